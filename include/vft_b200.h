@@ -1,0 +1,202 @@
+/*
+ * vft_b200.h -- C-ABI of the B200-native hot path of VeryFastTree's neighbour-joining phase.
+ *
+ * This is the drop-in boundary.  The reference's only plug-in seam is the
+ * per-element `Operations<Precision>` policy (src/operations/BasicOperations.h:16-39), whose
+ * calls are 4..20 elements wide; a GPU cannot live behind that seam (the reference's own
+ * CudaOperations.cu proves it).  The seam therefore moves one level up, to the loops of
+ * NeighbourJoining.tcc that *call* those primitives.  Every entry point below replaces one
+ * such loop and cites it; `veryfasttree_b200/csrc/B200Operations.h` is the C++ backend class a
+ * maintainer registers next to AVX256Operations, and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types cross this boundary;
+ *   - every function returns 0 on success, a negative VFT_E* code otherwise
+ *     (vft_last_error() gives the message; the C++ shim turns it into std::invalid_argument,
+ *     which main.cpp:673-678 reports and exits 1);
+ *   - buffers typed `void*` hold `float` when cfg.precision==32 and `double` when ==64
+ *     (the reference's `numeric_t`);
+ *   - node ids are the reference's: leaves 0..nSeqs-1, internal nodes nSeqs..2*nSeqs-1
+ *     (NeighbourJoining.tcc:229-231); codes are 0..nCodes-1, VFT_NOCODE for gap/unknown
+ *     (TransitionMatrix.h:7, NeighbourJoining.tcc:425,449-452);
+ *   - all calls on one context are serialised by the caller (the batch *replaces* the
+ *     reference's `omp for`); the library runs them on one CUDA stream per context.
+ *
+ * Arithmetic contract: results are bit-identical to the reference's "-mavx2" (no FMA)
+ * build run with `-threads 1` -- same expression types (P vs double), same evaluation order,
+ * same lane order in the P-typed dot products (AVX256Operations.tcc:5-26,58-138).
+ */
+#ifndef VFT_B200_H
+#define VFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFT_NOCODE 127          /* TransitionMatrix.h:7 */
+#define VFT_MAXCODES 20         /* DistanceMatrix.h:6   */
+
+#define VFT_OK            0
+#define VFT_EINVAL       -1     /* bad argument / precondition violated */
+#define VFT_ENODEVICE    -2     /* no usable CUDA device (never falls back to the CPU) */
+#define VFT_ECUDA        -3     /* CUDA runtime error */
+#define VFT_ENOMEM       -4
+
+/* lane order of the P-typed reductions (vector_multiply_sum / vector_multiply3_sum) */
+#define VFT_REDUCE_SCALAR 0     /* BasicOperations.tcc:17-41 : left to right            */
+#define VFT_REDUCE_AVX2   1     /* AVX256Operations.tcc:5-26 : lane accumulators + hadd */
+
+typedef struct vft_ctx vft_ctx;
+
+typedef struct vft_config {
+    int64_t nSeqs;              /* unique sequences (NeighbourJoining ctor, NJ.tcc:220)      */
+    int64_t nPos;               /* alignment columns                                          */
+    int32_t nCodes;             /* 4 (nt) or 20 (aa), Options.h:43                            */
+    int32_t precision;          /* 32 or 64 = sizeof(numeric_t)*8 (-double-precision)         */
+    int32_t useMatrix;          /* Options.useMatrix: 0 => %different (nt default,
+                                   VeryFastTree.cpp:96-98), 1 => tables from vft_upload_tables */
+    int32_t reduction;          /* VFT_REDUCE_*                                               */
+    int32_t device;             /* CUDA ordinal                                               */
+    int32_t reserved;
+    double  fPostTotalTolerance;/* Options.fPostTotalTolerance (Constants.h:37-38)            */
+} vft_config;
+
+/* -- life cycle: replaces CudaOperations() ctor / configCuda (CudaOperations.cu:169-175) ---- */
+int  vft_ctx_create(const vft_config *cfg, vft_ctx **out);
+int  vft_ctx_destroy(vft_ctx *ctx);
+const char *vft_last_error(void);
+/* name of the implementation behind this ABI: "cuda-sm100a" for the product library,
+   "oracle-cpu" for the test-only restatement under oracle/ */
+const char *vft_backend_name(void);
+
+/* -- model tables: after DistanceMatrix::setupDistanceMatrix (DistanceMatrix.tcc:102-153) -- */
+/* distances[20][20], eigenval[20], eigentot[20], codeFreq[20][20] (row = code, first nCodes
+   columns used; the reference pads rows to S, the padding is not part of the contract) */
+int  vft_upload_tables(vft_ctx *ctx, const void *distances, const void *eigenval,
+                       const void *eigentot, const void *codeFreq);
+
+/* -- leaves: end of seqsToProfiles (NJ.tcc:382-534) ----------------------------------------- */
+/* codes[nSeqs][nPos]; sets weights {0,1}, selfweight = nPos-nGaps (NJ.tcc:249-252), marks all
+   leaves active, no internal nodes */
+int  vft_upload_leaves(vft_ctx *ctx, const uint8_t *codes);
+
+/* -- out-profile: outProfile (NJ.tcc:729-815) / updateOutProfile (NJ.tcc:943-1010) ---------- */
+/* mean profile of the `n` nodes `ids` (ascending id order = the reference's accumulation order);
+   ids==NULL => all currently active nodes.  Also recomputes codeDist (setCodeDist, :873-898). */
+int  vft_outprofile_rebuild(vft_ctx *ctx, const int64_t *ids, int64_t n);
+int  vft_outprofile_update(vft_ctx *ctx, int64_t old1, int64_t old2, int64_t newnode,
+                           int64_t nActiveOld);
+
+/* -- join: averageProfile (NJ.tcc:2067-2135) + the self-distance at NJ.tcc:3040-3043 -------- */
+/* writes profile `out_id` = bionjWeight*id1 + (1-bionjWeight)*id2 (bionjWeight<0 => 0.5),
+   records diameter[out_id], marks id1,id2 inactive (parent set, NJ.tcc:2905-2906) and out_id
+   active, computes selfdist/selfweight[out_id] = profileDist(out,out). */
+int  vft_profile_average(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2,
+                         double bionjWeight, double diameter_out);
+int  vft_get_self(vft_ctx *ctx, int64_t id, double *selfdist, double *selfweight);
+
+/* -- out-distances: setOutDistance (NJ.tcc:1012-1053) --------------------------------------- */
+/* fresh value for each ids[k] at this nActive/totdiam against the current out-profile.
+   Pure: does not touch the context's own out-distance table (the caller decides what to commit,
+   mirroring the reference's lazy refresh, NJ.tcc:1092-1098). */
+int  vft_out_distance_batch(vft_ctx *ctx, const int64_t *ids, int64_t n, int64_t nActive,
+                            double totdiam, void *outDist);
+/* the loops NJ.tcc:257-260 / :4451-4464 / :3050-3055: every active node, committed to the
+   context's table (consumed by vft_dist_one_vs_all).  outDist[maxnode]: entries of inactive
+   nodes are left untouched. */
+int  vft_out_distance_all(vft_ctx *ctx, int64_t nActive, double totdiam, void *outDist,
+                          int64_t maxnode);
+
+/* -- candidate lists: the distance half of setDistCriterion (NJ.tcc:1115-1122) as called from
+      transferBestHits :4585-4612, uniqueBestHits :4823-4831, getBestFromTopHits :4287-4295 --- */
+/* per pair: leaf x leaf -> seqDist (NJ.tcc:1601-1624); else profileDist (NJ.tcc:1167-1190)
+   minus diameter[i]+diameter[j] (P arithmetic, :1120).  No criterion: the caller owns the lazy
+   out-distance state that setCriterion needs. */
+#define VFT_PAIRS_JOIN        0   /* setDistCriterion semantics as described above            */
+#define VFT_PAIRS_PROFILE_RAW 1   /* bare profileDist (NJ.tcc:1167-1190): no leaf shortcut, no
+                                     diameter correction -- the calls at NJ.tcc:3125-3127, :2945 */
+int  vft_dist_pairs(vft_ctx *ctx, const int64_t *i, const int64_t *j, int64_t n, int32_t flags,
+                    void *dist, void *weight);
+
+/* -- one-vs-all: setBestHit (NJ.tcc:3571-3639) + the psort/top-2m cut that always follows it
+      (NJ.tcc:3930, :4471-4472) --------------------------------------------------------------- */
+/* query vs every active node j < maxnode (self included, as the reference does), criterion
+   from the committed out-distance table (precondition: vft_out_distance_all at this nActive, or
+   the initial leaf state), then the K best in the order the reference's psort leaves them:
+   criterion ascending, ties by j DESCENDING (oracle/psort_probe.cpp).  *nOut = min(K, nActive).
+   Inactive nodes are not returned: their sentinel entries (NJ.tcc:3613-3617) sort after every
+   active entry and can be appended by the caller. */
+int  vft_dist_one_vs_all(vft_ctx *ctx, int64_t query, int64_t nActive, int64_t K,
+                         int64_t *j_out, void *dist, void *weight, void *criterion,
+                         int64_t *nOut);
+
+/* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
+      vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
+int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);
+
+/* running totals of work done through this context (feeds roofline accounting, Debug.h:12-15) */
+typedef struct vft_counters {
+    int64_t seqOps;          /* leaf x leaf distances                    */
+    int64_t profileOps;      /* profile distances (incl. out-profile)    */
+    int64_t outprofileOps;   /* of which vs the out-profile              */
+    int64_t profileAvgOps;   /* averageProfile calls                     */
+    int64_t launches;        /* kernels launched (0 for the CPU oracle)  */
+    int64_t algoBytes;       /* algorithmic bytes touched by the distance kernels */
+} vft_counters;
+int  vft_get_counters(vft_ctx *ctx, vft_counters *out);
+
+
+/* ============================================================================================
+ * Caller level (SURVEY.md §8 "next": the code either side of the kernels).
+ * vft_nj_build runs the whole metric phase -- NeighbourJoining ctor tail (NJ.tcc:237-260) +
+ * fastNJ() with the top-hits heuristic (NJ.tcc:2796-3155, :3746-4833) -- as a host-side batch
+ * producer over the entry points above (veryfasttree_b200/csrc/nj_host.cpp).  The join order,
+ * top-hit lists and branch lengths are those of the reference run with `-threads 1`.
+ * ==========================================================================================*/
+typedef struct vft_nj_options {
+    double  tophitsMult;        /* Options.h:20  (1.0)  */
+    double  tophitsClose;       /* Options.h:22  (-1.0 => log2(N)/(log2(N)+2), NJ.tcc:3747-3755) */
+    double  topvisibleMult;     /* Options.h:25  (1.5)  */
+    double  tophitsRefresh;     /* Options.h:28  (0.8)  */
+    double  staleOutLimit;      /* Options.h:36  (0.01) */
+    double  fResetOutProfile;   /* Options.h:38  (0.02) */
+    int32_t nResetOutProfile;   /* Options.h:40  (200)  */
+    int32_t bionj;              /* Options.h:18  (0)    */
+    int32_t prefetch;           /* 1 = batch the lazily refreshed out-distances / pair distances
+                                   ahead of the host loops (default); 0 = fetch one at a time
+                                   (same results, used by the tests to prove the prefetch is only
+                                   a hint) */
+    int32_t reserved;
+} vft_nj_options;
+
+void vft_nj_default_options(vft_nj_options *opt);
+
+typedef struct vft_nj_result {
+    /* caller-allocated, maxnodes = 2*nSeqs entries each (NJ.h:294-299) */
+    int64_t *parent;            /* -1 for the root                                  */
+    int32_t *nChild;
+    int64_t *child;             /* [maxnodes*3]                                     */
+    void    *branchlength;      /* P[maxnodes]                                      */
+    /* optional traces for parity checks (NULL to skip) */
+    int64_t *joins;             /* [(nSeqs-3)*2]  (i,j) of every join, in order     */
+    int64_t *leafTopHits;       /* [nSeqs*m]      top-hit list of every leaf after
+                                   setAllLeafTopHits (NJ.tcc:3746-4124), -1 padded  */
+    /* filled in */
+    int64_t root, maxnode, m;
+    int64_t nSeeds, nCloseUsed, nRefreshTopHits, nVisibleUpdate, nHillBetter;
+    int64_t nOutPrefetchHit, nOutSingleFetch, nPairPrefetchHit, nPairSingleFetch, nDeviceCalls;
+    double  secondsLeafTopHits, secondsJoins, secondsTotal;
+    vft_counters counters;
+} vft_nj_result;
+
+/* codes[nSeqs][nPos] as for vft_upload_leaves; tables==NULL unless cfg->useMatrix, else the four
+   arrays of vft_upload_tables in that order. */
+int  vft_nj_build(const vft_config *cfg, const vft_nj_options *opt, const uint8_t *codes,
+                  const void *const tables[4], vft_nj_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFT_B200_H */

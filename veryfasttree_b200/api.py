@@ -1,0 +1,323 @@
+"""ctypes binding of the C-ABI in include/vft_b200.h (plumbing only; the product is the library).
+
+`load()` opens the CUDA product library (veryfasttree_b200/lib/libvft_b200.so) and fails loudly
+when it is missing or when no CUDA device is usable -- there is no CPU fallback on this path.
+Tests may pass an explicit path (the test-only CPU double built under oracle/) to exercise the
+host logic on a box without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+NOCODE = 127
+HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(HERE, "lib", "libvft_b200.so")
+
+CODES_NT = "ACGT"                      # /root/reference/src/Constants.h:51
+CODES_AA = "ARNDCQEGHILKMFPSTWYV"      # /root/reference/src/Constants.h:50
+
+
+class VftConfig(C.Structure):
+    _fields_ = [("nSeqs", C.c_int64), ("nPos", C.c_int64), ("nCodes", C.c_int32),
+                ("precision", C.c_int32), ("useMatrix", C.c_int32), ("reduction", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32), ("fPostTotalTolerance", C.c_double)]
+
+
+class VftCounters(C.Structure):
+    _fields_ = [("seqOps", C.c_int64), ("profileOps", C.c_int64), ("outprofileOps", C.c_int64),
+                ("profileAvgOps", C.c_int64), ("launches", C.c_int64), ("algoBytes", C.c_int64)]
+
+
+class VftNjOptions(C.Structure):
+    _fields_ = [("tophitsMult", C.c_double), ("tophitsClose", C.c_double), ("topvisibleMult", C.c_double),
+                ("tophitsRefresh", C.c_double), ("staleOutLimit", C.c_double), ("fResetOutProfile", C.c_double),
+                ("nResetOutProfile", C.c_int32), ("bionj", C.c_int32), ("prefetch", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class VftNjResult(C.Structure):
+    _fields_ = [("parent", C.c_void_p), ("nChild", C.c_void_p), ("child", C.c_void_p),
+                ("branchlength", C.c_void_p), ("joins", C.c_void_p), ("leafTopHits", C.c_void_p),
+                ("root", C.c_int64), ("maxnode", C.c_int64), ("m", C.c_int64),
+                ("nSeeds", C.c_int64), ("nCloseUsed", C.c_int64), ("nRefreshTopHits", C.c_int64),
+                ("nVisibleUpdate", C.c_int64), ("nHillBetter", C.c_int64),
+                ("nOutPrefetchHit", C.c_int64), ("nOutSingleFetch", C.c_int64),
+                ("nPairPrefetchHit", C.c_int64), ("nPairSingleFetch", C.c_int64), ("nDeviceCalls", C.c_int64),
+                ("secondsLeafTopHits", C.c_double), ("secondsJoins", C.c_double), ("secondsTotal", C.c_double),
+                ("counters", VftCounters)]
+
+
+ABI_SYMBOLS = [
+    "vft_ctx_create", "vft_ctx_destroy", "vft_last_error", "vft_backend_name", "vft_upload_tables",
+    "vft_upload_leaves", "vft_outprofile_rebuild", "vft_outprofile_update", "vft_profile_average",
+    "vft_get_self", "vft_out_distance_batch", "vft_out_distance_all", "vft_dist_pairs",
+    "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
+]
+
+
+class VftError(RuntimeError):
+    pass
+
+
+class Lib:
+    """One loaded implementation of the ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise VftError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                           " (there is no CPU fallback for the CUDA path)")
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        d.vft_last_error.restype = C.c_char_p
+        d.vft_backend_name.restype = C.c_char_p
+        d.vft_ctx_create.argtypes = [C.POINTER(VftConfig), C.POINTER(vp)]
+        d.vft_ctx_destroy.argtypes = [vp]
+        d.vft_upload_tables.argtypes = [vp, vp, vp, vp, vp]
+        d.vft_upload_leaves.argtypes = [vp, vp]
+        d.vft_outprofile_rebuild.argtypes = [vp, vp, i64]
+        d.vft_outprofile_update.argtypes = [vp, i64, i64, i64, i64]
+        d.vft_profile_average.argtypes = [vp, i64, i64, i64, dbl, dbl]
+        d.vft_get_self.argtypes = [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]
+        d.vft_out_distance_batch.argtypes = [vp, vp, i64, i64, dbl, vp]
+        d.vft_out_distance_all.argtypes = [vp, i64, dbl, vp, i64]
+        d.vft_dist_pairs.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+        d.vft_dist_one_vs_all.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
+        d.vft_get_profile.argtypes = [vp, i64, vp, vp, vp]
+        d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
+        d.vft_nj_default_options.argtypes = [C.POINTER(VftNjOptions)]
+        d.vft_nj_build.argtypes = [C.POINTER(VftConfig), C.POINTER(VftNjOptions), vp, vp, C.POINTER(VftNjResult)]
+
+    @property
+    def backend(self) -> str:
+        return self.dll.vft_backend_name().decode()
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise VftError(f"{what} failed ({rc}): {self.dll.vft_last_error().decode()}")
+
+
+_product = None
+
+
+def load(path: str | None = None) -> Lib:
+    """The product library unless a test passes an explicit path."""
+    global _product
+    if path is not None:
+        return Lib(path)
+    if _product is None:
+        _product = Lib(PRODUCT_LIB)
+        if _product.backend != "cuda-sm100a":
+            raise VftError("product library reports backend %r" % _product.backend)
+    return _product
+
+
+def encode(chars: np.ndarray, kind: str) -> np.ndarray:
+    """ASCII alignment -> codes, as the reference does it: '.'->'-', U->T for nt
+    (Alignment.cpp:455-473), letters by position in codesString, everything else NOCODE
+    (NeighbourJoining.tcc:415-457)."""
+    lut = np.full(256, NOCODE, dtype=np.uint8)
+    alphabet = CODES_NT if kind == "nt" else CODES_AA
+    for k, ch in enumerate(alphabet):
+        lut[ord(ch)] = k
+        lut[ord(ch.lower())] = k
+    if kind == "nt":
+        lut[ord("U")] = lut[ord("T")]
+        lut[ord("u")] = lut[ord("T")]
+    return np.ascontiguousarray(lut[chars])
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def np_dtype(precision: int):
+    return np.float32 if precision == 32 else np.float64
+
+
+def make_config(n_seqs, n_pos, n_codes, precision, use_matrix=False, reduction=1, device=0) -> VftConfig:
+    tol = 1.0e-10 if precision == 32 else 1.0e-20     # Constants.h:37-38
+    return VftConfig(n_seqs, n_pos, n_codes, precision, int(use_matrix), reduction, device, 0, tol)
+
+
+class Context:
+    """Thin RAII wrapper over vft_ctx for kernel-level calls (tests, smoke, bench)."""
+
+    def __init__(self, lib: Lib, cfg: VftConfig):
+        self.lib, self.cfg = lib, cfg
+        self.h = C.c_void_p()
+        lib.check(lib.dll.vft_ctx_create(C.byref(cfg), C.byref(self.h)), "vft_ctx_create")
+        self.dt = np_dtype(cfg.precision)
+        self.M = 2 * cfg.nSeqs
+
+    def close(self):
+        if self.h:
+            self.lib.dll.vft_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload_tables(self, distances, eigenval, eigentot, code_freq):
+        arrs = [np.ascontiguousarray(x, dtype=self.dt) for x in (distances, eigenval, eigentot, code_freq)]
+        self.lib.check(self.lib.dll.vft_upload_tables(self.h, *[_ptr(a) for a in arrs]), "vft_upload_tables")
+
+    def upload_leaves(self, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        assert codes.shape == (self.cfg.nSeqs, self.cfg.nPos)
+        self.lib.check(self.lib.dll.vft_upload_leaves(self.h, _ptr(codes)), "vft_upload_leaves")
+
+    def outprofile_rebuild(self, ids=None):
+        if ids is None:
+            rc = self.lib.dll.vft_outprofile_rebuild(self.h, None, 0)
+        else:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            rc = self.lib.dll.vft_outprofile_rebuild(self.h, _ptr(ids), len(ids))
+        self.lib.check(rc, "vft_outprofile_rebuild")
+
+    def outprofile_update(self, old1, old2, new, n_active_old):
+        self.lib.check(self.lib.dll.vft_outprofile_update(self.h, old1, old2, new, n_active_old),
+                       "vft_outprofile_update")
+
+    def profile_average(self, out_id, id1, id2, bionj_weight=-1.0, diameter=0.0):
+        self.lib.check(self.lib.dll.vft_profile_average(self.h, out_id, id1, id2, bionj_weight, diameter),
+                       "vft_profile_average")
+
+    def get_self(self, node):
+        d, w = C.c_double(), C.c_double()
+        self.lib.check(self.lib.dll.vft_get_self(self.h, node, C.byref(d), C.byref(w)), "vft_get_self")
+        return d.value, w.value
+
+    def out_distance_batch(self, ids, n_active, totdiam):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty(len(ids), dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_out_distance_batch(self.h, _ptr(ids), len(ids), n_active, totdiam, _ptr(out)),
+                       "vft_out_distance_batch")
+        return out
+
+    def out_distance_all(self, n_active, totdiam):
+        out = np.zeros(self.M, dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_out_distance_all(self.h, n_active, totdiam, _ptr(out), self.M),
+                       "vft_out_distance_all")
+        return out
+
+    def dist_pairs(self, i, j, flags=0):
+        i = np.ascontiguousarray(i, dtype=np.int64)
+        j = np.ascontiguousarray(j, dtype=np.int64)
+        d = np.empty(len(i), dtype=self.dt)
+        w = np.empty(len(i), dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_dist_pairs(self.h, _ptr(i), _ptr(j), len(i), flags, _ptr(d), _ptr(w)),
+                       "vft_dist_pairs")
+        return d, w
+
+    def dist_one_vs_all(self, query, n_active, k):
+        j = np.empty(k, dtype=np.int64)
+        d = np.empty(k, dtype=self.dt)
+        w = np.empty(k, dtype=self.dt)
+        c = np.empty(k, dtype=self.dt)
+        n = C.c_int64()
+        self.lib.check(self.lib.dll.vft_dist_one_vs_all(self.h, query, n_active, k, _ptr(j), _ptr(d), _ptr(w),
+                                                        _ptr(c), C.byref(n)), "vft_dist_one_vs_all")
+        n = n.value
+        return j[:n], d[:n], w[:n], c[:n]
+
+    def get_profile(self, node):
+        L, A = self.cfg.nPos, self.cfg.nCodes
+        w = np.empty(L, dtype=self.dt)
+        cd = np.empty(L, dtype=np.uint8)
+        v = np.empty((L, A), dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_get_profile(self.h, node, _ptr(w), _ptr(cd), _ptr(v)), "vft_get_profile")
+        return w, cd, v
+
+    def counters(self) -> VftCounters:
+        c = VftCounters()
+        self.lib.check(self.lib.dll.vft_get_counters(self.h, C.byref(c)), "vft_get_counters")
+        return c
+
+
+@dataclass
+class NJTree:
+    n_seqs: int
+    precision: int
+    parent: np.ndarray
+    n_child: np.ndarray
+    child: np.ndarray
+    branchlength: np.ndarray
+    root: int
+    maxnode: int
+    m: int
+    joins: np.ndarray
+    leaf_top_hits: np.ndarray
+    stats: dict = field(default_factory=dict)
+
+    def newick(self, names) -> str:
+        """printNJ (NeighbourJoining.tcc:2706-2794) for an all-unique alignment."""
+        fmt = "%.5f" if self.precision == 32 else "%.9f"
+        out = []
+        stack = [(self.root, 0)]
+        while stack:
+            node, end = stack.pop()
+            if node < self.n_seqs:
+                if self.child[self.parent[node], 0] != node:
+                    out.append(",")
+                out.append(names[node])
+                out.append(":" + fmt % float(self.branchlength[node]))
+            elif end:
+                if node == self.root:
+                    out.append(")")
+                else:
+                    out.append("):" + fmt % float(self.branchlength[node]))
+            else:
+                if node != self.root and self.child[self.parent[node], 0] != node:
+                    out.append(",")
+                out.append("(")
+                stack.append((node, 1))
+                for k in range(int(self.n_child[node]) - 1, -1, -1):
+                    stack.append((int(self.child[node, k]), 0))
+        out.append(";")
+        return "".join(out)
+
+
+def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | None = None,
+             tables=None, device: int = 0, prefetch: bool = True, trace: bool = True,
+             reduction: int = 1) -> NJTree:
+    """The metric phase (NJ ctor tail + fastNJ) through vft_nj_build with HOST buffers."""
+    lib = lib or load()
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, L = codes.shape
+    dt = np_dtype(precision)
+    cfg = make_config(n, L, n_codes, precision, use_matrix=tables is not None, reduction=reduction, device=device)
+    opt = VftNjOptions()
+    lib.dll.vft_nj_default_options(C.byref(opt))
+    opt.prefetch = int(prefetch)
+    M = 2 * n
+    parent = np.full(M, -1, dtype=np.int64)
+    n_child = np.zeros(M, dtype=np.int32)
+    child = np.full((M, 3), -1, dtype=np.int64)
+    bl = np.zeros(M, dtype=dt)
+    m = int(0.5 + np.sqrt(n))
+    joins = np.full((max(n - 3, 0), 2), -1, dtype=np.int64) if trace else None
+    lth = np.full((n, max(m, 1)), -1, dtype=np.int64) if trace else None
+    res = VftNjResult()
+    res.parent, res.nChild, res.child, res.branchlength = _ptr(parent), _ptr(n_child), _ptr(child), _ptr(bl)
+    res.joins, res.leafTopHits = _ptr(joins), _ptr(lth)
+    tptr = None
+    keep = None
+    if tables is not None:
+        keep = [np.ascontiguousarray(t, dtype=dt) for t in tables]
+        arr = (C.c_void_p * 4)(*[t.ctypes.data for t in keep])
+        tptr = C.cast(arr, C.c_void_p)
+    rc = lib.dll.vft_nj_build(C.byref(cfg), C.byref(opt), _ptr(codes), tptr, C.byref(res))
+    lib.check(rc, "vft_nj_build")
+    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:22]}
+    stats.update({"counters": {k: getattr(res.counters, k) for k, _ in VftCounters._fields_}})
+    return NJTree(n, precision, parent, n_child, child, bl, res.root, res.maxnode, res.m,
+                  joins, lth, stats)

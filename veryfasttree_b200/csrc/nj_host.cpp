@@ -1,0 +1,985 @@
+// nj_host.cpp -- host-side caller of the B200 hot path: the NJ + TopHits phase.
+//
+// This is the code "either side of the kernels" (SURVEY.md §8): the reference's
+// NeighbourJoining ctor tail (NeighbourJoining.tcc:237-260) and fastNJ() with the top-hits
+// heuristic (NJ.tcc:2796-3155, :3746-4833), written from scratch as a *batch producer* for the
+// C-ABI in include/vft_b200.h.  The reference evaluates one pair at a time from inside OpenMP
+// loops and refreshes out-distances lazily from inside setCriterion; here every host loop is
+// preceded by a pre-scan that collects the pair distances and out-distances it can possibly
+// need, fetches them in ONE device call, and then replays the reference's decisions from the
+// fetched values.  The prefetch is only a hint: a value that was not prefetched is fetched on
+// demand (counted in nOutSingleFetch / nPairSingleFetch), so the decisions -- and therefore the
+// join order, the top-hit lists and the tree -- are exactly those of the reference at
+// `-threads 1`, whatever the hints are.
+//
+// Orderings: the reference sorts with non-strict comparators (NJ.tcc:7285-7311) through
+// boost's spinsort; oracle/psort_probe.cpp shows the outcome is always "key ascending, ties in
+// REVERSE input order".  rsort() below reproduces exactly that.
+//
+// Not supported (rejected with VFT_EINVAL, documented in DESIGN.md): -fastest / 2nd-level top
+// hits, topological constraints, -slow.
+#include "../../include/vft_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct Children { int nChild = 0; int64_t child[3] = {-1, -1, -1}; };
+
+// "key ascending, ties in reverse input order" == psort() with the reference's comparators
+template<class T, class Less>
+void rsort(std::vector<T> &v, Less strictLess) {
+    std::reverse(v.begin(), v.end());
+    std::stable_sort(v.begin(), v.end(), strictLess);
+}
+
+struct DeviceError { int code; };
+
+template<typename P>
+class NJ {
+public:
+    struct Hit { int64_t j; P dist; };                             // NJ.h:214-217
+    struct Besthit { int64_t i, j; P weight, dist, criterion; };   // NJ.h:192-200
+    struct TopHitsList { std::vector<Hit> hits; int64_t hitSource = -1; int64_t age = 0; };
+
+    NJ(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, vft_nj_result *res, const uint8_t *codes)
+            : ctx(ctx), cfg(cfg), opt(opt), res(res), nSeqs(cfg.nSeqs), nPos(cfg.nPos) {
+        maxnodes = 2 * nSeqs;
+        maxnode = nSeqs;
+        parent.assign(maxnodes, -1);
+        child.resize(maxnodes);
+        branchlength.assign(maxnodes, 0);
+        diameter.assign(maxnodes, 0);
+        varDiameter.assign(maxnodes, 0);
+        outDistances.assign(maxnodes, 0);
+        nOutDistActive.assign(maxnodes, nSeqs * 10);
+        freshVal.assign(maxnodes, 0);
+        freshEpoch.assign(maxnodes, -1);
+        wantEpoch.assign(maxnodes, -1);
+        // nGaps(i) = nPos - selfweight[i] (NJ.tcc:249-252, :3762): gap/unknown columns of leaf i
+        leafGaps.assign(nSeqs, 0);
+        for (int64_t i = 0; i < nSeqs; i++) {
+            int64_t g = 0;
+            for (int64_t p = 0; p < nPos; p++) g += codes[i * nPos + p] >= cfg.nCodes;
+            leafGaps[i] = g;
+        }
+    }
+
+    // ---- NeighbourJoining ctor tail, NJ.tcc:237-260 ------------------------------------------
+    void init() {
+        check(vft_outprofile_rebuild(ctx, nullptr, nSeqs));
+        totdiam = 0.0;
+        std::vector<P> od(maxnodes);
+        check(vft_out_distance_all(ctx, nSeqs, totdiam, od.data(), maxnodes));
+        for (int64_t i = 0; i < nSeqs; i++) { outDistances[i] = od[i]; nOutDistActive[i] = nSeqs; }
+        newEpoch(nSeqs);
+    }
+
+    void fastNJ();                       // NJ.tcc:2796-3155
+
+    int64_t root = -1;
+    int64_t maxnode;
+    std::vector<int64_t> parent;
+    std::vector<Children> child;
+    std::vector<P> branchlength;
+
+private:
+    vft_ctx *ctx;
+    vft_config cfg;
+    vft_nj_options opt;
+    vft_nj_result *res;
+    int64_t nSeqs, nPos, maxnodes;
+    std::vector<P> diameter, varDiameter, outDistances;
+    std::vector<int64_t> nOutDistActive;
+    double totdiam = 0;
+
+    // top-hits state, NJ.h:225-248
+    int64_t m = 0;
+    std::vector<TopHitsList> topHitsLists;
+    std::vector<Hit> visible;
+    std::vector<int64_t> topvisible;
+    int64_t topvisibleAge = 0;
+
+    void check(int rc) { res->nDeviceCalls++; if (rc != VFT_OK) throw DeviceError{rc}; }
+
+    // ---- fresh out-distance service ------------------------------------------------------------
+    // A fresh value is a pure function of (node, out-profile, nActive, totdiam); all three are
+    // fixed between two joins = one "epoch".
+    int64_t epoch = 0, epochActive = 0;
+    std::vector<P> freshVal;
+    std::vector<int64_t> freshEpoch, wantEpoch, leafGaps;
+    std::vector<int64_t> wantIds;
+    std::vector<P> wantVals;
+
+    void newEpoch(int64_t nActive) { epoch++; epochActive = nActive; pairCache.clear(); }
+
+    bool stale(int64_t i, int64_t nActive) const {       // trigger of NJ.tcc:1092-1098
+        int64_t nDiffAllow = opt.tophitsMult > 0 ? (int64_t) (nActive * opt.staleOutLimit) : 0;
+        return nOutDistActive[i] - nActive > nDiffAllow;
+    }
+
+    // hint: these nodes may get setOutDistance(.., nActive) soon
+    void wantOut(int64_t i, int64_t nActive, bool evenIfNotStale = false) {
+        if (!opt.prefetch || i < 0 || parent[i] >= 0) return;
+        if (nOutDistActive[i] == nActive || freshEpoch[i] == epoch || wantEpoch[i] == epoch) return;
+        if (!evenIfNotStale && !stale(i, nActive)) return;
+        wantEpoch[i] = epoch;             // queued; becomes valid (freshEpoch) in flushOut
+        wantIds.push_back(i);
+    }
+
+    void flushOut(int64_t nActive) {
+        if (wantIds.empty()) return;
+        wantVals.resize(wantIds.size());
+        check(vft_out_distance_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data()));
+        for (size_t k = 0; k < wantIds.size(); k++) { freshVal[wantIds[k]] = wantVals[k]; freshEpoch[wantIds[k]] = epoch; }
+        wantIds.clear();
+    }
+
+    // setOutDistance, NJ.tcc:1012-1053 (the arithmetic lives behind vft_out_distance_batch)
+    void setOutDistance(int64_t i, int64_t nActive) {
+        if (nOutDistActive[i] == nActive) return;
+        if (freshEpoch[i] == epoch && epochActive == nActive) {
+            res->nOutPrefetchHit++;
+        } else {
+            P v;
+            check(vft_out_distance_batch(ctx, &i, 1, nActive, totdiam, &v));
+            freshVal[i] = v;
+            if (epochActive == nActive) freshEpoch[i] = epoch;
+            res->nOutSingleFetch++;
+        }
+        outDistances[i] = freshVal[i];
+        nOutDistActive[i] = nActive;
+    }
+
+    // ---- pair distance service (distance half of setDistCriterion, NJ.tcc:1115-1122) -----------
+    struct DW { P dist, weight; };
+    std::unordered_map<uint64_t, DW> pairCache;
+    std::vector<int64_t> reqI, reqJ;
+    std::vector<P> reqD, reqW;
+
+    uint64_t pkey(int64_t i, int64_t j) const { return (uint64_t) i * (uint64_t) maxnodes + (uint64_t) j; }
+
+    void wantPair(int64_t i, int64_t j) {
+        if (!opt.prefetch) return;
+        if (pairCache.find(pkey(i, j)) != pairCache.end()) return;
+        pairCache[pkey(i, j)] = DW{0, -1};          // weight -1 marks "requested"
+        reqI.push_back(i); reqJ.push_back(j);
+    }
+
+    void flushPairs() {
+        if (reqI.empty()) return;
+        reqD.resize(reqI.size()); reqW.resize(reqI.size());
+        check(vft_dist_pairs(ctx, reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()));
+        for (size_t k = 0; k < reqI.size(); k++) pairCache[pkey(reqI[k], reqJ[k])] = DW{reqD[k], reqW[k]};
+        reqI.clear(); reqJ.clear();
+    }
+
+    DW pairDist(int64_t i, int64_t j) {
+        auto it = pairCache.find(pkey(i, j));
+        if (it != pairCache.end() && it->second.weight >= 0) { res->nPairPrefetchHit++; return it->second; }
+        DW r;
+        check(vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight));
+        res->nPairSingleFetch++;
+        return r;
+    }
+
+    // ---- criterion ------------------------------------------------------------------------------
+    // setCriterion, NJ.tcc:1085-1113
+    void setCriterion(int64_t nActive, Besthit &join) {
+        if (join.i < 0 || join.j < 0 || parent[join.i] >= 0 || parent[join.j] >= 0) return;
+        if (stale(join.i, nActive)) setOutDistance(join.i, nActive);
+        if (stale(join.j, nActive)) setOutDistance(join.j, nActive);
+        double outI = outDistances[join.i];
+        if (nOutDistActive[join.i] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[join.i] - 1);
+        double outJ = outDistances[join.j];
+        if (nOutDistActive[join.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[join.j] - 1);
+        join.criterion = (P) (join.dist - (outI + outJ) / (double) (nActive - 2));
+    }
+
+    void hintCriterion(int64_t nActive, int64_t i, int64_t j) {
+        if (i < 0 || j < 0 || parent[i] >= 0 || parent[j] >= 0) return;
+        wantOut(i, nActive); wantOut(j, nActive);
+    }
+
+    // setDistCriterion, NJ.tcc:1115-1124
+    void setDistCriterion(int64_t nActive, Besthit &hit) {
+        DW r = pairDist(hit.i, hit.j);
+        hit.dist = r.dist; hit.weight = r.weight;
+        setCriterion(nActive, hit);
+    }
+
+    int64_t activeAncestor(int64_t i) const {           // NJ.tcc:536-544
+        if (i < 0) return i;
+        while (parent[i] >= 0) i = parent[i];
+        return i;
+    }
+
+    static void hitToBestHit(int64_t i, const Hit &hit, Besthit &out) {   // NJ.tcc:4627-4633
+        out.i = i; out.j = hit.j; out.dist = hit.dist; out.criterion = (P) 1e20; out.weight = -1;
+    }
+
+    void hitsToBestHits(const std::vector<Hit> &hits, int64_t iNode, Besthit *out) {   // NJ.tcc:4615-4625
+        for (size_t k = 0; k < hits.size(); k++) hitToBestHit(iNode, hits[k], out[k]);
+    }
+
+    // getVisible, NJ.tcc:546-557
+    bool getVisible(int64_t nActive, int64_t iNode, Besthit &v) {
+        if (iNode < 0 || parent[iNode] >= 0) return false;
+        const Hit &h = visible[iNode];
+        if (h.j < 0 || parent[h.j] >= 0) return false;
+        hitToBestHit(iNode, h, v);
+        setCriterion(nActive, v);
+        return true;
+    }
+
+    void hintVisible(int64_t nActive, int64_t iNode) {
+        if (iNode < 0 || parent[iNode] >= 0) return;
+        hintCriterion(nActive, iNode, visible[iNode].j);
+    }
+
+    // updateBestHit, NJ.tcc:1626-1648
+    bool updateBestHit(int64_t nActive, Besthit &hit, bool bUpdateDist) {
+        int64_t i = activeAncestor(hit.i), j = activeAncestor(hit.j);
+        if (i < 0 || j < 0 || i == j) {
+            hit.i = -1; hit.j = -1; hit.weight = 0; hit.dist = (P) 1e20; hit.criterion = (P) 1e20;
+            return false;
+        }
+        if (i != hit.i || j != hit.j) {
+            hit.i = i; hit.j = j;
+            if (bUpdateDist) setDistCriterion(nActive, hit);
+            else { hit.dist = (P) -1e20; hit.criterion = (P) 1e20; }
+        }
+        return true;
+    }
+
+    static void sortByCriterion(std::vector<Besthit> &v) {     // psort(.., CompareHitsByCriterion), NJ.tcc:7301-7306
+        rsort(v, [](const Besthit &a, const Besthit &b) { return a.criterion < b.criterion; });
+    }
+
+    void sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int64_t nIn, int64_t nOut, bool sort);
+    void transferBestHits(int64_t nActive, int64_t iNode, const std::vector<Besthit> &oldhits, int64_t nOldHits,
+                          Besthit *newhits, bool updateDistances);
+    void uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out);
+    void uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out);
+    void setAllLeafTopHits();
+    void resetTopVisible(int64_t nActive);
+    void updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit);
+    void updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode);
+    void topHitNJSearch(int64_t nActive, Besthit &join);
+    void getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin);
+    void topHitJoin(int64_t newnode, int64_t nActive);
+    int64_t oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<Besthit> &out);
+    void fastNJSearch(int64_t nActive, std::vector<Besthit> &besthits, Besthit &join);
+    void setBestHitFull(int64_t node, int64_t nActive, Besthit &bestjoin, std::vector<Besthit> *allhits);
+};
+
+// setBestHit + psort + cut, through the device (NJ.tcc:3571-3639, :3930, :4471).  Returns the
+// number of *active* entries; entries [n, K) are the inactive sentinels in psort order.
+template<typename P>
+int64_t NJ<P>::oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<Besthit> &out) {
+    std::vector<int64_t> js(K);
+    std::vector<P> d(K), w(K), c(K);
+    int64_t n = 0;
+    check(vft_dist_one_vs_all(ctx, query, nActive, K, js.data(), d.data(), w.data(), c.data(), &n));
+    out.resize(K);
+    for (int64_t k = 0; k < n; k++) out[k] = Besthit{query, js[k], w[k], d[k], c[k]};
+    // sentinels of inactive nodes (NJ.tcc:3613-3617): criterion 1e20 ties, later index first
+    int64_t k = n;
+    for (int64_t j = maxnode - 1; j >= 0 && k < K; j--)
+        if (parent[j] >= 0) out[k++] = Besthit{-1, j, 0, (P) 1e20, (P) 1e20};
+    out.resize(k);
+    return n;
+}
+
+// sortSaveBestHits, NJ.tcc:4535-4578
+template<typename P>
+void NJ<P>::sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int64_t nIn, int64_t nOut, bool sort) {
+    if (sort) sortByCriterion(besthits);
+    if (nIn > (int64_t) besthits.size()) nIn = (int64_t) besthits.size();
+    int64_t nSave = 0, jLast = -1;
+    for (int64_t k = 0; k < nIn && nSave < nOut; k++) {
+        if (besthits[k].i < 0) continue;
+        int64_t j = besthits[k].j;
+        if (j != iNode && j != jLast && j >= 0) { nSave++; jLast = j; }
+    }
+    TopHitsList &l = topHitsLists[iNode];
+    l.hits.resize(nSave);
+    int64_t iSave = 0;
+    jLast = -1;
+    for (int64_t k = 0; k < nIn && iSave < nSave; k++) {
+        int64_t j = besthits[k].j;
+        if (j != iNode && j != jLast && j >= 0) {
+            l.hits[iSave].j = j; l.hits[iSave].dist = besthits[k].dist;
+            iSave++; jLast = j;
+        }
+    }
+}
+
+// transferBestHits, NJ.tcc:4580-4613.  Distances come from the pair service (prefetched by caller).
+template<typename P>
+void NJ<P>::transferBestHits(int64_t nActive, int64_t iNode, const std::vector<Besthit> &oldhits, int64_t nOldHits,
+                             Besthit *newhits, bool updateDistances) {
+    for (int64_t k = 0; k < nOldHits; k++) {
+        const Besthit &oldhit = oldhits[k];
+        Besthit &nh = newhits[k];
+        nh.i = iNode;
+        nh.j = activeAncestor(oldhit.j);
+        nh.dist = oldhit.dist; nh.weight = oldhit.weight; nh.criterion = oldhit.criterion;
+        if (nh.j < 0 || nh.j == iNode) {
+            nh.weight = 0; nh.dist = (P) -1e20; nh.criterion = (P) 1e20;
+        } else if (nh.i != oldhit.i || nh.j != oldhit.j) {
+            if (updateDistances) setDistCriterion(nActive, nh);
+            else { nh.dist = (P) -1e20; nh.criterion = (P) 1e20; }
+        } else {
+            if (updateDistances) setCriterion(nActive, nh);
+            else nh.criterion = (P) 1e20;
+        }
+    }
+}
+
+// uniqueBestHits, NJ.tcc:4786-4833, split around the device call:
+//   prepare = ancestor walk + psort by (i,j) + dedupe; finish = distances + criteria
+template<typename P>
+void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out) {
+    for (auto &h : combined) updateBestHit(nActive, h, false);
+    rsort(combined, [](const Besthit &a, const Besthit &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    out.clear();
+    out.reserve(combined.size());
+    int64_t iSavedLast = -1;
+    for (int64_t k = 0; k < (int64_t) combined.size(); k++) {
+        const Besthit &hit = combined[k];
+        if (hit.i < 0 || hit.j < 0) continue;
+        if (iSavedLast >= 0) {
+            const Besthit &saved = combined[iSavedLast];
+            if (saved.i == hit.i && saved.j == hit.j) continue;
+        }
+        out.push_back(hit);
+        iSavedLast = k;
+    }
+    for (auto &h : out) {
+        if (h.dist < 0.0) wantPair(h.i, h.j);
+        hintCriterion(nActive, h.i, h.j);
+    }
+}
+
+template<typename P>
+void NJ<P>::uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out) {
+    for (auto &h : out) {
+        if (h.dist < 0.0) setDistCriterion(nActive, h);
+        else setCriterion(nActive, h);
+    }
+}
+
+// setAllLeafTopHits, NJ.tcc:3746-4124 (the `-threads 1` branch, :3884-4015, without 2nd-level lists)
+template<typename P>
+void NJ<P>::setAllLeafTopHits() {
+    double close = opt.tophitsClose;
+    if (close < 0) {
+        double logN = std::log((double) nSeqs) / std::log(2.0);
+        close = logN / (logN + 2.0);
+    }
+    const std::vector<int64_t> &nGaps = leafGaps;                        // :3759-3763
+    std::vector<int64_t> seeds(nSeqs);
+    for (int64_t i = 0; i < nSeqs; i++) seeds[i] = i;
+    // psort(seeds, CompareSeeds), NJ.tcc:3770, :7285-7299
+    rsort(seeds, [&](int64_t a, int64_t b) {
+        if (nGaps[a] != nGaps[b]) return nGaps[a] < nGaps[b];
+        return outDistances[a] < outDistances[b];
+    });
+
+    std::vector<char> visited(nSeqs, 0);
+    std::vector<Besthit> besthitsSeed, besthitsNeighbor(2 * m);
+    std::vector<int64_t> closeNodes;
+    for (int64_t iSeed = 0; iSeed < nSeqs; iSeed++) {
+        int64_t seed = seeds[iSeed];
+        if (visited[seed]) continue;
+        visited[seed] = 1;
+        res->nSeeds++;
+        oneVsAll(seed, nSeqs, 2 * m, besthitsSeed);                      // setBestHit + sort, :3927-3930
+        sortSaveBestHits(seed, besthitsSeed, (int64_t) besthitsSeed.size(), m, /*sort*/false);
+
+        double neardist = besthitsSeed[2 * m - 1].dist * close;          // :3934
+        double nearweight = 0;
+        for (int64_t k = 0; k < 2 * m; k++) nearweight += besthitsSeed[k].weight;
+        nearweight = nearweight / (2.0 * m);
+        nearweight *= (1.0 - 2.0 * neardist / 3.0);
+        double nearcover = 1.0 - neardist / 2.0;
+
+        // which of the top m are close neighbours (:3953-3966); each j occurs once, so the set is
+        // known before any transfer is done and all their 2m-candidate lists go in ONE device call
+        closeNodes.clear();
+        for (int64_t iClose = 0; iClose < m; iClose++) {
+            const Besthit &closehit = besthitsSeed[iClose];
+            int64_t closeNode = closehit.j;
+            if (visited[closeNode]) continue;
+            bool isClose = closehit.dist <= neardist
+                           && (closehit.weight >= nearweight || closehit.weight >= (nPos - nGaps[closeNode]) * nearcover);
+            bool identical = closehit.dist < 1e-6
+                             && std::fabs(closehit.weight - (nPos - nGaps[seed])) < 1e-5
+                             && std::fabs(closehit.weight - (nPos - nGaps[closeNode])) < 1e-5;
+            if (isClose || identical) { closeNodes.push_back(closeNode); visited[closeNode] = 1; }
+        }
+        if (opt.prefetch) {
+            for (int64_t closeNode : closeNodes)
+                for (int64_t k = 0; k < 2 * m; k++) {
+                    int64_t j = besthitsSeed[k].j;
+                    if (j >= 0 && j != closeNode) wantPair(closeNode, j);
+                }
+            flushPairs();
+        }
+        for (int64_t closeNode : closeNodes) {
+            res->nCloseUsed++;
+            besthitsNeighbor.resize(2 * m);
+            transferBestHits(nSeqs, closeNode, besthitsSeed, 2 * m, besthitsNeighbor.data(), true);   // :3988
+            sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                            // :3991
+        }
+        pairCache.clear();
+    }
+
+    for (int64_t i = 0; i < nSeqs; i++) visible[i] = topHitsLists[i].hits[0];       // :4037-4044
+
+    // checking phase, NJ.tcc:4052-4119 (criteria only; every out-distance is fresh here)
+    int64_t nCheck = (int64_t) (0.5 + 2.0 * std::sqrt((double) m));
+    for (int64_t iNode = 0; iNode < nSeqs; iNode++) {
+        TopHitsList &lNode = topHitsLists[iNode];
+        for (int64_t iHit = 0; iHit < nCheck && iHit < (int64_t) lNode.hits.size(); iHit++) {
+            Besthit bh;
+            hitToBestHit(iNode, lNode.hits[iHit], bh);
+            setCriterion(nSeqs, bh);
+            TopHitsList &lTarget = topHitsLists[bh.j];
+            Besthit bhCheck;
+            hitToBestHit(bh.j, lTarget.hits[nCheck - 1], bhCheck);
+            setCriterion(nSeqs, bhCheck);
+            if (bhCheck.criterion < bh.criterion) continue;
+            bool bFound = false;
+            for (size_t k = 0; k < lTarget.hits.size() && !bFound; k++)
+                if (lTarget.hits[k].j == iNode) bFound = true;
+            if (bFound) continue;
+            int64_t iWorst = -1;
+            double dWorstCriterion = -1e20;
+            for (int64_t k = 0; k < (int64_t) lTarget.hits.size(); k++) {
+                Besthit bh2;
+                hitToBestHit(bh.j, lTarget.hits[k], bh2);
+                setCriterion(nSeqs, bh2);
+                if (bh2.criterion > dWorstCriterion) { iWorst = k; dWorstCriterion = bh2.criterion; }
+            }
+            if (dWorstCriterion > bh.criterion) {
+                lTarget.hits[iWorst].j = iNode;
+                lTarget.hits[iWorst].dist = bh.dist;
+                Besthit v;
+                getVisible(nSeqs, bh.j, v);
+                if (bh.criterion < v.criterion) visible[bh.j] = lTarget.hits[iWorst];
+            }
+        }
+    }
+}
+
+// resetTopVisible, NJ.tcc:4728-4784
+template<typename P>
+void NJ<P>::resetTopVisible(int64_t nActive) {
+    if (opt.prefetch) {
+        for (int64_t i = 0; i < maxnode; i++) hintVisible(nActive, i);
+        flushOut(nActive);
+    }
+    std::vector<Besthit> visibleSorted;
+    visibleSorted.reserve(nActive);
+    for (int64_t i = 0; i < maxnode; i++) {
+        if (parent[i] >= 0) continue;
+        Besthit v;
+        if (getVisible(nActive, i, v)) visibleSorted.push_back(v);
+    }
+    // The reference allocates nActive slots (:4729), fills nVisible of them and psorts ALL of
+    // them (:4744); the unfilled tail is value-initialised (i=j=0, criterion 0) and takes part in
+    // the sort, and only the first nVisible sorted slots are read (:4761).  Reproduced literally.
+    size_t nVisible = visibleSorted.size();
+    visibleSorted.resize((size_t) nActive, Besthit{0, 0, 0, 0, 0});
+    sortByCriterion(visibleSorted);
+    std::vector<int64_t> inTopVisible(maxnodes, -1);
+    size_t iSave = 0;
+    for (size_t k = 0; k < nVisible && iSave < topvisible.size(); k++) {
+        const Besthit &v = visibleSorted[k];
+        if (inTopVisible[v.i] != v.j) {
+            topvisible[iSave++] = v.i;
+            inTopVisible[v.i] = v.j;
+            inTopVisible[v.j] = v.i;
+        }
+    }
+    while (iSave < topvisible.size()) topvisible[iSave++] = -1;
+    topvisibleAge = 0;
+}
+
+// updateTopVisible, NJ.tcc:4661-4711
+template<typename P>
+void NJ<P>::updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit) {
+    bool bIn = false;
+    for (size_t k = 0; k < topvisible.size() && !bIn; k++) {
+        int64_t iNode = topvisible[k];
+        if (iNode == iIn) bIn = true;
+        else if (iNode < 0 || parent[iNode] >= 0) { bIn = true; topvisible[k] = iIn; }
+    }
+    if (bIn) return;
+    if (opt.prefetch) {
+        for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
+        hintCriterion(nActive, iIn, hit.j);
+        flushOut(nActive);
+    }
+    int64_t iPosWorst = -1;
+    double dCriterionWorst = -1e20;
+    for (size_t k = 0; k < topvisible.size() && !bIn; k++) {
+        int64_t iNode = topvisible[k];
+        Besthit v;
+        if (!getVisible(nActive, iNode, v)) { topvisible[k] = iIn; bIn = true; }
+        else if (v.i == hit.j && v.j == iIn) bIn = true;
+        else if (v.criterion >= dCriterionWorst) { iPosWorst = (int64_t) k; dCriterionWorst = v.criterion; }
+    }
+    if (!bIn && iPosWorst >= 0) {
+        Besthit v;
+        hitToBestHit(iIn, hit, v);
+        setCriterion(nActive, v);
+        if (v.criterion < dCriterionWorst) topvisible[iPosWorst] = iIn;
+    }
+}
+
+// updateVisible, NJ.tcc:4635-4658
+template<typename P>
+void NJ<P>::updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode) {
+    if (opt.prefetch) {
+        for (const Besthit &hit : tophitsNode) if (hit.i >= 0) hintVisible(nActive, hit.j);
+        flushOut(nActive);
+    }
+    for (Besthit &hit : tophitsNode) {
+        if (hit.i < 0) continue;
+        Besthit v;
+        bool bSuccess = getVisible(nActive, hit.j, v);
+        if (!bSuccess || hit.criterion < v.criterion) {
+            if (bSuccess) res->nVisibleUpdate++;
+            Hit &vis = visible[hit.j];
+            vis.j = hit.i;
+            vis.dist = hit.dist;
+            updateTopVisible(nActive, hit.j, vis);
+        }
+    }
+}
+
+// getBestFromTopHits, NJ.tcc:4267-4298
+template<typename P>
+void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin) {
+    TopHitsList &l = topHitsLists[iNode];
+    if (opt.prefetch) {
+        wantOut(iNode, nActive, /*evenIfNotStale*/true);
+        for (const Hit &h : l.hits) {
+            int64_t j = activeAncestor(h.j);
+            if (j < 0 || j == iNode) continue;
+            if (j != h.j) wantPair(iNode, j);
+            wantOut(j, nActive);
+        }
+        flushOut(nActive);
+        flushPairs();
+    }
+    setOutDistance(iNode, nActive);                                      // :4276
+    bestjoin.i = -1; bestjoin.j = -1; bestjoin.weight = 0;
+    bestjoin.dist = (P) 1e20; bestjoin.criterion = (P) 1e20;
+    for (size_t k = 0; k < l.hits.size(); k++) {
+        Besthit bh;
+        hitToBestHit(iNode, l.hits[k], bh);
+        if (updateBestHit(nActive, bh, true)) {
+            setCriterion(nActive, bh);
+            if (bh.criterion < bestjoin.criterion) bestjoin = bh;
+        }
+    }
+}
+
+// topHitNJSearch, NJ.tcc:4137-4264
+template<typename P>
+void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
+    if (opt.prefetch) {
+        for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
+        flushOut(nActive);
+    }
+    int64_t nCandidate = 0, iNodeBestCandidate = -1;
+    double dBestCriterion = 1e20;
+    for (size_t k = 0; k < topvisible.size(); k++) {
+        int64_t iNode = topvisible[k];
+        Besthit v;
+        if (getVisible(nActive, iNode, v)) {
+            nCandidate++;
+            if (iNodeBestCandidate < 0 || v.criterion < dBestCriterion) {
+                iNodeBestCandidate = iNode;
+                dBestCriterion = v.criterion;
+            }
+        }
+    }
+    topvisibleAge++;
+    if (2 * topvisibleAge > m
+        || (3 * nCandidate < (int64_t) topvisible.size() && 3 * nCandidate < nActive)) {
+        if (topvisibleAge <= 2) {                                        // :4171-4201
+            for (int64_t iNode = 0; iNode < maxnode; iNode++) {
+                if (parent[iNode] >= 0) continue;
+                Hit &v = visible[iNode];
+                int64_t newj = activeAncestor(v.j);
+                if (newj >= 0 && newj != v.j) {
+                    if (newj == iNode) {
+                        newj = 0;
+                        while (parent[newj] >= 0 || newj == iNode) newj++;
+                    }
+                    Besthit bh = {iNode, newj, (P) -1e20, (P) -1e20, (P) -1e20};
+                    setDistCriterion(nActive, bh);
+                    v.j = newj;
+                    v.dist = bh.dist;
+                }
+            }
+        }
+        resetTopVisible(nActive);
+        topHitNJSearch(nActive, join);
+        return;
+    }
+    getVisible(nActive, iNodeBestCandidate, join);                       // :4212
+
+    // hill-climbing, NJ.tcc:4222-4263 (single thread: bests[] has one entry)
+    bool changed;
+    do {
+        changed = false;
+        Besthit best;
+        getBestFromTopHits(join.i, nActive, best);
+        if (best.j != join.j && best.criterion < join.criterion) { changed = true; join = best; }
+        getBestFromTopHits(join.j, nActive, best);
+        if (best.j != join.i && best.criterion < join.criterion) { changed = true; join = best; }
+        if (changed) res->nHillBetter++;
+    } while (changed);
+}
+
+// topHitJoin, NJ.tcc:4306-4533 (no 2nd-level lists: hitSource is always -1)
+template<typename P>
+void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
+    TopHitsList &lNew = topHitsLists[newnode];
+    TopHitsList *lChild[2] = {&topHitsLists[child[newnode].child[0]], &topHitsLists[child[newnode].child[1]]};
+    size_t n0 = lChild[0]->hits.size();
+    std::vector<Besthit> combinedList(n0 + lChild[1]->hits.size());
+    hitsToBestHits(lChild[0]->hits, child[newnode].child[0], combinedList.data());
+    hitsToBestHits(lChild[1]->hits, child[newnode].child[1], combinedList.data() + n0);
+    std::vector<Besthit> uniqueList;
+    uniqueBestHitsPrepare(nActive, combinedList, uniqueList);
+    flushPairs(); flushOut(nActive);
+    uniqueBestHitsFinish(nActive, uniqueList);
+    int64_t nUnique = (int64_t) uniqueList.size();
+    lChild[0]->hits.clear(); lChild[0]->hits.shrink_to_fit();
+    lChild[1]->hits.clear(); lChild[1]->hits.shrink_to_fit();
+
+    lNew.age = (lChild[0]->age + lChild[1]->age + 1) / 2 + 1;            // :4342
+    int64_t tophitAgeLimit = std::max((int64_t) 1, (int64_t) (0.5 + std::log((double) m) / std::log(2.0)));
+    bool bUseUnique = nUnique == nActive - 1
+                      || (lNew.age <= tophitAgeLimit && nUnique >= (int64_t) (0.5 + m * opt.tophitsRefresh));
+    if (bUseUnique) {
+        int64_t nSave = std::min(nUnique, m);
+        sortSaveBestHits(newnode, uniqueList, nUnique, nSave, true);     // :4432
+        visible[newnode] = lNew.hits[0];
+        updateTopVisible(nActive, newnode, visible[newnode]);
+        uniqueList.resize(nSave);
+        updateVisible(nActive, uniqueList);
+        return;
+    }
+
+    // ---- refresh, NJ.tcc:4439-4517 ------------------------------------------------------------
+    res->nRefreshTopHits++;
+    lNew.age = 0;
+    {   // every out-distance up to date, :4451-4464
+        std::vector<P> od(maxnodes);
+        check(vft_out_distance_all(ctx, nActive, totdiam, od.data(), maxnodes));
+        for (int64_t i = 0; i < maxnode; i++)
+            if (parent[i] < 0) { outDistances[i] = od[i]; nOutDistActive[i] = nActive; }
+    }
+    std::vector<Besthit> allhits;
+    oneVsAll(newnode, nActive, 2 * m, allhits);                          // :4470-4471 (top 2m is all that is read)
+    sortSaveBestHits(newnode, allhits, (int64_t) allhits.size(), m, false);   // :4472
+
+    // expand the lists of the top m hits, :4477-4515.  The m iterations are independent (they
+    // read allhits and parent[], write only their own list), so their distance requests are
+    // gathered first and evaluated in one device call.
+    struct Work { int64_t iNode; std::vector<Besthit> unique; };
+    std::vector<Work> work;
+    for (int64_t iHit = 0; iHit < m && iHit < (int64_t) allhits.size(); iHit++) {
+        if (allhits[iHit].i < 0) continue;
+        int64_t iNode = allhits[iHit].j;
+        if (parent[iNode] >= 0) continue;
+        TopHitsList &l = topHitsLists[iNode];
+        int64_t nHitsOld = (int64_t) l.hits.size();
+        l.age = 0;
+        std::vector<Besthit> bothList(nHitsOld + 2 * m);
+        hitsToBestHits(l.hits, iNode, bothList.data());
+        for (int64_t k = 0; k < nHitsOld; k++) setCriterion(nActive, bothList[k]);
+        int64_t nAvail = std::min<int64_t>(2 * m, (int64_t) allhits.size());
+        bothList.resize(nHitsOld + nAvail);
+        transferBestHits(nActive, iNode, allhits, nAvail, bothList.data() + nHitsOld, false);
+        work.push_back(Work{iNode, {}});
+        uniqueBestHitsPrepare(nActive, bothList, work.back().unique);
+    }
+    flushPairs();
+    for (Work &wk : work) {
+        uniqueBestHitsFinish(nActive, wk.unique);
+        sortSaveBestHits(wk.iNode, wk.unique, (int64_t) wk.unique.size(), m, true);   // :4512
+        visible[wk.iNode] = topHitsLists[wk.iNode].hits[0];
+    }
+    pairCache.clear();
+    resetTopVisible(nActive);                                            // :4517
+}
+
+// setBestHit with the full allhits array (visible-set mode only, N tiny): NJ.tcc:3571-3639
+template<typename P>
+void NJ<P>::setBestHitFull(int64_t node, int64_t nActive, Besthit &bestjoin, std::vector<Besthit> *allhits) {
+    std::vector<Besthit> sorted;
+    int64_t n = oneVsAll(node, nActive, maxnode, sorted);
+    bestjoin = Besthit{node, -1, 0, (P) 1e20, (P) 1e20};
+    // arg-min with strict '<' scanning j ascending (:3627): lowest j among equal criteria
+    for (int64_t k = 0; k < n; k++) {
+        const Besthit &h = sorted[k];
+        if (h.j == node) continue;
+        if (h.criterion < bestjoin.criterion || (h.criterion == bestjoin.criterion && bestjoin.j >= 0 && h.j < bestjoin.j))
+            bestjoin = h;
+    }
+    if (allhits) {
+        allhits->assign(maxnode, Besthit{-1, -1, 0, (P) 1e20, (P) 1e20});
+        for (int64_t j = 0; j < maxnode; j++) (*allhits)[j].j = j;
+        for (int64_t k = 0; k < n; k++) (*allhits)[sorted[k].j] = sorted[k];
+    }
+}
+
+// fastNJSearch, NJ.tcc:3686-3744 (visible-set mode)
+template<typename P>
+void NJ<P>::fastNJSearch(int64_t nActive, std::vector<Besthit> &besthits, Besthit &join) {
+    join = Besthit{-1, -1, 0, (P) 1e20, (P) 1e20};
+    for (int64_t iNode = 0; iNode < maxnode; iNode++) {
+        int64_t jNode = besthits[iNode].j;
+        if (parent[iNode] < 0 && parent[jNode] < 0) {
+            setCriterion(nActive, besthits[iNode]);
+            if (besthits[iNode].criterion < join.criterion) join = besthits[iNode];
+        }
+    }
+    int changed;
+    do {
+        changed = 0;
+        setBestHitFull(join.i, nActive, besthits[join.i], nullptr);
+        if (besthits[join.i].j != join.j) changed = 1;
+        join.j = besthits[join.i].j; join.weight = besthits[join.i].weight;
+        join.dist = besthits[join.i].dist; join.criterion = besthits[join.i].criterion;
+        setBestHitFull(join.j, nActive, besthits[join.j], nullptr);
+        if (besthits[join.j].j != join.i) {
+            changed = 1;
+            join.i = besthits[join.j].j; join.weight = besthits[join.j].weight;
+            join.dist = besthits[join.j].dist; join.criterion = besthits[join.j].criterion;
+        }
+        if (changed) res->nHillBetter++;
+    } while (changed);
+}
+
+// fastNJ, NJ.tcc:2796-3155
+template<typename P>
+void NJ<P>::fastNJ() {
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    if (nSeqs < 3) {                                                     // :2798-2815
+        root = maxnode++;
+        child[root].nChild = (int) nSeqs;
+        for (int64_t i = 0; i < nSeqs; i++) { parent[i] = root; child[root].child[i] = i; }
+        if (nSeqs == 2) {
+            DW r = pairDist(0, 1);
+            branchlength[0] = (P) (r.dist / 2.0);
+            branchlength[1] = (P) (r.dist / 2.0);
+        }
+        return;
+    }
+    std::vector<Besthit> visibleSet, besthitNew;
+    m = 0;
+    if (opt.tophitsMult > 0) {
+        m = (int64_t) (0.5 + opt.tophitsMult * std::sqrt((double) nSeqs));
+        if (m < 4 || 2 * m >= nSeqs) m = 0;
+    }
+    res->m = m;
+    if (m > 0) {
+        topHitsLists.resize(maxnodes);
+        visible.assign(maxnodes, Hit{-1, (P) 1e20});
+        topvisible.assign((size_t) (0.5 + opt.topvisibleMult * m), -1);
+        setAllLeafTopHits();
+        if (res->leafTopHits) {
+            for (int64_t i = 0; i < nSeqs; i++)
+                for (int64_t k = 0; k < m; k++)
+                    res->leafTopHits[i * m + k] = k < (int64_t) topHitsLists[i].hits.size() ? topHitsLists[i].hits[k].j : -1;
+        }
+        resetTopVisible(nSeqs);
+    } else {
+        visibleSet.resize(maxnodes, Besthit{-1, -1, 0, (P) 1e20, (P) 1e20});
+        for (int64_t i = 0; i < nSeqs; i++) setBestHitFull(i, nSeqs, visibleSet[i], nullptr);
+    }
+    auto t1 = clk::now();
+    res->secondsLeafTopHits = std::chrono::duration<double>(t1 - t0).count();
+
+    int64_t nActiveOutProfileReset = nSeqs;
+    for (int64_t nActive = nSeqs; nActive > 3; nActive--) {
+        Besthit join;
+        if (m > 0) topHitNJSearch(nActive, join);
+        else fastNJSearch(nActive, visibleSet, join);
+
+        // :2897-2900 -- out-distances of the pair up to date, distance and weight recomputed
+        if (opt.prefetch) {
+            wantOut(join.i, nActive, true); wantOut(join.j, nActive, true);
+            wantPair(join.i, join.j);
+            flushOut(nActive); flushPairs();
+        }
+        setOutDistance(join.i, nActive);
+        setOutDistance(join.j, nActive);
+        setDistCriterion(nActive, join);
+
+        int64_t newnode = maxnode++;
+        parent[join.i] = newnode;
+        parent[join.j] = newnode;
+        child[newnode].nChild = 2;
+        child[newnode].child[0] = join.i < join.j ? join.i : join.j;
+        child[newnode].child[1] = join.i > join.j ? join.i : join.j;
+        if (res->joins) {
+            res->joins[2 * (nSeqs - nActive)] = child[newnode].child[0];
+            res->joins[2 * (nSeqs - nActive) + 1] = child[newnode].child[1];
+        }
+
+        // :2911-2916.  P + P + P is P arithmetic, then widened
+        double rawIJ = (P) ((P) (join.dist + diameter[join.i]) + diameter[join.j]);
+        double distIJ = join.dist;
+        double deltaDist = (P) (outDistances[join.i] - outDistances[join.j]) / (double) (nActive - 2);
+        branchlength[join.i] = (P) ((distIJ + deltaDist) / 2);
+        branchlength[join.j] = (P) ((distIJ - deltaDist) / 2);
+
+        double bionjWeight = 0.5;
+        double varIJ = rawIJ - varDiameter[join.i] - varDiameter[join.j];
+        if (opt.bionj && join.weight > 0.01 && varIJ > 0.001) {
+            throw DeviceError{VFT_EINVAL};       // BIONJ weighting (NJ.tcc:2921-2992) not built yet
+        }
+        // :3003-3007: double * (P+P) ...
+        diameter[newnode] = (P) (bionjWeight * (P) (branchlength[join.i] + diameter[join.i])
+                                 + (1 - bionjWeight) * (P) (branchlength[join.j] + diameter[join.j]));
+        varDiameter[newnode] = (P) (bionjWeight * varDiameter[join.i] + (1 - bionjWeight) * varDiameter[join.j]
+                                    + bionjWeight * (1 - bionjWeight) * varIJ);
+        check(vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
+                                  (double) diameter[newnode]));      // :3008 (+ :3040-3043)
+
+        // out-profile and total diameter, :3012-3037
+        int64_t changedActiveOutProfile = nActiveOutProfileReset - (nActive - 1);
+        if (changedActiveOutProfile >= opt.nResetOutProfile
+            && changedActiveOutProfile >= opt.fResetOutProfile * nActiveOutProfileReset) {
+            totdiam = 0;
+            for (int64_t i = 0; i < maxnode; i++) if (parent[i] < 0) totdiam += diameter[i];
+            check(vft_outprofile_rebuild(ctx, nullptr, nActive - 1));
+            nActiveOutProfileReset = nActive - 1;
+        } else {
+            check(vft_outprofile_update(ctx, join.i, join.j, newnode, nActive));
+            totdiam += (P) ((P) (diameter[newnode] - diameter[join.i]) - diameter[join.j]);
+        }
+        newEpoch(nActive - 1);
+
+        if (m > 0) {
+            topHitJoin(newnode, nActive - 1);
+        } else {
+            std::vector<P> od(maxnodes);
+            check(vft_out_distance_all(ctx, nActive - 1, totdiam, od.data(), maxnodes));
+            for (int64_t i = 0; i < maxnode; i++)
+                if (parent[i] < 0) { outDistances[i] = od[i]; nOutDistActive[i] = nActive - 1; }
+            setBestHitFull(newnode, nActive - 1, visibleSet[newnode], &besthitNew);
+            for (int64_t iNode = 0; iNode < maxnode; iNode++) {          // :3066-3095
+                if (parent[iNode] >= 0 || iNode == newnode) continue;
+                int64_t iOldVisible = visibleSet[iNode].j;
+                if (parent[iOldVisible] < 0) setCriterion(nActive - 1, visibleSet[iNode]);
+                if (parent[iOldVisible] >= 0 || besthitNew[iNode].criterion < visibleSet[iNode].criterion) {
+                    if (parent[iOldVisible] < 0) res->nVisibleUpdate++;
+                    visibleSet[iNode].j = newnode;
+                    visibleSet[iNode].dist = besthitNew[iNode].dist;
+                    visibleSet[iNode].criterion = besthitNew[iNode].criterion;
+                }
+            }
+        }
+    }
+
+    // root the last three nodes, NJ.tcc:3107-3135
+    int64_t top[3], nTop = 0;
+    for (int64_t i = 0; i < maxnode; i++) if (parent[i] < 0) top[nTop++] = i;
+    root = maxnode++;
+    child[root].nChild = 3;
+    for (nTop = 0; nTop < 3; nTop++) { parent[top[nTop]] = root; child[root].child[nTop] = top[nTop]; }
+    // bare profileDist of the three pairs, then "dist - diameter - diameter" in P (:3125-3132)
+    int64_t pi[3] = {top[0], top[0], top[1]}, pj[3] = {top[1], top[2], top[2]};
+    P pd[3], pw[3];
+    check(vft_dist_pairs(ctx, pi, pj, 3, VFT_PAIRS_PROFILE_RAW, pd, pw));
+    double d01 = (P) ((P) (pd[0] - diameter[top[0]]) - diameter[top[1]]);
+    double d02 = (P) ((P) (pd[1] - diameter[top[0]]) - diameter[top[2]]);
+    double d12 = (P) ((P) (pd[2] - diameter[top[1]]) - diameter[top[2]]);
+    branchlength[top[0]] = (P) ((d01 + d02 - d12) / 2);
+    branchlength[top[1]] = (P) ((d01 + d12 - d02) / 2);
+    branchlength[top[2]] = (P) ((d02 + d12 - d01) / 2);
+    res->secondsJoins = std::chrono::duration<double>(clk::now() - t1).count();
+}
+
+template<typename P>
+int run(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, const uint8_t *codes, vft_nj_result *res) {
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    NJ<P> nj(ctx, cfg, opt, res, codes);
+    try {
+        nj.init();
+        nj.fastNJ();
+    } catch (const DeviceError &e) {
+        return e.code;
+    }
+    int64_t M = 2 * cfg.nSeqs;
+    for (int64_t i = 0; i < M; i++) {
+        res->parent[i] = nj.parent[i];
+        res->nChild[i] = nj.child[i].nChild;
+        for (int k = 0; k < 3; k++) res->child[3 * i + k] = nj.child[i].child[k];
+        ((P *) res->branchlength)[i] = nj.branchlength[i];
+    }
+    res->root = nj.root;
+    res->maxnode = nj.maxnode;
+    res->secondsTotal = std::chrono::duration<double>(clk::now() - t0).count();
+    return VFT_OK;
+}
+
+}  // namespace
+
+extern "C" void vft_nj_default_options(vft_nj_options *o) {
+    std::memset(o, 0, sizeof *o);
+    o->tophitsMult = 1.0;        // Options.h:20
+    o->tophitsClose = -1.0;      // Options.h:22
+    o->topvisibleMult = 1.5;     // Options.h:25
+    o->tophitsRefresh = 0.8;     // Options.h:28
+    o->staleOutLimit = 0.01;     // Options.h:36
+    o->fResetOutProfile = 0.02;  // Options.h:38
+    o->nResetOutProfile = 200;   // Options.h:40
+    o->bionj = 0;
+    o->prefetch = 1;
+}
+
+extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in, const uint8_t *codes,
+                            const void *const tables[4], vft_nj_result *res) {
+    if (!cfg || !codes || !res || !res->parent || !res->nChild || !res->child || !res->branchlength) return VFT_EINVAL;
+    vft_nj_options opt;
+    if (opt_in) opt = *opt_in; else vft_nj_default_options(&opt);
+    if (opt.bionj) return VFT_EINVAL;
+    if (cfg->useMatrix && !tables) return VFT_EINVAL;
+    // zero the output counters, keep the caller's buffers
+    res->root = -1; res->maxnode = 0; res->m = 0;
+    res->nSeeds = res->nCloseUsed = res->nRefreshTopHits = res->nVisibleUpdate = res->nHillBetter = 0;
+    res->nOutPrefetchHit = res->nOutSingleFetch = res->nPairPrefetchHit = res->nPairSingleFetch = res->nDeviceCalls = 0;
+    res->secondsLeafTopHits = res->secondsJoins = res->secondsTotal = 0;
+    vft_ctx *ctx = nullptr;
+    int rc = vft_ctx_create(cfg, &ctx);
+    if (rc != VFT_OK) return rc;
+    if (cfg->useMatrix) rc = vft_upload_tables(ctx, tables[0], tables[1], tables[2], tables[3]);
+    if (rc == VFT_OK) rc = vft_upload_leaves(ctx, codes);
+    if (rc == VFT_OK) rc = cfg->precision == 32 ? run<float>(ctx, *cfg, opt, codes, res) : run<double>(ctx, *cfg, opt, codes, res);
+    if (rc == VFT_OK) vft_get_counters(ctx, &res->counters);
+    vft_ctx_destroy(ctx);
+    return rc;
+}
