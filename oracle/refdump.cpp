@@ -1,0 +1,286 @@
+// TEST INFRASTRUCTURE ONLY.
+//
+// White-box dumper: instantiates the reference's OWN templates
+// (veryfasttree::NeighbourJoining<P, AVX256Operations>, DistanceMatrix<P,32>) from the headers
+// where they lie under /root/reference/src -- nothing is copied or restated here -- and writes
+// kernel-level values for a given alignment as a flat list of named arrays.  The vectors pin
+// oracle/vft_oracle.c (and, through it, the CUDA kernels) at a finer grain than whole trees:
+// tests/golden/make_golden.py commits its output, tests/test_oracle_golden.py replays it.
+//
+// usage: refdump <fasta> <nt|aa> <32|64> <out.bin> [tophits]
+//
+// File format: repeated { u32 name_len, name, char dtype('f','d','q','B'), u32 ndim, i64 dims[], data }.
+#include <algorithm>
+#include <cinttypes>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <omp.h>
+
+// private members are reached with g++ -fno-access-control (see oracle/Makefile); a
+// `#define private public` would also rewrite the OpenMP private() clauses of the reference.
+#include "operations/AVX256Operations.h"
+#include "NeighbourJoining.h"
+
+using namespace veryfasttree;
+
+static FILE *g_out;
+
+static void put(const std::string &name, char dtype, const std::vector<int64_t> &dims, const void *data) {
+    uint32_t nl = (uint32_t) name.size(), nd = (uint32_t) dims.size();
+    size_t es = dtype == 'f' ? 4 : dtype == 'B' ? 1 : 8, n = 1;
+    for (auto d : dims) n *= (size_t) d;
+    fwrite(&nl, 4, 1, g_out); fwrite(name.data(), 1, nl, g_out); fwrite(&dtype, 1, 1, g_out);
+    fwrite(&nd, 4, 1, g_out); fwrite(dims.data(), 8, nd, g_out); fwrite(data, es, n, g_out);
+}
+template<typename P> static char dt() { return sizeof(P) == 4 ? 'f' : 'd'; }
+template<typename P> static void putv(const std::string &n, const std::vector<P> &v, std::vector<int64_t> dims = {}) {
+    if (dims.empty()) dims = {(int64_t) v.size()};
+    put(n, dt<P>(), dims, v.data());
+}
+static void putq(const std::string &n, const std::vector<int64_t> &v, std::vector<int64_t> dims = {}) {
+    if (dims.empty()) dims = {(int64_t) v.size()};
+    put(n, 'q', dims, v.data());
+}
+
+template<typename P>
+struct Dumper {
+    typedef NeighbourJoining<P, AVX256Operations> NJ;
+    typedef typename NJ::Profile Profile;
+    NJ &nj;
+    int64_t L, A, S;
+    explicit Dumper(NJ &nj) : nj(nj), L(nj.nPos), A(nj.options.nCodes), S(nj.nCodeSize) {}
+
+    void profile(const std::string &pfx, Profile &p) {           // dense expansion of the sparse Profile
+        std::vector<P> w(L), v(L * A, 0);
+        std::vector<uint8_t> c(L);
+        int64_t iv = 0;
+        for (int64_t i = 0; i < L; i++) {
+            w[i] = p.weights[i];
+            c[i] = (uint8_t) p.codes[i];
+            P *f = nj.getFreq(p, i, iv);
+            if (f) for (int64_t k = 0; k < A; k++) v[i * A + k] = f[k];
+        }
+        putv<P>(pfx + ".weights", w);
+        put(pfx + ".codes", 'B', {L}, c.data());
+        putv<P>(pfx + ".vectors", v, {L, A});
+        if (p.codeDistSize) {
+            std::vector<P> cd(p.codeDist, p.codeDist + L * A);
+            putv<P>(pfx + ".codeDist", cd, {L, A});
+        }
+    }
+};
+
+template<typename P>
+static int run(const std::string &fasta, bool aa, bool tophitsOnly) {
+    Options options;
+    options.verbose = 0;
+    options.showProgress = false;
+    options.threads = 1;
+    options.diskComputing = false;
+    options.nCodes = aa ? 20 : 4;
+    options.useMatrix = aa;
+    options.codesString = aa ? Constants::codesStringAA : Constants::codesStringNT;
+    options.doublePrecision = sizeof(P) == 8;
+    options.fPostTotalTolerance = sizeof(P) == 8 ? Constants::fPostTotalToleranceDouble : Constants::fPostTotalToleranceFloat;
+    options.MLMinBranchLength = sizeof(P) == 8 ? Constants::MLMinBranchLengthDouble : Constants::MLMinBranchLengthFloat;
+    options.MLMinRelBranchLength = sizeof(P) == 8 ? Constants::MLMinRelBranchLengthDouble : Constants::MLMinRelBranchLengthFloat;
+    omp_set_num_threads(1);
+
+    std::ifstream in(fasta);
+    if (!in) { std::fprintf(stderr, "cannot read %s\n", fasta.c_str()); return 2; }
+    std::ostringstream lg;
+    Alignment aln(options, in, lg);
+    aln.readAlignment();
+    std::vector<std::string> seqs = aln.seqs;     // keep a copy: the ctor releases its input strings
+    int64_t N = (int64_t) seqs.size(), L = aln.nPos;
+
+    typedef AVX256Operations<P> op_t;
+    static DistanceMatrix<P, op_t::ALIGNMENT> dmat{};
+    static TransitionMatrix<P, op_t::ALIGNMENT> transmat;
+    if (options.useMatrix) {
+        dmat.matrixBLOSUM45();
+        dmat.setupDistanceMatrix(options, lg);
+        std::vector<P> d(20 * 20), ev(20), et(20), cf(20 * 20);
+        for (int i = 0; i < 20; i++) {
+            ev[i] = dmat.eigenval[i]; et[i] = dmat.eigentot[i];
+            for (int j = 0; j < 20; j++) { d[i * 20 + j] = dmat.distances[i][j]; cf[i * 20 + j] = dmat.codeFreq[i][j]; }
+        }
+        putv<P>("tables.distances", d, {20, 20});
+        putv<P>("tables.eigenval", ev);
+        putv<P>("tables.eigentot", et);
+        putv<P>("tables.codeFreq", cf, {20, 20});
+    }
+
+    ProgressReport progress(false, 0, false);
+    std::vector<std::string> cons;
+    std::unique_ptr<DiskMemory> d1, d2;
+    NeighbourJoining<P, AVX256Operations> nj(options, lg, progress, seqs, L, cons, dmat, transmat, d1, d2);
+    Dumper<P> D(nj);
+    int64_t A = options.nCodes;
+    putq("shape", {N, L, A});
+
+    if (tophitsOnly) {
+        // the reference's own setAllLeafTopHits (NJ.tcc:3746-4124) at -threads 1: the top-hit list of
+        // every leaf, indices and distances -- the "identical top-hit indices" golden
+        int64_t m = (int64_t) (0.5 + options.tophitsMult * std::sqrt((double) N));
+        if (m < 4 || 2 * m >= N) { std::fprintf(stderr, "too few leaves for top hits\n"); return 3; }
+        nj.parent.assign(nj.maxnodes, -1);
+        typename NeighbourJoining<P, AVX256Operations>::TopHits tophits(options, nj.maxnodes, m);
+        nj.setAllLeafTopHits(tophits);
+        std::vector<int64_t> js(N * m, -1), vis(N);
+        std::vector<P> ds(N * m, 0);
+        for (int64_t i = 0; i < N; i++) {
+            auto &l = tophits.topHitsLists[i].hits;
+            for (size_t k = 0; k < l.size(); k++) { js[i * m + k] = l[k].j; ds[i * m + k] = l[k].dist; }
+            vis[i] = tophits.visible[i].j;
+        }
+        putq("tophits.m", {m});
+        putq("tophits.j", js, {N, m});
+        putv<P>("tophits.dist", ds, {N, m});
+        putq("tophits.visible", vis);
+        return 0;
+    }
+
+    // --- state right after the constructor (NJ.tcc:237-260)
+    D.profile("ctor.outprofile", nj.outprofile);
+    {
+        std::vector<P> od(nj.outDistances.begin(), nj.outDistances.begin() + N), sw(nj.selfweight.begin(), nj.selfweight.begin() + N);
+        putv<P>("ctor.outDistances", od);
+        putv<P>("ctor.selfweight", sw);
+    }
+
+    // --- leaf x leaf, seqDist (NJ.tcc:1601-1624)
+    {
+        std::vector<int64_t> pi, pj;
+        for (int64_t i = 0; i < std::min<int64_t>(N, 48); i++) {
+            pi.push_back(i); pj.push_back((i * 7 + 3) % N);
+            pi.push_back(i); pj.push_back(i);
+            pi.push_back(N - 1 - i); pj.push_back((i * 13 + 1) % N);
+        }
+        std::vector<P> dd(pi.size()), ww(pi.size());
+        for (size_t k = 0; k < pi.size(); k++) {
+            typename NeighbourJoining<P, AVX256Operations>::Besthit h;
+            nj.seqDist(nj.profiles[pi[k]].codes, nj.profiles[pj[k]].codes, h);
+            dd[k] = h.dist; ww[k] = h.weight;
+        }
+        putq("seq.i", pi); putq("seq.j", pj); putv<P>("seq.dist", dd); putv<P>("seq.weight", ww);
+    }
+
+    // --- a fixed script of joins: averageProfile (NJ.tcc:2067), selfdist (:3041), updateOutProfile (:943),
+    //     setOutDistance (:1012), profileDist (:1167); the test replays exactly this script
+    nj.parent.assign(nj.maxnodes, -1);
+    std::vector<int64_t> joins;
+    std::vector<double> diams;
+    std::vector<int64_t> active;
+    for (int64_t i = 0; i < N; i++) active.push_back(i);
+    int64_t nJoins = std::min<int64_t>(24, N - 4);
+    int64_t nActive = N;
+    std::vector<P> step_out_w, step_out_v;
+    for (int64_t k = 0; k < nJoins; k++) {
+        // alternate leaf+leaf, node+leaf, node+node picks, deterministic
+        int64_t a, b;
+        if (k % 3 == 0 || nj.maxnode - N < 2) { a = active[(k * 5) % active.size()]; b = active[(k * 5 + 1 + k) % active.size()]; }
+        else if (k % 3 == 1) { a = nj.maxnode - 1; b = active[(k * 11 + 2) % active.size()]; }
+        else { a = nj.maxnode - 1; b = nj.maxnode - 2; }
+        if (a == b || nj.parent[a] >= 0 || nj.parent[b] >= 0) {
+            a = active[0]; b = active[1];
+        }
+        int64_t nw = nj.maxnode++;
+        double diam = 0.003 * (double) (k + 1) + 0.001 * (double) (k % 4);
+        nj.diameter[nw] = (P) diam;
+        nj.averageProfile(nj.profiles[nw], nj.profiles[a], nj.profiles[b], -1.0);
+        typename NeighbourJoining<P, AVX256Operations>::Besthit sd;
+        nj.profileDist(nj.profiles[nw], nj.profiles[nw], sd);
+        nj.selfdist[nw] = sd.dist; nj.selfweight[nw] = sd.weight;
+        nj.updateOutProfile(nj.outprofile, nj.profiles[a], nj.profiles[b], nj.profiles[nw], nActive);
+        nj.totdiam += nj.diameter[nw] - nj.diameter[a] - nj.diameter[b];
+        nj.parent[a] = nw; nj.parent[b] = nw;
+        active.erase(std::find(active.begin(), active.end(), a));
+        active.erase(std::find(active.begin(), active.end(), b));
+        active.push_back(nw);
+        std::sort(active.begin(), active.end());
+        nActive--;
+        joins.push_back(a); joins.push_back(b); diams.push_back(diam);
+        D.profile("join" + std::to_string(k) + ".profile", nj.profiles[nw]);
+        std::vector<P> self = {nj.selfdist[nw], nj.selfweight[nw]};
+        putv<P>("join" + std::to_string(k) + ".self", self);
+        if (k == 0 || k == nJoins - 1) D.profile("join" + std::to_string(k) + ".outprofile", nj.outprofile);
+    }
+    putq("joins", joins, {nJoins, 2});
+    put("diameters", 'd', {nJoins}, diams.data());
+    double td = nj.totdiam;
+    put("totdiam", 'd', {1}, &td);
+    putq("nActive", {nActive});
+
+    // out-distances of every active node at this nActive (setOutDistance, NJ.tcc:1012-1053)
+    {
+        std::vector<P> od;
+        for (int64_t id : active) { nj.nOutDistActive[id] = -1; nj.setOutDistance(id, nActive); od.push_back(nj.outDistances[id]); }
+        putq("out.ids", active); putv<P>("out.dist", od);
+    }
+    // profile distances among internal nodes and leaves (profileDist, NJ.tcc:1167-1190), raw
+    {
+        std::vector<int64_t> pi, pj;
+        for (int64_t x = N; x < nj.maxnode; x++) {
+            pi.push_back(x); pj.push_back(x);
+            pi.push_back(x); pj.push_back((x * 3) % N);
+            pi.push_back((x * 5 + 1) % N); pj.push_back(x);
+            if (x + 1 < nj.maxnode) { pi.push_back(x); pj.push_back(x + 1); }
+            pi.push_back(nj.maxnode - 1); pj.push_back(x);
+        }
+        for (int64_t i = 0; i < std::min<int64_t>(N, 16); i++) { pi.push_back(i); pj.push_back((i * 7 + 3) % N); }  // leaf pairs through profileDist
+        std::vector<P> dd(pi.size()), ww(pi.size());
+        for (size_t k = 0; k < pi.size(); k++) {
+            typename NeighbourJoining<P, AVX256Operations>::Besthit h;
+            nj.profileDist(nj.profiles[pi[k]], nj.profiles[pj[k]], h);
+            dd[k] = h.dist; ww[k] = h.weight;
+        }
+        putq("prof.i", pi); putq("prof.j", pj); putv<P>("prof.dist", dd); putv<P>("prof.weight", ww);
+    }
+    // setDistCriterion's distance (NJ.tcc:1115-1122) for mixed pairs
+    {
+        std::vector<int64_t> pi, pj;
+        for (size_t x = 0; x + 1 < active.size() && x < 40; x++) { pi.push_back(active[x]); pj.push_back(active[active.size() - 1 - x]); }
+        std::vector<P> dd(pi.size()), ww(pi.size());
+        for (size_t k = 0; k < pi.size(); k++) {
+            typename NeighbourJoining<P, AVX256Operations>::Besthit h;
+            h.i = pi[k]; h.j = pj[k];
+            nj.nOutDistActive[h.i] = nActive; nj.nOutDistActive[h.j] = nActive;
+            nj.setDistCriterion(nActive, h);
+            dd[k] = h.dist; ww[k] = h.weight;
+        }
+        putq("join.i", pi); putq("join.j", pj); putv<P>("join.dist", dd); putv<P>("join.weight", ww);
+    }
+    // full out-profile rebuild over the active set (outProfile, NJ.tcc:729-815)
+    {
+        typedef typename NeighbourJoining<P, AVX256Operations>::Profile Profile;
+        std::vector<Profile *> ap;
+        for (int64_t id : active) ap.push_back(&nj.profiles[id]);
+        nj.outProfile(nj.outprofile, ap, (int64_t) ap.size());
+        D.profile("rebuild.outprofile", nj.outprofile);
+    }
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc != 5 && argc != 6) { std::fprintf(stderr, "usage: refdump <fasta> <nt|aa> <32|64> <out.bin> [tophits]\n"); return 2; }
+    bool th = argc == 6 && std::string(argv[5]) == "tophits";
+    g_out = std::fopen(argv[4], "wb");
+    if (!g_out) { std::perror(argv[4]); return 2; }
+    bool aa = std::string(argv[2]) == "aa";
+    int rc = std::string(argv[3]) == "64" ? run<double>(argv[1], aa, th) : run<float>(argv[1], aa, th);
+    std::fclose(g_out);
+    return rc;
+}

@@ -1,0 +1,150 @@
+"""Shared helpers of the parity tests: refdump reader, script replay through the C-ABI.
+
+`replay(lib, dump)` drives ANY implementation of include/vft_b200.h (the CUDA product library in
+the -m gpu tests, the CPU restatement in the CPU tests) through the script that
+oracle/refdump.cpp ran on the reference's own templates, and reports every array that is not
+bit-identical.
+"""
+from __future__ import annotations
+
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+from veryfasttree_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libvftoracle.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "VeryFastTree")
+REFDUMP_BIN = os.path.join(ROOT, "oracle", "_ref", "refdump")
+
+_DT = {b"f": np.float32, b"d": np.float64, b"q": np.int64, b"B": np.uint8}
+
+
+def read_refdump(path: str) -> dict:
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    o = 0
+    while o < len(data):
+        (nl,) = struct.unpack_from("<I", data, o); o += 4
+        name = data[o:o + nl].decode(); o += nl
+        dt = _DT[data[o:o + 1]]; o += 1
+        (nd,) = struct.unpack_from("<I", data, o); o += 4
+        dims = struct.unpack_from("<%dq" % nd, data, o); o += 8 * nd
+        n = int(np.prod(dims)) if nd else 1
+        arr = np.frombuffer(data, dtype=dt, count=n, offset=o).reshape(dims)
+        o += n * np.dtype(dt).itemsize
+        out[name] = arr
+    return out
+
+
+def ensure_oracle_built():
+    if not os.path.exists(ORACLE_LIB):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    return a.tobytes() == b.tobytes()
+
+
+def golden_case(name: str):
+    """(chars, kind) of a named golden alignment; regenerated from its seed, never stored."""
+    n, L, kind, seed = CASES[name]
+    chars = synth.make_alignment(n, L, kind, seed)
+    chars = chars[synth.unique_rows(chars)]
+    return chars, kind
+
+
+# name -> (n, nPos, kind, seed)
+CASES = {
+    "nt60": (60, 150, "nt", 5),
+    "aa60": (60, 120, "aa", 3),
+    "c1": (250, 500, "nt", 1),          # BASELINE.json configs[0]
+    "nt1000": (1000, 300, "nt", 7),
+    "aa300": (300, 200, "aa", 9),
+}
+
+
+def replay(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: int, device: int = 0):
+    """Returns a list of names of arrays that differ (empty = bit-exact)."""
+    bad = []
+
+    def cmp(name, got):
+        want = dump[name]
+        if not bits_equal(np.asarray(got, dtype=want.dtype).reshape(want.shape), want):
+            bad.append(name)
+
+    N, L, A = [int(x) for x in dump["shape"]]
+    codes = api.encode(chars, kind)
+    assert codes.shape == (N, L)
+    use_matrix = kind == "aa"
+    cfg = api.make_config(N, L, A, precision, use_matrix=use_matrix, reduction=1, device=device)
+    with api.Context(lib, cfg) as ctx:
+        if use_matrix:
+            ctx.upload_tables(dump["tables.distances"], dump["tables.eigenval"], dump["tables.eigentot"],
+                              dump["tables.codeFreq"])
+        ctx.upload_leaves(codes)
+        # constructor tail: outProfile over all leaves + out-distances
+        ctx.outprofile_rebuild()
+        w, cd, v = ctx.get_profile(-1)
+        cmp("ctor.outprofile.weights", w)
+        cmp("ctor.outprofile.vectors", v)
+        od = ctx.out_distance_all(N, 0.0)
+        cmp("ctor.outDistances", od[:N])
+        cmp("ctor.selfweight", [ctx.get_self(i)[1] for i in range(N)])
+        # also through the batch entry point
+        ids = np.arange(0, N, 3)
+        cmp_batch = ctx.out_distance_batch(ids, N, 0.0)
+        if not bits_equal(cmp_batch, dump["ctor.outDistances"][ids]):
+            bad.append("ctor.outDistances(batch)")
+        # leaf x leaf
+        d, wt = ctx.dist_pairs(dump["seq.i"], dump["seq.j"])
+        cmp("seq.dist", d)
+        cmp("seq.weight", wt)
+        # the join script
+        joins = dump["joins"]
+        n_active = N
+        totdiam = 0.0
+        diam = np.zeros(2 * N, dtype=ctx.dt)
+        for k in range(joins.shape[0]):
+            a, b = int(joins[k, 0]), int(joins[k, 1])
+            nw = N + k
+            ctx.profile_average(nw, a, b, -1.0, float(dump["diameters"][k]))
+            diam[nw] = ctx.dt(dump["diameters"][k])
+            ctx.outprofile_update(a, b, nw, n_active)
+            # totdiam += diameter[new] - diameter[a] - diameter[b]  (P arithmetic, NJ.tcc:3036)
+            totdiam += float(ctx.dt(ctx.dt(diam[nw] - diam[a]) - diam[b]))
+            n_active -= 1
+            w, cd, v = ctx.get_profile(nw)
+            cmp("join%d.profile.weights" % k, w)
+            cmp("join%d.profile.codes" % k, cd)
+            cmp("join%d.profile.vectors" % k, v)
+            cmp("join%d.self" % k, list(ctx.get_self(nw)))
+            if ("join%d.outprofile.weights" % k) in dump:
+                w, cd, v = ctx.get_profile(-1)
+                cmp("join%d.outprofile.weights" % k, w)
+                cmp("join%d.outprofile.vectors" % k, v)
+        assert n_active == int(dump["nActive"][0])
+        if abs(totdiam - float(dump["totdiam"][0])) != 0.0:
+            bad.append("totdiam")
+        cmp("out.dist", ctx.out_distance_batch(dump["out.ids"], n_active, totdiam))
+        d, wt = ctx.dist_pairs(dump["prof.i"], dump["prof.j"], flags=1)
+        cmp("prof.dist", d)
+        cmp("prof.weight", wt)
+        d, wt = ctx.dist_pairs(dump["join.i"], dump["join.j"], flags=0)
+        cmp("join.dist", d)
+        cmp("join.weight", wt)
+        ctx.outprofile_rebuild()
+        w, cd, v = ctx.get_profile(-1)
+        cmp("rebuild.outprofile.weights", w)
+        cmp("rebuild.outprofile.vectors", v)
+    return bad

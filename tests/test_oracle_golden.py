@@ -1,0 +1,90 @@
+"""CPU tests (no GPU): pin the oracle restatement and the host NJ driver to the reference.
+
+  - oracle/vft_oracle.c replays the white-box script that oracle/refdump.cpp ran on the
+    reference's own templates: every array bit-identical (nt / aa, fp32 / fp64);
+  - the product's host driver (nj_host.cpp) on top of the oracle reproduces the reference
+    binary's NJ tree byte for byte and the reference's leaf top-hit index lists exactly;
+  - the prefetch hints do not change a single decision.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import replay
+from veryfasttree_b200 import api
+
+
+@pytest.fixture(scope="module")
+def olib():
+    replay.ensure_oracle_built()
+    lib = api.load(replay.ORACLE_LIB)
+    assert lib.backend == "oracle-cpu"
+    return lib
+
+
+def tables_for(kind, prec):
+    if kind != "aa":
+        return None
+    z = np.load(os.path.join(replay.GOLDEN, "blosum45_f%d.npz" % prec))
+    return [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60"])
+def test_oracle_matches_reference_templates(olib, name, prec):
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d.refdump.bin" % (name, prec)))
+    chars, kind = replay.golden_case(name)
+    assert replay.replay(olib, dump, chars, kind, prec) == []
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60", "c1", "aa300", "nt1000"])
+def test_nj_tree_identical_to_reference(olib, name, prec):
+    chars, kind = replay.golden_case(name)
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=olib,
+                        tables=tables_for(kind, prec))
+    names = ["t%d" % i for i in range(chars.shape[0])]
+    assert tree.newick(names) == want
+    assert tree.stats["nOutSingleFetch"] == 0 and tree.stats["nPairSingleFetch"] == 0
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["c1", "aa300"])
+def test_leaf_top_hits_identical_to_reference(olib, name, prec):
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d.tophits.bin" % (name, prec)))
+    chars, kind = replay.golden_case(name)
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=olib,
+                        tables=tables_for(kind, prec))
+    assert tree.m == int(dump["tophits.m"][0])
+    assert np.array_equal(tree.leaf_top_hits, dump["tophits.j"])
+
+
+def test_prefetch_is_only_a_hint(olib):
+    chars, kind = replay.golden_case("c1")
+    codes = api.encode(chars, kind)
+    a = api.nj_build(codes, 4, 32, lib=olib, prefetch=True)
+    b = api.nj_build(codes, 4, 32, lib=olib, prefetch=False)
+    assert np.array_equal(a.joins, b.joins)
+    assert a.branchlength.tobytes() == b.branchlength.tobytes()
+    assert b.stats["nOutPrefetchHit"] == 0 and b.stats["nOutSingleFetch"] > 0
+
+
+def test_tiny_inputs_visible_set_mode(olib, tmp_path):
+    # fewer than 13 leaves: top-hits are switched off (m < 4, NJ.tcc:2829) and the visible-set
+    # search (fastNJSearch, NJ.tcc:3686) is used.  Compared with the reference binary when it is here.
+    import sys
+    sys.path.insert(0, replay.GOLDEN)
+    from veryfasttree_b200 import synth
+    for n in (3, 4, 5, 9, 12, 15, 20):
+        chars, kind = replay.golden_case("nt60")
+        chars = chars[:n]
+        t = api.nj_build(api.encode(chars, kind), 4, 64, lib=olib)
+        assert (t.m == 0) == (n < 13)
+        assert t.root == 2 * n - 3 and (t.parent[:t.root] >= 0).all()
+        if os.path.exists(replay.REF_BIN):
+            import make_golden
+            fa = str(tmp_path / ("tiny%d.fa" % n))
+            synth.write_fasta(fa, chars)
+            assert t.newick(["t%d" % i for i in range(n)]) == make_golden.ref_tree(fa, kind, 64)
