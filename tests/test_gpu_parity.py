@@ -1,0 +1,175 @@
+"""GPU parity tests (B200): the CUDA product library, called through the C-ABI, against
+  (1) the white-box vectors of the reference's own templates (tests/golden/*.refdump.bin),
+  (2) the CPU restatement (oracle/) on seeded inputs, every output array bit-identical,
+  (3) the NJ trees / top-hit lists of the unmodified reference binary (tests/golden/*.nj.tree),
+  (4) size-independent properties at the bench size.
+Bit-exact means bit-exact: float payloads are compared as bytes, indices as integers.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import replay
+from veryfasttree_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def glib():
+    lib = api.load()                      # fails loudly when the CUDA library is missing
+    assert lib.backend == "cuda-sm100a"
+    return lib
+
+
+@pytest.fixture(scope="module")
+def olib():
+    replay.ensure_oracle_built()
+    return api.load(replay.ORACLE_LIB)
+
+
+def tables_for(kind, prec):
+    if kind != "aa":
+        return None
+    z = np.load(os.path.join(replay.GOLDEN, "blosum45_f%d.npz" % prec))
+    return [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60"])
+def test_cuda_matches_reference_templates(glib, name, prec):
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d.refdump.bin" % (name, prec)))
+    chars, kind = replay.golden_case(name)
+    assert replay.replay(glib, dump, chars, kind, prec) == []
+
+
+def run_script(lib, codes, n_codes, prec, tables, seed, n_joins, k_top):
+    """A seeded sequence of ABI calls; returns every output for comparison."""
+    rs = np.random.RandomState(seed)
+    N, L = codes.shape
+    out = {}
+    cfg = api.make_config(N, L, n_codes, prec, use_matrix=tables is not None)
+    with api.Context(lib, cfg) as ctx:
+        if tables is not None:
+            ctx.upload_tables(*tables)
+        ctx.upload_leaves(codes)
+        ctx.outprofile_rebuild()
+        out["od0"] = ctx.out_distance_all(N, 0.0)
+        for q in rs.randint(0, N, size=3):
+            j, d, w, c = ctx.dist_one_vs_all(int(q), N, k_top)
+            out["ova0_%d" % q] = [j, d, w, c]
+        pi, pj = rs.randint(0, N, size=500), rs.randint(0, N, size=500)
+        out["leafpairs"] = list(ctx.dist_pairs(pi, pj))
+        active = list(range(N))
+        diam = np.zeros(2 * N, dtype=ctx.dt)
+        totdiam = 0.0
+        n_active = N
+        for k in range(n_joins):
+            a, b = rs.choice(len(active), size=2, replace=False)
+            a, b = active[a], active[b]
+            nw = N + k
+            dm = float(ctx.dt(0.001 * (1 + k % 7)))
+            ctx.profile_average(nw, a, b, -1.0, dm)
+            diam[nw] = dm
+            ctx.outprofile_update(a, b, nw, n_active)
+            totdiam += float(ctx.dt(ctx.dt(diam[nw] - diam[a]) - diam[b]))
+            active.remove(a); active.remove(b); active.append(nw)
+            n_active -= 1
+            if k % 16 == 5:
+                ctx.outprofile_rebuild()
+        out["self"] = [ctx.get_self(N + k) for k in range(n_joins)]
+        out["outprofile"] = list(ctx.get_profile(-1))
+        out["lastprofile"] = list(ctx.get_profile(N + n_joins - 1))
+        ids = np.array(sorted(active))[::3]
+        out["od_batch"] = ctx.out_distance_batch(ids, n_active, totdiam)
+        out["od_all"] = ctx.out_distance_all(n_active, totdiam)
+        for q in [N + n_joins - 1, active[0], active[len(active) // 2]]:
+            j, d, w, c = ctx.dist_one_vs_all(int(q), n_active, k_top)
+            out["ova1_%d" % q] = [j, d, w, c]
+        act = np.array(active)
+        pi, pj = act[rs.randint(0, len(act), size=800)], act[rs.randint(0, len(act), size=800)]
+        out["pairs_join"] = list(ctx.dist_pairs(pi, pj, 0))
+        out["pairs_raw"] = list(ctx.dist_pairs(pi, pj, 1))
+        cn = ctx.counters()
+        out["ops"] = np.array([cn.seqOps, cn.profileOps, cn.outprofileOps, cn.profileAvgOps])
+    return out
+
+
+def flatten(o, pfx=""):
+    if isinstance(o, dict):
+        for k, v in o.items():
+            yield from flatten(v, pfx + "/" + str(k))
+    elif isinstance(o, (list, tuple)):
+        for k, v in enumerate(o):
+            yield from flatten(v, pfx + "/" + str(k))
+    else:
+        yield pfx, np.asarray(o)
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("kind,n,L,joins", [("nt", 700, 333, 300), ("aa", 400, 207, 150), ("nt", 5000, 200, 600)])
+def test_cuda_bit_exact_vs_oracle(glib, olib, kind, n, L, joins, prec):
+    chars = synth.make_alignment(n, L, kind, seed=100 + n)
+    chars[::17, ::5] = ord("-")           # ragged gaps, also in nt
+    chars[3] = ord("-")                   # an all-gap sequence: weight 0.01 / dist 1 sentinels
+    codes = api.encode(chars, kind)
+    A = 4 if kind == "nt" else 20
+    k_top = 2 * int(0.5 + np.sqrt(n))
+    a = run_script(glib, codes, A, prec, tables_for(kind, prec), 7, joins, k_top)
+    b = run_script(olib, codes, A, prec, tables_for(kind, prec), 7, joins, k_top)
+    bad = [ka for (ka, va), (kb, vb) in zip(flatten(a), flatten(b)) if not replay.bits_equal(va, vb)]
+    assert bad == []
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60", "c1", "aa300", "nt1000"])
+def test_nj_tree_identical_to_reference(glib, name, prec):
+    chars, kind = replay.golden_case(name)
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=glib,
+                        tables=tables_for(kind, prec))
+    assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+    assert tree.stats["counters"]["launches"] > 0
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["c1", "aa300"])
+def test_leaf_top_hits_identical_to_reference(glib, name, prec):
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d.tophits.bin" % (name, prec)))
+    chars, kind = replay.golden_case(name)
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=glib,
+                        tables=tables_for(kind, prec))
+    assert np.array_equal(tree.leaf_top_hits, dump["tophits.j"])
+
+
+def test_bench_size_properties_and_reference(glib, tmp_path):
+    """BASELINE.json configs[1] shape scaled to what the reference finishes in ~10 s here (4000 taxa):
+    same tree as the reference binary when it travelled with the snapshot; always: a valid binary
+    tree over all leaves, every join between active nodes, one-vs-all sorted and self on top."""
+    n, L = 4000, 200
+    chars = synth.make_alignment(n, L, "nt", seed=1)
+    chars = chars[synth.unique_rows(chars)]
+    n = chars.shape[0]
+    codes = api.encode(chars, "nt")
+    tree = api.nj_build(codes, 4, 32, lib=glib)
+    assert tree.root == 2 * n - 3 and tree.maxnode == 2 * n - 2
+    assert (tree.parent[:tree.root] >= 0).all() and tree.parent[tree.root] == -1
+    assert (np.bincount(tree.parent[:tree.root], minlength=2 * n)[n:tree.root] == 2).all()
+    seen = np.zeros(2 * n, dtype=bool)
+    for k, (a, b) in enumerate(tree.joins):
+        assert not seen[a] and not seen[b] and max(a, b) < n + k
+        seen[a] = seen[b] = True
+    if os.path.exists(replay.REF_BIN):
+        import sys
+        sys.path.insert(0, replay.GOLDEN)
+        import make_golden
+        fa = str(tmp_path / "b.fa")
+        synth.write_fasta(fa, chars)
+        assert tree.newick(["t%d" % i for i in range(n)]) == make_golden.ref_tree(fa, "nt", 32)
+
+
+def test_no_device_argument_errors(glib):
+    cfg = api.make_config(10, 20, 4, 32, device=99)
+    with pytest.raises(api.VftError):
+        api.Context(glib, cfg)

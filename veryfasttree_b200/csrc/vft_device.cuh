@@ -1,0 +1,320 @@
+// vft_device.cuh -- device-side arithmetic of the NJ hot path (sm_100a).
+//
+// Everything here is "reference-order arithmetic": each value is produced by the same sequence
+// of individually rounded operations, in the same types, as the reference's -mavx2 (no FMA)
+// build evaluates it (citations: /root/reference/src, NJ.tcc = NeighbourJoining.tcc).  That is
+// what makes the top-hit indices identical to the reference rather than merely close: the
+// criterion has many exact and near ties, and the order of the double-precision accumulation
+// over positions decides them.  Consequences for the kernel design:
+//   - a pair's distance is accumulated by ONE thread, positions in ascending order (the
+//     per-position work is cheap; parallelism comes from the thousands of pairs in a batch);
+//   - mul and add are kept separate (__dmul_rn/__dadd_rn, __fmul_rn/__fadd_rn; the file is also
+//     compiled with -fmad=false);
+//   - the P-typed 20-wide dot products reproduce the lane order of AVX256Operations.tcc.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define VFT_DEV_NOCODE 127u
+
+namespace vft {
+
+// ---- separately rounded arithmetic in P and in double ------------------------------------------
+__device__ __forceinline__ float  pmul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ double pmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  padd(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ double padd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float  psub(float a, float b)   { return __fsub_rn(a, b); }
+__device__ __forceinline__ double psub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+
+template<typename P>
+struct Store {
+    // profile slab (HBM): leaves are 1 byte/position, internal nodes are dense
+    uint8_t *codes;        // [2*nSeqs][Lp]            NOCODE in the padding
+    P *weights;            // [nSeqs][Lp]              internal node id -> row id-nSeqs; 0 in the padding
+    P *vecs;               // [nSeqs][Lp][A]
+    // out-profile (always dense, NJ.tcc:746)
+    P *ow, *ov, *ocd;      // [Lp], [Lp][A], [Lp][A] (codeDist, matrix mode)
+    // per node
+    P *diameter, *selfdist, *selfweight, *outDist;   // [2*nSeqs]
+    uint8_t *active;       // [2*nSeqs]
+    // tables (DistanceMatrix.h:15-33), row stride 20
+    const P *distances, *eigenval, *eigentot, *codeFreq;
+    int64_t nSeqs, L, Lp;
+    int reduction;         // VFT_REDUCE_*
+    double fPostTotalTolerance;
+};
+
+// ---- lane-ordered reductions: BasicOperations.tcc:17-41, AVX256Operations.tcc:5-26,58-138 -------
+template<typename P, int A>
+__device__ __forceinline__ P lane_fold(const P (&prod)[A], int mode) {
+    if (mode == 0) {
+        P out = 0;
+#pragma unroll
+        for (int i = 0; i < A; i++) out = padd(out, prod[i]);
+        return out;
+    }
+    if (sizeof(P) == 8) {                       // 4 lane accumulators, then (l0+l1)+(l2+l3)
+        P l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+#pragma unroll
+        for (int i = 0; i < A; i += 4) {
+            l0 = padd(prod[i], l0); l1 = padd(prod[i + 1], l1); l2 = padd(prod[i + 2], l2); l3 = padd(prod[i + 3], l3);
+        }
+        return padd(padd(l0, l1), padd(l2, l3));
+    }
+    if (A == 4) return padd(padd(prod[0], prod[1]), padd(prod[2], prod[3]));
+    {                                           // float, A == 20: two 8-lane blocks + a 4-lane tail
+        P l[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) l[k] = 0;
+        constexpr int m = A - (A % 8);
+#pragma unroll
+        for (int i = 0; i < m; i += 8)
+#pragma unroll
+            for (int k = 0; k < 8; k++) l[k] = padd(prod[i + k], l[k]);
+        P t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = padd(l[k], prod[(m + k) < A ? (m + k) : 0]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = padd(l[4 + k], t[k]);
+        return padd(padd(t[0], t[1]), padd(t[2], t[3]));
+    }
+}
+
+template<typename P, int A>
+__device__ __forceinline__ P vec_mul_sum(const P *f1, const P *f2, int mode) {        // vector_multiply_sum
+    P prod[A];
+#pragma unroll
+    for (int i = 0; i < A; i++) prod[i] = pmul(f1[i], f2[i]);
+    return lane_fold<P, A>(prod, mode);
+}
+
+template<typename P, int A>
+__device__ __forceinline__ P vec_mul3_sum(const P *f1, const P *f2, const P *f3, int mode) {   // vector_multiply3_sum
+    P prod[A];
+#pragma unroll
+    for (int i = 0; i < A; i++) prod[i] = pmul(pmul(f1[i], f2[i]), f3[i]);
+    return lane_fold<P, A>(prod, mode);
+}
+
+// ---- a node as the distance loops see it -------------------------------------------------------
+template<typename P, int A>
+struct View {
+    const uint8_t *codes;   // nullptr for the out-profile (every code is NOCODE)
+    const P *w;             // nullptr for leaves (weight = code != NOCODE)
+    const P *v;             // nullptr for leaves
+    const P *cd;            // codeDist (out-profile, matrix mode) or nullptr
+};
+
+template<typename P, int A>
+__device__ __forceinline__ View<P, A> make_view(const Store<P> &s, int64_t id) {
+    View<P, A> r;
+    if (id < 0) { r.codes = nullptr; r.w = s.ow; r.v = s.ov; r.cd = s.ocd; }
+    else if (id < s.nSeqs) { r.codes = s.codes + id * s.Lp; r.w = nullptr; r.v = nullptr; r.cd = nullptr; }
+    else {
+        int64_t row = id - s.nSeqs;
+        r.codes = s.codes + id * s.Lp; r.w = s.weights + row * s.Lp; r.v = s.vecs + row * s.Lp * A; r.cd = nullptr;
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t code_of(const uint4 &q, int b) {
+    uint32_t w = (b < 4) ? q.x : (b < 8) ? q.y : (b < 12) ? q.z : q.w;
+    return (w >> ((b & 3) * 8)) & 0xFFu;
+}
+
+// profileDistPiece, NJ.tcc:900-941, for a position where both weights are > 0
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ double piece(const Store<P> &s, uint32_t c1, uint32_t c2,
+                                        const P *f1, const P *f2, const P *cd2) {
+    if (MATRIX) {
+        if (c1 != VFT_DEV_NOCODE && c2 != VFT_DEV_NOCODE) return (double) s.distances[c1 * 20 + c2];
+        if (cd2 != nullptr && c1 != VFT_DEV_NOCODE) return (double) cd2[c1];
+        P a[A], b[A], e[A];
+        const P *p1 = (c1 != VFT_DEV_NOCODE) ? s.codeFreq + c1 * 20 : f1;
+        const P *p2 = (c2 != VFT_DEV_NOCODE) ? s.codeFreq + c2 * 20 : f2;
+#pragma unroll
+        for (int k = 0; k < A; k++) { a[k] = p1[k]; b[k] = p2[k]; e[k] = s.eigenval[k]; }
+        return (double) vec_mul3_sum<P, A>(a, b, e, s.reduction);
+    } else {
+        if (c1 != VFT_DEV_NOCODE) {
+            if (c2 != VFT_DEV_NOCODE) return c1 == c2 ? 0.0 : 1.0;
+            return xsub(1.0, (double) f2[c1]);
+        }
+        if (c2 != VFT_DEV_NOCODE) return xsub(1.0, (double) f1[c2]);
+        double pc = 1.0;
+#pragma unroll
+        for (int k = 0; k < A; k++) pc = xsub(pc, (double) pmul(f1[k], f2[k]));
+        return pc;
+    }
+}
+
+// profileDist, NJ.tcc:1167-1190: one thread, positions in ascending order
+template<typename P, int A, bool MATRIX>
+__device__ void profile_dist(const Store<P> &s, const View<P, A> &p1, const View<P, A> &p2, P &dist, P &weight) {
+    double top = 0, denom = 0;
+    const int64_t Lp = s.Lp;
+    for (int64_t base = 0; base < Lp; base += 16) {
+        uint4 q1 = p1.codes ? *reinterpret_cast<const uint4 *>(p1.codes + base)
+                            : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+        uint4 q2 = p2.codes ? *reinterpret_cast<const uint4 *>(p2.codes + base)
+                            : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int64_t pos = base + b;
+            const uint32_t c1 = code_of(q1, b), c2 = code_of(q2, b);
+            const P w1 = p1.w ? p1.w[pos] : (c1 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+            const P w2 = p2.w ? p2.w[pos] : (c2 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+            if (w1 > 0 && w2 > 0) {
+                const double wt = (double) pmul(w1, w2);                                  // :1176
+                denom = xadd(denom, wt);
+                const double pc = piece<P, A, MATRIX>(s, c1, c2, p1.v ? p1.v + pos * A : nullptr,
+                                                      p2.v ? p2.v + pos * A : nullptr, p2.cd ? p2.cd + pos * A : nullptr);
+                top = xadd(top, xmul(wt, pc));
+            }
+        }
+    }
+    weight = (P) (denom > 0 ? denom : 0.01);                                              // :1187
+    dist = (P) (denom > 0 ? top / denom : 1.0);                                           // :1188
+}
+
+// seqDist, NJ.tcc:1601-1624
+template<typename P, bool MATRIX>
+__device__ void seq_dist(const Store<P> &s, const uint8_t *c1, const uint8_t *c2, P &dist, P &weight) {
+    const int64_t Lp = s.Lp;
+    int nUse = 0;
+    double top = 0;
+    if (!MATRIX) {
+        int nDiff = 0;
+        for (int64_t base = 0; base < Lp; base += 16) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(c1 + base);
+            const uint4 b = *reinterpret_cast<const uint4 *>(c2 + base);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // per-byte masks: 0xFF where the byte is a real code on both sides / where they differ
+                const uint32_t use = __vcmpne4(aw[k], 0x7F7F7F7Fu) & __vcmpne4(bw[k], 0x7F7F7F7Fu);
+                const uint32_t ne = __vcmpne4(aw[k], bw[k]);
+                nUse += __popc(use) >> 3;
+                nDiff += __popc(use & ne) >> 3;
+            }
+        }
+        top = (double) nDiff;
+    } else {
+        for (int64_t base = 0; base < Lp; base += 16) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(c1 + base);
+            const uint4 b = *reinterpret_cast<const uint4 *>(c2 + base);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t x = code_of(a, k), y = code_of(b, k);
+                if (x != VFT_DEV_NOCODE && y != VFT_DEV_NOCODE) { nUse++; top = xadd(top, (double) s.distances[x * 20 + y]); }
+            }
+        }
+    }
+    weight = (P) (double) nUse;                                                           // :1621
+    dist = (P) (nUse > 0 ? top / (double) nUse : 1.0);                                    // :1622
+}
+
+// distance half of setDistCriterion, NJ.tcc:1115-1122
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void join_dist(const Store<P> &s, int64_t i, int64_t j, bool raw, P &dist, P &weight) {
+    if (!raw && i < s.nSeqs && j < s.nSeqs) {
+        seq_dist<P, MATRIX>(s, s.codes + i * s.Lp, s.codes + j * s.Lp, dist, weight);
+    } else {
+        const View<P, A> v1 = make_view<P, A>(s, i), v2 = make_view<P, A>(s, j);
+        profile_dist<P, A, MATRIX>(s, v1, v2, dist, weight);
+        if (raw) return;
+        dist = psub(dist, padd(s.diameter[i], s.diameter[j]));                            // :1120
+    }
+    dist = (P) xadd((double) dist, 0.0);                 // :1122, constraintWeight * 0 (no constraints)
+}
+
+// setOutDistance, NJ.tcc:1012-1053
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ P out_distance(const Store<P> &s, int64_t iNode, int64_t nActive, double totdiam) {
+    P ddist, dweight;
+    const View<P, A> v1 = make_view<P, A>(s, iNode), vo = make_view<P, A>(s, -1);
+    profile_dist<P, A, MATRIX>(s, v1, vo, ddist, dweight);
+    const P pN = (P) nActive, pN1 = (P) (nActive - 1);
+    const P t4 = psub(pmul(pmul(ddist, dweight), pN), pmul(s.selfweight[iNode], s.selfdist[iNode]));   // :1046
+    const double top = (double) pmul(pN1, t4);
+    const double bottom = (double) psub(pmul(dweight, pN), s.selfweight[iNode]);                        // :1047
+    const double pd = top / bottom;                                                                       // :1048
+    const P dn = pmul(s.diameter[iNode], pN1);
+    const double r = bottom > 0.01 ? xsub(xsub(pd, (double) dn), xsub(totdiam, (double) s.diameter[iNode])) : 3.0;
+    return (P) r;
+}
+
+// addToFreq / normalizeFreq on a register-resident frequency vector, NJ.tcc:821-871
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void add_to_freq(const Store<P> &s, P (&f)[A], double weight, uint32_t codeIn, const P *fIn) {
+    if (fIn != nullptr) {
+        const P w = (P) weight;
+#pragma unroll
+        for (int k = 0; k < A; k++) f[k] = padd(f[k], pmul(fIn[k], w));
+    } else if (MATRIX) {
+        const P w = (P) weight;
+        const P *cf = s.codeFreq + codeIn * 20;
+#pragma unroll
+        for (int k = 0; k < A; k++) f[k] = padd(f[k], pmul(cf[k], w));
+    } else {
+#pragma unroll
+        for (int k = 0; k < A; k++) if ((uint32_t) k == codeIn) f[k] = (P) xadd((double) f[k], weight);   // :831
+    }
+}
+
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void normalize_freq(const Store<P> &s, P (&f)[A]) {
+    double total = 0;
+    if (MATRIX) {
+        P e[A];
+#pragma unroll
+        for (int k = 0; k < A; k++) e[k] = s.eigentot[k];
+        total = (double) vec_mul_sum<P, A>(f, e, s.reduction);                            // :849
+    } else {
+#pragma unroll
+        for (int k = 0; k < A; k++) total = xadd(total, (double) f[k]);                   // :851-853
+    }
+    if (total > s.fPostTotalTolerance) {
+        const P inv = (P) (1.0 / total);                                                  // :856
+#pragma unroll
+        for (int k = 0; k < A; k++) f[k] = pmul(f[k], inv);
+    } else if (!MATRIX) {
+#pragma unroll
+        for (int k = 0; k < A; k++) f[k] = (P) (1.0 / A);
+    } else {
+#pragma unroll
+        for (int k = 0; k < A; k++) f[k] = s.codeFreq[k];
+    }
+}
+
+// setCodeDist for one position of the out-profile, NJ.tcc:873-898 (code1 = NOCODE, f = the vector)
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void code_dist_row(const Store<P> &s, const P (&f)[A], P *cdRow) {
+    if (!MATRIX) return;
+    P e[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) e[k] = s.eigenval[k];
+    for (int c = 0; c < A; c++) {
+        P b[A];
+#pragma unroll
+        for (int k = 0; k < A; k++) b[k] = s.codeFreq[c * 20 + k];
+        cdRow[c] = (P) (double) vec_mul3_sum<P, A>(f, b, e, s.reduction);
+    }
+}
+
+// orderable keys: ascending unsigned order == ascending floating order
+__device__ __forceinline__ uint64_t order_key(float x) {
+    uint32_t u = __float_as_uint(x);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (uint64_t) u;
+}
+__device__ __forceinline__ uint64_t order_key(double x) {
+    uint64_t u = (uint64_t) __double_as_longlong(x);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+}  // namespace vft
