@@ -120,6 +120,12 @@ int  vft_out_distance_all(vft_ctx *ctx, int64_t nActive, double totdiam, void *o
 int  vft_dist_pairs(vft_ctx *ctx, const int64_t *i, const int64_t *j, int64_t n, int32_t flags,
                     void *dist, void *weight);
 
+/* the two list kinds above in ONE device call (one launch, one synchronisation): the per-join
+   requests of the host loops are small, so their cost is latency, not bandwidth */
+int  vft_eval_batch(vft_ctx *ctx, const int64_t *out_ids, int64_t nOut, int64_t nActive, double totdiam,
+                    void *outDist, const int64_t *i, const int64_t *j, int64_t nPairs, int32_t flags,
+                    void *dist, void *weight);
+
 /* -- one-vs-all: setBestHit (NJ.tcc:3571-3639) + the psort/top-2m cut that always follows it
       (NJ.tcc:3930, :4471-4472) --------------------------------------------------------------- */
 /* query vs every active node j < maxnode (self included, as the reference does), criterion
@@ -144,8 +150,23 @@ typedef struct vft_counters {
     int64_t profileAvgOps;   /* averageProfile calls                     */
     int64_t launches;        /* kernels launched (0 for the CPU oracle)  */
     int64_t algoBytes;       /* algorithmic bytes touched by the distance kernels */
+    int64_t h2dBytes;        /* bytes copied host->device through this context */
+    int64_t d2hBytes;        /* bytes copied device->host through this context */
+    /* filled only when cfg.reserved & VFT_CFG_PROFILE: device time per kernel class, CUDA events
+       on the launching stream (ms), and the algorithmic bytes of that class */
+    double  msDist;          /* k_dist_pairs + k_one_vs_all + k_out_distance (the distance sweep) */
+    double  msSelect;        /* top-K sort/merge/gather                                             */
+    double  msProfile;       /* k_average + k_outprofile_update + k_outprofile_rebuild             */
+    int64_t distLaunches;
+    int64_t distBytes;
 } vft_counters;
+#define VFT_CFG_PROFILE 1    /* vft_config.reserved bit: time every kernel with CUDA events */
 int  vft_get_counters(vft_ctx *ctx, vft_counters *out);
+
+/* device-side stopwatch on the context's stream (CUDA events; wall clock in the CPU oracle):
+   brackets a host-driven sequence of calls for bench.py */
+int  vft_timer_start(vft_ctx *ctx);
+int  vft_timer_stop(vft_ctx *ctx, double *milliseconds);
 
 
 /* ============================================================================================
@@ -188,6 +209,8 @@ typedef struct vft_nj_result {
     int64_t nSeeds, nCloseUsed, nRefreshTopHits, nVisibleUpdate, nHillBetter;
     int64_t nOutPrefetchHit, nOutSingleFetch, nPairPrefetchHit, nPairSingleFetch, nDeviceCalls;
     double  secondsLeafTopHits, secondsJoins, secondsTotal;
+    double  deviceMsResident;   /* vft_timer around ctor tail + fastNJ: leaves already in HBM  */
+    double  secondsEndToEnd;    /* host clock around everything incl. context + upload + result */
     vft_counters counters;
 } vft_nj_result;
 

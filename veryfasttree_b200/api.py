@@ -29,7 +29,9 @@ class VftConfig(C.Structure):
 
 class VftCounters(C.Structure):
     _fields_ = [("seqOps", C.c_int64), ("profileOps", C.c_int64), ("outprofileOps", C.c_int64),
-                ("profileAvgOps", C.c_int64), ("launches", C.c_int64), ("algoBytes", C.c_int64)]
+                ("profileAvgOps", C.c_int64), ("launches", C.c_int64), ("algoBytes", C.c_int64),
+                ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64), ("msDist", C.c_double), ("msSelect", C.c_double),
+                ("msProfile", C.c_double), ("distLaunches", C.c_int64), ("distBytes", C.c_int64)]
 
 
 class VftNjOptions(C.Structure):
@@ -48,6 +50,7 @@ class VftNjResult(C.Structure):
                 ("nOutPrefetchHit", C.c_int64), ("nOutSingleFetch", C.c_int64),
                 ("nPairPrefetchHit", C.c_int64), ("nPairSingleFetch", C.c_int64), ("nDeviceCalls", C.c_int64),
                 ("secondsLeafTopHits", C.c_double), ("secondsJoins", C.c_double), ("secondsTotal", C.c_double),
+                ("deviceMsResident", C.c_double), ("secondsEndToEnd", C.c_double),
                 ("counters", VftCounters)]
 
 
@@ -56,6 +59,7 @@ ABI_SYMBOLS = [
     "vft_upload_leaves", "vft_outprofile_rebuild", "vft_outprofile_update", "vft_profile_average",
     "vft_get_self", "vft_out_distance_batch", "vft_out_distance_all", "vft_dist_pairs",
     "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
+    "vft_timer_start", "vft_timer_stop", "vft_eval_batch",
 ]
 
 
@@ -87,6 +91,7 @@ class Lib:
         d.vft_out_distance_batch.argtypes = [vp, vp, i64, i64, dbl, vp]
         d.vft_out_distance_all.argtypes = [vp, i64, dbl, vp, i64]
         d.vft_dist_pairs.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+        d.vft_eval_batch.argtypes = [vp, vp, i64, i64, dbl, vp, vp, vp, i64, i32, vp, vp]
         d.vft_dist_one_vs_all.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_get_profile.argtypes = [vp, i64, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -288,13 +293,14 @@ class NJTree:
 
 def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | None = None,
              tables=None, device: int = 0, prefetch: bool = True, trace: bool = True,
-             reduction: int = 1) -> NJTree:
+             reduction: int = 1, profile: bool = False) -> NJTree:
     """The metric phase (NJ ctor tail + fastNJ) through vft_nj_build with HOST buffers."""
     lib = lib or load()
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     n, L = codes.shape
     dt = np_dtype(precision)
     cfg = make_config(n, L, n_codes, precision, use_matrix=tables is not None, reduction=reduction, device=device)
+    cfg.reserved = 1 if profile else 0
     opt = VftNjOptions()
     lib.dll.vft_nj_default_options(C.byref(opt))
     opt.prefetch = int(prefetch)
@@ -317,7 +323,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
         tptr = C.cast(arr, C.c_void_p)
     rc = lib.dll.vft_nj_build(C.byref(cfg), C.byref(opt), _ptr(codes), tptr, C.byref(res))
     lib.check(rc, "vft_nj_build")
-    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:22]}
+    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:24]}
     stats.update({"counters": {k: getattr(res.counters, k) for k, _ in VftCounters._fields_}})
     return NJTree(n, precision, parent, n_child, child, bl, res.root, res.maxnode, res.m,
                   joins, lth, stats)

@@ -135,13 +135,21 @@ private:
         wantIds.push_back(i);
     }
 
-    void flushOut(int64_t nActive) {
-        if (wantIds.empty()) return;
+    // ONE device call for everything queued so far: out-distance requests and pair requests
+    void flush(int64_t nActive) {
+        if (wantIds.empty() && reqI.empty()) return;
         wantVals.resize(wantIds.size());
-        check(vft_out_distance_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data()));
+        reqD.resize(reqI.size()); reqW.resize(reqI.size());
+        check(vft_eval_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data(),
+                             reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()));
         for (size_t k = 0; k < wantIds.size(); k++) { freshVal[wantIds[k]] = wantVals[k]; freshEpoch[wantIds[k]] = epoch; }
+        for (size_t k = 0; k < reqI.size(); k++)
+            if (reqCached[k]) pairCache[pkey(reqI[k], reqJ[k])] = DW{reqD[k], reqW[k]};
         wantIds.clear();
+        reqI.clear(); reqJ.clear(); reqCached.clear();
     }
+    void flushOut(int64_t nActive) { flush(nActive); }
+    void flushPairs() { flush(epochActive); }
 
     // setOutDistance, NJ.tcc:1012-1053 (the arithmetic lives behind vft_out_distance_batch)
     void setOutDistance(int64_t i, int64_t nActive) {
@@ -163,23 +171,26 @@ private:
     struct DW { P dist, weight; };
     std::unordered_map<uint64_t, DW> pairCache;
     std::vector<int64_t> reqI, reqJ;
-    std::vector<P> reqD, reqW;
+    std::vector<P> reqD, reqW;        // results of the last flush, by request slot
 
     uint64_t pkey(int64_t i, int64_t j) const { return (uint64_t) i * (uint64_t) maxnodes + (uint64_t) j; }
 
+    std::vector<char> reqCached;
+
+    // hint for a pair looked up later through pairDist() (small, sporadic lists)
     void wantPair(int64_t i, int64_t j) {
         if (!opt.prefetch) return;
         if (pairCache.find(pkey(i, j)) != pairCache.end()) return;
         pairCache[pkey(i, j)] = DW{0, -1};          // weight -1 marks "requested"
-        reqI.push_back(i); reqJ.push_back(j);
+        reqI.push_back(i); reqJ.push_back(j); reqCached.push_back(1);
     }
 
-    void flushPairs() {
-        if (reqI.empty()) return;
-        reqD.resize(reqI.size()); reqW.resize(reqI.size());
-        check(vft_dist_pairs(ctx, reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()));
-        for (size_t k = 0; k < reqI.size(); k++) pairCache[pkey(reqI[k], reqJ[k])] = DW{reqD[k], reqW[k]};
-        reqI.clear(); reqJ.clear();
+    // positional request for the big lists: the result is read back from slot s of reqD/reqW
+    // right after the next flush (no hashing); -1 when prefetching is off
+    int64_t slotPair(int64_t i, int64_t j) {
+        if (!opt.prefetch) return -1;
+        reqI.push_back(i); reqJ.push_back(j); reqCached.push_back(0);
+        return (int64_t) reqI.size() - 1;
     }
 
     DW pairDist(int64_t i, int64_t j) {
@@ -267,8 +278,9 @@ private:
     void sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int64_t nIn, int64_t nOut, bool sort);
     void transferBestHits(int64_t nActive, int64_t iNode, const std::vector<Besthit> &oldhits, int64_t nOldHits,
                           Besthit *newhits, bool updateDistances);
-    void uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out);
-    void uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out);
+    void uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out,
+                               std::vector<int64_t> &slots);
+    void uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out, const std::vector<int64_t> &slots);
     void setAllLeafTopHits();
     void resetTopVisible(int64_t nActive);
     void updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit);
@@ -348,7 +360,8 @@ void NJ<P>::transferBestHits(int64_t nActive, int64_t iNode, const std::vector<B
 // uniqueBestHits, NJ.tcc:4786-4833, split around the device call:
 //   prepare = ancestor walk + psort by (i,j) + dedupe; finish = distances + criteria
 template<typename P>
-void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out) {
+void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out,
+                                  std::vector<int64_t> &slots) {
     for (auto &h : combined) updateBestHit(nActive, h, false);
     rsort(combined, [](const Besthit &a, const Besthit &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
     out.clear();
@@ -364,17 +377,22 @@ void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combine
         out.push_back(hit);
         iSavedLast = k;
     }
-    for (auto &h : out) {
-        if (h.dist < 0.0) wantPair(h.i, h.j);
+    slots.assign(out.size(), -1);
+    for (size_t k = 0; k < out.size(); k++) {
+        const Besthit &h = out[k];
+        if (h.dist < 0.0) slots[k] = slotPair(h.i, h.j);
         hintCriterion(nActive, h.i, h.j);
     }
 }
 
 template<typename P>
-void NJ<P>::uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out) {
-    for (auto &h : out) {
-        if (h.dist < 0.0) setDistCriterion(nActive, h);
-        else setCriterion(nActive, h);
+void NJ<P>::uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out, const std::vector<int64_t> &slots) {
+    for (size_t k = 0; k < out.size(); k++) {
+        Besthit &h = out[k];
+        if (h.dist < 0.0) {                                      // :4826-4827
+            if (slots[k] >= 0) { h.dist = reqD[slots[k]]; h.weight = reqW[slots[k]]; res->nPairPrefetchHit++; setCriterion(nActive, h); }
+            else setDistCriterion(nActive, h);
+        } else setCriterion(nActive, h);
     }
 }
 
@@ -428,18 +446,33 @@ void NJ<P>::setAllLeafTopHits() {
             if (isClose || identical) { closeNodes.push_back(closeNode); visited[closeNode] = 1; }
         }
         if (opt.prefetch) {
+            // all 2m-candidate lists of this seed's close neighbours in ONE device call, results by slot
             for (int64_t closeNode : closeNodes)
                 for (int64_t k = 0; k < 2 * m; k++) {
                     int64_t j = besthitsSeed[k].j;
-                    if (j >= 0 && j != closeNode) wantPair(closeNode, j);
+                    if (j >= 0 && j != closeNode) slotPair(closeNode, j);
                 }
-            flushPairs();
-        }
-        for (int64_t closeNode : closeNodes) {
-            res->nCloseUsed++;
-            besthitsNeighbor.resize(2 * m);
-            transferBestHits(nSeqs, closeNode, besthitsSeed, 2 * m, besthitsNeighbor.data(), true);   // :3988
-            sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                            // :3991
+            flush(nSeqs);
+            size_t r = 0;
+            for (int64_t closeNode : closeNodes) {
+                res->nCloseUsed++;
+                besthitsNeighbor.resize(2 * m);
+                for (int64_t k = 0; k < 2 * m; k++) {                    // transferBestHits, :4585-4612
+                    const Besthit &oldhit = besthitsSeed[k];
+                    Besthit &nh = besthitsNeighbor[k];
+                    nh.i = closeNode; nh.j = oldhit.j;                   // every leaf is its own active ancestor
+                    if (nh.j < 0 || nh.j == closeNode) { nh.weight = 0; nh.dist = (P) -1e20; nh.criterion = (P) 1e20; }
+                    else { nh.dist = reqD[r]; nh.weight = reqW[r]; r++; res->nPairPrefetchHit++; setCriterion(nSeqs, nh); }
+                }
+                sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                        // :3991
+            }
+        } else {
+            for (int64_t closeNode : closeNodes) {
+                res->nCloseUsed++;
+                besthitsNeighbor.resize(2 * m);
+                transferBestHits(nSeqs, closeNode, besthitsSeed, 2 * m, besthitsNeighbor.data(), true);   // :3988
+                sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                            // :3991
+            }
         }
         pairCache.clear();
     }
@@ -666,9 +699,10 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     hitsToBestHits(lChild[0]->hits, child[newnode].child[0], combinedList.data());
     hitsToBestHits(lChild[1]->hits, child[newnode].child[1], combinedList.data() + n0);
     std::vector<Besthit> uniqueList;
-    uniqueBestHitsPrepare(nActive, combinedList, uniqueList);
-    flushPairs(); flushOut(nActive);
-    uniqueBestHitsFinish(nActive, uniqueList);
+    std::vector<int64_t> uniqueSlots;
+    uniqueBestHitsPrepare(nActive, combinedList, uniqueList, uniqueSlots);
+    flush(nActive);
+    uniqueBestHitsFinish(nActive, uniqueList, uniqueSlots);
     int64_t nUnique = (int64_t) uniqueList.size();
     lChild[0]->hits.clear(); lChild[0]->hits.shrink_to_fit();
     lChild[1]->hits.clear(); lChild[1]->hits.shrink_to_fit();
@@ -703,7 +737,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     // expand the lists of the top m hits, :4477-4515.  The m iterations are independent (they
     // read allhits and parent[], write only their own list), so their distance requests are
     // gathered first and evaluated in one device call.
-    struct Work { int64_t iNode; std::vector<Besthit> unique; };
+    struct Work { int64_t iNode; std::vector<Besthit> unique; std::vector<int64_t> slots; };
     std::vector<Work> work;
     for (int64_t iHit = 0; iHit < m && iHit < (int64_t) allhits.size(); iHit++) {
         if (allhits[iHit].i < 0) continue;
@@ -718,12 +752,12 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         int64_t nAvail = std::min<int64_t>(2 * m, (int64_t) allhits.size());
         bothList.resize(nHitsOld + nAvail);
         transferBestHits(nActive, iNode, allhits, nAvail, bothList.data() + nHitsOld, false);
-        work.push_back(Work{iNode, {}});
-        uniqueBestHitsPrepare(nActive, bothList, work.back().unique);
+        work.push_back(Work{iNode, {}, {}});
+        uniqueBestHitsPrepare(nActive, bothList, work.back().unique, work.back().slots);
     }
-    flushPairs();
+    flush(nActive);
     for (Work &wk : work) {
-        uniqueBestHitsFinish(nActive, wk.unique);
+        uniqueBestHitsFinish(nActive, wk.unique, wk.slots);
         sortSaveBestHits(wk.iNode, wk.unique, (int64_t) wk.unique.size(), m, true);   // :4512
         visible[wk.iNode] = topHitsLists[wk.iNode].hits[0];
     }
@@ -928,8 +962,10 @@ int run(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, const ui
     auto t0 = clk::now();
     NJ<P> nj(ctx, cfg, opt, res, codes);
     try {
+        vft_timer_start(ctx);
         nj.init();
         nj.fastNJ();
+        vft_timer_stop(ctx, &res->deviceMsResident);
     } catch (const DeviceError &e) {
         return e.code;
     }
@@ -973,6 +1009,8 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     res->nSeeds = res->nCloseUsed = res->nRefreshTopHits = res->nVisibleUpdate = res->nHillBetter = 0;
     res->nOutPrefetchHit = res->nOutSingleFetch = res->nPairPrefetchHit = res->nPairSingleFetch = res->nDeviceCalls = 0;
     res->secondsLeafTopHits = res->secondsJoins = res->secondsTotal = 0;
+    res->deviceMsResident = res->secondsEndToEnd = 0;
+    auto e2e0 = std::chrono::steady_clock::now();
     vft_ctx *ctx = nullptr;
     int rc = vft_ctx_create(cfg, &ctx);
     if (rc != VFT_OK) return rc;
@@ -981,5 +1019,6 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     if (rc == VFT_OK) rc = cfg->precision == 32 ? run<float>(ctx, *cfg, opt, codes, res) : run<double>(ctx, *cfg, opt, codes, res);
     if (rc == VFT_OK) vft_get_counters(ctx, &res->counters);
     vft_ctx_destroy(ctx);
+    res->secondsEndToEnd = std::chrono::duration<double>(std::chrono::steady_clock::now() - e2e0).count();
     return rc;
 }

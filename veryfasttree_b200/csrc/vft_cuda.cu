@@ -5,7 +5,7 @@
 //   weights  P     [N][Lp]         internal nodes only (row = id - N)
 //   vecs     P     [N][Lp][A]      internal nodes only, dense (unused where the code is known)
 //   out-profile ow[Lp], ov[Lp][A], ocd[Lp][A]; per-node scalars diameter/selfdist/selfweight/outDist/active
-// Lp = nPos rounded up to 16 so that code rows are read with 128-bit loads.
+// Lp = nPos rounded up to 32: code rows are read with 128-bit loads and a warp covers 32 positions.
 //
 // Kernels (one thread accumulates one pair, see vft_device.cuh for why):
 //   k_dist_pairs      candidate lists           (transferBestHits / uniqueBestHits / getBestFromTopHits)
@@ -39,23 +39,55 @@ static int cuda_fail(cudaError_t e, const char *what) {
 // kernels
 // =================================================================================================
 
+// One launch evaluates a mixed request list (vft_eval_batch): items [0,nOutItems) are
+// setOutDistance requests (a = node), the rest are pair-distance requests (a,b).  Each warp owns G
+// consecutive items: leaf x leaf pairs are done by their own lane (seqDist is byte work), every other
+// item is evaluated by the whole warp, one after the other (profile_dist_warp).  G=1 for the small
+// per-join lists (latency), larger for the refresh batches (throughput).
+// ia/ib/r0/r1 live in pinned host memory mapped into the device address space (zero-copy): a
+// request costs one launch and one stream synchronisation, no separate memcpy.
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_dist_pairs(Store<P> s, const int64_t *__restrict__ pi, const int64_t *__restrict__ pj, int64_t n, int raw,
-             P *__restrict__ dist, P *__restrict__ weight) {
-    const int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    P d, w;
-    join_dist<P, A, MATRIX>(s, pi[t], pj[t], raw != 0, d, w);
-    dist[t] = d;
-    weight[t] = w;
+k_eval(Store<P> s, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib, int64_t n, int64_t nOutItems, int G,
+       int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1) {
+    __shared__ double smAll[4][64];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    double *sm = smAll[threadIdx.x >> 5];
+    const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+    const int64_t item = warp * G + lane;
+    const bool valid = lane < G && item < n;
+    const int64_t a = valid ? ia[item] : -1, b = valid ? ib[item] : -1;
+    const bool isOut = valid && item < nOutItems;
+    const bool isSeq = valid && !isOut && !raw && a < s.nSeqs && b < s.nSeqs;
+    P d = 0, w = 0;
+    if (isSeq) {
+        seq_dist<P, MATRIX>(s, s.codes + a * s.Lp, s.codes + b * s.Lp, d, w);
+        d = (P) xadd((double) d, 0.0);                                                    // NJ.tcc:1122
+    }
+    unsigned mask = __ballot_sync(full, valid && !isSeq);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t aa = __shfl_sync(full, a, src), bb = __shfl_sync(full, b, src);
+        const bool io = __shfl_sync(full, (int) isOut, src) != 0;
+        if (io) {
+            const P v = out_distance_warp<P, A, MATRIX>(s, aa, nActive, totdiam, sm);
+            if (lane == src) d = v;
+        } else {
+            P dd, ww;
+            join_dist_warp<P, A, MATRIX>(s, aa, bb, raw != 0, sm, dd, ww);
+            if (lane == src) { d = dd; w = ww; }
+        }
+    }
+    if (valid) { r0[item] = d; r1[item] = w; }
 }
 
-// setBestHit (NJ.tcc:3571-3639): one thread per node slot j < maxnode
+// setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_one_vs_all(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, P *__restrict__ dist,
-             P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, P *__restrict__ dist,
+                  P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
     const int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     if (j >= maxnode) return;
     if (!s.active[j]) { keys[j] = ~0ull; return; }
@@ -66,6 +98,60 @@ k_one_vs_all(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, P *__r
     const P c = (P) xsub((double) d, xadd(outI, outJ) / (double) (nActive - 2));
     dist[j] = d; weight[j] = w; crit[j] = c;
     keys[j] = order_key(c);
+}
+
+// setBestHit for an INTERNAL query: every distance is a profileDist; each warp owns G node slots
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(128)
+k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int G, P *__restrict__ dist,
+                  P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+    __shared__ double smAll[4][64];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    double *sm = smAll[threadIdx.x >> 5];
+    const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+    const int64_t j = warp * G + lane;
+    const bool valid = lane < G && j < maxnode;
+    const bool act = valid && s.active[j];
+    P d = 0, w = 0;
+    unsigned mask = __ballot_sync(full, act);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t jj = __shfl_sync(full, j, src);
+        P dd, ww;
+        join_dist_warp<P, A, MATRIX>(s, query, jj, false, sm, dd, ww);
+        if (lane == src) { d = dd; w = ww; }
+    }
+    if (!valid) return;
+    if (!act) { keys[j] = ~0ull; return; }
+    const double outI = (double) s.outDist[query], outJ = (double) s.outDist[j];
+    const P c = (P) xsub((double) d, xadd(outI, outJ) / (double) (nActive - 2));
+    dist[j] = d; weight[j] = w; crit[j] = c;
+    keys[j] = order_key(c);
+}
+
+// setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(128)
+k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam, P *__restrict__ out) {
+    __shared__ double smAll[4][64];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    double *sm = smAll[threadIdx.x >> 5];
+    const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+    const int64_t j = warp * G + lane;
+    const bool act = lane < G && j < maxnode && s.active[j];
+    P v = 0;
+    unsigned mask = __ballot_sync(full, act);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t jj = __shfl_sync(full, j, src);
+        const P r = out_distance_warp<P, A, MATRIX>(s, jj, nActive, totdiam, sm);
+        if (lane == src) v = r;
+    }
+    if (act) { out[j] = v; s.outDist[j] = v; }
 }
 
 // ---- top-K in psort order: key ascending, ties by index DESCENDING -----------------------------
@@ -138,20 +224,6 @@ __global__ void k_gather_topk(const uint32_t *__restrict__ idx, int K, const P *
     if (t >= K) return;
     const uint32_t j = idx[t];
     out[t].j = j; out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j];
-}
-
-// setOutDistance for a list of nodes (ids != nullptr) or for every active node (ids == nullptr)
-template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(128)
-k_out_distance(Store<P> s, const int64_t *__restrict__ ids, int64_t n, int64_t nActive, double totdiam,
-               P *__restrict__ out, int commit) {
-    const int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int64_t id = ids ? ids[t] : t;
-    if (!ids && !s.active[id]) return;
-    const P v = out_distance<P, A, MATRIX>(s, id, nActive, totdiam);
-    out[t] = v;
-    if (commit) s.outDist[id] = v;
 }
 
 // averageProfile (NJ.tcc:2067-2135) + profileDist(new,new) (NJ.tcc:3040-3043); ONE CTA:
@@ -249,7 +321,8 @@ k_outprofile_update(Store<P> s, int64_t o1, int64_t o2, int64_t nw, int64_t nAct
 }
 
 // outProfile, NJ.tcc:729-815: one thread per position walks the node list in ascending order
-// (the accumulation order of the reference at -threads 1)
+// (the accumulation order of the reference at -threads 1); the loads of 16 nodes are issued
+// together, the accumulation stays strictly in order.
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(64)
 k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
@@ -260,19 +333,30 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
     P f[A];
 #pragma unroll
     for (int k = 0; k < A; k++) f[k] = 0;
-    for (int64_t in = 0; in < n; in++) {
-        const int64_t id = ids[in];
-        const uint32_t c = s.codes[id * s.Lp + pos];
-        P w;
-        const P *fIn = nullptr;
-        if (id < s.nSeqs) w = c != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
-        else {
-            const int64_t row = id - s.nSeqs;
-            w = s.weights[row * s.Lp + pos];
-            if (c == VFT_DEV_NOCODE) fIn = s.vecs + (row * s.Lp + pos) * A;
+    constexpr int U = 16;
+    for (int64_t in0 = 0; in0 < n; in0 += U) {
+        int64_t id[U];
+        uint32_t c[U];
+        P w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            id[u] = in0 + u < n ? ids[in0 + u] : -1;
+            c[u] = id[u] >= 0 ? (uint32_t) s.codes[id[u] * s.Lp + pos] : VFT_DEV_NOCODE;
         }
-        wout = (P) xadd((double) wout, xmul((double) w, inweight));                        // :741
-        if (w > 0) add_to_freq<P, A, MATRIX>(s, f, (double) w, c, fIn);                    // :771-774
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (id[u] < 0) w[u] = 0;
+            else if (id[u] < s.nSeqs) w[u] = c[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+            else w[u] = s.weights[(id[u] - s.nSeqs) * s.Lp + pos];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            wout = (P) xadd((double) wout, xmul((double) w[u], inweight));                 // :741 (+0.0 for padding)
+            if (w[u] > 0) {
+                const P *fIn = (id[u] >= s.nSeqs && c[u] == VFT_DEV_NOCODE) ? s.vecs + ((id[u] - s.nSeqs) * s.Lp + pos) * A : nullptr;
+                add_to_freq<P, A, MATRIX>(s, f, (double) w[u], c[u], fIn);                 // :771-774
+            }
+        }
     }
     if (wout <= 0) wout = (P) 1e-20;                                                       // :743-745
     s.ow[pos] = wout;
@@ -317,8 +401,51 @@ struct vft_ctx {
     void *h_in, *h_out;
     size_t hCap;
     std::vector<uint8_t> activeHost;
+    int64_t nActLeaf, nActInternal;
     vft_counters cnt;
+    // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
+    cudaEvent_t tmr0, tmr1;
+    bool profile;
+    struct Pending { cudaEvent_t a, b; int cls; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
 };
+
+enum { CLS_DIST = 0, CLS_SELECT = 1, CLS_PROFILE = 2 };
+
+static void prof_begin(vft_ctx *c, int cls) {
+    if (!c->profile) return;
+    vft_ctx::Pending p;
+    for (cudaEvent_t *e : {&p.a, &p.b}) {
+        if (c->pool.empty()) cudaEventCreate(e);
+        else { *e = c->pool.back(); c->pool.pop_back(); }
+    }
+    p.cls = cls;
+    cudaEventRecord(p.a, c->stream);
+    c->pending.push_back(p);
+}
+static void prof_end(vft_ctx *c) {
+    if (!c->profile) return;
+    cudaEventRecord(c->pending.back().b, c->stream);
+}
+// call only after the stream has been synchronised
+static void prof_resolve(vft_ctx *c) {
+    if (!c->profile) return;
+    for (auto &p : c->pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        if (p.cls == CLS_DIST) { c->cnt.msDist += ms; c->cnt.distLaunches++; }
+        else if (p.cls == CLS_SELECT) c->cnt.msSelect += ms;
+        else c->cnt.msProfile += ms;
+        c->pool.push_back(p.a); c->pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
+static cudaError_t sync_stream(vft_ctx *c) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) prof_resolve(c);
+    return e;
+}
 
 template<typename P>
 static Store<P> make_store(vft_ctx *c) {
@@ -386,9 +513,11 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaSetDevice(cfg->device));
     vft_ctx *c = new vft_ctx();      // value-initialised: every pointer starts out null
     c->cfg = *cfg; c->A = cfg->nCodes; c->N = cfg->nSeqs; c->M = 2 * cfg->nSeqs; c->L = cfg->nPos;
-    c->Lp = (cfg->nPos + 15) / 16 * 16; c->ps = cfg->precision / 8; c->maxnode = 0;
+    c->Lp = (cfg->nPos + 31) / 32 * 32; c->ps = cfg->precision / 8; c->maxnode = 0;
     std::memset(&c->cnt, 0, sizeof c->cnt);
+    c->profile = (cfg->reserved & VFT_CFG_PROFILE) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->tmr0)); CK(cudaEventCreate(&c->tmr1));
     const size_t ps = c->ps, Lp = (size_t) c->Lp, A = (size_t) c->A, N = (size_t) c->N, M = (size_t) c->M;
     CK(cudaMalloc(&c->codes, M * Lp));
     CK(cudaMalloc(&c->weights, N * Lp * ps));
@@ -418,7 +547,7 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     if (rc != VFT_OK) return rc;
     cudaFuncSetAttribute(k_topk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
     cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     *out = c;
     return VFT_OK;
 }
@@ -432,6 +561,9 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->pool) cudaEventDestroy(e);
+    cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
     cudaStreamDestroy(c->stream);
     delete c;
     return VFT_OK;
@@ -445,7 +577,7 @@ extern "C" int vft_upload_tables(vft_ctx *c, const void *distances, const void *
     std::memcpy(h, distances, 400 * ps); std::memcpy(h + 400 * ps, eigenval, 20 * ps);
     std::memcpy(h + 420 * ps, eigentot, 20 * ps); std::memcpy(h + 440 * ps, codeFreq, 400 * ps);
     CK(cudaMemcpyAsync(c->tables, h, 840 * ps, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     return VFT_OK;
 }
 
@@ -459,15 +591,17 @@ extern "C" int vft_upload_leaves(vft_ctx *c, const uint8_t *codes) {
             padded[(size_t) i * c->Lp + p] = cd >= c->A ? VFT_NOCODE : cd;
         }
     CK(cudaMemcpyAsync(c->codes, padded.data(), padded.size(), cudaMemcpyHostToDevice, c->stream));
+    c->cnt.h2dBytes += (int64_t) padded.size();
     CK(cudaMemsetAsync(c->active, 0, c->M, c->stream));
 #define CALL_INIT(P, A_, MX) k_init_leaves<P><<<(unsigned) ((c->N + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c))
     if (c->cfg.precision == 32) { CALL_INIT(float, 0, 0); } else { CALL_INIT(double, 0, 0); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     c->cnt.launches++;
     std::fill(c->activeHost.begin(), c->activeHost.end(), 0);
     std::fill(c->activeHost.begin(), c->activeHost.begin() + c->N, 1);
     c->maxnode = c->N;
+    c->nActLeaf = c->N; c->nActInternal = 0;
     return VFT_OK;
 }
 
@@ -483,10 +617,13 @@ extern "C" int vft_outprofile_rebuild(vft_ctx *c, const int64_t *ids, int64_t n)
     rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
     std::memcpy(c->h_in, ids, (size_t) n * 8);
     CK(cudaMemcpyAsync(c->d_ids, c->h_in, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
+    c->cnt.h2dBytes += n * 8;
 #define CALL_REB(P, A_, MX) k_outprofile_rebuild<P, A_, MX><<<(unsigned) ((c->L + 63) / 64), 64, 0, c->stream>>>(make_store<P>(c), c->d_ids, n)
+    prof_begin(c, CLS_PROFILE);
     VFT_DISPATCH(c, CALL_REB);
+    prof_end(c);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));     // h_in is reused by the next call
+    CK(sync_stream(c));     // h_in is reused by the next call
     c->cnt.launches++;
     return VFT_OK;
 }
@@ -496,7 +633,9 @@ extern "C" int vft_outprofile_update(vft_ctx *c, int64_t old1, int64_t old2, int
         || old2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad argument");
 #define CALL_UPD(P, A_, MX) k_outprofile_update<P, A_, MX><<<(unsigned) ((c->L + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), old1, old2, newnode, nActiveOld)
+    prof_begin(c, CLS_PROFILE);
     VFT_DISPATCH(c, CALL_UPD);
+    prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;
     return VFT_OK;            // asynchronous: ordered on the context's stream
@@ -514,10 +653,14 @@ extern "C" int vft_profile_average(vft_ctx *c, int64_t out_id, int64_t id1, int6
         k_average<P, A_, MX><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out); \
     } while (0)
     if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the single-CTA average kernel");
+    prof_begin(c, CLS_PROFILE);
     VFT_DISPATCH(c, CALL_AVG);
+    prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++; c->cnt.profileAvgOps++; c->cnt.profileOps++;
-    c->activeHost[id1] = 0; c->activeHost[id2] = 0; c->activeHost[out_id] = 1;
+    for (int64_t ch : {id1, id2})
+        if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
+    if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
     return VFT_OK;            // asynchronous
 }
@@ -527,7 +670,7 @@ extern "C" int vft_get_self(vft_ctx *c, int64_t id, double *selfdist, double *se
     char buf[16];
     CK(cudaMemcpyAsync(buf, (char *) c->selfdist + id * c->ps, c->ps, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(buf + 8, (char *) c->selfweight + id * c->ps, c->ps, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     if (c->ps == 4) { *selfdist = *(float *) buf; *selfweight = *(float *) (buf + 8); }
     else { *selfdist = *(double *) buf; *selfweight = *(double *) (buf + 8); }
     return VFT_OK;
@@ -537,37 +680,81 @@ static int64_t profile_bytes(vft_ctx *c, int64_t id) {      // algorithmic bytes
     return id >= 0 && id < c->N ? c->L : c->L * ((int64_t) c->A * c->ps + c->ps + 1);
 }
 
+static int pick_group(int64_t nItems) {
+    // items per warp: 1 while the batch cannot fill the machine, more once it can (148 SMs x 16 warps)
+    int64_t g = (nItems + 2367) / 2368;
+    return (int) std::min<int64_t>(32, std::max<int64_t>(1, g));
+}
+
+// One request = one launch + one synchronisation.  Inputs are packed as int32 into pinned host
+// memory that the kernel reads directly (zero-copy); results come back the same way.
+extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, int64_t nActive, double totdiam,
+                              void *outDist, const int64_t *pi, const int64_t *pj, int64_t nPairs, int32_t flags,
+                              void *dist, void *weight) {
+    if (!c) return fail(VFT_EINVAL, "null argument");
+    if ((nOut > 0 && (!out_ids || !outDist)) || (nPairs > 0 && (!pi || !pj || !dist || !weight)) || nOut < 0 || nPairs < 0)
+        return fail(VFT_EINVAL, "null argument");
+    const int64_t n = nOut + nPairs;
+    if (n == 0) return VFT_OK;
+    int rc = ensure_pinned(c, (size_t) n * 16); if (rc) return rc;
+    int32_t *ha = (int32_t *) c->h_in, *hb = ha + n;
+    const bool raw = (flags & VFT_PAIRS_PROFILE_RAW) != 0;
+    for (int64_t k = 0; k < nOut; k++) {
+        if (out_ids[k] < 0 || out_ids[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        ha[k] = (int32_t) out_ids[k]; hb[k] = -1;
+        c->cnt.algoBytes += profile_bytes(c, out_ids[k]);
+    }
+    if (nOut) { c->cnt.algoBytes += profile_bytes(c, -1); c->cnt.profileOps += nOut; c->cnt.outprofileOps += nOut; }
+    int64_t lastQuery = -2;
+    for (int64_t k = 0; k < nPairs; k++) {
+        if (pi[k] < 0 || pj[k] < 0 || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        ha[nOut + k] = (int32_t) pi[k]; hb[nOut + k] = (int32_t) pj[k];
+        if (!raw && pi[k] < c->N && pj[k] < c->N) { c->cnt.seqOps++; c->cnt.algoBytes += c->L; }
+        else { c->cnt.profileOps++; c->cnt.algoBytes += profile_bytes(c, pj[k]); }
+        if (pi[k] != lastQuery) { c->cnt.algoBytes += profile_bytes(c, pi[k]); lastQuery = pi[k]; }   // a list shares its query
+    }
+    const int G = pick_group(n);
+    const int64_t warps = (n + G - 1) / G;
+    const unsigned blocks = (unsigned) ((warps + 3) / 4);
+    void *r0 = c->h_out, *r1 = (char *) c->h_out + (size_t) n * 8;
+#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), ha, hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1)
+    prof_begin(c, CLS_DIST);
+    VFT_DISPATCH(c, CALL_EVAL);
+    prof_end(c);
+    CK(cudaGetLastError());
+    CK(sync_stream(c));
+    c->cnt.launches++;
+    c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += n * 2 * (int64_t) c->ps;
+    if (nOut) std::memcpy(outDist, r0, (size_t) nOut * c->ps);
+    if (nPairs) {
+        std::memcpy(dist, (char *) r0 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+        std::memcpy(weight, (char *) r1 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+    }
+    return VFT_OK;
+}
+
 extern "C" int vft_out_distance_batch(vft_ctx *c, const int64_t *ids, int64_t n, int64_t nActive, double totdiam,
                                       void *outDist) {
-    if (!c || (n > 0 && (!ids || !outDist))) return fail(VFT_EINVAL, "null argument");
-    if (n == 0) return VFT_OK;
-    for (int64_t k = 0; k < n; k++) if (ids[k] < 0 || ids[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
-    int rc = ensure_lists(c, n); if (rc) return rc;
-    rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
-    std::memcpy(c->h_in, ids, (size_t) n * 8);
-    CK(cudaMemcpyAsync(c->d_ids, c->h_in, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
-#define CALL_OD(P, A_, MX) k_out_distance<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), c->d_ids, n, nActive, totdiam, (P *) c->d_out1, 0)
-    VFT_DISPATCH(c, CALL_OD);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_out, c->d_out1, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    std::memcpy(outDist, c->h_out, (size_t) n * c->ps);
-    c->cnt.launches++; c->cnt.profileOps += n; c->cnt.outprofileOps += n;
-    for (int64_t k = 0; k < n; k++) c->cnt.algoBytes += profile_bytes(c, ids[k]);
-    c->cnt.algoBytes += profile_bytes(c, -1);
-    return VFT_OK;
+    return vft_eval_batch(c, ids, n, nActive, totdiam, outDist, nullptr, nullptr, 0, 0, nullptr, nullptr);
+}
+
+extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, int64_t n, int32_t flags, void *dist,
+                              void *weight) {
+    return vft_eval_batch(c, nullptr, 0, 0, 0.0, nullptr, pi, pj, n, flags, dist, weight);
 }
 
 extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam, void *outDist, int64_t maxnode) {
     if (!c || !outDist || maxnode < c->maxnode) return fail(VFT_EINVAL, "bad argument");
     const int64_t n = c->maxnode;
-    int rc = ensure_lists(c, n); if (rc) return rc;
-    rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
-#define CALL_ODA(P, A_, MX) k_out_distance<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), nullptr, n, nActive, totdiam, (P *) c->d_out1, 1)
+    int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
+    const int G = pick_group(n);
+    const int64_t warps = (n + G - 1) / G;
+#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
+    prof_begin(c, CLS_DIST);
     VFT_DISPATCH(c, CALL_ODA);
+    prof_end(c);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_out, c->d_out1, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     int64_t nAct = 0;
     for (int64_t i = 0; i < n; i++)
         if (c->activeHost[i]) {
@@ -576,35 +763,7 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
         }
     c->cnt.launches++; c->cnt.profileOps += nAct; c->cnt.outprofileOps += nAct;
     c->cnt.algoBytes += profile_bytes(c, -1);
-    return VFT_OK;
-}
-
-extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, int64_t n, int32_t flags, void *dist,
-                              void *weight) {
-    if (!c || (n > 0 && (!pi || !pj || !dist || !weight))) return fail(VFT_EINVAL, "null argument");
-    if (n == 0) return VFT_OK;
-    int rc = ensure_lists(c, n); if (rc) return rc;
-    rc = ensure_pinned(c, (size_t) n * 16); if (rc) return rc;
-    int64_t *h = (int64_t *) c->h_in;
-    const bool raw = (flags & VFT_PAIRS_PROFILE_RAW) != 0;
-    for (int64_t k = 0; k < n; k++) {
-        if (pi[k] < 0 || pj[k] < 0 || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
-        h[k] = pi[k]; h[n + k] = pj[k];
-        if (!raw && pi[k] < c->N && pj[k] < c->N) { c->cnt.seqOps++; c->cnt.algoBytes += c->L; }
-        else { c->cnt.profileOps++; c->cnt.algoBytes += profile_bytes(c, pj[k]); }
-    }
-    c->cnt.algoBytes += profile_bytes(c, pi[0]);     // lists share their query; count it once
-    CK(cudaMemcpyAsync(c->d_pi, h, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_pj, h + n, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
-#define CALL_DP(P, A_, MX) k_dist_pairs<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), c->d_pi, c->d_pj, n, raw ? 1 : 0, (P *) c->d_out1, (P *) c->d_out2)
-    VFT_DISPATCH(c, CALL_DP);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_out, c->d_out1, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync((char *) c->h_out + (size_t) n * 8, c->d_out2, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    std::memcpy(dist, c->h_out, (size_t) n * c->ps);
-    std::memcpy(weight, (char *) c->h_out + (size_t) n * 8, (size_t) n * c->ps);
-    c->cnt.launches++;
+    c->cnt.d2hBytes += nAct * (int64_t) c->ps;
     return VFT_OK;
 }
 
@@ -621,13 +780,19 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
         if (K > SORT_N) return fail(VFT_EINVAL, "K larger than 4096 is not supported yet");
         Kc = SORT_N;
     }
-#define CALL_OVA(P, A_, MX) k_one_vs_all<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-    VFT_DISPATCH(c, CALL_OVA);
+    const int Gq = pick_group(n);
+    const int64_t warpsQ = (n + Gq - 1) / Gq;
+#define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+    prof_begin(c, CLS_DIST);
+    if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
+    prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;
     // chunk sort, then a merge tree until one list is left
     int nLists = (int) ((n + SORT_N - 1) / SORT_N);
     const int KcStage = std::min(Kc, SORT_N);
+    prof_begin(c, CLS_SELECT);
     k_topk_chunks<<<nLists, SORT_T, SORT_N * 12, c->stream>>>(c->d_keys, n, KcStage, c->d_tkA, c->d_tvA);
     CK(cudaGetLastError());
     c->cnt.launches++;
@@ -646,12 +811,13 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
     const int64_t nRet = std::min<int64_t>(std::min<int64_t>(K, nActive), KcStage);
     const size_t recSz = c->ps == 4 ? sizeof(Rec<float>) : sizeof(Rec<double>);
     int rc = ensure_pinned(c, (size_t) nRet * recSz); if (rc) return rc;
-    if (c->ps == 4) k_gather_topk<float><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->d_rec);
-    else k_gather_topk<double><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->d_rec);
+    if (c->ps == 4) k_gather_topk<float><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
+    else k_gather_topk<double><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->h_out);
     CK(cudaGetLastError());
     c->cnt.launches++;
-    CK(cudaMemcpyAsync(c->h_out, c->d_rec, (size_t) nRet * recSz, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    prof_end(c);
+    c->cnt.d2hBytes += (int64_t) (nRet * recSz);
+    CK(sync_stream(c));
     if (c->ps == 4) {
         const Rec<float> *r = (const Rec<float> *) c->h_out;
         for (int64_t k = 0; k < nRet; k++) { j_out[k] = r[k].j; ((float *) dist)[k] = r[k].dist; ((float *) weight)[k] = r[k].weight; ((float *) criterion)[k] = r[k].crit; }
@@ -661,11 +827,10 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
     }
     *nOut = nRet;
     // accounting: one distance per active node
-    for (int64_t j = 0; j < n; j++)
-        if (c->activeHost[j]) {
-            if (query < c->N && j < c->N) { c->cnt.seqOps++; c->cnt.algoBytes += c->L; }
-            else { c->cnt.profileOps++; c->cnt.algoBytes += profile_bytes(c, j); }
-        }
+    if (query < c->N) { c->cnt.seqOps += c->nActLeaf; c->cnt.algoBytes += c->nActLeaf * c->L; }
+    else { c->cnt.profileOps += c->nActLeaf; c->cnt.algoBytes += c->nActLeaf * profile_bytes(c, 0); }
+    c->cnt.profileOps += c->nActInternal;
+    c->cnt.algoBytes += c->nActInternal * profile_bytes(c, c->N);
     c->cnt.algoBytes += profile_bytes(c, query);
     return VFT_OK;
 }
@@ -673,7 +838,7 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
 extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *codes, void *vectors) {
     if (!c || id < -1 || id >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
     const size_t ps = c->ps, L = (size_t) c->L, Lp = (size_t) c->Lp, A = (size_t) c->A;
-    CK(cudaStreamSynchronize(c->stream));
+    CK(sync_stream(c));
     if (id < 0) {
         if (weights) CK(cudaMemcpy(weights, c->ow, L * ps, cudaMemcpyDeviceToHost));
         if (codes) std::memset(codes, VFT_NOCODE, L);
@@ -698,6 +863,24 @@ extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *c
 
 extern "C" int vft_get_counters(vft_ctx *c, vft_counters *out) {
     if (!c || !out) return fail(VFT_EINVAL, "null argument");
+    CK(sync_stream(c));
+    c->cnt.distBytes = c->cnt.algoBytes;      // only the distance kernels account algorithmic bytes
     *out = c->cnt;
+    return VFT_OK;
+}
+
+extern "C" int vft_timer_start(vft_ctx *c) {
+    if (!c) return fail(VFT_EINVAL, "null argument");
+    CK(cudaEventRecord(c->tmr0, c->stream));
+    return VFT_OK;
+}
+
+extern "C" int vft_timer_stop(vft_ctx *c, double *ms) {
+    if (!c || !ms) return fail(VFT_EINVAL, "null argument");
+    CK(cudaEventRecord(c->tmr1, c->stream));
+    CK(cudaEventSynchronize(c->tmr1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->tmr0, c->tmr1));
+    *ms = f;
     return VFT_OK;
 }

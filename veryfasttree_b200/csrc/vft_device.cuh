@@ -306,6 +306,77 @@ __device__ __forceinline__ void code_dist_row(const Store<P> &s, const P (&f)[A]
     }
 }
 
+
+// profileDist, NJ.tcc:1167-1190, by one WARP: the 32 lanes evaluate 32 consecutive positions in
+// parallel (coalesced loads along the node-major rows), then lane 0 / lane 1 add the 32
+// per-position terms of `denom` / `top` IN POSITION ORDER from shared memory.  The additions are
+// the reference's, in the reference's order; positions the reference skips contribute +0.0, and
+// x + (+0.0) == x for every value the accumulators can take (they are never -0.0), so the result is
+// bit-identical to the one-thread loop above -- at 1/30th of its latency.
+// `sm` = 64 doubles of shared memory private to the calling warp.  Result valid in every lane.
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void profile_dist_warp(const Store<P> &s, const View<P, A> &p1, const View<P, A> &p2,
+                                                  double *sm, P &dist, P &weight) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    double acc = 0;                                   // lane 0: denom, lane 1: top
+    const int64_t Lp = s.Lp;
+    for (int64_t base = 0; base < Lp; base += 32) {
+        const int64_t pos = base + lane;
+        const uint32_t c1 = p1.codes ? (uint32_t) p1.codes[pos] : VFT_DEV_NOCODE;
+        const uint32_t c2 = p2.codes ? (uint32_t) p2.codes[pos] : VFT_DEV_NOCODE;
+        const P w1 = p1.w ? p1.w[pos] : (c1 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+        const P w2 = p2.w ? p2.w[pos] : (c2 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+        double wt = 0, tt = 0;
+        const bool on = w1 > 0 && w2 > 0;
+        if (on) {
+            wt = (double) pmul(w1, w2);                                                    // :1176
+            tt = xmul(wt, piece<P, A, MATRIX>(s, c1, c2, p1.v ? p1.v + pos * A : nullptr,
+                                              p2.v ? p2.v + pos * A : nullptr, p2.cd ? p2.cd + pos * A : nullptr));
+        }
+        if (__ballot_sync(full, on) == 0) continue;   // nothing to add in this chunk
+        sm[lane] = wt;
+        sm[32 + lane] = tt;
+        __syncwarp();
+        if (lane < 2) {
+            const double *src = sm + 32 * lane;
+#pragma unroll
+            for (int k = 0; k < 32; k++) acc = xadd(acc, src[k]);
+        }
+        __syncwarp();
+    }
+    const double denom = __shfl_sync(full, acc, 0), top = __shfl_sync(full, acc, 1);
+    weight = (P) (denom > 0 ? denom : 0.01);                                              // :1187
+    dist = (P) (denom > 0 ? top / denom : 1.0);                                           // :1188
+}
+
+// distance half of setDistCriterion for a pair that is NOT leaf x leaf (or raw), by one warp
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void join_dist_warp(const Store<P> &s, int64_t i, int64_t j, bool raw, double *sm,
+                                               P &dist, P &weight) {
+    const View<P, A> v1 = make_view<P, A>(s, i), v2 = make_view<P, A>(s, j);
+    profile_dist_warp<P, A, MATRIX>(s, v1, v2, sm, dist, weight);
+    if (raw) return;
+    dist = psub(dist, padd(s.diameter[i], s.diameter[j]));                                // :1120
+    dist = (P) xadd((double) dist, 0.0);                                                  // :1122
+}
+
+// setOutDistance, NJ.tcc:1012-1053, by one warp
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ P out_distance_warp(const Store<P> &s, int64_t iNode, int64_t nActive, double totdiam, double *sm) {
+    P ddist, dweight;
+    const View<P, A> v1 = make_view<P, A>(s, iNode), vo = make_view<P, A>(s, -1);
+    profile_dist_warp<P, A, MATRIX>(s, v1, vo, sm, ddist, dweight);
+    const P pN = (P) nActive, pN1 = (P) (nActive - 1);
+    const P t4 = psub(pmul(pmul(ddist, dweight), pN), pmul(s.selfweight[iNode], s.selfdist[iNode]));   // :1046
+    const double top = (double) pmul(pN1, t4);
+    const double bottom = (double) psub(pmul(dweight, pN), s.selfweight[iNode]);                        // :1047
+    const double pd = top / bottom;                                                                       // :1048
+    const P dn = pmul(s.diameter[iNode], pN1);
+    const double r = bottom > 0.01 ? xsub(xsub(pd, (double) dn), xsub(totdiam, (double) s.diameter[iNode])) : 3.0;
+    return (P) r;
+}
+
 // orderable keys: ascending unsigned order == ascending floating order
 __device__ __forceinline__ uint64_t order_key(float x) {
     uint32_t u = __float_as_uint(x);
