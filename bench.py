@@ -225,7 +225,13 @@ def main():
         dev_ms_max, e2e_max, taxa_total, launches_total = dev_ms, e2e_s, float(n_unique), float(launches)
 
     # one extra profiled pass: per-kernel-class device time from CUDA events on the launching stream
-    prof = one_step(profile=True).stats["counters"]
+    ptree = one_step(profile=True)
+    prof = ptree.stats["counters"]
+    if rank == 0:
+        st = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in tr.stats.items() if k not in ("counters",)}
+        st["secondsHost"] = [round(x, 3) for x in tr.stats["secondsHost"]]
+        print("[bench] last timed step:", json.dumps(st), file=sys.stderr)
+        print("[bench] profiled pass counters:", json.dumps(prof), file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

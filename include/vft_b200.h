@@ -189,7 +189,9 @@ typedef struct vft_nj_options {
                                    ahead of the host loops (default); 0 = fetch one at a time
                                    (same results, used by the tests to prove the prefetch is only
                                    a hint) */
-    int32_t reserved;
+    int32_t hostThreads;        /* OpenMP threads for the per-list host work of the refreshes and the
+                                   leaf transfers (the reference parallelises the same loops,
+                                   NJ.tcc:4477, :3838); 0 = min(16, cores).  Results do not depend on it. */
 } vft_nj_options;
 
 void vft_nj_default_options(vft_nj_options *opt);
@@ -211,6 +213,9 @@ typedef struct vft_nj_result {
     double  secondsLeafTopHits, secondsJoins, secondsTotal;
     double  deviceMsResident;   /* vft_timer around ctor tail + fastNJ: leaves already in HBM  */
     double  secondsEndToEnd;    /* host clock around everything incl. context + upload + result */
+    double  secondsInCalls;     /* host clock spent inside the kernel-level ABI calls              */
+    double  secondsHost[8];     /* host-only time: 0 leaf top-hits, 1 first top-visible, 2 join search,
+                                   3 join bookkeeping (incl. 4), 4 topHitJoin (incl. 5), 5 refreshes  */
     vft_counters counters;
 } vft_nj_result;
 

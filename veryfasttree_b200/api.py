@@ -38,7 +38,7 @@ class VftNjOptions(C.Structure):
     _fields_ = [("tophitsMult", C.c_double), ("tophitsClose", C.c_double), ("topvisibleMult", C.c_double),
                 ("tophitsRefresh", C.c_double), ("staleOutLimit", C.c_double), ("fResetOutProfile", C.c_double),
                 ("nResetOutProfile", C.c_int32), ("bionj", C.c_int32), ("prefetch", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("hostThreads", C.c_int32)]
 
 
 class VftNjResult(C.Structure):
@@ -50,7 +50,7 @@ class VftNjResult(C.Structure):
                 ("nOutPrefetchHit", C.c_int64), ("nOutSingleFetch", C.c_int64),
                 ("nPairPrefetchHit", C.c_int64), ("nPairSingleFetch", C.c_int64), ("nDeviceCalls", C.c_int64),
                 ("secondsLeafTopHits", C.c_double), ("secondsJoins", C.c_double), ("secondsTotal", C.c_double),
-                ("deviceMsResident", C.c_double), ("secondsEndToEnd", C.c_double),
+                ("deviceMsResident", C.c_double), ("secondsEndToEnd", C.c_double), ("secondsInCalls", C.c_double), ("secondsHost", C.c_double * 8),
                 ("counters", VftCounters)]
 
 
@@ -293,7 +293,7 @@ class NJTree:
 
 def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | None = None,
              tables=None, device: int = 0, prefetch: bool = True, trace: bool = True,
-             reduction: int = 1, profile: bool = False) -> NJTree:
+             reduction: int = 1, profile: bool = False, host_threads: int = 0) -> NJTree:
     """The metric phase (NJ ctor tail + fastNJ) through vft_nj_build with HOST buffers."""
     lib = lib or load()
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -304,6 +304,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
     opt = VftNjOptions()
     lib.dll.vft_nj_default_options(C.byref(opt))
     opt.prefetch = int(prefetch)
+    opt.hostThreads = host_threads
     M = 2 * n
     parent = np.full(M, -1, dtype=np.int64)
     n_child = np.zeros(M, dtype=np.int32)
@@ -323,7 +324,8 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
         tptr = C.cast(arr, C.c_void_p)
     rc = lib.dll.vft_nj_build(C.byref(cfg), C.byref(opt), _ptr(codes), tptr, C.byref(res))
     lib.check(rc, "vft_nj_build")
-    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:24]}
+    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:25]}
+    stats["secondsHost"] = [float(x) for x in res.secondsHost]
     stats.update({"counters": {k: getattr(res.counters, k) for k, _ in VftCounters._fields_}})
     return NJTree(n, precision, parent, n_child, child, bl, res.root, res.maxnode, res.m,
                   joins, lth, stats)

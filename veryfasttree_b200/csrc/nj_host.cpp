@@ -21,6 +21,7 @@
 #include "../../include/vft_b200.h"
 
 #include <algorithm>
+#include <omp.h>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -43,6 +44,26 @@ void rsort(std::vector<T> &v, Less strictLess) {
 
 struct DeviceError { int code; };
 
+// orderable integer keys: ascending unsigned order == ascending floating order
+inline uint64_t orderKey(float x) { if (x == 0) x = 0; uint32_t u; std::memcpy(&u, &x, 4); return (u & 0x80000000u) ? (uint32_t) ~u : (u | 0x80000000u); }
+inline uint64_t orderKey(double x) { if (x == 0) x = 0; uint64_t u; std::memcpy(&u, &x, 8); return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull); }
+
+// psort order for an array of records with an integer key: key ascending, ties by input position
+// DESCENDING.  Sorts 16-byte (key, position) pairs and permutes once; scratch is per thread.
+template<class T, class KeyFn>
+void rsortByKey(std::vector<T> &v, KeyFn keyOf) {
+    const size_t n = v.size();
+    if (n < 2) return;
+    static thread_local std::vector<std::pair<uint64_t, uint32_t>> kv;
+    static thread_local std::vector<T> tmp;
+    kv.resize(n);
+    for (size_t k = 0; k < n; k++) kv[k] = {keyOf(v[k]), (uint32_t) (n - 1 - k)};   // reversed position: plain pair order
+    std::sort(kv.begin(), kv.end());
+    tmp.resize(n);
+    for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - kv[k].second];
+    v.swap(tmp);
+}
+
 template<typename P>
 class NJ {
 public:
@@ -64,6 +85,7 @@ public:
         freshVal.assign(maxnodes, 0);
         freshEpoch.assign(maxnodes, -1);
         wantEpoch.assign(maxnodes, -1);
+        hostThreads = opt.hostThreads > 0 ? opt.hostThreads : std::max(1, std::min(16, omp_get_num_procs()));
         // nGaps(i) = nPos - selfweight[i] (NJ.tcc:249-252, :3762): gap/unknown columns of leaf i
         leafGaps.assign(nSeqs, 0);
         for (int64_t i = 0; i < nSeqs; i++) {
@@ -75,10 +97,10 @@ public:
 
     // ---- NeighbourJoining ctor tail, NJ.tcc:237-260 ------------------------------------------
     void init() {
-        check(vft_outprofile_rebuild(ctx, nullptr, nSeqs));
+        check(timed([&] { return vft_outprofile_rebuild(ctx, nullptr, nSeqs); }));
         totdiam = 0.0;
         std::vector<P> od(maxnodes);
-        check(vft_out_distance_all(ctx, nSeqs, totdiam, od.data(), maxnodes));
+        check(timed([&] { return vft_out_distance_all(ctx, nSeqs, totdiam, od.data(), maxnodes); }));
         for (int64_t i = 0; i < nSeqs; i++) { outDistances[i] = od[i]; nOutDistActive[i] = nSeqs; }
         newEpoch(nSeqs);
     }
@@ -109,6 +131,22 @@ private:
     int64_t topvisibleAge = 0;
 
     void check(int rc) { res->nDeviceCalls++; if (rc != VFT_OK) throw DeviceError{rc}; }
+    // wall time spent inside ABI calls (device + its synchronisation), for the host/device split
+    // host-side time per section of the phase (wall clock minus time inside ABI calls)
+    struct Section {
+        NJ *nj; int k; std::chrono::steady_clock::time_point t0; double calls0;
+        Section(NJ *nj, int k) : nj(nj), k(k), t0(std::chrono::steady_clock::now()), calls0(nj->res->secondsInCalls) {}
+        ~Section() {
+            double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            nj->res->secondsHost[k] += wall - (nj->res->secondsInCalls - calls0);
+        }
+    };
+    template<class F> int timed(F f) {
+        auto t0 = std::chrono::steady_clock::now();
+        int rc = f();
+        res->secondsInCalls += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
 
     // ---- fresh out-distance service ------------------------------------------------------------
     // A fresh value is a pure function of (node, out-profile, nActive, totdiam); all three are
@@ -140,8 +178,8 @@ private:
         if (wantIds.empty() && reqI.empty()) return;
         wantVals.resize(wantIds.size());
         reqD.resize(reqI.size()); reqW.resize(reqI.size());
-        check(vft_eval_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data(),
-                             reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()));
+        check(timed([&] { return vft_eval_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data(),
+                             reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()); }));
         for (size_t k = 0; k < wantIds.size(); k++) { freshVal[wantIds[k]] = wantVals[k]; freshEpoch[wantIds[k]] = epoch; }
         for (size_t k = 0; k < reqI.size(); k++)
             if (reqCached[k]) pairCache[pkey(reqI[k], reqJ[k])] = DW{reqD[k], reqW[k]};
@@ -158,7 +196,7 @@ private:
             res->nOutPrefetchHit++;
         } else {
             P v;
-            check(vft_out_distance_batch(ctx, &i, 1, nActive, totdiam, &v));
+            check(timed([&] { return vft_out_distance_batch(ctx, &i, 1, nActive, totdiam, &v); }));
             freshVal[i] = v;
             if (epochActive == nActive) freshEpoch[i] = epoch;
             res->nOutSingleFetch++;
@@ -197,8 +235,17 @@ private:
         auto it = pairCache.find(pkey(i, j));
         if (it != pairCache.end() && it->second.weight >= 0) { res->nPairPrefetchHit++; return it->second; }
         DW r;
-        check(vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight));
+        check(timed([&] { return vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight); }));
         res->nPairSingleFetch++;
+        return r;
+    }
+
+    DW pairDistNoCache(int64_t i, int64_t j) {       // callable from host threads: no shared counters
+        DW r;
+        int rc;
+#pragma omp critical(vft_device_call)
+        rc = vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight);
+        if (rc != VFT_OK) throw DeviceError{rc};
         return r;
     }
 
@@ -251,6 +298,18 @@ private:
         return true;
     }
 
+    // what getBestFromTopHits(iNode) will ask for (NJ.tcc:4267-4298)
+    void hintList(int64_t nActive, int64_t iNode) {
+        if (iNode < 0 || parent[iNode] >= 0) return;
+        wantOut(iNode, nActive, /*evenIfNotStale*/true);
+        for (const Hit &h : topHitsLists[iNode].hits) {
+            int64_t j = activeAncestor(h.j);
+            if (j < 0 || j == iNode) continue;
+            if (j != h.j) wantPair(iNode, j);
+            wantOut(j, nActive);
+        }
+    }
+
     void hintVisible(int64_t nActive, int64_t iNode) {
         if (iNode < 0 || parent[iNode] >= 0) return;
         hintCriterion(nActive, iNode, visible[iNode].j);
@@ -272,7 +331,7 @@ private:
     }
 
     static void sortByCriterion(std::vector<Besthit> &v) {     // psort(.., CompareHitsByCriterion), NJ.tcc:7301-7306
-        rsort(v, [](const Besthit &a, const Besthit &b) { return a.criterion < b.criterion; });
+        rsortByKey(v, [](const Besthit &a) { return orderKey(a.criterion); });
     }
 
     void sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int64_t nIn, int64_t nOut, bool sort);
@@ -281,6 +340,8 @@ private:
     void uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out,
                                std::vector<int64_t> &slots);
     void uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out, const std::vector<int64_t> &slots);
+    void uniqueCore(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out);
+    int hostThreads = 1;
     void setAllLeafTopHits();
     void resetTopVisible(int64_t nActive);
     void updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit);
@@ -300,7 +361,7 @@ int64_t NJ<P>::oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<B
     std::vector<int64_t> js(K);
     std::vector<P> d(K), w(K), c(K);
     int64_t n = 0;
-    check(vft_dist_one_vs_all(ctx, query, nActive, K, js.data(), d.data(), w.data(), c.data(), &n));
+    check(timed([&] { return vft_dist_one_vs_all(ctx, query, nActive, K, js.data(), d.data(), w.data(), c.data(), &n); }));
     out.resize(K);
     for (int64_t k = 0; k < n; k++) out[k] = Besthit{query, js[k], w[k], d[k], c[k]};
     // sentinels of inactive nodes (NJ.tcc:3613-3617): criterion 1e20 ties, later index first
@@ -362,8 +423,22 @@ void NJ<P>::transferBestHits(int64_t nActive, int64_t iNode, const std::vector<B
 template<typename P>
 void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out,
                                   std::vector<int64_t> &slots) {
+    uniqueCore(nActive, combined, out);
+    slots.assign(out.size(), -1);
+    for (size_t k = 0; k < out.size(); k++) {
+        const Besthit &h = out[k];
+        if (h.dist < 0.0) slots[k] = slotPair(h.i, h.j);
+        hintCriterion(nActive, h.i, h.j);
+    }
+}
+
+// the part of uniqueBestHits that touches no shared state: ancestor walk, psort by (i,j), dedupe
+template<typename P>
+void NJ<P>::uniqueCore(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out) {
     for (auto &h : combined) updateBestHit(nActive, h, false);
-    rsort(combined, [](const Besthit &a, const Besthit &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    {   // psort by (i,j), NJ.tcc:4797, :7309-7311; ids fit 31 bits, -1 sorts first
+        rsortByKey(combined, [](const Besthit &a) { return ((uint64_t) (uint32_t) (a.i + 1) << 32) | (uint32_t) (a.j + 1); });
+    }
     out.clear();
     out.reserve(combined.size());
     int64_t iSavedLast = -1;
@@ -376,12 +451,6 @@ void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combine
         }
         out.push_back(hit);
         iSavedLast = k;
-    }
-    slots.assign(out.size(), -1);
-    for (size_t k = 0; k < out.size(); k++) {
-        const Besthit &h = out[k];
-        if (h.dist < 0.0) slots[k] = slotPair(h.i, h.j);
-        hintCriterion(nActive, h.i, h.j);
     }
 }
 
@@ -453,18 +522,28 @@ void NJ<P>::setAllLeafTopHits() {
                     if (j >= 0 && j != closeNode) slotPair(closeNode, j);
                 }
             flush(nSeqs);
-            size_t r = 0;
-            for (int64_t closeNode : closeNodes) {
-                res->nCloseUsed++;
-                besthitsNeighbor.resize(2 * m);
+            // slot offsets per close node, then the lists are completed by the host threads
+            std::vector<size_t> firstSlot(closeNodes.size() + 1, 0);
+            for (size_t ci = 0; ci < closeNodes.size(); ci++) {
+                size_t cnt = 0;
+                for (int64_t k = 0; k < 2 * m; k++) { int64_t j = besthitsSeed[k].j; cnt += (j >= 0 && j != closeNodes[ci]); }
+                firstSlot[ci + 1] = firstSlot[ci] + cnt;
+            }
+            res->nCloseUsed += (int64_t) closeNodes.size();
+            res->nPairPrefetchHit += (int64_t) firstSlot.back();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(hostThreads)
+            for (int64_t ci = 0; ci < (int64_t) closeNodes.size(); ci++) {
+                const int64_t closeNode = closeNodes[ci];
+                std::vector<Besthit> nb(2 * m);
+                size_t r = firstSlot[ci];
                 for (int64_t k = 0; k < 2 * m; k++) {                    // transferBestHits, :4585-4612
                     const Besthit &oldhit = besthitsSeed[k];
-                    Besthit &nh = besthitsNeighbor[k];
+                    Besthit &nh = nb[k];
                     nh.i = closeNode; nh.j = oldhit.j;                   // every leaf is its own active ancestor
                     if (nh.j < 0 || nh.j == closeNode) { nh.weight = 0; nh.dist = (P) -1e20; nh.criterion = (P) 1e20; }
-                    else { nh.dist = reqD[r]; nh.weight = reqW[r]; r++; res->nPairPrefetchHit++; setCriterion(nSeqs, nh); }
+                    else { nh.dist = reqD[r]; nh.weight = reqW[r]; r++; setCriterion(nSeqs, nh); }
                 }
-                sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                        // :3991
+                sortSaveBestHits(closeNode, nb, 2 * m, m, true);                                      // :3991
             }
         } else {
             for (int64_t closeNode : closeNodes) {
@@ -518,33 +597,50 @@ void NJ<P>::setAllLeafTopHits() {
 // resetTopVisible, NJ.tcc:4728-4784
 template<typename P>
 void NJ<P>::resetTopVisible(int64_t nActive) {
-    if (opt.prefetch) {
-        for (int64_t i = 0; i < maxnode; i++) hintVisible(nActive, i);
-        flushOut(nActive);
-    }
-    std::vector<Besthit> visibleSorted;
-    visibleSorted.reserve(nActive);
+    // pass 1: which nodes have a live visible hit (getVisible's tests, :546-553) + staleness hints
+    static thread_local std::vector<int64_t> cand;
+    cand.clear();
     for (int64_t i = 0; i < maxnode; i++) {
         if (parent[i] >= 0) continue;
-        Besthit v;
-        if (getVisible(nActive, i, v)) visibleSorted.push_back(v);
+        const Hit &h = visible[i];
+        if (h.j < 0 || parent[h.j] >= 0) continue;
+        cand.push_back(i);
+        if (opt.prefetch) { wantOut(i, nActive); wantOut(h.j, nActive); }
     }
-    // The reference allocates nActive slots (:4729), fills nVisible of them and psorts ALL of
-    // them (:4744); the unfilled tail is value-initialised (i=j=0, criterion 0) and takes part in
-    // the sort, and only the first nVisible sorted slots are read (:4761).  Reproduced literally.
-    size_t nVisible = visibleSorted.size();
-    visibleSorted.resize((size_t) nActive, Besthit{0, 0, 0, 0, 0});
-    sortByCriterion(visibleSorted);
-    std::vector<int64_t> inTopVisible(maxnodes, -1);
+    flush(nActive);
+    // pass 2: criteria, in ascending node order = the order of visibleSorted[] in the reference
+    const size_t nVisible = cand.size();
+    static thread_local std::vector<Besthit> vis;
+    vis.resize(nVisible);
+    for (size_t k = 0; k < nVisible; k++) getVisible(nActive, cand[k], vis[k]);
+    // The reference allocates nActive slots (:4729), fills nVisible of them and psorts ALL of them
+    // (:4744); the unfilled tail is value-initialised (i=j=0, criterion 0) and takes part in the
+    // sort, and only the first nVisible sorted slots are read (:4761).  Reproduced literally, but
+    // only as much of the order as is consumed is materialised: (key, reversed position) pairs,
+    // partially sorted, extended on demand.
+    const size_t nAll = (size_t) std::max<int64_t>(nActive, (int64_t) nVisible);
+    static thread_local std::vector<std::pair<uint64_t, uint32_t>> kv;
+    kv.resize(nAll);
+    const uint64_t zeroKey = orderKey((P) 0);
+    for (size_t k = 0; k < nAll; k++) kv[k] = {k < nVisible ? orderKey(vis[k].criterion) : zeroKey, (uint32_t) (nAll - 1 - k)};
+    size_t sorted = std::min(nAll, 4 * topvisible.size() + 64);
+    std::partial_sort(kv.begin(), kv.begin() + sorted, kv.end());
+    static thread_local std::vector<int64_t> inTopVisible;
+    static thread_local std::vector<int64_t> touched;
+    if ((int64_t) inTopVisible.size() < maxnodes) inTopVisible.assign(maxnodes, -1);
+    touched.clear();
     size_t iSave = 0;
     for (size_t k = 0; k < nVisible && iSave < topvisible.size(); k++) {
-        const Besthit &v = visibleSorted[k];
-        if (inTopVisible[v.i] != v.j) {
-            topvisible[iSave++] = v.i;
-            inTopVisible[v.i] = v.j;
-            inTopVisible[v.j] = v.i;
+        if (k >= sorted) { std::sort(kv.begin() + sorted, kv.end()); sorted = nAll; }
+        const size_t src = nAll - 1 - kv[k].second;
+        const int64_t vi = src < nVisible ? vis[src].i : 0, vj = src < nVisible ? vis[src].j : 0;
+        if (inTopVisible[vi] != vj) {
+            topvisible[iSave++] = vi;
+            inTopVisible[vi] = vj; touched.push_back(vi);
+            inTopVisible[vj] = vi; touched.push_back(vj);
         }
     }
+    for (int64_t t : touched) inTopVisible[t] = -1;
     while (iSave < topvisible.size()) topvisible[iSave++] = -1;
     topvisibleAge = 0;
 }
@@ -606,17 +702,7 @@ void NJ<P>::updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode) {
 template<typename P>
 void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin) {
     TopHitsList &l = topHitsLists[iNode];
-    if (opt.prefetch) {
-        wantOut(iNode, nActive, /*evenIfNotStale*/true);
-        for (const Hit &h : l.hits) {
-            int64_t j = activeAncestor(h.j);
-            if (j < 0 || j == iNode) continue;
-            if (j != h.j) wantPair(iNode, j);
-            wantOut(j, nActive);
-        }
-        flushOut(nActive);
-        flushPairs();
-    }
+    if (opt.prefetch) { hintList(nActive, iNode); flush(nActive); }
     setOutDistance(iNode, nActive);                                      // :4276
     bestjoin.i = -1; bestjoin.j = -1; bestjoin.weight = 0;
     bestjoin.dist = (P) 1e20; bestjoin.criterion = (P) 1e20;
@@ -635,7 +721,29 @@ template<typename P>
 void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
     if (opt.prefetch) {
         for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
-        flushOut(nActive);
+        // Speculation: guess the join from the values we already hold (stale out-distances rescaled,
+        // no refresh) and queue what the hill-climb over its two top-hit lists and the join itself
+        // will ask for, so that the whole search usually costs ONE device call.  Only a hint: the
+        // exact search below decides, and fetches whatever the guess did not cover.
+        int64_t g1 = -1, g2 = -1;
+        double c1 = 1e300, c2 = 1e300;
+        for (int64_t iNode : topvisible) {
+            if (iNode < 0 || parent[iNode] >= 0) continue;
+            const Hit &h = visible[iNode];
+            if (h.j < 0 || parent[h.j] >= 0) continue;
+            double outI = outDistances[iNode], outJ = outDistances[h.j];
+            if (nOutDistActive[iNode] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[iNode] - 1);
+            if (nOutDistActive[h.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[h.j] - 1);
+            double c = h.dist - (outI + outJ) / (double) (nActive - 2);
+            if (c < c1) { c2 = c1; g2 = g1; c1 = c; g1 = iNode; } else if (c < c2) { c2 = c; g2 = iNode; }
+        }
+        for (int64_t g : {g1, g2}) {
+            if (g < 0) continue;
+            const int64_t gj = visible[g].j;
+            hintList(nActive, g); hintList(nActive, gj);
+            wantPair(g, gj);
+        }
+        flush(nActive);
     }
     int64_t nCandidate = 0, iNodeBestCandidate = -1;
     double dBestCriterion = 1e20;
@@ -701,6 +809,10 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     std::vector<Besthit> uniqueList;
     std::vector<int64_t> uniqueSlots;
     uniqueBestHitsPrepare(nActive, combinedList, uniqueList, uniqueSlots);
+    if (opt.prefetch) {      // what updateTopVisible / updateVisible below can touch (a superset)
+        for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
+        for (const Besthit &h : uniqueList) hintVisible(nActive, h.j);
+    }
     flush(nActive);
     uniqueBestHitsFinish(nActive, uniqueList, uniqueSlots);
     int64_t nUnique = (int64_t) uniqueList.size();
@@ -722,11 +834,12 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     }
 
     // ---- refresh, NJ.tcc:4439-4517 ------------------------------------------------------------
+    Section secRefresh(this, 5);
     res->nRefreshTopHits++;
     lNew.age = 0;
     {   // every out-distance up to date, :4451-4464
         std::vector<P> od(maxnodes);
-        check(vft_out_distance_all(ctx, nActive, totdiam, od.data(), maxnodes));
+        check(timed([&] { return vft_out_distance_all(ctx, nActive, totdiam, od.data(), maxnodes); }));
         for (int64_t i = 0; i < maxnode; i++)
             if (parent[i] < 0) { outDistances[i] = od[i]; nOutDistActive[i] = nActive; }
     }
@@ -743,24 +856,46 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         if (allhits[iHit].i < 0) continue;
         int64_t iNode = allhits[iHit].j;
         if (parent[iNode] >= 0) continue;
+        work.push_back(Work{iNode, {}, {}});
+    }
+    const int64_t nAvail = std::min<int64_t>(2 * m, (int64_t) allhits.size());
+    // host threads over the lists, as the reference does (NJ.tcc:4477): every out-distance is fresh
+    // here, so setCriterion is a pure function and the iterations share nothing they write
+#pragma omp parallel for schedule(dynamic, 2) num_threads(hostThreads)
+    for (int64_t wi = 0; wi < (int64_t) work.size(); wi++) {
+        Work &wk = work[wi];
+        const int64_t iNode = wk.iNode;
         TopHitsList &l = topHitsLists[iNode];
         int64_t nHitsOld = (int64_t) l.hits.size();
         l.age = 0;
-        std::vector<Besthit> bothList(nHitsOld + 2 * m);
+        std::vector<Besthit> bothList(nHitsOld + nAvail);
         hitsToBestHits(l.hits, iNode, bothList.data());
         for (int64_t k = 0; k < nHitsOld; k++) setCriterion(nActive, bothList[k]);
-        int64_t nAvail = std::min<int64_t>(2 * m, (int64_t) allhits.size());
-        bothList.resize(nHitsOld + nAvail);
         transferBestHits(nActive, iNode, allhits, nAvail, bothList.data() + nHitsOld, false);
-        work.push_back(Work{iNode, {}, {}});
-        uniqueBestHitsPrepare(nActive, bothList, work.back().unique, work.back().slots);
+        uniqueCore(nActive, bothList, wk.unique);
+    }
+    for (Work &wk : work) {
+        wk.slots.assign(wk.unique.size(), -1);
+        for (size_t k = 0; k < wk.unique.size(); k++)
+            if (wk.unique[k].dist < 0.0) wk.slots[k] = slotPair(wk.unique[k].i, wk.unique[k].j);
     }
     flush(nActive);
-    for (Work &wk : work) {
-        uniqueBestHitsFinish(nActive, wk.unique, wk.slots);
+    int64_t hits = 0;
+#pragma omp parallel for schedule(dynamic, 2) num_threads(hostThreads) reduction(+ : hits)
+    for (int64_t wi = 0; wi < (int64_t) work.size(); wi++) {
+        Work &wk = work[wi];
+        for (size_t k = 0; k < wk.unique.size(); k++) {            // uniqueBestHits tail, :4823-4831
+            Besthit &h = wk.unique[k];
+            if (h.dist < 0.0) {
+                if (wk.slots[k] >= 0) { h.dist = reqD[wk.slots[k]]; h.weight = reqW[wk.slots[k]]; hits++; }
+                else { DW r = pairDistNoCache(h.i, h.j); h.dist = r.dist; h.weight = r.weight; }
+            }
+            setCriterion(nActive, h);
+        }
         sortSaveBestHits(wk.iNode, wk.unique, (int64_t) wk.unique.size(), m, true);   // :4512
         visible[wk.iNode] = topHitsLists[wk.iNode].hits[0];
     }
+    res->nPairPrefetchHit += hits;
     pairCache.clear();
     resetTopVisible(nActive);                                            // :4517
 }
@@ -840,13 +975,13 @@ void NJ<P>::fastNJ() {
         topHitsLists.resize(maxnodes);
         visible.assign(maxnodes, Hit{-1, (P) 1e20});
         topvisible.assign((size_t) (0.5 + opt.topvisibleMult * m), -1);
-        setAllLeafTopHits();
+        { Section sec(this, 0); setAllLeafTopHits(); }
         if (res->leafTopHits) {
             for (int64_t i = 0; i < nSeqs; i++)
                 for (int64_t k = 0; k < m; k++)
                     res->leafTopHits[i * m + k] = k < (int64_t) topHitsLists[i].hits.size() ? topHitsLists[i].hits[k].j : -1;
         }
-        resetTopVisible(nSeqs);
+        { Section sec(this, 1); resetTopVisible(nSeqs); }
     } else {
         visibleSet.resize(maxnodes, Besthit{-1, -1, 0, (P) 1e20, (P) 1e20});
         for (int64_t i = 0; i < nSeqs; i++) setBestHitFull(i, nSeqs, visibleSet[i], nullptr);
@@ -857,8 +992,12 @@ void NJ<P>::fastNJ() {
     int64_t nActiveOutProfileReset = nSeqs;
     for (int64_t nActive = nSeqs; nActive > 3; nActive--) {
         Besthit join;
-        if (m > 0) topHitNJSearch(nActive, join);
-        else fastNJSearch(nActive, visibleSet, join);
+        {
+            Section sec(this, 2);
+            if (m > 0) topHitNJSearch(nActive, join);
+            else fastNJSearch(nActive, visibleSet, join);
+        }
+        Section secJoin(this, 3);
 
         // :2897-2900 -- out-distances of the pair up to date, distance and weight recomputed
         if (opt.prefetch) {
@@ -898,8 +1037,8 @@ void NJ<P>::fastNJ() {
                                  + (1 - bionjWeight) * (P) (branchlength[join.j] + diameter[join.j]));
         varDiameter[newnode] = (P) (bionjWeight * varDiameter[join.i] + (1 - bionjWeight) * varDiameter[join.j]
                                     + bionjWeight * (1 - bionjWeight) * varIJ);
-        check(vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
-                                  (double) diameter[newnode]));      // :3008 (+ :3040-3043)
+        check(timed([&] { return vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
+                                  (double) diameter[newnode]); }));      // :3008 (+ :3040-3043)
 
         // out-profile and total diameter, :3012-3037
         int64_t changedActiveOutProfile = nActiveOutProfileReset - (nActive - 1);
@@ -907,19 +1046,20 @@ void NJ<P>::fastNJ() {
             && changedActiveOutProfile >= opt.fResetOutProfile * nActiveOutProfileReset) {
             totdiam = 0;
             for (int64_t i = 0; i < maxnode; i++) if (parent[i] < 0) totdiam += diameter[i];
-            check(vft_outprofile_rebuild(ctx, nullptr, nActive - 1));
+            check(timed([&] { return vft_outprofile_rebuild(ctx, nullptr, nActive - 1); }));
             nActiveOutProfileReset = nActive - 1;
         } else {
-            check(vft_outprofile_update(ctx, join.i, join.j, newnode, nActive));
+            check(timed([&] { return vft_outprofile_update(ctx, join.i, join.j, newnode, nActive); }));
             totdiam += (P) ((P) (diameter[newnode] - diameter[join.i]) - diameter[join.j]);
         }
         newEpoch(nActive - 1);
 
         if (m > 0) {
+            Section sec(this, 4);
             topHitJoin(newnode, nActive - 1);
         } else {
             std::vector<P> od(maxnodes);
-            check(vft_out_distance_all(ctx, nActive - 1, totdiam, od.data(), maxnodes));
+            check(timed([&] { return vft_out_distance_all(ctx, nActive - 1, totdiam, od.data(), maxnodes); }));
             for (int64_t i = 0; i < maxnode; i++)
                 if (parent[i] < 0) { outDistances[i] = od[i]; nOutDistActive[i] = nActive - 1; }
             setBestHitFull(newnode, nActive - 1, visibleSet[newnode], &besthitNew);
@@ -946,7 +1086,7 @@ void NJ<P>::fastNJ() {
     // bare profileDist of the three pairs, then "dist - diameter - diameter" in P (:3125-3132)
     int64_t pi[3] = {top[0], top[0], top[1]}, pj[3] = {top[1], top[2], top[2]};
     P pd[3], pw[3];
-    check(vft_dist_pairs(ctx, pi, pj, 3, VFT_PAIRS_PROFILE_RAW, pd, pw));
+    check(timed([&] { return vft_dist_pairs(ctx, pi, pj, 3, VFT_PAIRS_PROFILE_RAW, pd, pw); }));
     double d01 = (P) ((P) (pd[0] - diameter[top[0]]) - diameter[top[1]]);
     double d02 = (P) ((P) (pd[1] - diameter[top[0]]) - diameter[top[2]]);
     double d12 = (P) ((P) (pd[2] - diameter[top[1]]) - diameter[top[2]]);
@@ -995,6 +1135,7 @@ extern "C" void vft_nj_default_options(vft_nj_options *o) {
     o->nResetOutProfile = 200;   // Options.h:40
     o->bionj = 0;
     o->prefetch = 1;
+    o->hostThreads = 0;
 }
 
 extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in, const uint8_t *codes,
@@ -1009,7 +1150,8 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     res->nSeeds = res->nCloseUsed = res->nRefreshTopHits = res->nVisibleUpdate = res->nHillBetter = 0;
     res->nOutPrefetchHit = res->nOutSingleFetch = res->nPairPrefetchHit = res->nPairSingleFetch = res->nDeviceCalls = 0;
     res->secondsLeafTopHits = res->secondsJoins = res->secondsTotal = 0;
-    res->deviceMsResident = res->secondsEndToEnd = 0;
+    res->deviceMsResident = res->secondsEndToEnd = res->secondsInCalls = 0;
+    for (double &x : res->secondsHost) x = 0;
     auto e2e0 = std::chrono::steady_clock::now();
     vft_ctx *ctx = nullptr;
     int rc = vft_ctx_create(cfg, &ctx);
