@@ -46,18 +46,24 @@ static int cuda_fail(cudaError_t e, const char *what) {
 // per-join lists (latency), larger for the refresh batches (throughput).
 // ia/ib/r0/r1 live in pinned host memory mapped into the device address space (zero-copy): a
 // request costs one launch and one stream synchronisation, no separate memcpy.
+constexpr int INLINE_ITEMS = 384;
+struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 3 KB of kernel parameters
+
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_eval(Store<P> s, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib, int64_t n, int64_t nOutItems, int G,
-       int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1) {
-    __shared__ double smAll[4][64];
+k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
+       int64_t n, int64_t nOutItems, int G, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
+       unsigned int *__restrict__ doneCount, volatile unsigned int *__restrict__ doneFlag, unsigned int seq) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = smAll[threadIdx.x >> 5];
+    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t item = warp * G + lane;
     const bool valid = lane < G && item < n;
-    const int64_t a = valid ? ia[item] : -1, b = valid ? ib[item] : -1;
+    // small lists travel in the kernel parameters (no PCIe read at kernel start), large ones are
+    // read from the mapped pinned buffer
+    const int64_t a = !valid ? -1 : (ia ? ia[item] : inl.a[item]), b = !valid ? -1 : (ib ? ib[item] : inl.b[item]);
     const bool isOut = valid && item < nOutItems;
     const bool isSeq = valid && !isOut && !raw && a < s.nSeqs && b < s.nSeqs;
     P d = 0, w = 0;
@@ -80,7 +86,15 @@ k_eval(Store<P> s, const int32_t *__restrict__ ia, const int32_t *__restrict__ i
             if (lane == src) { d = dd; w = ww; }
         }
     }
-    if (valid) { r0[item] = d; r1[item] = w; }
+    if (valid) { r0[item] = d; r1[item] = w; __threadfence_system(); }
+    // completion: the last CTA to finish publishes `seq` in mapped host memory; the host spins on it
+    // instead of going through cudaStreamSynchronize (a few microseconds per request)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int done = atomicAdd(doneCount, 1u) + 1u;
+        if (done == gridDim.x) { *doneCount = 0u; __threadfence_system(); *doneFlag = seq; }
+    }
 }
 
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
@@ -105,10 +119,10 @@ template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
 k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int G, P *__restrict__ dist,
                   P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
-    __shared__ double smAll[4][64];
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = smAll[threadIdx.x >> 5];
+    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t j = warp * G + lane;
     const bool valid = lane < G && j < maxnode;
@@ -135,10 +149,10 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
 k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam, P *__restrict__ out) {
-    __shared__ double smAll[4][64];
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = smAll[threadIdx.x >> 5];
+    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t j = warp * G + lane;
     const bool act = lane < G && j < maxnode && s.active[j];
@@ -402,6 +416,9 @@ struct vft_ctx {
     size_t hCap;
     std::vector<uint8_t> activeHost;
     int64_t nActLeaf, nActInternal;
+    unsigned int seq;
+    unsigned int *d_doneCount;
+    volatile unsigned int *h_flag;
     vft_counters cnt;
     // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
     cudaEvent_t tmr0, tmr1;
@@ -542,9 +559,23 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->active, 0, M, c->stream));
     CK(cudaMemsetAsync(c->tables, 0, 840 * ps, c->stream));
     c->activeHost.assign(M, 0);
+    CK(cudaMalloc(&c->d_doneCount, 4));
+    CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
+    { void *f = nullptr; CK(cudaHostAlloc(&f, 64, cudaHostAllocMapped)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
+    c->seq = 0;
     int rc = ensure_lists(c, 4096);
     if (rc == VFT_OK) rc = ensure_pinned(c, 1 << 20);
     if (rc != VFT_OK) return rc;
+    {
+        const int need = (int) (4 * warp_smem_bytes(c->Lp));
+        if (need > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-warp term buffers (nPos > 3200)");
+        if (need > 48 * 1024) {
+#define SET_SMEM(P, A_, MX) do { cudaFuncSetAttribute(k_eval<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+            cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+            cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
+            VFT_DISPATCH(c, SET_SMEM);
+        }
+    }
     cudaFuncSetAttribute(k_topk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
     cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
     CK(sync_stream(c));
@@ -561,6 +592,8 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_flag) cudaFreeHost((void *) c->h_flag);
+    if (c->d_doneCount) cudaFree(c->d_doneCount);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
     cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
@@ -717,12 +750,29 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     const int64_t warps = (n + G - 1) / G;
     const unsigned blocks = (unsigned) ((warps + 3) / 4);
     void *r0 = c->h_out, *r1 = (char *) c->h_out + (size_t) n * 8;
-#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), ha, hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1)
+    const size_t smem = 4 * warp_smem_bytes(c->Lp);
+    const bool inlineItems = n <= INLINE_ITEMS;
+    InlineItems inl;
+    if (inlineItems) { std::memcpy(inl.a, ha, (size_t) n * 4); std::memcpy(inl.b, hb, (size_t) n * 4); }
+    const unsigned int seq = ++c->seq;
+#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, smem, c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : ha, inlineItems ? nullptr : hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, c->h_flag, seq)
     prof_begin(c, CLS_DIST);
     VFT_DISPATCH(c, CALL_EVAL);
     prof_end(c);
     CK(cudaGetLastError());
-    CK(sync_stream(c));
+    if (c->profile) { CK(sync_stream(c)); }
+    else {
+        // spin on the completion word the kernel writes into mapped host memory
+        volatile unsigned int *flag = c->h_flag;
+        uint64_t spins = 0;
+        while (*flag != seq) {
+            if ((++spins & 0xFFFFF) == 0) {                       // ~every few ms: surface device errors
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "k_eval");
+                if (e == cudaSuccess && *flag != seq) return fail(VFT_ECUDA, "k_eval finished without publishing its completion flag");
+            }
+        }
+    }
     c->cnt.launches++;
     c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += n * 2 * (int64_t) c->ps;
     if (nOut) std::memcpy(outDist, r0, (size_t) nOut * c->ps);
@@ -749,7 +799,7 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
     const int G = pick_group(n);
     const int64_t warps = (n + G - 1) / G;
-#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
+#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
     prof_begin(c, CLS_DIST);
     VFT_DISPATCH(c, CALL_ODA);
     prof_end(c);
@@ -783,7 +833,7 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
     const int Gq = pick_group(n);
     const int64_t warpsQ = (n + Gq - 1) / Gq;
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), query, nActive, n, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
     prof_begin(c, CLS_DIST);
     if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
     prof_end(c);

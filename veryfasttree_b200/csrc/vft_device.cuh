@@ -307,44 +307,101 @@ __device__ __forceinline__ void code_dist_row(const Store<P> &s, const P (&f)[A]
 }
 
 
-// profileDist, NJ.tcc:1167-1190, by one WARP: the 32 lanes evaluate 32 consecutive positions in
-// parallel (coalesced loads along the node-major rows), then lane 0 / lane 1 add the 32
-// per-position terms of `denom` / `top` IN POSITION ORDER from shared memory.  The additions are
-// the reference's, in the reference's order; positions the reference skips contribute +0.0, and
-// x + (+0.0) == x for every value the accumulators can take (they are never -0.0), so the result is
-// bit-identical to the one-thread loop above -- at 1/30th of its latency.
-// `sm` = 64 doubles of shared memory private to the calling warp.  Result valid in every lane.
+// profileDistPiece for the 4-state %different case with both vectors already in registers
+template<typename P>
+__device__ __forceinline__ P pick4(const P (&f)[4], uint32_t c) {
+    return c == 0 ? f[0] : c == 1 ? f[1] : c == 2 ? f[2] : f[3];
+}
+template<typename P>
+__device__ __forceinline__ double piece4(uint32_t c1, uint32_t c2, const P (&f1)[4], const P (&f2)[4]) {
+    if (c1 != VFT_DEV_NOCODE) {                                                            // NJ.tcc:920-926
+        if (c2 != VFT_DEV_NOCODE) return c1 == c2 ? 0.0 : 1.0;
+        return xsub(1.0, (double) pick4(f2, c1));
+    }
+    if (c2 != VFT_DEV_NOCODE) return xsub(1.0, (double) pick4(f1, c2));                    // :928-930
+    double pc = 1.0;                                                                       // :933-937
+#pragma unroll
+    for (int k = 0; k < 4; k++) pc = xsub(pc, (double) pmul(f1[k], f2[k]));
+    return pc;
+}
+
+template<typename P> struct Vec4T;
+template<> struct Vec4T<float> { typedef float4 type; };
+template<> struct Vec4T<double> { typedef double4 type; };
+
+// profileDist, NJ.tcc:1167-1190, by one WARP.
+//   phase 1  the 32 lanes evaluate the positions in parallel (coalesced loads along the node-major
+//            rows, 8 x 32 positions in flight at a time) and store the per-position terms
+//            w1*w2 and w1*w2*piece to shared memory;
+//   phase 2  lane 0 adds the `denom` terms and lane 1 the `top` terms IN POSITION ORDER.
+// The additions are the reference's, in the reference's order; positions the reference skips
+// contribute +0.0, and x + (+0.0) == x for every value the accumulators can take (they are never
+// -0.0), so the result is bit-identical to the one-thread loop above.  Zero `top` terms (equal
+// codes, the common case between close relatives) are compacted away before the ordered pass.
+// `sm` = 2*Lp doubles (+Lp/32 ints) of shared memory private to the calling warp: see warp_smem_bytes().
+__host__ __device__ inline size_t warp_smem_bytes(int64_t Lp) { return (size_t) Lp * 16; }
+
 template<typename P, int A, bool MATRIX>
 __device__ __forceinline__ void profile_dist_warp(const Store<P> &s, const View<P, A> &p1, const View<P, A> &p2,
                                                   double *sm, P &dist, P &weight) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double acc = 0;                                   // lane 0: denom, lane 1: top
     const int64_t Lp = s.Lp;
-    for (int64_t base = 0; base < Lp; base += 32) {
-        const int64_t pos = base + lane;
-        const uint32_t c1 = p1.codes ? (uint32_t) p1.codes[pos] : VFT_DEV_NOCODE;
-        const uint32_t c2 = p2.codes ? (uint32_t) p2.codes[pos] : VFT_DEV_NOCODE;
-        const P w1 = p1.w ? p1.w[pos] : (c1 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
-        const P w2 = p2.w ? p2.w[pos] : (c2 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
-        double wt = 0, tt = 0;
-        const bool on = w1 > 0 && w2 > 0;
-        if (on) {
-            wt = (double) pmul(w1, w2);                                                    // :1176
-            tt = xmul(wt, piece<P, A, MATRIX>(s, c1, c2, p1.v ? p1.v + pos * A : nullptr,
-                                              p2.v ? p2.v + pos * A : nullptr, p2.cd ? p2.cd + pos * A : nullptr));
-        }
-        if (__ballot_sync(full, on) == 0) continue;   // nothing to add in this chunk
-        sm[lane] = wt;
-        sm[32 + lane] = tt;
-        __syncwarp();
-        if (lane < 2) {
-            const double *src = sm + 32 * lane;
+    double *termW = sm, *termT = sm + Lp;
+    int nTop = 0;                                     // compacted count of non-zero top terms (uniform)
+    constexpr int UC = 8;                             // chunks of 32 positions with their loads in flight together
+    for (int64_t base = 0; base < Lp; base += 32 * UC) {
+        uint32_t c1[UC], c2[UC];
+        P w1[UC], w2[UC];
+        constexpr bool PRE = (A == 4 && !MATRIX);     // 4-state vectors are prefetched with the weights
+        P v1[PRE ? UC : 1][4], v2[PRE ? UC : 1][4];
 #pragma unroll
-            for (int k = 0; k < 32; k++) acc = xadd(acc, src[k]);
+        for (int u = 0; u < UC; u++) {
+            const int64_t pos = base + 32 * u + lane;
+            const bool in = pos < Lp;
+            c1[u] = (in && p1.codes) ? (uint32_t) p1.codes[pos] : VFT_DEV_NOCODE;
+            c2[u] = (in && p2.codes) ? (uint32_t) p2.codes[pos] : VFT_DEV_NOCODE;
+            w1[u] = (in && p1.w) ? p1.w[pos] : (P) -1;
+            w2[u] = (in && p2.w) ? p2.w[pos] : (P) -1;
+            if (PRE) {
+                typedef typename Vec4T<P>::type V4;
+                if (in && p1.v) { const V4 t = *reinterpret_cast<const V4 *>(p1.v + pos * 4); v1[u][0] = t.x; v1[u][1] = t.y; v1[u][2] = t.z; v1[u][3] = t.w; }
+                else { v1[u][0] = v1[u][1] = v1[u][2] = v1[u][3] = 0; }
+                if (in && p2.v) { const V4 t = *reinterpret_cast<const V4 *>(p2.v + pos * 4); v2[u][0] = t.x; v2[u][1] = t.y; v2[u][2] = t.z; v2[u][3] = t.w; }
+                else { v2[u][0] = v2[u][1] = v2[u][2] = v2[u][3] = 0; }
+            }
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < UC; u++) {
+            const int64_t pos = base + 32 * u + lane;
+            if (base + 32 * u >= Lp) break;           // uniform
+            const P a1 = p1.w ? w1[u] : (c1[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+            const P a2 = p2.w ? w2[u] : (c2[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+            double wt = 0, tt = 0;
+            if (a1 > 0 && a2 > 0) {
+                wt = (double) pmul(a1, a2);                                                // :1176
+                double pc;
+                if constexpr (PRE) pc = piece4<P>(c1[u], c2[u], v1[u], v2[u]);
+                else pc = piece<P, A, MATRIX>(s, c1[u], c2[u], p1.v ? p1.v + pos * A : nullptr,
+                                             p2.v ? p2.v + pos * A : nullptr, p2.cd ? p2.cd + pos * A : nullptr);
+                tt = xmul(wt, pc);
+            }
+            termW[pos] = wt;
+            const unsigned nz = __ballot_sync(full, tt != 0.0);
+            if (tt != 0.0) termT[nTop + __popc(nz & ((1u << lane) - 1u))] = tt;
+            nTop += __popc(nz);
+        }
     }
+    __syncwarp();
+    double acc = 0;
+    if (lane == 0) {
+        for (int64_t k = 0; k < Lp; k += 4) {
+            acc = xadd(acc, termW[k]); acc = xadd(acc, termW[k + 1]); acc = xadd(acc, termW[k + 2]); acc = xadd(acc, termW[k + 3]);
+        }
+    } else if (lane == 1) {
+        for (int k = 0; k < nTop; k++) acc = xadd(acc, termT[k]);
+    }
+    __syncwarp();
     const double denom = __shfl_sync(full, acc, 0), top = __shfl_sync(full, acc, 1);
     weight = (P) (denom > 0 ? denom : 0.01);                                              // :1187
     dist = (P) (denom > 0 ? top / denom : 1.0);                                           // :1188
