@@ -95,6 +95,10 @@ int  vft_outprofile_update(vft_ctx *ctx, int64_t old1, int64_t old2, int64_t new
    active, computes selfdist/selfweight[out_id] = profileDist(out,out). */
 int  vft_profile_average(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2,
                          double bionjWeight, double diameter_out);
+/* vft_profile_average followed by vft_outprofile_update(id1, id2, out_id, nActiveOld) in one launch:
+   the join of NJ.tcc:3008 + :3035 when the out-profile is not rebuilt */
+int  vft_profile_average_update(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2,
+                                double bionjWeight, double diameter_out, int64_t nActiveOld);
 int  vft_get_self(vft_ctx *ctx, int64_t id, double *selfdist, double *selfweight);
 
 /* -- out-distances: setOutDistance (NJ.tcc:1012-1053) --------------------------------------- */

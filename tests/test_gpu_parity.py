@@ -70,9 +70,12 @@ def run_script(lib, codes, n_codes, prec, tables, seed, n_joins, k_top):
             a, b = active[a], active[b]
             nw = N + k
             dm = float(ctx.dt(0.001 * (1 + k % 7)))
-            ctx.profile_average(nw, a, b, -1.0, dm)
+            if k % 2:
+                ctx.profile_average_update(nw, a, b, n_active, -1.0, dm)      # the fused join launch
+            else:
+                ctx.profile_average(nw, a, b, -1.0, dm)
+                ctx.outprofile_update(a, b, nw, n_active)
             diam[nw] = dm
-            ctx.outprofile_update(a, b, nw, n_active)
             totdiam += float(ctx.dt(ctx.dt(diam[nw] - diam[a]) - diam[b]))
             active.remove(a); active.remove(b); active.append(nw)
             n_active -= 1

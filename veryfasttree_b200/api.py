@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "vft_upload_leaves", "vft_outprofile_rebuild", "vft_outprofile_update", "vft_profile_average",
     "vft_get_self", "vft_out_distance_batch", "vft_out_distance_all", "vft_dist_pairs",
     "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
-    "vft_timer_start", "vft_timer_stop", "vft_eval_batch",
+    "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
 ]
 
 
@@ -87,6 +87,7 @@ class Lib:
         d.vft_outprofile_rebuild.argtypes = [vp, vp, i64]
         d.vft_outprofile_update.argtypes = [vp, i64, i64, i64, i64]
         d.vft_profile_average.argtypes = [vp, i64, i64, i64, dbl, dbl]
+        d.vft_profile_average_update.argtypes = [vp, i64, i64, i64, dbl, dbl, i64]
         d.vft_get_self.argtypes = [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]
         d.vft_out_distance_batch.argtypes = [vp, vp, i64, i64, dbl, vp]
         d.vft_out_distance_all.argtypes = [vp, i64, dbl, vp, i64]
@@ -195,6 +196,10 @@ class Context:
     def profile_average(self, out_id, id1, id2, bionj_weight=-1.0, diameter=0.0):
         self.lib.check(self.lib.dll.vft_profile_average(self.h, out_id, id1, id2, bionj_weight, diameter),
                        "vft_profile_average")
+
+    def profile_average_update(self, out_id, id1, id2, n_active_old, bionj_weight=-1.0, diameter=0.0):
+        self.lib.check(self.lib.dll.vft_profile_average_update(self.h, out_id, id1, id2, bionj_weight, diameter,
+                                                               n_active_old), "vft_profile_average_update")
 
     def get_self(self, node):
         d, w = C.c_double(), C.c_double()

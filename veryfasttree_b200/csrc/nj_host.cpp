@@ -1037,19 +1037,19 @@ void NJ<P>::fastNJ() {
                                  + (1 - bionjWeight) * (P) (branchlength[join.j] + diameter[join.j]));
         varDiameter[newnode] = (P) (bionjWeight * varDiameter[join.i] + (1 - bionjWeight) * varDiameter[join.j]
                                     + bionjWeight * (1 - bionjWeight) * varIJ);
-        check(timed([&] { return vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
-                                  (double) diameter[newnode]); }));      // :3008 (+ :3040-3043)
-
-        // out-profile and total diameter, :3012-3037
+        // averageProfile (:3008, + the self-distance of :3040-3043) and the out-profile (:3012-3037)
         int64_t changedActiveOutProfile = nActiveOutProfileReset - (nActive - 1);
         if (changedActiveOutProfile >= opt.nResetOutProfile
             && changedActiveOutProfile >= opt.fResetOutProfile * nActiveOutProfileReset) {
+            check(timed([&] { return vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
+                                                         (double) diameter[newnode]); }));
             totdiam = 0;
             for (int64_t i = 0; i < maxnode; i++) if (parent[i] < 0) totdiam += diameter[i];
             check(timed([&] { return vft_outprofile_rebuild(ctx, nullptr, nActive - 1); }));
             nActiveOutProfileReset = nActive - 1;
         } else {
-            check(timed([&] { return vft_outprofile_update(ctx, join.i, join.j, newnode, nActive); }));
+            check(timed([&] { return vft_profile_average_update(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
+                                                                (double) diameter[newnode], nActive); }));
             totdiam += (P) ((P) (diameter[newnode] - diameter[join.i]) - diameter[join.j]);
         }
         newEpoch(nActive - 1);

@@ -86,15 +86,9 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
             if (lane == src) { d = dd; w = ww; }
         }
     }
-    if (valid) { r0[item] = d; r1[item] = w; __threadfence_system(); }
-    // completion: the last CTA to finish publishes `seq` in mapped host memory; the host spins on it
-    // instead of going through cudaStreamSynchronize (a few microseconds per request)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned int done = atomicAdd(doneCount, 1u) + 1u;
-        if (done == gridDim.x) { *doneCount = 0u; __threadfence_system(); *doneFlag = seq; }
-    }
+    if (valid) { r0[item] = d; r1[item] = w; }
+    // (a completion word in mapped memory + host spin was tried instead of cudaStreamSynchronize:
+    //  the system-scope fences it needs cost more than the synchronisation they replace)
 }
 
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
@@ -242,9 +236,9 @@ __global__ void k_gather_topk(const uint32_t *__restrict__ idx, int K, const P *
 
 // averageProfile (NJ.tcc:2067-2135) + profileDist(new,new) (NJ.tcc:3040-3043); ONE CTA:
 // positions in parallel, then thread 0 adds the per-position self-distance terms in order.
-template<typename P, int A, bool MATRIX>
+template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
-k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut) {
+k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *termW = reinterpret_cast<double *>(smem);            // [Lp] w*w
     double *termT = termW + s.Lp;                                // [Lp] w*w*piece
@@ -280,6 +274,27 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
             oc[pos] = (uint8_t) co;
 #pragma unroll
             for (int k = 0; k < A; k++) ov[pos * A + k] = f[k];
+            if (UPDATE) {
+                // updateOutProfile for this position (NJ.tcc:943-1010), fused: the three profiles it
+                // needs are already in registers
+                P g[A];
+#pragma unroll
+                for (int k = 0; k < A; k++) g[k] = s.ov[pos * A + k];
+                const double originalMult = (double) pmul(s.ow[pos], (P) nActiveOld);     // :962
+                const double newMult = xsub(xsub(xadd(originalMult, (double) wo), (double) w1), (double) w2);   // :963
+                P wout = (P) (newMult / (double) (nActiveOld - 1));                        // :964
+                if (wout <= 0) wout = (P) 1e-20;
+                s.ow[pos] = wout;
+#pragma unroll
+                for (int k = 0; k < A; k++) g[k] = (P) xmul((double) g[k], originalMult);  // :969-971
+                if (w1 > 0) add_to_freq<P, A, MATRIX>(s, g, (double) (-w1), c1, (c1 == VFT_DEV_NOCODE && p1.v) ? p1.v + pos * A : nullptr);
+                if (w2 > 0) add_to_freq<P, A, MATRIX>(s, g, (double) (-w2), c2, (c2 == VFT_DEV_NOCODE && p2.v) ? p2.v + pos * A : nullptr);
+                if (wo > 0) add_to_freq<P, A, MATRIX>(s, g, (double) wo, co, hasVec ? f : nullptr);
+                normalize_freq<P, A, MATRIX>(s, g);                                        // :984
+#pragma unroll
+                for (int k = 0; k < A; k++) s.ov[pos * A + k] = g[k];
+                if (MATRIX) code_dist_row<P, A, MATRIX>(s, g, s.ocd + pos * A);            // :1001-1003
+            }
             if (wo > 0) {                                       // self-distance term, profileDist(out,out)
                 const double wt = (double) pmul(wo, wo);
                 tw = wt;
@@ -334,50 +349,75 @@ k_outprofile_update(Store<P> s, int64_t o1, int64_t o2, int64_t nw, int64_t nAct
     if (MATRIX) code_dist_row<P, A, MATRIX>(s, f, s.ocd + pos * A);                        // :1001-1003
 }
 
-// outProfile, NJ.tcc:729-815: one thread per position walks the node list in ascending order
-// (the accumulation order of the reference at -threads 1); the loads of 16 nodes are issued
-// together, the accumulation stays strictly in order.
+// outProfile, NJ.tcc:729-815.  The reference accumulates node after node (ascending id) into every
+// position; the order matters (P-typed sums), so the node loop stays sequential -- but its loads do
+// not have to be: ONE WARP per position, the 32 lanes fetch 32 consecutive nodes' (code, weight,
+// vector) for that position at once (and the next 32 while these are being added), then the values
+// are broadcast lane by lane, in node order, into the accumulators that every lane keeps identically.
 template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
-    const int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t pos = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     if (pos >= s.L) return;
     const double inweight = 1.0 / (double) n;                                              // :732
     P wout = 0;
     P f[A];
 #pragma unroll
     for (int k = 0; k < A; k++) f[k] = 0;
-    constexpr int U = 16;
-    for (int64_t in0 = 0; in0 < n; in0 += U) {
-        int64_t id[U];
-        uint32_t c[U];
-        P w[U];
+
+    struct Item { uint32_t c; P w; bool vec; P v[A]; };
+    auto fetch = [&](int64_t in, Item &it) {
+        it.c = VFT_DEV_NOCODE; it.w = 0; it.vec = false;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            id[u] = in0 + u < n ? ids[in0 + u] : -1;
-            c[u] = id[u] >= 0 ? (uint32_t) s.codes[id[u] * s.Lp + pos] : VFT_DEV_NOCODE;
-        }
+        for (int k = 0; k < A; k++) it.v[k] = 0;
+        if (in >= n) return;
+        const int64_t id = ids[in];
+        it.c = (uint32_t) s.codes[id * s.Lp + pos];
+        if (id < s.nSeqs) it.w = it.c != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+        else {
+            const int64_t row = id - s.nSeqs;
+            it.w = s.weights[row * s.Lp + pos];
+            if (it.c == VFT_DEV_NOCODE && it.w > 0) {
+                it.vec = true;
+                const P *src = s.vecs + (row * s.Lp + pos) * A;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (id[u] < 0) w[u] = 0;
-            else if (id[u] < s.nSeqs) w[u] = c[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
-            else w[u] = s.weights[(id[u] - s.nSeqs) * s.Lp + pos];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            wout = (P) xadd((double) wout, xmul((double) w[u], inweight));                 // :741 (+0.0 for padding)
-            if (w[u] > 0) {
-                const P *fIn = (id[u] >= s.nSeqs && c[u] == VFT_DEV_NOCODE) ? s.vecs + ((id[u] - s.nSeqs) * s.Lp + pos) * A : nullptr;
-                add_to_freq<P, A, MATRIX>(s, f, (double) w[u], c[u], fIn);                 // :771-774
+                for (int k = 0; k < A; k++) it.v[k] = src[k];
             }
         }
+    };
+    Item cur, nxt;
+    fetch(lane, cur);
+    for (int64_t in0 = 0; in0 < n; in0 += 32) {
+        fetch(in0 + 32 + lane, nxt);                  // in flight while `cur` is consumed
+        const int cnt = (int) min((int64_t) 32, n - in0);
+        for (int u = 0; u < cnt; u++) {
+            const P w = __shfl_sync(full, cur.w, u);
+            wout = (P) xadd((double) wout, xmul((double) w, inweight));                    // :741
+            if (w > 0) {                                                                   // uniform
+                const uint32_t c = __shfl_sync(full, cur.c, u);
+                const bool vec = __shfl_sync(full, (int) cur.vec, u) != 0;
+                if (vec) {
+                    P fin[A];
+#pragma unroll
+                    for (int k = 0; k < A; k++) fin[k] = __shfl_sync(full, cur.v[k], u);
+                    add_to_freq<P, A, MATRIX>(s, f, (double) w, c, fin);                   // :771-774
+                } else {
+                    add_to_freq<P, A, MATRIX>(s, f, (double) w, c, nullptr);
+                }
+            }
+        }
+        cur = nxt;
     }
     if (wout <= 0) wout = (P) 1e-20;                                                       // :743-745
-    s.ow[pos] = wout;
     normalize_freq<P, A, MATRIX>(s, f);                                                    // :789-794
+    if (lane == 0) {
+        s.ow[pos] = wout;
 #pragma unroll
-    for (int k = 0; k < A; k++) s.ov[pos * A + k] = f[k];
-    if (MATRIX) code_dist_row<P, A, MATRIX>(s, f, s.ocd + pos * A);                        // :801-803
+        for (int k = 0; k < A; k++) s.ov[pos * A + k] = f[k];
+        if (MATRIX) code_dist_row<P, A, MATRIX>(s, f, s.ocd + pos * A);                    // :801-803
+    }
 }
 
 // leaves: selfweight = nPos - nGaps (NJ.tcc:249-252), active, padding of the code rows
@@ -651,7 +691,7 @@ extern "C" int vft_outprofile_rebuild(vft_ctx *c, const int64_t *ids, int64_t n)
     std::memcpy(c->h_in, ids, (size_t) n * 8);
     CK(cudaMemcpyAsync(c->d_ids, c->h_in, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
     c->cnt.h2dBytes += n * 8;
-#define CALL_REB(P, A_, MX) k_outprofile_rebuild<P, A_, MX><<<(unsigned) ((c->L + 63) / 64), 64, 0, c->stream>>>(make_store<P>(c), c->d_ids, n)
+#define CALL_REB(P, A_, MX) k_outprofile_rebuild<P, A_, MX><<<(unsigned) ((c->L + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), c->d_ids, n)
     prof_begin(c, CLS_PROFILE);
     VFT_DISPATCH(c, CALL_REB);
     prof_end(c);
@@ -674,18 +714,24 @@ extern "C" int vft_outprofile_update(vft_ctx *c, int64_t old1, int64_t old2, int
     return VFT_OK;            // asynchronous: ordered on the context's stream
 }
 
-extern "C" int vft_profile_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight,
-                                   double diameter_out) {
+static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight, double diameter_out,
+                          int64_t nActiveOld, bool update) {
     if (!c || out_id < c->N || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad node id");
+    if (update && nActiveOld < 2) return fail(VFT_EINVAL, "bad nActiveOld");
     if (bionjWeight < 0) bionjWeight = 0.5;
     const size_t smem = (size_t) c->Lp * 16;
+    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the single-CTA average kernel");
 #define CALL_AVG(P, A_, MX)                                                                                   \
     do {                                                                                                      \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-        k_average<P, A_, MX><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out); \
+        if (update) {                                                                                         \
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+            k_average<P, A_, MX, true><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld); \
+        } else {                                                                                              \
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+            k_average<P, A_, MX, false><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld); \
+        }                                                                                                     \
     } while (0)
-    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the single-CTA average kernel");
     prof_begin(c, CLS_PROFILE);
     VFT_DISPATCH(c, CALL_AVG);
     prof_end(c);
@@ -695,7 +741,17 @@ extern "C" int vft_profile_average(vft_ctx *c, int64_t out_id, int64_t id1, int6
         if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
     if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
-    return VFT_OK;            // asynchronous
+    return VFT_OK;            // asynchronous: ordered on the context's stream
+}
+
+extern "C" int vft_profile_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight,
+                                   double diameter_out) {
+    return launch_average(c, out_id, id1, id2, bionjWeight, diameter_out, 0, false);
+}
+
+extern "C" int vft_profile_average_update(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight,
+                                          double diameter_out, int64_t nActiveOld) {
+    return launch_average(c, out_id, id1, id2, bionjWeight, diameter_out, nActiveOld, true);
 }
 
 extern "C" int vft_get_self(vft_ctx *c, int64_t id, double *selfdist, double *selfweight) {
@@ -760,19 +816,7 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     VFT_DISPATCH(c, CALL_EVAL);
     prof_end(c);
     CK(cudaGetLastError());
-    if (c->profile) { CK(sync_stream(c)); }
-    else {
-        // spin on the completion word the kernel writes into mapped host memory
-        volatile unsigned int *flag = c->h_flag;
-        uint64_t spins = 0;
-        while (*flag != seq) {
-            if ((++spins & 0xFFFFF) == 0) {                       // ~every few ms: surface device errors
-                cudaError_t e = cudaStreamQuery(c->stream);
-                if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "k_eval");
-                if (e == cudaSuccess && *flag != seq) return fail(VFT_ECUDA, "k_eval finished without publishing its completion flag");
-            }
-        }
-    }
+    CK(sync_stream(c));
     c->cnt.launches++;
     c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += n * 2 * (int64_t) c->ps;
     if (nOut) std::memcpy(outDist, r0, (size_t) nOut * c->ps);
