@@ -88,3 +88,19 @@ def test_tiny_inputs_visible_set_mode(olib, tmp_path):
             fa = str(tmp_path / ("tiny%d.fa" % n))
             synth.write_fasta(fa, chars)
             assert t.newick(["t%d" % i for i in range(n)]) == make_golden.ref_tree(fa, kind, 64)
+
+
+def test_b200operations_drops_into_reference_templates(tmp_path):
+    """oracle/_ref/plugin_probe = the reference's own NeighbourJoining<> compiled over B200Operations<>
+    (built only where /root/reference exists): same NJ tree as BasicOperations."""
+    import subprocess
+    probe = os.path.join(replay.ROOT, "oracle", "_ref", "plugin_probe")
+    if not os.path.exists(probe):
+        pytest.skip("oracle/_ref/plugin_probe not built on this box")
+    from veryfasttree_b200 import synth
+    for kind, name in (("nt", "nt60"), ("aa", "aa300")):
+        chars, _ = replay.golden_case(name)
+        fa = str(tmp_path / (name + ".fa"))
+        synth.write_fasta(fa, chars)
+        out = subprocess.run([probe, fa, kind], capture_output=True, text=True)
+        assert out.returncode == 0 and "IDENTICAL" in out.stdout

@@ -85,6 +85,8 @@ public:
         freshVal.assign(maxnodes, 0);
         freshEpoch.assign(maxnodes, -1);
         wantEpoch.assign(maxnodes, -1);
+        up.resize(maxnodes);
+        for (int64_t i = 0; i < maxnodes; i++) up[i] = i;
         hostThreads = opt.hostThreads > 0 ? opt.hostThreads : std::max(1, std::min(16, omp_get_num_procs()));
         // nGaps(i) = nPos - selfweight[i] (NJ.tcc:249-252, :3762): gap/unknown columns of leaf i
         leafGaps.assign(nSeqs, 0);
@@ -274,9 +276,14 @@ private:
         setCriterion(nActive, hit);
     }
 
-    int64_t activeAncestor(int64_t i) const {           // NJ.tcc:536-544
+    // activeAncestor, NJ.tcc:536-544: the root of the subtree that contains i.  Same answer as
+    // walking parent[], but over a union-find shortcut array with path halving (the walk can be
+    // hundreds of levels deep on ladder-like trees); halving is skipped inside host-thread regions.
+    std::vector<int64_t> up;
+    int64_t activeAncestor(int64_t i) {
         if (i < 0) return i;
-        while (parent[i] >= 0) i = parent[i];
+        if (omp_in_parallel()) { while (up[i] != i) i = up[i]; return i; }
+        while (up[i] != i) { const int64_t g = up[up[i]]; up[i] = g; i = g; }
         return i;
     }
 
@@ -1012,6 +1019,7 @@ void NJ<P>::fastNJ() {
         int64_t newnode = maxnode++;
         parent[join.i] = newnode;
         parent[join.j] = newnode;
+        up[join.i] = newnode; up[join.j] = newnode;
         child[newnode].nChild = 2;
         child[newnode].child[0] = join.i < join.j ? join.i : join.j;
         child[newnode].child[1] = join.i > join.j ? join.i : join.j;
