@@ -142,6 +142,34 @@ int  vft_dist_one_vs_all(vft_ctx *ctx, int64_t query, int64_t nActive, int64_t K
                          int64_t *j_out, void *dist, void *weight, void *criterion,
                          int64_t *nOut);
 
+/* ============================================================================================
+ * Likelihood kernels: pairLogLk and posteriorProfile under JC
+ * (nucleotides, no transition matrix) or an eigen-decomposed rate matrix (GTR nt / JTT-WAG-LG aa),
+ * with CAT rate categories.  Profiles are the same device slab; in the ML phase they hold the
+ * rotated frequencies the reference keeps (VeryFastTreeImpl.tcc:253-256).
+ * ==========================================================================================*/
+/* after TransitionMatrix::create*() (TransitionMatrix.tcc:158-281).  NULL codeFreq => Jukes-Cantor
+   (no transition matrix, NJ.tcc:1202).  codeFreq[(nCodes+1)][nCodes]: rows 0..nCodes-1 the codes,
+   LAST row the NOCODE (gap) row transmat.codeFreq[NOCODE]; eigeninv[nCodes][nCodes] (row j = the
+   vector of NJ.tcc:2426); eigeninvT[nCodes][nCodes] (nt only, NJ.tcc:2333; may be NULL for aa);
+   eigenval[nCodes]; statinv[nCodes]. */
+int  vft_upload_transmat(vft_ctx *ctx, const void *codeFreq, const void *eigenval, const void *eigeninv,
+                         const void *eigeninvT, const void *statinv);
+/* Rates (NJ.h:163-174) + the scalar options the two kernels read: rates[nRateCats] (P),
+   ratecat[nPos], Options.MLMinRelBranchLength / MLMinBranchLength (Constants.h:32-36),
+   Options.fastexp level 0..3 (BasicOperations.tcc:121-216) */
+int  vft_sync_rates(vft_ctx *ctx, const void *rates, int64_t nRateCats, const int64_t *ratecat,
+                    double MLMinRelBranchLength, double MLMinBranchLength, int32_t fastexpLevel);
+/* pairLogLk (NJ.tcc:1192-1447) for n (pair, length) items -- the Brent abscissae of onedimenmin
+   (NJ.tcc:7024), the per-node calls of treeLogLk (NJ.tcc:5123).  loglk[n] doubles.  siteLk: NULL,
+   or [n][nPos] doubles receiving the per-site lkAB (what the reference multiplies into
+   site_likelihoods[], :1263-1265; positions it skips get 1.0). */
+int  vft_pair_loglk_batch(vft_ctx *ctx, const int64_t *i, const int64_t *j, const double *length,
+                          int64_t n, double *loglk, double *siteLk);
+/* posteriorProfile (NJ.tcc:2137-2447, exactML): profile out_id (an internal-node row) = posterior of
+   the parent of id1,id2 at distances len1,len2 */
+int  vft_posterior_profile(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2, double len1, double len2);
+
 /* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
       vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
 int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);

@@ -82,6 +82,111 @@ struct Dumper {
     }
 };
 
+// ---- "ml" mode: pairLogLk (NJ.tcc:1192) and posteriorProfile (NJ.tcc:2137) of the reference, on ML-phase
+//      profiles built by the reference's own posteriorProfile; model = jc | gtr (nt) | jtt (aa)
+template<typename P>
+static int runML(const std::string &fasta, bool aa, const std::string &model, int fastexpLvl) {
+    Options options;
+    options.verbose = 0; options.showProgress = false; options.threads = 1; options.diskComputing = false;
+    options.nCodes = aa ? 20 : 4; options.useMatrix = aa;
+    options.codesString = aa ? Constants::codesStringAA : Constants::codesStringNT;
+    options.doublePrecision = sizeof(P) == 8;
+    options.fastexp = fastexpLvl;
+    options.fPostTotalTolerance = sizeof(P) == 8 ? Constants::fPostTotalToleranceDouble : Constants::fPostTotalToleranceFloat;
+    options.MLMinBranchLength = sizeof(P) == 8 ? Constants::MLMinBranchLengthDouble : Constants::MLMinBranchLengthFloat;
+    options.MLMinRelBranchLength = sizeof(P) == 8 ? Constants::MLMinRelBranchLengthDouble : Constants::MLMinRelBranchLengthFloat;
+    omp_set_num_threads(1);
+    std::ifstream in(fasta);
+    if (!in) { std::fprintf(stderr, "cannot read %s\n", fasta.c_str()); return 2; }
+    std::ostringstream lg;
+    Alignment aln(options, in, lg);
+    aln.readAlignment();
+    std::vector<std::string> seqs = aln.seqs;
+    int64_t N = (int64_t) seqs.size(), L = aln.nPos, A = options.nCodes;
+    typedef AVX256Operations<P> op_t;
+    typedef NeighbourJoining<P, AVX256Operations> NJ;
+    static DistanceMatrix<P, op_t::ALIGNMENT> dmat{};
+    static TransitionMatrix<P, op_t::ALIGNMENT> transmat;
+    if (aa) { dmat.matrixBLOSUM45(); dmat.setupDistanceMatrix(options, lg); }
+    if (model == "jtt") transmat.createTransitionMatrixJTT92(options);
+    else if (model == "gtr") {
+        double r[6] = {1.3, 3.1, 0.7, 0.9, 4.2, 1.0}, f[4] = {0.31, 0.19, 0.23, 0.27};
+        transmat.createGTR(options, r, f);
+    }
+    ProgressReport progress(false, 0, false);
+    std::vector<std::string> cons;
+    std::unique_ptr<DiskMemory> d1, d2;
+    NJ nj(options, lg, progress, seqs, L, cons, dmat, transmat, d1, d2);
+    Dumper<P> D(nj);
+    putq("shape", {N, L, A});
+    putq("ml.fastexp", {fastexpLvl});
+    putq("ml.hasTransmat", {(int64_t) (bool) transmat});
+    double mins[2] = {options.MLMinRelBranchLength, options.MLMinBranchLength};
+    put("ml.minlen", 'd', {2}, mins);
+    if (transmat) {
+        std::vector<P> cf((A + 1) * A), ev(A), ei(A * A), eit(A * A), si(A);
+        for (int64_t i = 0; i < A; i++) {
+            ev[i] = transmat.eigenval[i]; si[i] = transmat.statinv[i];
+            for (int64_t j = 0; j < A; j++) { cf[i * A + j] = transmat.codeFreq[i][j]; ei[i * A + j] = transmat.eigeninv[i][j]; eit[i * A + j] = transmat.eigeninvT[i][j]; }
+        }
+        for (int64_t j = 0; j < A; j++) cf[A * A + j] = transmat.codeFreq[NOCODE][j];
+        putv<P>("ml.codeFreq", cf, {A + 1, A}); putv<P>("ml.eigenval", ev); putv<P>("ml.eigeninv", ei, {A, A});
+        putv<P>("ml.eigeninvT", eit, {A, A}); putv<P>("ml.statinv", si);
+    }
+    // CAT rates: 4 categories, position i in category (i*7+i/3) % 4
+    const int64_t nCat = 4;
+    nj.rates.reset(nCat, L);
+    const double rv[4] = {0.25, 0.8, 1.0, 2.6};
+    std::vector<P> rates(nCat);
+    std::vector<int64_t> ratecat(L);
+    for (int64_t c = 0; c < nCat; c++) { nj.rates.rates[c] = (P) rv[c]; rates[c] = nj.rates.rates[c]; }
+    for (int64_t i = 0; i < L; i++) { nj.rates.ratecat[i] = (i * 7 + i / 3) % nCat; ratecat[i] = nj.rates.ratecat[i]; }
+    putv<P>("ml.rates", rates); putq("ml.ratecat", ratecat);
+
+    // posterior profiles: a script of (out, a, b, len1, len2)
+    nj.parent.assign(nj.maxnodes, -1);
+    int64_t K = std::min<int64_t>(14, N - 2);
+    std::vector<int64_t> script;
+    std::vector<double> lens;
+    for (int64_t k = 0; k < K; k++) {
+        int64_t a, b;
+        if (k % 3 == 0) { a = (k * 5) % N; b = (k * 5 + 3) % N; }
+        else if (k % 3 == 1) { a = N + k - 1; b = (k * 11 + 2) % N; }
+        else { a = N + k - 1; b = N + k - 2; }
+        double l1 = k == 4 ? 1e-7 : 0.02 + 0.013 * (double) k, l2 = k == 7 ? 0.0 : 0.11 - 0.006 * (double) k;
+        int64_t out = N + k;
+        nj.posteriorProfile(nj.profiles[out], nj.profiles[a], nj.profiles[b], l1, l2);
+        nj.maxnode = out + 1;
+        script.push_back(out); script.push_back(a); script.push_back(b);
+        lens.push_back(l1); lens.push_back(l2);
+        D.profile("post" + std::to_string(k), nj.profiles[out]);
+    }
+    putq("ml.post.script", script, {K, 3});
+    put("ml.post.lens", 'd', {K, 2}, lens.data());
+
+    // pair log-likelihoods over leaves and the posterior profiles
+    std::vector<int64_t> pi, pj;
+    std::vector<double> pl;
+    for (int64_t x = 0; x < N + K; x += 2) {
+        pi.push_back(x); pj.push_back((x * 3 + 1) % (N + K)); pl.push_back(0.01 + 0.004 * (double) (x % 37));
+        pi.push_back((x * 5 + 2) % N); pj.push_back(N + (x % K)); pl.push_back(0.3 + 0.05 * (double) (x % 9));
+    }
+    pi.push_back(N + K - 1); pj.push_back(N + K - 2); pl.push_back(1e-9);      // below MLMinRelBranchLength
+    pi.push_back(0); pj.push_back(0); pl.push_back(0.5);
+    pi.push_back(N + 1); pj.push_back(N + 1); pl.push_back(2.5);
+    std::vector<double> ll(pi.size());
+    std::vector<double> site(L * 3, 1.0);
+    for (size_t k = 0; k < pi.size(); k++) {
+        double *sl = k < 3 ? &site[k * L] : nullptr;
+        ll[k] = nj.pairLogLk(nj.profiles[pi[k]], nj.profiles[pj[k]], pl[k], sl);
+    }
+    putq("ml.lk.i", pi); putq("ml.lk.j", pj);
+    put("ml.lk.len", 'd', {(int64_t) pl.size()}, pl.data());
+    put("ml.lk.loglk", 'd', {(int64_t) ll.size()}, ll.data());
+    put("ml.lk.site", 'd', {3, L}, site.data());
+    return 0;
+}
+
 template<typename P>
 static int run(const std::string &fasta, bool aa, bool tophitsOnly) {
     Options options;
@@ -275,8 +380,17 @@ static int run(const std::string &fasta, bool aa, bool tophitsOnly) {
 }
 
 int main(int argc, char **argv) {
-    if (argc != 5 && argc != 6) { std::fprintf(stderr, "usage: refdump <fasta> <nt|aa> <32|64> <out.bin> [tophits]\n"); return 2; }
+    if (argc < 5 || argc > 8) { std::fprintf(stderr, "usage: refdump <fasta> <nt|aa> <32|64> <out.bin> [tophits | ml <jc|gtr|jtt> <fastexp>]\n"); return 2; }
     bool th = argc == 6 && std::string(argv[5]) == "tophits";
+    if (argc == 8 && std::string(argv[5]) == "ml") {
+        g_out = std::fopen(argv[4], "wb");
+        if (!g_out) { std::perror(argv[4]); return 2; }
+        bool aa2 = std::string(argv[2]) == "aa";
+        int lvl = std::atoi(argv[7]);
+        int rc2 = std::string(argv[3]) == "64" ? runML<double>(argv[1], aa2, argv[6], lvl) : runML<float>(argv[1], aa2, argv[6], lvl);
+        std::fclose(g_out);
+        return rc2;
+    }
     g_out = std::fopen(argv[4], "wb");
     if (!g_out) { std::perror(argv[4]); return 2; }
     bool aa = std::string(argv[2]) == "aa";

@@ -3,6 +3,7 @@ where /root/reference exists; `make -C oracle ref` first).
 
   *.refdump.bin   kernel-level vectors from the reference's own templates (oracle/refdump.cpp)
   *.tophits.bin   leaf top-hit lists from the reference's own setAllLeafTopHits
+  *.mldump.bin    pairLogLk / posteriorProfile of the reference (refdump "ml" mode: JC, GTR, JTT; CAT rates)
   *.nj.tree       the `NJ` line of the reference binary's -log (tree after the metric phase),
                   run with -threads 1 -ext AVX2 [-nt] [-double-precision] -noml -nni 0 -spr 0 -nosupport
   blosum45_f{32,64}.npz   the BLOSUM45 tables as the reference hands them to its kernels
@@ -58,6 +59,14 @@ def main():
                     with open(os.path.join(HERE, "%s_f%d.nj.tree" % (name, prec)), "w") as f:
                         f.write(ref_tree(fasta, kind, prec) + "\n")
                 print("golden", name, prec)
+        for name, (n, L, kind, seed, model, combos) in replay.ML_CASES.items():
+            chars, kind, model = replay.ml_case_chars(name)
+            fasta = os.path.join(td, name + ".fa")
+            synth.write_fasta(fasta, chars)
+            for prec, lvl in combos:
+                subprocess.run([replay.REFDUMP_BIN, fasta, kind, str(prec),
+                                os.path.join(HERE, "%s_f%d_e%d.mldump.bin" % (name, prec, lvl)), "ml", model, str(lvl)], check=True)
+                print("golden", name, prec, lvl)
         for prec in (32, 64):
             d = replay.read_refdump(os.path.join(HERE, "aa60_f%d.refdump.bin" % prec))
             np.savez(os.path.join(HERE, "blosum45_f%d.npz" % prec), distances=d["tables.distances"],

@@ -148,3 +148,80 @@ def replay(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: in
         cmp("rebuild.outprofile.weights", w)
         cmp("rebuild.outprofile.vectors", v)
     return bad
+
+
+# name -> (n, nPos, kind, seed, model, [(precision, fastexp level), ...])
+ML_CASES = {
+    "ml_jc": (30, 90, "nt", 6, "jc", [(32, 0), (64, 0)]),
+    "ml_gtr": (30, 90, "nt", 6, "gtr", [(32, 3), (64, 2), (64, 0)]),
+    "ml_jtt": (30, 90, "aa", 6, "jtt", [(32, 3), (64, 2), (32, 0)]),
+}
+
+
+def ml_case_chars(name):
+    n, L, kind, seed, model, _ = ML_CASES[name]
+    chars = synth.make_alignment(n, L, kind, seed)
+    return chars[synth.unique_rows(chars)], kind, model
+
+
+def replay_ml(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: int, exact_log: bool, device: int = 0):
+    """Replays oracle/refdump.cpp's "ml" script (posteriorProfile + pairLogLk of the reference) through
+    an implementation of the ABI.  Posterior profiles are compared bit for bit when the model has no libm
+    call in them (rational fastexp levels 2/3); log-likelihoods within the north_star tolerance (1e-5
+    relative fp32, 1e-12 fp64), or bit for bit when `exact_log` (same libm: the CPU oracle).
+    Returns (list of mismatching arrays, max relative log-lk error)."""
+    import ctypes as C
+    bad = []
+    N, L, A = [int(x) for x in dump["shape"]]
+    codes = api.encode(chars, kind)
+    lvl = int(dump["ml.fastexp"][0])
+    has_tm = bool(dump["ml.hasTransmat"][0])
+    cfg = api.make_config(N, L, A, precision, use_matrix=False, reduction=1, device=device)
+    dt = api.np_dtype(precision)
+    with api.Context(lib, cfg) as ctx:
+        ctx.upload_leaves(codes)
+        d = lib.dll
+        if has_tm:
+            arrs = [np.ascontiguousarray(dump[k], dtype=dt) for k in ("ml.codeFreq", "ml.eigenval", "ml.eigeninv", "ml.eigeninvT", "ml.statinv")]
+            lib.check(d.vft_upload_transmat(ctx.h, *[api._ptr(a) for a in arrs]), "vft_upload_transmat")
+        else:
+            lib.check(d.vft_upload_transmat(ctx.h, None, None, None, None, None), "vft_upload_transmat")
+        rates = np.ascontiguousarray(dump["ml.rates"], dtype=dt)
+        ratecat = np.ascontiguousarray(dump["ml.ratecat"], dtype=np.int64)
+        lib.check(d.vft_sync_rates(ctx.h, api._ptr(rates), len(rates), api._ptr(ratecat), float(dump["ml.minlen"][0]),
+                                   float(dump["ml.minlen"][1]), lvl), "vft_sync_rates")
+        libm_free = has_tm and lvl >= 2
+        for k, (out, a, b) in enumerate(dump["ml.post.script"]):
+            l1, l2 = [float(x) for x in dump["ml.post.lens"][k]]
+            lib.check(d.vft_posterior_profile(ctx.h, int(out), int(a), int(b), l1, l2), "vft_posterior_profile")
+            w, cd, v = ctx.get_profile(int(out))
+            want_w, want_c, want_v = dump["post%d.weights" % k], dump["post%d.codes" % k], dump["post%d.vectors" % k]
+            if not np.array_equal(cd, want_c):
+                bad.append("post%d.codes" % k)
+            if libm_free or exact_log:
+                if not bits_equal(w, want_w): bad.append("post%d.weights" % k)
+                if not bits_equal(v.reshape(want_v.shape), want_v): bad.append("post%d.vectors" % k)
+            else:
+                tol = 2e-6 if precision == 32 else 1e-13
+                if not np.allclose(w, want_w, rtol=tol, atol=tol): bad.append("post%d.weights~" % k)
+                if not np.allclose(v.reshape(want_v.shape), want_v, rtol=tol, atol=tol): bad.append("post%d.vectors~" % k)
+        pi = np.ascontiguousarray(dump["ml.lk.i"]); pj = np.ascontiguousarray(dump["ml.lk.j"])
+        pl = np.ascontiguousarray(dump["ml.lk.len"], dtype=np.float64)
+        ll = np.empty(len(pi), dtype=np.float64)
+        site = np.empty((3, L), dtype=np.float64)
+        lib.check(d.vft_pair_loglk_batch(ctx.h, api._ptr(pi), api._ptr(pj), api._ptr(pl), len(pi), api._ptr(ll), None), "vft_pair_loglk_batch")
+        lib.check(d.vft_pair_loglk_batch(ctx.h, api._ptr(pi[:3].copy()), api._ptr(pj[:3].copy()), api._ptr(pl[:3].copy()), 3,
+                                         api._ptr(np.empty(3)), api._ptr(site)), "vft_pair_loglk_batch(site)")
+        want = dump["ml.lk.loglk"]
+        rel = float(np.max(np.abs(ll - want) / np.maximum(1e-300, np.abs(want))))
+        if exact_log and (libm_free or True):
+            if not bits_equal(ll, want): bad.append("ml.lk.loglk")
+            if not bits_equal(site, dump["ml.lk.site"]): bad.append("ml.lk.site")
+        else:
+            tol = 1e-5 if precision == 32 else 1e-12
+            if rel > tol: bad.append("ml.lk.loglk rel=%g" % rel)
+            stol = 2e-6 if precision == 32 else 1e-13
+            if libm_free:
+                if not bits_equal(site, dump["ml.lk.site"]): bad.append("ml.lk.site")
+            elif not np.allclose(site, dump["ml.lk.site"], rtol=stol, atol=0): bad.append("ml.lk.site~")
+    return bad, rel

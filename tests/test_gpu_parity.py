@@ -176,3 +176,18 @@ def test_no_device_argument_errors(glib):
     cfg = api.make_config(10, 20, 4, 32, device=99)
     with pytest.raises(api.VftError):
         api.Context(glib, cfg)
+
+
+ML_PARAMS = [(name, prec, lvl) for name, case in replay.ML_CASES.items() for prec, lvl in case[5]]
+
+
+@pytest.mark.parametrize("name,prec,lvl", ML_PARAMS)
+def test_cuda_likelihood_matches_reference(glib, name, prec, lvl):
+    """k_pair_loglk / k_posterior vs the reference's own pairLogLk / posteriorProfile (tests/golden/*.mldump.bin).
+    Bit-identical posterior profiles and per-site likelihoods wherever the reference makes no libm call
+    (-fastexp 2/3 with a transition matrix); otherwise, and for the final log(), the north_star tolerance:
+    1e-5 relative (fp32) / 1e-12 (fp64)."""
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d_e%d.mldump.bin" % (name, prec, lvl)))
+    chars, kind, model = replay.ml_case_chars(name)
+    bad, rel = replay.replay_ml(glib, dump, chars, kind, prec, exact_log=False)
+    assert bad == [], (bad, rel)

@@ -104,3 +104,16 @@ def test_b200operations_drops_into_reference_templates(tmp_path):
         synth.write_fasta(fa, chars)
         out = subprocess.run([probe, fa, kind], capture_output=True, text=True)
         assert out.returncode == 0 and "IDENTICAL" in out.stdout
+
+
+ML_PARAMS = [(name, prec, lvl) for name, case in replay.ML_CASES.items() for prec, lvl in case[5]]
+
+
+@pytest.mark.parametrize("name,prec,lvl", ML_PARAMS)
+def test_oracle_likelihood_matches_reference(olib, name, prec, lvl):
+    """pairLogLk (NJ.tcc:1192) and posteriorProfile (NJ.tcc:2137) of the restatement vs the reference's own
+    functions: posterior profiles, per-site likelihoods and log-likelihoods bit-identical (same libm)."""
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d_e%d.mldump.bin" % (name, prec, lvl)))
+    chars, kind, model = replay.ml_case_chars(name)
+    bad, rel = replay.replay_ml(olib, dump, chars, kind, prec, exact_log=True)
+    assert bad == [] and rel == 0.0

@@ -60,6 +60,7 @@ ABI_SYMBOLS = [
     "vft_get_self", "vft_out_distance_batch", "vft_out_distance_all", "vft_dist_pairs",
     "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
     "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
+    "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
 ]
 
 
@@ -88,6 +89,11 @@ class Lib:
         d.vft_outprofile_update.argtypes = [vp, i64, i64, i64, i64]
         d.vft_profile_average.argtypes = [vp, i64, i64, i64, dbl, dbl]
         d.vft_profile_average_update.argtypes = [vp, i64, i64, i64, dbl, dbl, i64]
+        if hasattr(d, "vft_upload_transmat"):
+            d.vft_upload_transmat.argtypes = [vp, vp, vp, vp, vp, vp]
+            d.vft_sync_rates.argtypes = [vp, vp, i64, vp, dbl, dbl, i32]
+            d.vft_pair_loglk_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+            d.vft_posterior_profile.argtypes = [vp, i64, i64, i64, dbl, dbl]
         d.vft_get_self.argtypes = [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]
         d.vft_out_distance_batch.argtypes = [vp, vp, i64, i64, dbl, vp]
         d.vft_out_distance_all.argtypes = [vp, i64, dbl, vp, i64]

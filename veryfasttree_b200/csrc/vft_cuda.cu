@@ -17,6 +17,7 @@
 // There is no CPU fallback: without a usable device vft_ctx_create returns VFT_ENODEVICE.
 #include "../../include/vft_b200.h"
 #include "vft_device.cuh"
+#include "vft_ml.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -420,6 +421,58 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
     }
 }
 
+// pairLogLk (NJ.tcc:1192-1447): one warp per (pair, length) item
+template<typename P, int A>
+__global__ void __launch_bounds__(128)
+k_pair_loglk(Store<P> s, MLModel<P> m, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
+             const double *__restrict__ len, int64_t n, double *__restrict__ loglk, double *__restrict__ siteLk) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int64_t item = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+    const size_t perWarp = (size_t) s.Lp * 8 + 64 * 20 * 8;
+    unsigned char *mine = smemRaw + (threadIdx.x >> 5) * perWarp;
+    if (item >= n) return;
+    const double v = pair_loglk_warp<P, A>(s, m, ia[item], ib[item], len[item], reinterpret_cast<double *>(mine),
+                                           mine + (size_t) s.Lp * 8, siteLk ? siteLk + item * s.L : nullptr);
+    if ((threadIdx.x & 31) == 0) loglk[item] = v;
+}
+
+// posteriorProfile (NJ.tcc:2137-2447): one thread per position; the two expEigenRates tables (or the
+// JC pSame/pDiff vectors) are built once per CTA in shared memory
+template<typename P, int A>
+__global__ void __launch_bounds__(128)
+k_posterior(Store<P> s, MLModel<P> m, int64_t oid, int64_t id1, int64_t id2, double len1, double len2) {
+    __shared__ __align__(16) unsigned char tab[2 * 64 * 20 * 8];
+    if (len1 < m.MLMinBranchLength) len1 = m.MLMinBranchLength;                            // :2139-2144
+    if (len2 < m.MLMinBranchLength) len2 = m.MLMinBranchLength;
+    P *ee1 = reinterpret_cast<P *>(tab), *ee2 = reinterpret_cast<P *>(tab + 64 * 20 * 8);
+    double *PS1 = reinterpret_cast<double *>(tab), *PD1 = PS1 + 64, *PS2 = reinterpret_cast<double *>(tab + 64 * 20 * 8), *PD2 = PS2 + 64;
+    if (m.codeFreq) {
+        exp_eigen_rates<P, A>(m, len1, ee1, threadIdx.x, blockDim.x);
+        exp_eigen_rates<P, A>(m, len2, ee2, threadIdx.x, blockDim.x);
+    } else {
+        jc_tables<P>(m, len1, PS1, PD1, threadIdx.x, blockDim.x);
+        jc_tables<P>(m, len2, PS2, PD2, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    const int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    if (pos >= s.Lp) return;
+    const int64_t row = oid - s.nSeqs;
+    P wOut = 0;
+    uint32_t cOut = VFT_DEV_NOCODE;
+    P f[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) f[k] = 0;
+    if (pos < s.L) {
+        const View<P, A> p1 = make_view<P, A>(s, id1), p2 = make_view<P, A>(s, id2);
+        posterior_site<P, A>(s, m, p1, p2, pos, ee1, ee2, PS1, PD1, PS2, PD2, wOut, cOut, f);
+    }
+    s.weights[row * s.Lp + pos] = wOut;
+    s.codes[oid * s.Lp + pos] = (uint8_t) cOut;
+#pragma unroll
+    for (int k = 0; k < A; k++) s.vecs[(row * s.Lp + pos) * A + k] = f[k];
+    if (pos == 0) s.active[oid] = 1;
+}
+
 // leaves: selfweight = nPos - nGaps (NJ.tcc:249-252), active, padding of the code rows
 template<typename P>
 __global__ void k_init_leaves(Store<P> s) {
@@ -456,6 +509,12 @@ struct vft_ctx {
     size_t hCap;
     std::vector<uint8_t> activeHost;
     int64_t nActLeaf, nActInternal;
+    // ML model
+    void *mlTables, *mlRates;
+    int32_t *mlRatecat;
+    bool hasTransmat, hasRates;
+    int nRateCats, fastexp;
+    double MLMinRel, MLMinBr;
     unsigned int seq;
     unsigned int *d_doneCount;
     volatile unsigned int *h_flag;
@@ -599,6 +658,9 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->active, 0, M, c->stream));
     CK(cudaMemsetAsync(c->tables, 0, 840 * ps, c->stream));
     c->activeHost.assign(M, 0);
+    CK(cudaMalloc(&c->mlTables, 1300 * ps)); CK(cudaMalloc(&c->mlRates, 64 * ps)); CK(cudaMalloc(&c->mlRatecat, Lp * 4));
+    CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
+    c->hasTransmat = false; c->hasRates = false;
     CK(cudaMalloc(&c->d_doneCount, 4));
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
     { void *f = nullptr; CK(cudaHostAlloc(&f, 64, cudaHostAllocMapped)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
@@ -628,7 +690,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_tkA, c->d_tkB,
-                    c->d_tvA, c->d_tvB, c->d_rec, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2};
+                    c->d_tvA, c->d_tvB, c->d_rec, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -927,6 +989,111 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
     c->cnt.algoBytes += c->nActInternal * profile_bytes(c, c->N);
     c->cnt.algoBytes += profile_bytes(c, query);
     return VFT_OK;
+}
+
+template<typename P>
+static MLModel<P> make_model(vft_ctx *c) {
+    MLModel<P> m;
+    const P *t = (const P *) c->mlTables;
+    const int A = c->A;
+    m.codeFreq = c->hasTransmat ? t : nullptr;
+    m.eigenval = t + (A + 1) * A; m.eigeninv = m.eigenval + A; m.eigeninvT = m.eigeninv + A * A; m.statinv = m.eigeninvT + A * A;
+    m.rates = (const P *) c->mlRates; m.ratecat = c->mlRatecat;
+    m.nRateCats = c->nRateCats; m.fastexp = c->fastexp;
+    m.MLMinRelBranchLength = c->MLMinRel; m.MLMinBranchLength = c->MLMinBr;
+    return m;
+}
+
+extern "C" int vft_upload_transmat(vft_ctx *c, const void *codeFreq, const void *eigenval, const void *eigeninv,
+                                   const void *eigeninvT, const void *statinv) {
+    if (!c) return fail(VFT_EINVAL, "null argument");
+    c->hasTransmat = codeFreq != nullptr;
+    if (!codeFreq) return VFT_OK;
+    if (!eigenval || !eigeninv || !statinv) return fail(VFT_EINVAL, "null argument");
+    const size_t ps = c->ps, A = (size_t) c->A;
+    std::vector<char> h(1300 * ps, 0);
+    char *q = h.data();
+    std::memcpy(q, codeFreq, (A + 1) * A * ps); q += (A + 1) * A * ps;
+    std::memcpy(q, eigenval, A * ps); q += A * ps;
+    std::memcpy(q, eigeninv, A * A * ps); q += A * A * ps;
+    if (eigeninvT) std::memcpy(q, eigeninvT, A * A * ps);
+    q += A * A * ps;
+    std::memcpy(q, statinv, A * ps);
+    CK(cudaMemcpyAsync(c->mlTables, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(sync_stream(c));
+    return VFT_OK;
+}
+
+extern "C" int vft_sync_rates(vft_ctx *c, const void *rates, int64_t nRateCats, const int64_t *ratecat,
+                              double MLMinRelBranchLength, double MLMinBranchLength, int32_t fastexpLevel) {
+    if (!c || !rates || !ratecat || nRateCats < 1 || nRateCats > 64 || fastexpLevel < 0 || fastexpLevel > 3)
+        return fail(VFT_EINVAL, "bad argument");
+    std::vector<int32_t> rc((size_t) c->Lp, 0);
+    for (int64_t i = 0; i < c->L; i++) {
+        if (ratecat[i] < 0 || ratecat[i] >= nRateCats) return fail(VFT_EINVAL, "bad rate category");
+        rc[(size_t) i] = (int32_t) ratecat[i];
+    }
+    CK(cudaMemcpyAsync(c->mlRates, rates, (size_t) nRateCats * c->ps, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->mlRatecat, rc.data(), rc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(sync_stream(c));
+    c->nRateCats = (int) nRateCats; c->fastexp = fastexpLevel; c->MLMinRel = MLMinRelBranchLength; c->MLMinBr = MLMinBranchLength;
+    c->hasRates = true;
+    return VFT_OK;
+}
+
+extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t *pj, const double *length, int64_t n,
+                                    double *loglk, double *siteLk) {
+    if (!c || (n > 0 && (!pi || !pj || !length || !loglk))) return fail(VFT_EINVAL, "null argument");
+    if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
+    if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
+    if (n == 0) return VFT_OK;
+    const size_t need = (size_t) n * 24 + (siteLk ? (size_t) n * c->L * 8 : 0);
+    int rc = ensure_pinned(c, need); if (rc) return rc;
+    int32_t *ha = (int32_t *) c->h_in, *hb = ha + n;
+    double *hl = (double *) ((char *) c->h_in + (size_t) n * 8);
+    for (int64_t k = 0; k < n; k++) {
+        if (pi[k] < 0 || pj[k] < 0 || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        ha[k] = (int32_t) pi[k]; hb[k] = (int32_t) pj[k]; hl[k] = length[k];
+        c->cnt.algoBytes += profile_bytes(c, pi[k]) + profile_bytes(c, pj[k]) + c->L * 4;
+    }
+    double *outLk = (double *) c->h_out, *outSite = siteLk ? outLk + n : nullptr;
+    const size_t perWarp = (size_t) c->Lp * 8 + 64 * 20 * 8;
+    const size_t smem = 4 * perWarp;
+    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-warp likelihood buffers");
+    const unsigned blocks = (unsigned) ((n + 3) / 4);
+#define CALL_LK(P, A_)                                                                                          \
+    do {                                                                                                        \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_pair_loglk<P, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        k_pair_loglk<P, A_><<<blocks, 128, smem, c->stream>>>(make_store<P>(c), make_model<P>(c), ha, hb, hl, n, outLk, outSite); \
+    } while (0)
+    prof_begin(c, CLS_DIST);
+    if (c->cfg.precision == 32) { if (c->A == 4) CALL_LK(float, 4); else CALL_LK(float, 20); }
+    else { if (c->A == 4) CALL_LK(double, 4); else CALL_LK(double, 20); }
+    prof_end(c);
+    CK(cudaGetLastError());
+    CK(sync_stream(c));
+    c->cnt.launches++;
+    std::memcpy(loglk, outLk, (size_t) n * 8);
+    if (siteLk) std::memcpy(siteLk, outSite, (size_t) n * c->L * 8);
+    return VFT_OK;
+}
+
+extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double len1, double len2) {
+    if (!c || out_id < c->N || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode)
+        return fail(VFT_EINVAL, "bad node id");
+    if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
+    if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
+    const unsigned blocks = (unsigned) ((c->Lp + 127) / 128);
+#define CALL_POST(P, A_) k_posterior<P, A_><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), make_model<P>(c), out_id, id1, id2, len1, len2)
+    prof_begin(c, CLS_PROFILE);
+    if (c->cfg.precision == 32) { if (c->A == 4) CALL_POST(float, 4); else CALL_POST(float, 20); }
+    else { if (c->A == 4) CALL_POST(double, 4); else CALL_POST(double, 20); }
+    prof_end(c);
+    CK(cudaGetLastError());
+    c->cnt.launches++;
+    if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
+    if (out_id >= c->maxnode) c->maxnode = out_id + 1;
+    return VFT_OK;            // asynchronous
 }
 
 extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *codes, void *vectors) {
