@@ -213,16 +213,9 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # max over ranks of the device-timed and end-to-end sums
-    tt = torch.tensor([dev_ms, e2e_s, float(n_unique), float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, e2e_max, taxa_total, launches_total = mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item()
-    else:
-        dev_ms_max, e2e_max, taxa_total, launches_total = dev_ms, e2e_s, float(n_unique), float(launches)
+    # max over ranks of the device-timed and end-to-end sums, sum of the units (veryfasttree_b200/dist.py)
+    from veryfasttree_b200 import dist as vdist
+    dev_ms_max, e2e_max, taxa_total, launches_total = vdist.aggregate_step_times(dev_ms, e2e_s, float(n_unique), float(launches), device="cuda")
 
     # one extra profiled pass: per-kernel-class device time from CUDA events on the launching stream
     ptree = one_step(profile=True)

@@ -141,6 +141,11 @@ int  vft_eval_batch(vft_ctx *ctx, const int64_t *out_ids, int64_t nOut, int64_t 
 int  vft_dist_one_vs_all(vft_ctx *ctx, int64_t query, int64_t nActive, int64_t K,
                          int64_t *j_out, void *dist, void *weight, void *criterion,
                          int64_t *nOut);
+/* the same sweep restricted to the candidate block jBegin <= j < jEnd: the unit of multi-GPU sharding
+    -- each rank evaluates its block, the K records per rank are all-gathered and merged */
+int  vft_dist_one_vs_all_range(vft_ctx *ctx, int64_t query, int64_t nActive, int64_t K, int64_t jBegin,
+                               int64_t jEnd, int64_t *j_out, void *dist, void *weight, void *criterion,
+                               int64_t *nOut);
 
 /* ============================================================================================
  * Likelihood kernels: pairLogLk and posteriorProfile under JC

@@ -1,0 +1,80 @@
+"""world_size-2 gloo tests (CPU) of the N>1 path: the measurement aggregation bench.py uses for its
+replicas, and the candidate-sharded one-vs-all (per-rank block + all_gather + merge) against the
+unsharded call.  The ABI implementation behind the ranks is the CPU oracle (tests only)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import replay
+    from veryfasttree_b200 import api, synth, dist as vdist
+    lib = api.load(replay.ORACLE_LIB)
+    # --- replicas: each rank builds its own tree; aggregation = max time, sum taxa
+    chars = synth.make_alignment(200 + 40 * rank, 120, "nt", seed=1 + rank)
+    chars = chars[synth.unique_rows(chars)]
+    tree = api.nj_build(api.encode(chars, "nt"), 4, 32, lib=lib, trace=False)
+    dev_ms, e2e, taxa, launches = vdist.aggregate_step_times(100.0 + 10 * rank, 1.0 + rank, float(chars.shape[0]), 7.0)
+    # --- sharded one-vs-all on a replicated slab
+    chars2 = synth.make_alignment(300, 150, "nt", seed=9)
+    codes = api.encode(chars2, "nt")
+    cfg = api.make_config(codes.shape[0], codes.shape[1], 4, 64)
+    with api.Context(lib, cfg) as ctx:
+        ctx.upload_leaves(codes)
+        ctx.outprofile_rebuild()
+        ctx.out_distance_all(codes.shape[0], 0.0)
+        n_active = codes.shape[0]
+        for k in range(40):           # some internal nodes so that both kernels' paths are exercised
+            ctx.profile_average_update(300 + k, 2 * k, 2 * k + 1, n_active)
+            n_active -= 1
+        ctx.out_distance_all(n_active, 0.0)
+        full = ctx.dist_one_vs_all(320, n_active, 34)
+        shard = vdist.sharded_one_vs_all(ctx, 320, n_active, 34)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), agg=np.array([dev_ms, e2e, taxa, launches]), n=chars.shape[0],
+             root=tree.root, full_j=full[0], shard_j=shard[0], full_c=full[3], shard_c=shard[3], full_d=full[1], shard_d=shard[1])
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path):
+    import replay
+    replay.ensure_oracle_built()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    # aggregation: max of the times, sum of the units -- identical on both ranks
+    assert np.array_equal(r0["agg"], r1["agg"])
+    assert r0["agg"][0] == 110.0 and r0["agg"][1] == 2.0
+    assert r0["agg"][2] == float(r0["n"] + r1["n"]) and r0["agg"][3] == 14.0
+    assert int(r0["root"]) == 2 * int(r0["n"]) - 3 and int(r1["root"]) == 2 * int(r1["n"]) - 3
+    # sharded sweep == unsharded sweep, bit for bit, on every rank
+    for r in (r0, r1):
+        assert np.array_equal(r["full_j"], r["shard_j"])
+        assert r["full_c"].tobytes() == r["shard_c"].tobytes() and r["full_d"].tobytes() == r["shard_d"].tobytes()
+
+
+def test_candidate_blocks_cover_everything():
+    from veryfasttree_b200 import dist as vdist
+    for n in (1, 7, 100, 32001):
+        for world in (1, 2, 3, 8):
+            blocks = [vdist.candidate_block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))

@@ -61,6 +61,7 @@ ABI_SYMBOLS = [
     "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
     "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
     "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
+    "vft_dist_one_vs_all_range",
 ]
 
 
@@ -100,6 +101,7 @@ class Lib:
         d.vft_dist_pairs.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         d.vft_eval_batch.argtypes = [vp, vp, i64, i64, dbl, vp, vp, vp, i64, i32, vp, vp]
         d.vft_dist_one_vs_all.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
+        d.vft_dist_one_vs_all_range.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_get_profile.argtypes = [vp, i64, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
         d.vft_nj_default_options.argtypes = [C.POINTER(VftNjOptions)]
@@ -166,6 +168,7 @@ class Context:
         lib.check(lib.dll.vft_ctx_create(C.byref(cfg), C.byref(self.h)), "vft_ctx_create")
         self.dt = np_dtype(cfg.precision)
         self.M = 2 * cfg.nSeqs
+        self._maxnode = 0
 
     def close(self):
         if self.h:
@@ -186,6 +189,7 @@ class Context:
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         assert codes.shape == (self.cfg.nSeqs, self.cfg.nPos)
         self.lib.check(self.lib.dll.vft_upload_leaves(self.h, _ptr(codes)), "vft_upload_leaves")
+        self._maxnode = self.cfg.nSeqs
 
     def outprofile_rebuild(self, ids=None):
         if ids is None:
@@ -202,10 +206,12 @@ class Context:
     def profile_average(self, out_id, id1, id2, bionj_weight=-1.0, diameter=0.0):
         self.lib.check(self.lib.dll.vft_profile_average(self.h, out_id, id1, id2, bionj_weight, diameter),
                        "vft_profile_average")
+        self._maxnode = max(self._maxnode, out_id + 1)
 
     def profile_average_update(self, out_id, id1, id2, n_active_old, bionj_weight=-1.0, diameter=0.0):
         self.lib.check(self.lib.dll.vft_profile_average_update(self.h, out_id, id1, id2, bionj_weight, diameter,
                                                                n_active_old), "vft_profile_average_update")
+        self._maxnode = max(self._maxnode, out_id + 1)
 
     def get_self(self, node):
         d, w = C.c_double(), C.c_double()
@@ -234,14 +240,19 @@ class Context:
                        "vft_dist_pairs")
         return d, w
 
-    def dist_one_vs_all(self, query, n_active, k):
+    def maxnode(self):
+        return self._maxnode
+
+    def dist_one_vs_all(self, query, n_active, k, j_begin=0, j_end=None):
         j = np.empty(k, dtype=np.int64)
         d = np.empty(k, dtype=self.dt)
         w = np.empty(k, dtype=self.dt)
         c = np.empty(k, dtype=self.dt)
         n = C.c_int64()
-        self.lib.check(self.lib.dll.vft_dist_one_vs_all(self.h, query, n_active, k, _ptr(j), _ptr(d), _ptr(w),
-                                                        _ptr(c), C.byref(n)), "vft_dist_one_vs_all")
+        if j_end is None:
+            j_end = self._maxnode
+        self.lib.check(self.lib.dll.vft_dist_one_vs_all_range(self.h, query, n_active, k, j_begin, j_end, _ptr(j), _ptr(d),
+                                                              _ptr(w), _ptr(c), C.byref(n)), "vft_dist_one_vs_all_range")
         n = n.value
         return j[:n], d[:n], w[:n], c[:n]
 

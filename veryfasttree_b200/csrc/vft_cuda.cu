@@ -95,11 +95,11 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, P *__restrict__ dist,
-                  P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd,
+                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
     const int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     if (j >= maxnode) return;
-    if (!s.active[j]) { keys[j] = ~0ull; return; }
+    if (!s.active[j] || j < jBegin || j >= jEnd) { keys[j] = ~0ull; return; }
     P d, w;
     join_dist<P, A, MATRIX>(s, query, j, false, d, w);
     // setCriterion (NJ.tcc:1099-1107) with every out-distance fresh at this nActive
@@ -112,8 +112,8 @@ k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, P
 // setBestHit for an INTERNAL query: every distance is a profileDist; each warp owns G node slots
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int G, P *__restrict__ dist,
-                  P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd, int G,
+                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -121,7 +121,7 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t j = warp * G + lane;
     const bool valid = lane < G && j < maxnode;
-    const bool act = valid && s.active[j];
+    const bool act = valid && s.active[j] && j >= jBegin && j < jEnd;
     P d = 0, w = 0;
     unsigned mask = __ballot_sync(full, act);
     while (mask) {
@@ -927,6 +927,12 @@ static int next_pow2(int64_t x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, int64_t K, int64_t *j_out, void *dist,
                                    void *weight, void *criterion, int64_t *nOut) {
+    if (!c) return fail(VFT_EINVAL, "null argument");
+    return vft_dist_one_vs_all_range(c, query, nActive, K, 0, c->maxnode, j_out, dist, weight, criterion, nOut);
+}
+
+extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nActive, int64_t K, int64_t jBegin, int64_t jEnd,
+                                         int64_t *j_out, void *dist, void *weight, void *criterion, int64_t *nOut) {
     if (!c || !j_out || !dist || !weight || !criterion || !nOut) return fail(VFT_EINVAL, "null argument");
     if (query < 0 || query >= c->maxnode || !c->activeHost[query]) return fail(VFT_EINVAL, "query must be an active node");
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
@@ -938,8 +944,8 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
     }
     const int Gq = pick_group(n);
     const int64_t warpsQ = (n + Gq - 1) / Gq;
-#define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), query, nActive, n, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
     prof_begin(c, CLS_DIST);
     if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
     prof_end(c);
@@ -964,7 +970,12 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
         std::swap(inK, outK); std::swap(inV, outV);
         nLists = nOutLists;
     }
-    const int64_t nRet = std::min<int64_t>(std::min<int64_t>(K, nActive), KcStage);
+    int64_t inBlock = nActive;
+    if (jBegin > 0 || jEnd < n) {
+        inBlock = 0;
+        for (int64_t j = std::max<int64_t>(0, jBegin); j < std::min(jEnd, n); j++) inBlock += c->activeHost[j];
+    }
+    const int64_t nRet = std::min<int64_t>(std::min<int64_t>(K, inBlock), KcStage);
     const size_t recSz = c->ps == 4 ? sizeof(Rec<float>) : sizeof(Rec<double>);
     int rc = ensure_pinned(c, (size_t) nRet * recSz); if (rc) return rc;
     if (c->ps == 4) k_gather_topk<float><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
