@@ -200,11 +200,13 @@ def main():
     sampler.start()
     barrier()
     dev_ms, e2e_s, launches, h2d, d2h = 0.0, 0.0, 0, 0, 0
+    per_step = []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         tr = one_step()
         dev_ms += tr.stats["deviceMsResident"]
         e2e_s += tr.stats["secondsEndToEnd"]
+        per_step.append((round(tr.stats["deviceMsResident"], 1), round(tr.stats["secondsEndToEnd"] * 1e3, 1)))
         launches += tr.stats["counters"]["launches"]
         h2d += tr.stats["counters"]["h2dBytes"]
         d2h += tr.stats["counters"]["d2hBytes"] + 4 * 2 * n_unique * 4     # + tree read-back
@@ -225,6 +227,7 @@ def main():
         st["secondsHost"] = [round(x, 3) for x in tr.stats["secondsHost"]]
         print("[bench] last timed step:", json.dumps(st), file=sys.stderr)
         print("[bench] profiled pass counters:", json.dumps(prof), file=sys.stderr)
+        print("[bench] per step (device ms, end-to-end ms):", per_step, file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -259,9 +262,10 @@ def main():
     value = taxa_total * args.steps / (dev_ms_max * 1e-3)
     line = {"metric": "taxa/sec on initial NJ+TopHits build", "value": value, "unit": "taxa/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, f64 accumulation (as the reference)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "taxa_per_gpu": int(n_unique), "columns": WORKLOAD["pos"],
                        "parallelism": "replicas x%d" % args.gpus, "l2": "flushed between steps (256 MiB write)",
+                       "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)",
                        "parity": "join order, top-hit lists and branch lengths identical to the reference at -threads 1"},
             "e2e": {"value": taxa_total * args.steps / e2e_max, "unit": "taxa/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps},

@@ -169,70 +169,114 @@ __device__ __forceinline__ bool kv_less(uint64_t ka, uint32_t ia, uint64_t kb, u
     return ka < kb || (ka == kb && ia > ib);
 }
 
-constexpr int SORT_N = 4096;        // elements sorted per CTA
-constexpr int SORT_T = 1024;
+template<typename P>
+struct Rec { int64_t j; P dist, weight, crit; };
 
-__device__ void bitonic_sort_smem(uint64_t *k, uint32_t *v) {
-    for (int size = 2; size <= SORT_N; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < SORT_N / 2; t += SORT_T) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const uint64_t ka = k[lo], kb = k[hi];
-                const uint32_t ia = v[lo], ib = v[hi];
-                const bool swap = up ? kv_less(kb, ib, ka, ia) : kv_less(ka, ia, kb, ib);
-                if (swap) { k[lo] = kb; k[hi] = ka; v[lo] = ib; v[hi] = ia; }
+// ---- top-K in ONE kernel: radix select + small sort -------------------------------------------------
+// The K best of n keys in psort order = the K smallest COMPOSITE keys (criterion bits, 0xFFFFFFFF - index):
+// composites are unique, so ties need no special casing.  One CTA finds the K-th composite with an
+// 8-bit-per-pass MSB radix select over the keys (L2-resident: n*8 bytes per pass), compacts the K
+// selected elements into shared memory, sorts them with a bitonic network and writes the result
+// records straight into mapped host memory.  KEYBYTES = 4 (float criterion) or 8 (double).
+constexpr int SEL_T = 1024;
+constexpr int SEL_MAXK = 4096;
+
+template<typename P, int KEYBYTES>
+__global__ void __launch_bounds__(SEL_T)
+k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__restrict__ dist, const P *__restrict__ weight,
+              const P *__restrict__ crit, Rec<P> *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem);                    // [32 warps][256]
+    uint64_t *sk = reinterpret_cast<uint64_t *>(smem + 32 * 256 * 4);              // [SEL_MAXK] sort keys
+    uint32_t *sv = reinterpret_cast<uint32_t *>(smem + 32 * 256 * 4 + SEL_MAXK * 8);   // [SEL_MAXK] node ids
+    __shared__ uint64_t prefKey, maskKey;
+    __shared__ uint32_t prefIdx, maskIdx;
+    __shared__ unsigned int need, cnt;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int PASSES = KEYBYTES + 4;
+    if (tid == 0) { prefKey = 0; maskKey = 0; prefIdx = 0; maskIdx = 0; need = (unsigned) K; cnt = 0; }
+    __syncthreads();
+    for (int p = 0; p < PASSES; p++) {
+        for (int t = tid; t < 32 * 256; t += SEL_T) hist[t] = 0;
+        __syncthreads();
+        const uint64_t pk = prefKey, mk = maskKey;
+        const uint32_t pi = prefIdx, mi = maskIdx;
+        const bool onKey = p < KEYBYTES;
+        const int shift = onKey ? 8 * (KEYBYTES - 1 - p) : 8 * (3 - (p - KEYBYTES));
+        for (int64_t base = 0; base < n; base += SEL_T) {
+            const int64_t i = base + tid;
+            bool in = false;
+            unsigned int digit = 0;
+            if (i < n) {
+                const uint64_t k = keys[i];
+                const uint32_t ni = 0xFFFFFFFFu - (uint32_t) i;
+                in = ((k & mk) == pk) && ((ni & mi) == pi);
+                digit = onKey ? (unsigned int) ((k >> shift) & 0xFFu) : ((ni >> shift) & 0xFFu);
+            }
+            // warp-aggregated increment of the warp-private histogram
+            const unsigned act = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) hist[wid * 256 + digit] += __popc(peers);
+            }
+        }
+        __syncthreads();
+        // fold the 32 private histograms, then thread 0 walks the 256 bins
+        if (tid < 256) {
+            unsigned int tot = 0;
+            for (int w = 0; w < 32; w++) tot += hist[w * 256 + tid];
+            hist[tid] = tot;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int cum = 0, want = need;
+            int d = 0;
+            for (; d < 256; d++) { if (cum + hist[d] >= want) break; cum += hist[d]; }
+            if (d == 256) d = 255;
+            need = want - cum;
+            if (onKey) { prefKey |= (uint64_t) d << shift; maskKey |= (uint64_t) 0xFFu << shift; }
+            else { prefIdx |= (uint32_t) d << shift; maskIdx |= 0xFFu << shift; }
+        }
+        __syncthreads();
+    }
+    // the K-th composite is (prefKey, prefIdx): select everything <= it
+    const uint64_t tk = prefKey;
+    const uint32_t ti = prefIdx;
+    for (int64_t base = 0; base < n; base += SEL_T) {
+        const int64_t i = base + tid;
+        if (i < n) {
+            const uint64_t k = keys[i];
+            const uint32_t ni = 0xFFFFFFFFu - (uint32_t) i;
+            if (k < tk || (k == tk && ni <= ti)) {
+                const unsigned int slot = atomicAdd(&cnt, 1u);
+                if (slot < SEL_MAXK) { sk[slot] = k; sv[slot] = (uint32_t) i; }
             }
         }
     }
     __syncthreads();
-}
-
-// stage 1: CTA b sorts slots [b*SORT_N, (b+1)*SORT_N) and keeps its Kc best
-__global__ void __launch_bounds__(SORT_T)
-k_topk_chunks(const uint64_t *__restrict__ keys, int64_t n, int Kc, uint64_t *__restrict__ outK, uint32_t *__restrict__ outV) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *k = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *v = reinterpret_cast<uint32_t *>(smem + sizeof(uint64_t) * SORT_N);
-    const int64_t base = (int64_t) blockIdx.x * SORT_N;
-    for (int t = threadIdx.x; t < SORT_N; t += SORT_T) {
-        const int64_t j = base + t;
-        k[t] = j < n ? keys[j] : ~0ull;
-        v[t] = (uint32_t) (j < n ? j : 0xFFFFFFFFu - t);      // padding: distinct indices, sorts after all
+    const int have = min((int) cnt, SEL_MAXK);
+    int np2 = 1;
+    while (np2 < have) np2 <<= 1;
+    for (int t = tid; t < np2; t += SEL_T) if (t >= have) { sk[t] = ~0ull; sv[t] = 0u; }
+    // bitonic sort of np2 elements: key ascending, index descending
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < np2 / 2; t += SEL_T) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const uint64_t ka = sk[lo], kb = sk[hi];
+                const uint32_t ia = sv[lo], ib = sv[hi];
+                const bool sw = up ? kv_less(kb, ib, ka, ia) : kv_less(ka, ia, kb, ib);
+                if (sw) { sk[lo] = kb; sk[hi] = ka; sv[lo] = ib; sv[hi] = ia; }
+            }
+        }
     }
-    bitonic_sort_smem(k, v);
-    for (int t = threadIdx.x; t < Kc; t += SORT_T) { outK[(int64_t) blockIdx.x * Kc + t] = k[t]; outV[(int64_t) blockIdx.x * Kc + t] = v[t]; }
-}
-
-// stage 2..: CTA b merges `R` sorted lists of Kc entries (R*Kc <= SORT_N) and keeps the Kc best
-__global__ void __launch_bounds__(SORT_T)
-k_topk_merge(const uint64_t *__restrict__ inK, const uint32_t *__restrict__ inV, int nLists, int R, int Kc,
-             uint64_t *__restrict__ outK, uint32_t *__restrict__ outV) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *k = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *v = reinterpret_cast<uint32_t *>(smem + sizeof(uint64_t) * SORT_N);
-    const int first = blockIdx.x * R;
-    const int have = min(R, nLists - first) * Kc;
-    for (int t = threadIdx.x; t < SORT_N; t += SORT_T) {
-        if (t < have) { k[t] = inK[(int64_t) first * Kc + t]; v[t] = inV[(int64_t) first * Kc + t]; }
-        else { k[t] = ~0ull; v[t] = 0u; }
+    __syncthreads();
+    for (int t = tid; t < K && t < have; t += SEL_T) {
+        const uint32_t j = sv[t];
+        out[t].j = j; out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j];
     }
-    bitonic_sort_smem(k, v);
-    for (int t = threadIdx.x; t < Kc; t += SORT_T) { outK[(int64_t) blockIdx.x * Kc + t] = k[t]; outV[(int64_t) blockIdx.x * Kc + t] = v[t]; }
-}
-
-template<typename P>
-struct Rec { int64_t j; P dist, weight, crit; };
-
-template<typename P>
-__global__ void k_gather_topk(const uint32_t *__restrict__ idx, int K, const P *__restrict__ dist,
-                              const P *__restrict__ weight, const P *__restrict__ crit, Rec<P> *__restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= K) return;
-    const uint32_t j = idx[t];
-    out[t].j = j; out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j];
 }
 
 // averageProfile (NJ.tcc:2067-2135) + profileDist(new,new) (NJ.tcc:3040-3043); ONE CTA:
@@ -644,10 +688,7 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMalloc(&c->tables, 840 * ps));
     CK(cudaMalloc(&c->d_dist, M * ps)); CK(cudaMalloc(&c->d_weight, M * ps)); CK(cudaMalloc(&c->d_crit, M * ps));
     CK(cudaMalloc(&c->d_keys, M * 8));
-    const size_t nChunks = (M + SORT_N - 1) / SORT_N;
-    CK(cudaMalloc(&c->d_tkA, nChunks * SORT_N * 8)); CK(cudaMalloc(&c->d_tkB, nChunks * SORT_N * 8));
-    CK(cudaMalloc(&c->d_tvA, nChunks * SORT_N * 4)); CK(cudaMalloc(&c->d_tvB, nChunks * SORT_N * 4));
-    CK(cudaMalloc(&c->d_rec, SORT_N * 32));
+    c->d_tkA = c->d_tkB = nullptr; c->d_tvA = c->d_tvB = nullptr; c->d_rec = nullptr;
     CK(cudaMemsetAsync(c->codes, VFT_NOCODE, M * Lp, c->stream));
     CK(cudaMemsetAsync(c->weights, 0, N * Lp * ps, c->stream));
     CK(cudaMemsetAsync(c->ow, 0, Lp * ps, c->stream));
@@ -665,8 +706,10 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
     { void *f = nullptr; CK(cudaHostAlloc(&f, 64, cudaHostAllocMapped)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
     c->seq = 0;
-    int rc = ensure_lists(c, 4096);
-    if (rc == VFT_OK) rc = ensure_pinned(c, 1 << 20);
+    int rc = ensure_lists(c, std::max<int64_t>(4096, c->M));
+    // pinned request/response buffers sized once for the largest list the NJ driver produces
+    // (m lists of 2m pairs at a refresh, m = sqrt(N); every active node in the all-node sweeps)
+    if (rc == VFT_OK) rc = ensure_pinned(c, std::max<size_t>((size_t) 1 << 20, (size_t) 48 * (size_t) c->N + (size_t) 16 * (size_t) c->M + 4096));
     if (rc != VFT_OK) return rc;
     {
         const int need = (int) (4 * warp_smem_bytes(c->Lp));
@@ -678,8 +721,8 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
             VFT_DISPATCH(c, SET_SMEM);
         }
     }
-    cudaFuncSetAttribute(k_topk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
-    cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_N * 12);
+    cudaFuncSetAttribute(k_topk_select<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
+    cudaFuncSetAttribute(k_topk_select<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     CK(sync_stream(c));
     *out = c;
     return VFT_OK;
@@ -937,11 +980,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     if (query < 0 || query >= c->maxnode || !c->activeHost[query]) return fail(VFT_EINVAL, "query must be an active node");
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
     const int64_t n = c->maxnode;
-    int Kc = next_pow2(std::min<int64_t>(K, n));
-    if (Kc > SORT_N / 2) {
-        if (K > SORT_N) return fail(VFT_EINVAL, "K larger than 4096 is not supported yet");
-        Kc = SORT_N;
-    }
+    if (K > SEL_MAXK) return fail(VFT_EINVAL, "K larger than 4096 is not supported");
     const int Gq = pick_group(n);
     const int64_t warpsQ = (n + Gq - 1) / Gq;
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
@@ -951,39 +990,24 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;
-    // chunk sort, then a merge tree until one list is left
-    int nLists = (int) ((n + SORT_N - 1) / SORT_N);
-    const int KcStage = std::min(Kc, SORT_N);
-    prof_begin(c, CLS_SELECT);
-    k_topk_chunks<<<nLists, SORT_T, SORT_N * 12, c->stream>>>(c->d_keys, n, KcStage, c->d_tkA, c->d_tvA);
-    CK(cudaGetLastError());
-    c->cnt.launches++;
-    uint64_t *inK = c->d_tkA, *outK = c->d_tkB;
-    uint32_t *inV = c->d_tvA, *outV = c->d_tvB;
-    while (nLists > 1) {
-        int R = std::max(2, SORT_N / KcStage);
-        if (KcStage == SORT_N) return fail(VFT_EINVAL, "K larger than 2048 needs more than one chunk: not supported yet");
-        int nOutLists = (nLists + R - 1) / R;
-        k_topk_merge<<<nOutLists, SORT_T, SORT_N * 12, c->stream>>>(inK, inV, nLists, R, KcStage, outK, outV);
-        CK(cudaGetLastError());
-        c->cnt.launches++;
-        std::swap(inK, outK); std::swap(inV, outV);
-        nLists = nOutLists;
-    }
     int64_t inBlock = nActive;
     if (jBegin > 0 || jEnd < n) {
         inBlock = 0;
         for (int64_t j = std::max<int64_t>(0, jBegin); j < std::min(jEnd, n); j++) inBlock += c->activeHost[j];
     }
-    const int64_t nRet = std::min<int64_t>(std::min<int64_t>(K, inBlock), KcStage);
+    const int64_t nRet = std::min<int64_t>(K, inBlock);
     const size_t recSz = c->ps == 4 ? sizeof(Rec<float>) : sizeof(Rec<double>);
-    int rc = ensure_pinned(c, (size_t) nRet * recSz); if (rc) return rc;
-    if (c->ps == 4) k_gather_topk<float><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
-    else k_gather_topk<double><<<(unsigned) ((nRet + 127) / 128), 128, 0, c->stream>>>(inV, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->h_out);
-    CK(cudaGetLastError());
-    c->cnt.launches++;
-    prof_end(c);
-    c->cnt.d2hBytes += (int64_t) (nRet * recSz);
+    int rc = ensure_pinned(c, (size_t) std::max<int64_t>(nRet, 1) * recSz); if (rc) return rc;
+    if (nRet > 0) {
+        const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12;
+        prof_begin(c, CLS_SELECT);
+        if (c->ps == 4) k_topk_select<float, 4><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
+        else k_topk_select<double, 8><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->h_out);
+        prof_end(c);
+        CK(cudaGetLastError());
+        c->cnt.launches++;
+        c->cnt.d2hBytes += (int64_t) (nRet * recSz);
+    }
     CK(sync_stream(c));
     if (c->ps == 4) {
         const Rec<float> *r = (const Rec<float> *) c->h_out;
