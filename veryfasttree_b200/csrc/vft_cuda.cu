@@ -213,11 +213,15 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
                 in = ((k & mk) == pk) && ((ni & mi) == pi);
                 digit = onKey ? (unsigned int) ((k >> shift) & 0xFFu) : ((ni >> shift) & 0xFFu);
             }
-            // warp-aggregated increment of the warp-private histogram
+            // warp-aggregated increment of the warp-private histogram; fast path: the whole warp
+            // agrees on the digit (the usual case: criteria share their leading bits)
             const unsigned act = __ballot_sync(0xFFFFFFFFu, in);
-            if (in) {
-                const unsigned peers = __match_any_sync(act, digit);
-                if (lane == __ffs(peers) - 1) hist[wid * 256 + digit] += __popc(peers);
+            if (act) {
+                const int leader = __ffs(act) - 1;
+                const unsigned int d0 = __shfl_sync(0xFFFFFFFFu, digit, leader);
+                const unsigned same = __ballot_sync(0xFFFFFFFFu, in && digit == d0);
+                if (same == act) { if (lane == leader) hist[wid * 256 + d0] += __popc(act); }
+                else if (in) atomicAdd(&hist[wid * 256 + digit], 1u);
             }
         }
         __syncthreads();
@@ -228,14 +232,28 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
             hist[tid] = tot;
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned int cum = 0, want = need;
-            int d = 0;
-            for (; d < 256; d++) { if (cum + hist[d] >= want) break; cum += hist[d]; }
-            if (d == 256) d = 255;
-            need = want - cum;
-            if (onKey) { prefKey |= (uint64_t) d << shift; maskKey |= (uint64_t) 0xFFu << shift; }
-            else { prefIdx |= (uint32_t) d << shift; maskIdx |= 0xFFu << shift; }
+        if (wid == 0) {
+            // warp 0 scans the 256 bins: 8 bins per lane, exclusive prefix over lanes, then the lane
+            // whose range contains the `need`-th element walks its 8 bins
+            unsigned int loc[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) { loc[b] = hist[lane * 8 + b]; sum += loc[b]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+            const unsigned int excl = incl - sum, want = need;
+            const bool mine = excl < want && want <= incl;
+            const unsigned who = __ballot_sync(0xFFFFFFFFu, mine);
+            const int owner = who ? __ffs(who) - 1 : 31;
+            if (lane == owner) {
+                unsigned int cum = excl;
+                int b = 0;
+                for (; b < 7; b++) { if (cum + loc[b] >= want) break; cum += loc[b]; }
+                const int d = lane * 8 + b;
+                need = want - cum;
+                if (onKey) { prefKey |= (uint64_t) d << shift; maskKey |= (uint64_t) 0xFFu << shift; }
+                else { prefIdx |= (uint32_t) d << shift; maskIdx |= 0xFFu << shift; }
+            }
         }
         __syncthreads();
     }
@@ -965,8 +983,6 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     c->cnt.d2hBytes += nAct * (int64_t) c->ps;
     return VFT_OK;
 }
-
-static int next_pow2(int64_t x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, int64_t K, int64_t *j_out, void *dist,
                                    void *weight, void *criterion, int64_t *nOut) {
