@@ -67,8 +67,11 @@ void rsortByKey(std::vector<T> &v, KeyFn keyOf) {
 template<typename P>
 class NJ {
 public:
-    struct Hit { int64_t j; P dist; };                             // NJ.h:214-217
-    struct Besthit { int64_t i, j; P weight, dist, criterion; };   // NJ.h:192-200
+    // node ids fit 31 bits (maxnodes = 2N < 2^31, checked in vft_nj_build): 32-bit ids halve the
+    // memory of the top-hit lists (the reference's are int64_t, NJ.h:192-217) and the copy traffic
+    typedef int32_t id_t;
+    struct Hit { id_t j; P dist; };                                // NJ.h:214-217
+    struct Besthit { id_t i, j; P weight, dist, criterion; };      // NJ.h:192-200
     struct TopHitsList { std::vector<Hit> hits; int64_t hitSource = -1; int64_t age = 0; };
 
     NJ(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, vft_nj_result *res, const uint8_t *codes)
@@ -370,11 +373,11 @@ int64_t NJ<P>::oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<B
     int64_t n = 0;
     check(timed([&] { return vft_dist_one_vs_all(ctx, query, nActive, K, js.data(), d.data(), w.data(), c.data(), &n); }));
     out.resize(K);
-    for (int64_t k = 0; k < n; k++) out[k] = Besthit{query, js[k], w[k], d[k], c[k]};
+    for (int64_t k = 0; k < n; k++) out[k] = Besthit{(id_t) query, (id_t) js[k], w[k], d[k], c[k]};
     // sentinels of inactive nodes (NJ.tcc:3613-3617): criterion 1e20 ties, later index first
     int64_t k = n;
     for (int64_t j = maxnode - 1; j >= 0 && k < K; j--)
-        if (parent[j] >= 0) out[k++] = Besthit{-1, j, 0, (P) 1e20, (P) 1e20};
+        if (parent[j] >= 0) out[k++] = Besthit{-1, (id_t) j, 0, (P) 1e20, (P) 1e20};
     out.resize(k);
     return n;
 }
@@ -444,7 +447,7 @@ template<typename P>
 void NJ<P>::uniqueCore(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out) {
     for (auto &h : combined) updateBestHit(nActive, h, false);
     {   // psort by (i,j), NJ.tcc:4797, :7309-7311; ids fit 31 bits, -1 sorts first
-        rsortByKey(combined, [](const Besthit &a) { return ((uint64_t) (uint32_t) (a.i + 1) << 32) | (uint32_t) (a.j + 1); });
+        rsortByKey(combined, [](const Besthit &a) { return ((uint64_t) (uint32_t) ((int64_t) a.i + 1) << 32) | (uint32_t) ((int64_t) a.j + 1); });
     }
     out.clear();
     out.reserve(combined.size());
@@ -778,7 +781,7 @@ void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
                         newj = 0;
                         while (parent[newj] >= 0 || newj == iNode) newj++;
                     }
-                    Besthit bh = {iNode, newj, (P) -1e20, (P) -1e20, (P) -1e20};
+                    Besthit bh = {(id_t) iNode, (id_t) newj, (P) -1e20, (P) -1e20, (P) -1e20};
                     setDistCriterion(nActive, bh);
                     v.j = newj;
                     v.dist = bh.dist;
@@ -912,7 +915,7 @@ template<typename P>
 void NJ<P>::setBestHitFull(int64_t node, int64_t nActive, Besthit &bestjoin, std::vector<Besthit> *allhits) {
     std::vector<Besthit> sorted;
     int64_t n = oneVsAll(node, nActive, maxnode, sorted);
-    bestjoin = Besthit{node, -1, 0, (P) 1e20, (P) 1e20};
+    bestjoin = Besthit{(id_t) node, -1, 0, (P) 1e20, (P) 1e20};
     // arg-min with strict '<' scanning j ascending (:3627): lowest j among equal criteria
     for (int64_t k = 0; k < n; k++) {
         const Besthit &h = sorted[k];
@@ -1149,6 +1152,7 @@ extern "C" void vft_nj_default_options(vft_nj_options *o) {
 extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in, const uint8_t *codes,
                             const void *const tables[4], vft_nj_result *res) {
     if (!cfg || !codes || !res || !res->parent || !res->nChild || !res->child || !res->branchlength) return VFT_EINVAL;
+    if (cfg->nSeqs >= (int64_t) 1 << 30) return VFT_EINVAL;
     vft_nj_options opt;
     if (opt_in) opt = *opt_in; else vft_nj_default_options(&opt);
     if (opt.bionj) return VFT_EINVAL;

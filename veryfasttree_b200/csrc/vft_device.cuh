@@ -337,7 +337,8 @@ template<> struct Vec4T<double> { typedef double4 type; };
 // The additions are the reference's, in the reference's order; positions the reference skips
 // contribute +0.0, and x + (+0.0) == x for every value the accumulators can take (they are never
 // -0.0), so the result is bit-identical to the one-thread loop above.  Zero `top` terms (equal
-// codes, the common case between close relatives) are compacted away before the ordered pass.
+// codes, the common case between close relatives) are compacted away before the ordered pass, and
+// the `denom` pass is replaced by a tree sum whenever that is provably exact (see below).
 // `sm` = 2*Lp doubles (+Lp/32 ints) of shared memory private to the calling warp: see warp_smem_bytes().
 __host__ __device__ inline size_t warp_smem_bytes(int64_t Lp) { return (size_t) Lp * 16; }
 
@@ -392,13 +393,44 @@ __device__ __forceinline__ void profile_dist_warp(const Store<P> &s, const View<
             nTop += __popc(nz);
         }
     }
+    // `denom` fast path: when every partial sum of the w1*w2 terms is exactly representable (all
+    // terms are multiples of 2^LB and the total stays below 2^(LB+53)), every addition in ANY order
+    // is exact, so the ordered sum equals a tree sum.  True for the 0/1 and small dyadic weights
+    // that NJ profiles carry in fp32; checked per pair, never assumed.
+    double dLocal = 0;
+    int minLB = 4096, maxE = -4096, cntNZ = 0;
+    for (int64_t pos = lane; pos < Lp; pos += 32) {
+        const double t = termW[pos];                  // own writes: visible without a barrier
+        if (t > 0) {
+            const unsigned long long bits = (unsigned long long) __double_as_longlong(t);
+            const int e = (int) ((bits >> 52) & 0x7FF) - 1023;
+            const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | 0x10000000000000ull;
+            const int lb = e - 52 + (__ffsll((long long) mant) - 1);
+            minLB = min(minLB, lb); maxE = max(maxE, e); cntNZ++;
+            dLocal += t;                              // exactness of this partial sum is covered by the test below
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        minLB = min(minLB, __shfl_xor_sync(full, minLB, o));
+        maxE = max(maxE, __shfl_xor_sync(full, maxE, o));
+        cntNZ += __shfl_xor_sync(full, cntNZ, o);
+    }
+    int lg = 0;
+    while ((1 << lg) < cntNZ) lg++;
+    const bool exactDenom = cntNZ == 0 || (maxE + 1 + lg - minLB <= 53 && minLB > -1000);
     __syncwarp();
     double acc = 0;
-    if (lane == 0) {
+    if (exactDenom) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dLocal += __shfl_xor_sync(full, dLocal, o);
+        if (lane == 0) acc = dLocal;
+    } else if (lane == 0) {
         for (int64_t k = 0; k < Lp; k += 4) {
             acc = xadd(acc, termW[k]); acc = xadd(acc, termW[k + 1]); acc = xadd(acc, termW[k + 2]); acc = xadd(acc, termW[k + 3]);
         }
-    } else if (lane == 1) {
+    }
+    if (lane == 1) {
         for (int k = 0; k < nTop; k++) acc = xadd(acc, termT[k]);
     }
     __syncwarp();
