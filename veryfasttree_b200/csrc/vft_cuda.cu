@@ -58,7 +58,7 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
+    unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t item = warp * G + lane;
     const bool valid = lane < G && item < n;
@@ -72,24 +72,17 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
         seq_dist<P, MATRIX>(s, s.codes + a * s.Lp, s.codes + b * s.Lp, d, w);
         d = (P) xadd((double) d, 0.0);                                                    // NJ.tcc:1122
     }
-    unsigned mask = __ballot_sync(full, valid && !isSeq);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t aa = __shfl_sync(full, a, src), bb = __shfl_sync(full, b, src);
-        const bool io = __shfl_sync(full, (int) isOut, src) != 0;
-        if (io) {
-            const P v = out_distance_warp<P, A, MATRIX>(s, aa, nActive, totdiam, sm);
-            if (lane == src) d = v;
-        } else {
-            P dd, ww;
-            join_dist_warp<P, A, MATRIX>(s, aa, bb, raw != 0, sm, dd, ww);
-            if (lane == src) { d = dd; w = ww; }
-        }
+    const bool isProf = valid && !isSeq;
+    const unsigned mask = __ballot_sync(full, isProf);
+    double den, top;
+    group_profile_dist<P, A, MATRIX>(s, a, isOut ? (int64_t) -1 : b, mask, G, smw, den, top);
+    if (isProf) {
+        P dd, ww;
+        finish_dist<P>(den, top, dd, ww);
+        if (isOut) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
+        else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
     }
     if (valid) { r0[item] = d; r1[item] = w; }
-    // (a completion word in mapped memory + host spin was tried instead of cudaStreamSynchronize:
-    //  the system-scope fences it needs cost more than the synchronisation they replace)
 }
 
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
@@ -117,23 +110,19 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
+    unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t j = warp * G + lane;
     const bool valid = lane < G && j < maxnode;
     const bool act = valid && s.active[j] && j >= jBegin && j < jEnd;
-    P d = 0, w = 0;
-    unsigned mask = __ballot_sync(full, act);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t jj = __shfl_sync(full, j, src);
-        P dd, ww;
-        join_dist_warp<P, A, MATRIX>(s, query, jj, false, sm, dd, ww);
-        if (lane == src) { d = dd; w = ww; }
-    }
+    const unsigned mask = __ballot_sync(full, act);
+    double den, top;
+    group_profile_dist<P, A, MATRIX>(s, query, j, mask, G, smw, den, top);
     if (!valid) return;
     if (!act) { keys[j] = ~0ull; return; }
+    P d, w;
+    finish_dist<P>(den, top, d, w);
+    d = join_correct<P>(s, query, j, d);
     const double outI = (double) s.outDist[query], outJ = (double) s.outDist[j];
     const P c = (P) xsub((double) d, xadd(outI, outJ) / (double) (nActive - 2));
     dist[j] = d; weight[j] = w; crit[j] = c;
@@ -147,20 +136,19 @@ k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double t
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    double *sm = reinterpret_cast<double *>(smemRaw + (threadIdx.x >> 5) * warp_smem_bytes(s.Lp));
+    unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t j = warp * G + lane;
     const bool act = lane < G && j < maxnode && s.active[j];
-    P v = 0;
-    unsigned mask = __ballot_sync(full, act);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t jj = __shfl_sync(full, j, src);
-        const P r = out_distance_warp<P, A, MATRIX>(s, jj, nActive, totdiam, sm);
-        if (lane == src) v = r;
+    const unsigned mask = __ballot_sync(full, act);
+    double den, top;
+    group_profile_dist<P, A, MATRIX>(s, j, (int64_t) -1, mask, G, smw, den, top);
+    if (act) {
+        P dd, ww;
+        finish_dist<P>(den, top, dd, ww);
+        const P v = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
+        out[j] = v; s.outDist[j] = v;
     }
-    if (act) { out[j] = v; s.outDist[j] = v; }
 }
 
 // ---- top-K in psort order: key ascending, ties by index DESCENDING -----------------------------
@@ -730,14 +718,12 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     if (rc == VFT_OK) rc = ensure_pinned(c, std::max<size_t>((size_t) 1 << 20, (size_t) 48 * (size_t) c->N + (size_t) 16 * (size_t) c->M + 4096));
     if (rc != VFT_OK) return rc;
     {
-        const int need = (int) (4 * warp_smem_bytes(c->Lp));
-        if (need > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-warp term buffers (nPos > 3200)");
-        if (need > 48 * 1024) {
-#define SET_SMEM(P, A_, MX) do { cudaFuncSetAttribute(k_eval<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
-            cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
-            cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
-            VFT_DISPATCH(c, SET_SMEM);
-        }
+        // the grouped distance kernels use up to 4 warps x R rows of the [R][C] term tile
+#define SET_SMEM(P, A_, MX) do { const int need = (int) (4 * group_smem_bytes<P, A_, MX>(TileShape<A_, MX>::R)); \
+        cudaFuncSetAttribute(k_eval<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+        cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+        cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
+        VFT_DISPATCH(c, SET_SMEM);
     }
     cudaFuncSetAttribute(k_topk_select<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     cudaFuncSetAttribute(k_topk_select<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
@@ -892,10 +878,12 @@ static int64_t profile_bytes(vft_ctx *c, int64_t id) {      // algorithmic bytes
     return id >= 0 && id < c->N ? c->L : c->L * ((int64_t) c->A * c->ps + c->ps + 1);
 }
 
-static int pick_group(int64_t nItems) {
-    // items per warp: 1 while the batch cannot fill the machine, more once it can (148 SMs x 16 warps)
+static int pick_group(vft_ctx *c, int64_t nItems) {
+    // items per warp: 1 while the batch cannot fill the machine, more once it can (148 SMs x 16 warps),
+    // up to the rows of the term tile (TileShape<A, MATRIX>::R)
+    const int R = (c->A == 4 && !c->cfg.useMatrix) ? 8 : 32;
     int64_t g = (nItems + 2367) / 2368;
-    return (int) std::min<int64_t>(32, std::max<int64_t>(1, g));
+    return (int) std::min<int64_t>(R, std::max<int64_t>(1, g));
 }
 
 // One request = one launch + one synchronisation.  Inputs are packed as int32 into pinned host
@@ -925,16 +913,15 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         else { c->cnt.profileOps++; c->cnt.algoBytes += profile_bytes(c, pj[k]); }
         if (pi[k] != lastQuery) { c->cnt.algoBytes += profile_bytes(c, pi[k]); lastQuery = pi[k]; }   // a list shares its query
     }
-    const int G = pick_group(n);
+    const int G = pick_group(c, n);
     const int64_t warps = (n + G - 1) / G;
     const unsigned blocks = (unsigned) ((warps + 3) / 4);
     void *r0 = c->h_out, *r1 = (char *) c->h_out + (size_t) n * 8;
-    const size_t smem = 4 * warp_smem_bytes(c->Lp);
     const bool inlineItems = n <= INLINE_ITEMS;
     InlineItems inl;
     if (inlineItems) { std::memcpy(inl.a, ha, (size_t) n * 4); std::memcpy(inl.b, hb, (size_t) n * 4); }
     const unsigned int seq = ++c->seq;
-#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, smem, c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : ha, inlineItems ? nullptr : hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, c->h_flag, seq)
+#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : ha, inlineItems ? nullptr : hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, c->h_flag, seq)
     prof_begin(c, CLS_DIST);
     VFT_DISPATCH(c, CALL_EVAL);
     prof_end(c);
@@ -964,9 +951,9 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     if (!c || !outDist || maxnode < c->maxnode) return fail(VFT_EINVAL, "bad argument");
     const int64_t n = c->maxnode;
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
-    const int G = pick_group(n);
+    const int G = pick_group(c, n);
     const int64_t warps = (n + G - 1) / G;
-#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
+#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
     prof_begin(c, CLS_DIST);
     VFT_DISPATCH(c, CALL_ODA);
     prof_end(c);
@@ -997,10 +984,10 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
     const int64_t n = c->maxnode;
     if (K > SEL_MAXK) return fail(VFT_EINVAL, "K larger than 4096 is not supported");
-    const int Gq = pick_group(n);
+    const int Gq = pick_group(c, n);
     const int64_t warpsQ = (n + Gq - 1) / Gq;
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * warp_smem_bytes(c->Lp), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
     prof_begin(c, CLS_DIST);
     if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
     prof_end(c);

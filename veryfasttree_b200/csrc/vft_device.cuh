@@ -329,133 +329,301 @@ template<typename P> struct Vec4T;
 template<> struct Vec4T<float> { typedef float4 type; };
 template<> struct Vec4T<double> { typedef double4 type; };
 
-// profileDist, NJ.tcc:1167-1190, by one WARP.
-//   phase 1  the 32 lanes evaluate the positions in parallel (coalesced loads along the node-major
-//            rows, 8 x 32 positions in flight at a time) and store the per-position terms
-//            w1*w2 and w1*w2*piece to shared memory;
-//   phase 2  lane 0 adds the `denom` terms and lane 1 the `top` terms IN POSITION ORDER.
-// The additions are the reference's, in the reference's order; positions the reference skips
-// contribute +0.0, and x + (+0.0) == x for every value the accumulators can take (they are never
-// -0.0), so the result is bit-identical to the one-thread loop above.  Zero `top` terms (equal
-// codes, the common case between close relatives) are compacted away before the ordered pass, and
-// the `denom` pass is replaced by a tree sum whenever that is provably exact (see below).
-// `sm` = 2*Lp doubles (+Lp/32 ints) of shared memory private to the calling warp: see warp_smem_bytes().
-__host__ __device__ inline size_t warp_smem_bytes(int64_t Lp) { return (size_t) Lp * 16; }
+// profileDist, NJ.tcc:1167-1190, for a GROUP of pairs by one WARP ("tile-transposed" ordered
+// accumulation).  The reference adds the per-position terms of a pair in position order into two
+// doubles; the order decides the last bit of top/denom and with it the exact and near ties of the NJ
+// criterion, so it is reproduced: a pair's terms are still added one after the other, by ONE lane --
+// but up to R pairs are in flight per warp instead of one:
+//   phase 1  for every pair (row) of the group, the 32 lanes evaluate C = 32*PPL consecutive positions
+//            (PPL positions per lane, 128-bit loads along the node-major rows) and store the two terms
+//            w1*w2 and w1*w2*piece into that row of a padded [R][C] shared-memory tile;
+//   phase 2  lane k adds row k, left to right, into ITS pair's denom / top accumulators: R
+//            independent ordered chains (denom and top interleaved: one DADD latency per position).
+// Positions the reference skips contribute +0.0, and x + (+0.0) == x for every value the accumulators
+// can take (they start at +0.0 and never become -0.0), so the sums are bit-identical to the
+// one-thread loop in profile_dist().  Loads are software-pipelined across units (unit = one pair x C
+// positions), also across chunk boundaries, so a single pair (the per-join lists) streams its rows
+// without a dependent-load stall per chunk.  Consecutive pairs that share their first node (every
+// list the NJ driver produces) reuse its registers.
+// Tile shapes: 4-state %different profiles (nt): PPL=4, R=8, C=128; 20-state / matrix: PPL=1, R=32, C=32.
+template<int A, bool MATRIX> struct TileShape {
+    static constexpr int PPL = (A == 4 && !MATRIX) ? 4 : 1;
+    static constexpr int R = 32 / PPL, C = 32 * PPL;
+};
+template<typename P, int A, bool MATRIX>
+__host__ __device__ inline size_t group_smem_bytes(int rows) {      // per warp, independent of the alignment length
+    constexpr int C = TileShape<A, MATRIX>::C;
+    constexpr int WS = sizeof(P) == 4 ? C + 4 : C + 2;
+    return (size_t) rows * ((C + 2) * 8 + WS * sizeof(P));
+}
+
+template<typename P> struct VecLd;
+template<> struct VecLd<float>  { typedef float4 type;  static constexpr int N = 4; };
+template<> struct VecLd<double> { typedef double2 type; static constexpr int N = 2; };
+
+// n consecutive P's from a 16-byte aligned address with 128-bit loads
+template<typename P, int N_>
+__device__ __forceinline__ void load_vec(const P *__restrict__ src, P *v) {
+    typedef typename VecLd<P>::type V;
+    constexpr int N = VecLd<P>::N;
+    if constexpr (N_ % N == 0) {
+        const V *q = reinterpret_cast<const V *>(src);
+#pragma unroll
+        for (int k = 0; k < N_ / N; k++) {
+            const V t = q[k];
+            if constexpr (N == 4) { v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+            else { v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N_; k++) v[k] = src[k];
+    }
+}
 
 template<typename P, int A, bool MATRIX>
-__device__ __forceinline__ void profile_dist_warp(const Store<P> &s, const View<P, A> &p1, const View<P, A> &p2,
-                                                  double *sm, P &dist, P &weight) {
+__device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t myA, int64_t myB, unsigned mask, int rows,
+                                                   unsigned char *smw, double &denomOut, double &topOut) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    const int64_t Lp = s.Lp;
-    double *termW = sm, *termT = sm + Lp;
-    int nTop = 0;                                     // compacted count of non-zero top terms (uniform)
-    constexpr int UC = 8;                             // chunks of 32 positions with their loads in flight together
-    for (int64_t base = 0; base < Lp; base += 32 * UC) {
-        uint32_t c1[UC], c2[UC];
-        P w1[UC], w2[UC];
-        constexpr bool PRE = (A == 4 && !MATRIX);     // 4-state vectors are prefetched with the weights
-        P v1[PRE ? UC : 1][4], v2[PRE ? UC : 1][4];
+    constexpr int PPL = TileShape<A, MATRIX>::PPL, C = TileShape<A, MATRIX>::C;
+    constexpr bool REGV = (MATRIX || A == 4);          // vectors staged in registers (the generic !MATRIX A=20 case reads them in place)
+    constexpr bool VCOND = MATRIX;                     // matrix mode: vectors (or codeFreq rows / table entries) are fetched once codes and weights are known
+    constexpr int TS = C + 2;                          // row strides: 16-byte aligned rows, conflict-free 128-bit row reads
+    constexpr int WS = sizeof(P) == 4 ? C + 4 : C + 2;
+    double *T = reinterpret_cast<double *>(smw);       // [rows][TS]
+    P *W = reinterpret_cast<P *>(smw + (size_t) rows * TS * 8);   // [rows][WS]; w1*w2 is a P product: exact in P
+    const int nItems = __popc(mask);                   // <= rows <= R (caller's contract)
+    denomOut = 0; topOut = 0;
+    if (nItems == 0) return;
+    // compact the group: lane k takes the k-th item (its row), and will accumulate it
+    const int srcLane = lane < nItems ? __fns(mask, 0, lane + 1) : 0;
+    const int rowA = (int) __shfl_sync(full, myA, srcLane), rowB = (int) __shfl_sync(full, myB, srcLane);
+    const uint32_t Lp = (uint32_t) s.Lp, nSeqs = (uint32_t) s.nSeqs;
+    const int nChunks = (int) ((Lp + C - 1) / C);
+    P eig[MATRIX ? A : 1];
+    if constexpr (MATRIX) {
 #pragma unroll
-        for (int u = 0; u < UC; u++) {
-            const int64_t pos = base + 32 * u + lane;
-            const bool in = pos < Lp;
-            c1[u] = (in && p1.codes) ? (uint32_t) p1.codes[pos] : VFT_DEV_NOCODE;
-            c2[u] = (in && p2.codes) ? (uint32_t) p2.codes[pos] : VFT_DEV_NOCODE;
-            w1[u] = (in && p1.w) ? p1.w[pos] : (P) -1;
-            w2[u] = (in && p2.w) ? p2.w[pos] : (P) -1;
-            if (PRE) {
-                typedef typename Vec4T<P>::type V4;
-                if (in && p1.v) { const V4 t = *reinterpret_cast<const V4 *>(p1.v + pos * 4); v1[u][0] = t.x; v1[u][1] = t.y; v1[u][2] = t.z; v1[u][3] = t.w; }
-                else { v1[u][0] = v1[u][1] = v1[u][2] = v1[u][3] = 0; }
-                if (in && p2.v) { const V4 t = *reinterpret_cast<const V4 *>(p2.v + pos * 4); v2[u][0] = t.x; v2[u][1] = t.y; v2[u][2] = t.z; v2[u][3] = t.w; }
-                else { v2[u][0] = v2[u][1] = v2[u][2] = v2[u][3] = 0; }
+        for (int k = 0; k < A; k++) eig[k] = s.eigenval[k];
+    }
+
+    // one side of a unit: where its codes / weights / vectors live (nullptr: leaf or out-profile conventions of View)
+    struct Side { const uint8_t *codes; const P *w; const P *v; };
+    auto side = [&](int id) {
+        Side r;
+        if (id < 0) { r.codes = nullptr; r.w = s.ow; r.v = s.ov; }
+        else {
+            r.codes = s.codes + (uint64_t) (uint32_t) id * Lp;
+            if ((uint32_t) id < nSeqs) { r.w = nullptr; r.v = nullptr; }
+            else {
+                const uint64_t off = (uint64_t) ((uint32_t) id - nSeqs) * Lp;
+                r.w = s.weights + off; r.v = s.vecs + off * A;
             }
         }
+        return r;
+    };
+    struct CW { uint32_t c1[PPL], c2[PPL]; P w1[PPL], w2[PPL]; };
+    struct VV { P v1[REGV ? PPL * A : 1], v2[REGV ? PPL * A : 1]; P pre[VCOND ? PPL : 1]; };
+    struct Unit { int k, c, na, nb; uint32_t pos; bool in; };
+    auto unitAt = [&](int k, int c) {
+        Unit u;
+        u.k = k; u.c = c;
+        u.na = __shfl_sync(full, rowA, k); u.nb = __shfl_sync(full, rowB, k);
+        u.pos = (uint32_t) c * C + lane * PPL;
+        u.in = u.pos < Lp;                             // Lp is a multiple of 32 >= PPL: a lane's PPL positions are all in or all out
+        return u;
+    };
+    auto nextUnit = [&](const Unit &u) { return (u.k + 1 < nItems) ? unitAt(u.k + 1, u.c) : unitAt(0, u.c + 1); };
+    auto loadCodes = [&](const uint8_t *row, uint32_t pos, uint32_t (&c)[PPL]) {
+        if (row == nullptr) {
 #pragma unroll
-        for (int u = 0; u < UC; u++) {
-            const int64_t pos = base + 32 * u + lane;
-            if (base + 32 * u >= Lp) break;           // uniform
-            const P a1 = p1.w ? w1[u] : (c1[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
-            const P a2 = p2.w ? w2[u] : (c2[u] != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
-            double wt = 0, tt = 0;
-            if (a1 > 0 && a2 > 0) {
-                wt = (double) pmul(a1, a2);                                                // :1176
-                double pc;
-                if constexpr (PRE) pc = piece4<P>(c1[u], c2[u], v1[u], v2[u]);
-                else pc = piece<P, A, MATRIX>(s, c1[u], c2[u], p1.v ? p1.v + pos * A : nullptr,
-                                             p2.v ? p2.v + pos * A : nullptr, p2.cd ? p2.cd + pos * A : nullptr);
-                tt = xmul(wt, pc);
+            for (int i = 0; i < PPL; i++) c[i] = VFT_DEV_NOCODE;
+        } else if constexpr (PPL == 4) {
+            const uint32_t q = *reinterpret_cast<const uint32_t *>(row + pos);
+#pragma unroll
+            for (int i = 0; i < 4; i++) c[i] = (q >> (8 * i)) & 0xFFu;
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPL; i++) c[i] = (uint32_t) row[pos + i];
+        }
+    };
+    // stage A: codes + weights; in %different mode also the (narrow) vectors, unconditionally
+    auto loadA = [&](const Unit &u, CW &o, VV &q) {
+        if (!u.in) {
+#pragma unroll
+            for (int i = 0; i < PPL; i++) { o.c1[i] = o.c2[i] = VFT_DEV_NOCODE; o.w1[i] = o.w2[i] = 0; }
+            return;
+        }
+        const Side s1 = side(u.na), s2 = side(u.nb);
+        loadCodes(s1.codes, u.pos, o.c1);
+        loadCodes(s2.codes, u.pos, o.c2);
+        if (s1.w) load_vec<P, PPL>(s1.w + u.pos, o.w1);
+        else {
+#pragma unroll
+            for (int i = 0; i < PPL; i++) o.w1[i] = o.c1[i] != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+        }
+        if (s2.w) load_vec<P, PPL>(s2.w + u.pos, o.w2);
+        else {
+#pragma unroll
+            for (int i = 0; i < PPL; i++) o.w2[i] = o.c2[i] != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+        }
+        if constexpr (REGV && !VCOND) {
+            if (s1.v) load_vec<P, PPL * A>(s1.v + (uint64_t) u.pos * A, q.v1);
+            else {
+#pragma unroll
+                for (int k = 0; k < PPL * A; k++) q.v1[k] = 0;
             }
-            termW[pos] = wt;
-            const unsigned nz = __ballot_sync(full, tt != 0.0);
-            if (tt != 0.0) termT[nTop + __popc(nz & ((1u << lane) - 1u))] = tt;
-            nTop += __popc(nz);
-        }
-    }
-    // `denom` fast path: when every partial sum of the w1*w2 terms is exactly representable (all
-    // terms are multiples of 2^LB and the total stays below 2^(LB+53)), every addition in ANY order
-    // is exact, so the ordered sum equals a tree sum.  True for the 0/1 and small dyadic weights
-    // that NJ profiles carry in fp32; checked per pair, never assumed.
-    double dLocal = 0;
-    int minLB = 4096, maxE = -4096, cntNZ = 0;
-    for (int64_t pos = lane; pos < Lp; pos += 32) {
-        const double t = termW[pos];                  // own writes: visible without a barrier
-        if (t > 0) {
-            const unsigned long long bits = (unsigned long long) __double_as_longlong(t);
-            const int e = (int) ((bits >> 52) & 0x7FF) - 1023;
-            const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | 0x10000000000000ull;
-            const int lb = e - 52 + (__ffsll((long long) mant) - 1);
-            minLB = min(minLB, lb); maxE = max(maxE, e); cntNZ++;
-            dLocal += t;                              // exactness of this partial sum is covered by the test below
-        }
-    }
+            if (s2.v) load_vec<P, PPL * A>(s2.v + (uint64_t) u.pos * A, q.v2);
+            else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        minLB = min(minLB, __shfl_xor_sync(full, minLB, o));
-        maxE = max(maxE, __shfl_xor_sync(full, maxE, o));
-        cntNZ += __shfl_xor_sync(full, cntNZ, o);
-    }
-    int lg = 0;
-    while ((1 << lg) < cntNZ) lg++;
-    const bool exactDenom = cntNZ == 0 || (maxE + 1 + lg - minLB <= 53 && minLB > -1000);
-    __syncwarp();
-    double acc = 0;
-    if (exactDenom) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dLocal += __shfl_xor_sync(full, dLocal, o);
-        if (lane == 0) acc = dLocal;
-    } else if (lane == 0) {
-        for (int64_t k = 0; k < Lp; k += 4) {
-            acc = xadd(acc, termW[k]); acc = xadd(acc, termW[k + 1]); acc = xadd(acc, termW[k + 2]); acc = xadd(acc, termW[k + 3]);
+                for (int k = 0; k < PPL * A; k++) q.v2[k] = 0;
+            }
         }
+    };
+    // stage B (matrix mode), once codes and weights are known: per position either the table entry that
+    // IS the piece (code x code, or code x codeDist of the out-profile) or the two vectors of the 3-way
+    // dot product -- the profile's own vector, or the codeFreq row that stands in for a known code
+    // (profileDistPiece, NJ.tcc:900-916)
+    auto loadB = [&](const Unit &u, const CW &cw, VV &q) {
+        if constexpr (VCOND) {
+            if (!u.in) return;
+            const Side s1 = side(u.na), s2 = side(u.nb);
+#pragma unroll
+            for (int i = 0; i < PPL; i++) {
+                const uint32_t c1 = cw.c1[i], c2 = cw.c2[i];
+                q.pre[i] = 0;
+                if (cw.w1[i] > 0 && cw.w2[i] > 0) {
+                    if (c1 != VFT_DEV_NOCODE && c2 != VFT_DEV_NOCODE) q.pre[i] = s.distances[c1 * 20 + c2];
+                    else if (u.nb < 0 && c1 != VFT_DEV_NOCODE) q.pre[i] = s.ocd[(uint64_t) (u.pos + i) * A + c1];
+                    else {
+                        const P *f1 = c1 != VFT_DEV_NOCODE ? s.codeFreq + c1 * 20 : s1.v + (uint64_t) (u.pos + i) * A;
+                        const P *f2 = c2 != VFT_DEV_NOCODE ? s.codeFreq + c2 * 20 : s2.v + (uint64_t) (u.pos + i) * A;
+                        load_vec<P, A>(f1, q.v1 + i * A);
+                        load_vec<P, A>(f2, q.v2 + i * A);
+                    }
+                }
+            }
+        }
+    };
+
+    double den = 0, top = 0;
+    auto compute = [&](const Unit &u, const CW &cw, const VV &q) {
+        double tt[PPL];
+        P wt[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; i++) {
+            const uint32_t c1 = cw.c1[i], c2 = cw.c2[i];
+            const bool on = cw.w1[i] > 0 && cw.w2[i] > 0;
+            wt[i] = on ? pmul(cw.w1[i], cw.w2[i]) : (P) 0;                               // :1176
+            double pc;
+            if constexpr (MATRIX) {
+                const bool table = (c1 != VFT_DEV_NOCODE && c2 != VFT_DEV_NOCODE) || (u.nb < 0 && c1 != VFT_DEV_NOCODE);
+                pc = (double) q.pre[i];
+                if (on && !table) pc = (double) vec_mul3_sum<P, A>(q.v1 + i * A, q.v2 + i * A, eig, s.reduction);
+            } else if constexpr (A == 4) {
+                // profileDistPiece's four %different cases (NJ.tcc:918-939) in one branch-free form: a known code
+                // acts as the indicator vector of that code; 1*f and 0*f are exact, and subtracting +0.0 is exact,
+                // so "1 - f2[c1]", "c1==c2 ? 0 : 1" and the full "1 - sum f1*f2" all come out of the same chain
+                pc = 1.0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const P g1 = c1 != VFT_DEV_NOCODE ? (c1 == (uint32_t) k ? (P) 1 : (P) 0) : q.v1[i * 4 + k];
+                    const P g2 = c2 != VFT_DEV_NOCODE ? (c2 == (uint32_t) k ? (P) 1 : (P) 0) : q.v2[i * 4 + k];
+                    pc = xsub(pc, (double) pmul(g1, g2));
+                }
+            } else {
+                pc = 0;
+                if (on) {
+                    const View<P, A> v1 = make_view<P, A>(s, u.na), v2 = make_view<P, A>(s, u.nb);
+                    pc = piece<P, A, false>(s, c1, c2, v1.v ? v1.v + (uint64_t) (u.pos + i) * A : nullptr,
+                                            v2.v ? v2.v + (uint64_t) (u.pos + i) * A : nullptr, nullptr);
+                }
+            }
+            tt[i] = on ? xmul((double) wt[i], pc) : 0.0;
+        }
+        double *tr = T + u.k * TS + lane * PPL;
+        P *wr = W + u.k * WS + lane * PPL;
+        if constexpr (PPL == 4) {
+            *reinterpret_cast<double2 *>(tr) = make_double2(tt[0], tt[1]);
+            *reinterpret_cast<double2 *>(tr + 2) = make_double2(tt[2], tt[3]);
+            if constexpr (sizeof(P) == 4) *reinterpret_cast<float4 *>(wr) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+            else { *reinterpret_cast<double2 *>(wr) = make_double2(wt[0], wt[1]); *reinterpret_cast<double2 *>(wr + 2) = make_double2(wt[2], wt[3]); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPL; i++) { tr[i] = tt[i]; wr[i] = wt[i]; }
+        }
+        // end of a chunk: every row holds its C terms -> ordered accumulation, one lane per pair
+        if (u.k + 1 == nItems) {
+            __syncwarp();
+            if (lane < nItems) {
+                const double *trow = T + lane * TS;
+                const P *wrow = W + lane * WS;
+#pragma unroll
+                for (int j = 0; j < C; j += 4) {
+                    const double2 ta = *reinterpret_cast<const double2 *>(trow + j), tb = *reinterpret_cast<const double2 *>(trow + j + 2);
+                    P w4[4];
+                    load_vec<P, 4>(wrow + j, w4);
+                    den = xadd(den, (double) w4[0]); top = xadd(top, ta.x);
+                    den = xadd(den, (double) w4[1]); top = xadd(top, ta.y);
+                    den = xadd(den, (double) w4[2]); top = xadd(top, tb.x);
+                    den = xadd(den, (double) w4[3]); top = xadd(top, tb.y);
+                }
+            }
+            __syncwarp();
+        }
+    };
+
+    const int U = nChunks * nItems;
+    // Two register buffers (X, Y) alternate between "being computed" and "being loaded": the loop is
+    // unrolled by two so that no buffer is ever copied.  Matrix mode adds a second, earlier stage for the
+    // codes + weights (a few registers, rotated).
+    Unit uX = unitAt(0, 0), uY = uX, uZ = uX;
+    CW cwX, cwY, cwZ;
+    VV qX, qY;
+    loadA(uX, cwX, qX);
+    if (U > 1) { uY = nextUnit(uX); loadA(uY, cwY, qY); }
+    loadB(uX, cwX, qX);
+    for (int u = 0; u < U; u += 2) {
+        // ---- even unit: compute X; Y is one ahead ---------------------------------------------------
+        if constexpr (VCOND) {
+            if (u + 2 < U) { uZ = nextUnit(uY); loadA(uZ, cwZ, qX /*unused*/); }
+            if (u + 1 < U) loadB(uY, cwY, qY);
+        }
+        compute(uX, cwX, qX);
+        if constexpr (VCOND) { uX = uZ; cwX = cwZ; }                       // X now describes unit u+2 (codes + weights loaded)
+        else if (u + 2 < U) { uX = nextUnit(uY); loadA(uX, cwX, qX); }
+        if (u + 1 >= U) break;
+        // ---- odd unit: compute Y; X is one ahead ----------------------------------------------------
+        if constexpr (VCOND) {
+            if (u + 3 < U) { uZ = nextUnit(uX); loadA(uZ, cwZ, qY /*unused*/); }
+            if (u + 2 < U) loadB(uX, cwX, qX);
+        }
+        compute(uY, cwY, qY);
+        if constexpr (VCOND) { uY = uZ; cwY = cwZ; }
+        else if (u + 3 < U) { uY = nextUnit(uX); loadA(uY, cwY, qY); }
     }
-    if (lane == 1) {
-        for (int k = 0; k < nTop; k++) acc = xadd(acc, termT[k]);
-    }
-    __syncwarp();
-    const double denom = __shfl_sync(full, acc, 0), top = __shfl_sync(full, acc, 1);
-    weight = (P) (denom > 0 ? denom : 0.01);                                              // :1187
-    dist = (P) (denom > 0 ? top / denom : 1.0);                                           // :1188
+    // hand each item's sums back to the lane that owns it
+    const int rank = __popc(mask & ((1u << lane) - 1u));
+    denomOut = __shfl_sync(full, den, rank);
+    topOut = __shfl_sync(full, top, rank);
 }
 
-// distance half of setDistCriterion for a pair that is NOT leaf x leaf (or raw), by one warp
-template<typename P, int A, bool MATRIX>
-__device__ __forceinline__ void join_dist_warp(const Store<P> &s, int64_t i, int64_t j, bool raw, double *sm,
-                                               P &dist, P &weight) {
-    const View<P, A> v1 = make_view<P, A>(s, i), v2 = make_view<P, A>(s, j);
-    profile_dist_warp<P, A, MATRIX>(s, v1, v2, sm, dist, weight);
-    if (raw) return;
+// profileDist's tail, NJ.tcc:1187-1188
+template<typename P>
+__device__ __forceinline__ void finish_dist(double denom, double top, P &dist, P &weight) {
+    weight = (P) (denom > 0 ? denom : 0.01);
+    dist = (P) (denom > 0 ? top / denom : 1.0);
+}
+
+// distance half of setDistCriterion (NJ.tcc:1115-1122) applied to a finished profileDist
+template<typename P>
+__device__ __forceinline__ P join_correct(const Store<P> &s, int64_t i, int64_t j, P dist) {
     dist = psub(dist, padd(s.diameter[i], s.diameter[j]));                                // :1120
-    dist = (P) xadd((double) dist, 0.0);                                                  // :1122
+    return (P) xadd((double) dist, 0.0);                                                  // :1122
 }
 
-// setOutDistance, NJ.tcc:1012-1053, by one warp
-template<typename P, int A, bool MATRIX>
-__device__ __forceinline__ P out_distance_warp(const Store<P> &s, int64_t iNode, int64_t nActive, double totdiam, double *sm) {
-    P ddist, dweight;
-    const View<P, A> v1 = make_view<P, A>(s, iNode), vo = make_view<P, A>(s, -1);
-    profile_dist_warp<P, A, MATRIX>(s, v1, vo, sm, ddist, dweight);
+// setOutDistance's algebra, NJ.tcc:1046-1052, applied to profileDist(node, out-profile)
+template<typename P>
+__device__ __forceinline__ P out_distance_finish(const Store<P> &s, int64_t iNode, int64_t nActive, double totdiam, P ddist, P dweight) {
     const P pN = (P) nActive, pN1 = (P) (nActive - 1);
     const P t4 = psub(pmul(pmul(ddist, dweight), pN), pmul(s.selfweight[iNode], s.selfdist[iNode]));   // :1046
     const double top = (double) pmul(pN1, t4);
