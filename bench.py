@@ -226,8 +226,11 @@ def main():
         st = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in tr.stats.items() if k not in ("counters",)}
         st["secondsHost"] = [round(x, 3) for x in tr.stats["secondsHost"]]
         print("[bench] last timed step:", json.dumps(st), file=sys.stderr)
-        print("[bench] profiled pass counters:", json.dumps(prof), file=sys.stderr)
+        print("[bench] profiled pass counters:", json.dumps({k: v for k, v in prof.items() if k not in ("msKernel", "nKernel")}), file=sys.stderr)
         print("[bench] per step (device ms, end-to-end ms):", per_step, file=sys.stderr)
+        for nm, ms, cnt in zip(api.KERNEL_NAMES, prof["msKernel"], prof["nKernel"]):
+            if cnt:
+                print("[bench] profiled pass  %-24s %7d launches %9.2f ms  %8.2f us/launch" % (nm, cnt, ms, 1e3 * ms / cnt), file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

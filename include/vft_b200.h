@@ -70,6 +70,10 @@ const char *vft_last_error(void);
 /* name of the implementation behind this ABI: "cuda-sm100a" for the product library,
    "oracle-cpu" for the test-only restatement under oracle/ */
 const char *vft_backend_name(void);
+/* Contexts come and go once per tree; the library parks the device / pinned blocks of a destroyed context
+   in a process-wide cache (exact-size reuse, never the contents) so that the next vft_ctx_create does not
+   pay the driver's allocation calls again.  This returns the parked blocks to the driver. */
+int  vft_release_cached_memory(void);
 
 /* -- model tables: after DistanceMatrix::setupDistanceMatrix (DistanceMatrix.tcc:102-153) -- */
 /* distances[20][20], eigenval[20], eigentot[20], codeFreq[20][20] (row = code, first nCodes
@@ -147,6 +151,28 @@ int  vft_dist_one_vs_all_range(vft_ctx *ctx, int64_t query, int64_t nActive, int
                                int64_t jEnd, int64_t *j_out, void *dist, void *weight, void *criterion,
                                int64_t *nOut);
 
+/* -- top-hits refresh: the list-merging loop of topHitJoin's refresh branch (NJ.tcc:4477-4515) ------
+   After a refresh's one-vs-all of `newnode` (NJ.tcc:4470-4472) the reference rebuilds the top-hit list
+   of each of its m best hits iNode[l] from  (own list of iNode) + (the nAvail best hits of newnode):
+     transferBestHits(.., updateDistances=false) :4580-4613  -- candidate j keeps its distance only when
+                                                               iNode == newnode, otherwise it is unknown
+     uniqueBestHits :4786-4833   -- psort by (i,j) (ties: reverse input order), first of each run of equal
+                                    j kept, distance computed where unknown (setDistCriterion, :1115-1124),
+                                    criterion for every survivor (setCriterion, :1085-1113)
+     sortSaveBestHits :4535-4578 -- psort by criterion, the first m hits
+   This entry point does those three steps for all nLists lists in one device pass.
+   Inputs: own lists concatenated (ownOffset[nLists+1]); ownJ[k] = active ancestor of the stored hit
+   (activeAncestor, :536-544; <0 if none), ownDist[k] = the cached distance, or any NEGATIVE value when the
+   ancestor differs from the stored j (updateBestHit, :1626-1648) -- a negative distance is recomputed, as in
+   the reference (:4826).  allJ/allDist[nAvail]: the sorted hits of newnode exactly as vft_dist_one_vs_all
+   returned them (all active).  Criteria use the context's committed out-distance table: precondition
+   vft_out_distance_all at this nActive (every out-distance fresh, so setCriterion has no side effect).
+   Outputs: outCount[nLists] (= min(m, survivors)), outJ / outDist [nLists*m]. */
+int  vft_tophits_merge(vft_ctx *ctx, int64_t newnode, int64_t nActive, int64_t m, int64_t nLists,
+                       const int64_t *iNode, const int64_t *ownOffset, const int64_t *ownJ, const void *ownDist,
+                       int64_t nAvail, const int64_t *allJ, const void *allDist,
+                       int64_t *outCount, int64_t *outJ, void *outDist);
+
 /* ============================================================================================
  * Likelihood kernels: pairLogLk and posteriorProfile under JC
  * (nucleotides, no transition matrix) or an eigen-decomposed rate matrix (GTR nt / JTT-WAG-LG aa),
@@ -196,7 +222,13 @@ typedef struct vft_counters {
     double  msProfile;       /* k_average + k_outprofile_update + k_outprofile_rebuild             */
     int64_t distLaunches;
     int64_t distBytes;
+    /* the same event timings per kernel (VFT_CFG_PROFILE only): ms and launch counts, indexed as VFT_KERNEL_NAMES */
+    double  msKernel[12];
+    int64_t nKernel[12];
 } vft_counters;
+#define VFT_KERNEL_NAMES "k_eval(list<=384)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", \
+                         "k_merge_prep+finish", "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", \
+                         "k_posterior", "-"
 #define VFT_CFG_PROFILE 1    /* vft_config.reserved bit: time every kernel with CUDA events */
 int  vft_get_counters(vft_ctx *ctx, vft_counters *out);
 

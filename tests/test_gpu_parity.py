@@ -94,6 +94,26 @@ def run_script(lib, codes, n_codes, prec, tables, seed, n_joins, k_top):
         pi, pj = act[rs.randint(0, len(act), size=800)], act[rs.randint(0, len(act), size=800)]
         out["pairs_join"] = list(ctx.dist_pairs(pi, pj, 0))
         out["pairs_raw"] = list(ctx.dist_pairs(pi, pj, 1))
+        # the list-merging pass of a top-hits refresh (vft_tophits_merge): own lists with stale entries (negative
+        # distance), entries without an ancestor (-1), self hits and duplicates of the transferred hits
+        q = N + n_joins - 1
+        m = max(4, k_top // 2)
+        aj, ad, aw, ac = ctx.dist_one_vs_all(q, n_active, 2 * m)
+        lists = [int(x) for x in aj[:m]]
+        if q not in lists:
+            lists[-1] = q                                   # the iNode == newnode case keeps the transferred distances
+        own_off, own_j, own_d = [0], [], []
+        for ln in lists:
+            k_own = int(rs.randint(0, m + 1))
+            js = act[rs.randint(0, len(act), size=k_own)].astype(np.int64)
+            ds = rs.random_sample(k_own).astype(ctx.dt)
+            ds[rs.random_sample(k_own) < 0.3] = -1e20       # ancestor changed: distance unknown
+            js[rs.random_sample(k_own) < 0.1] = -1          # no active ancestor
+            if k_own > 2:
+                js[0] = ln                                  # self
+                js[1] = aj[min(3, len(aj) - 1)]             # duplicate of a transferred hit
+            own_j += list(js); own_d += list(ds); own_off.append(len(own_j))
+        out["merge"] = list(ctx.tophits_merge(q, n_active, m, lists, own_off, own_j, np.array(own_d, dtype=ctx.dt), aj, ad))
         cn = ctx.counters()
         out["ops"] = np.array([cn.seqOps, cn.profileOps, cn.outprofileOps, cn.profileAvgOps])
     return out

@@ -31,7 +31,12 @@ class VftCounters(C.Structure):
     _fields_ = [("seqOps", C.c_int64), ("profileOps", C.c_int64), ("outprofileOps", C.c_int64),
                 ("profileAvgOps", C.c_int64), ("launches", C.c_int64), ("algoBytes", C.c_int64),
                 ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64), ("msDist", C.c_double), ("msSelect", C.c_double),
-                ("msProfile", C.c_double), ("distLaunches", C.c_int64), ("distBytes", C.c_int64)]
+                ("msProfile", C.c_double), ("distLaunches", C.c_int64), ("distBytes", C.c_int64),
+                ("msKernel", C.c_double * 12), ("nKernel", C.c_int64 * 12)]
+
+
+KERNEL_NAMES = ["k_eval(list<=384)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
+                "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", "k_posterior", "-"]
 
 
 class VftNjOptions(C.Structure):
@@ -61,7 +66,7 @@ ABI_SYMBOLS = [
     "vft_dist_one_vs_all", "vft_get_profile", "vft_get_counters", "vft_nj_default_options", "vft_nj_build",
     "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
     "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
-    "vft_dist_one_vs_all_range",
+    "vft_dist_one_vs_all_range", "vft_tophits_merge", "vft_release_cached_memory",
 ]
 
 
@@ -103,6 +108,8 @@ class Lib:
         d.vft_dist_one_vs_all.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_dist_one_vs_all_range.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_get_profile.argtypes = [vp, i64, vp, vp, vp]
+        if hasattr(d, "vft_tophits_merge"):
+            d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
         d.vft_nj_default_options.argtypes = [C.POINTER(VftNjOptions)]
         d.vft_nj_build.argtypes = [C.POINTER(VftConfig), C.POINTER(VftNjOptions), vp, vp, C.POINTER(VftNjResult)]
@@ -256,6 +263,23 @@ class Context:
         n = n.value
         return j[:n], d[:n], w[:n], c[:n]
 
+    def tophits_merge(self, newnode, n_active, m, i_nodes, own_offset, own_j, own_dist, all_j, all_dist):
+        """vft_tophits_merge: returns (count[nLists], j[nLists, m], dist[nLists, m])."""
+        i_nodes = np.ascontiguousarray(i_nodes, dtype=np.int64)
+        own_offset = np.ascontiguousarray(own_offset, dtype=np.int64)
+        own_j = np.ascontiguousarray(own_j, dtype=np.int64)
+        own_dist = np.ascontiguousarray(own_dist, dtype=self.dt)
+        all_j = np.ascontiguousarray(all_j, dtype=np.int64)
+        all_dist = np.ascontiguousarray(all_dist, dtype=self.dt)
+        n_lists = len(i_nodes)
+        cnt = np.zeros(n_lists, dtype=np.int64)
+        oj = np.full((n_lists, m), -1, dtype=np.int64)
+        od = np.zeros((n_lists, m), dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_tophits_merge(self.h, newnode, n_active, m, n_lists, _ptr(i_nodes), _ptr(own_offset), _ptr(own_j),
+                                                      _ptr(own_dist), len(all_j), _ptr(all_j), _ptr(all_dist),
+                                                      _ptr(cnt), _ptr(oj), _ptr(od)), "vft_tophits_merge")
+        return cnt, oj, od
+
     def get_profile(self, node):
         L, A = self.cfg.nPos, self.cfg.nCodes
         w = np.empty(L, dtype=self.dt)
@@ -348,6 +372,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
     lib.check(rc, "vft_nj_build")
     stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:25]}
     stats["secondsHost"] = [float(x) for x in res.secondsHost]
-    stats.update({"counters": {k: getattr(res.counters, k) for k, _ in VftCounters._fields_}})
+    stats.update({"counters": {k: (list(getattr(res.counters, k)) if k in ("msKernel", "nKernel") else getattr(res.counters, k))
+                               for k, _ in VftCounters._fields_}})
     return NJTree(n, precision, parent, n_child, child, bl, res.root, res.maxnode, res.m,
                   joins, lth, stats)

@@ -25,6 +25,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -32,6 +34,15 @@
 #include <vector>
 
 namespace {
+
+#ifdef VFT_HOSTPROF
+static double g_hp[32]; static const char *g_hpName[32]; static double *g_hpCalls = nullptr; static long g_hpN[32];
+struct HP { int k; std::chrono::steady_clock::time_point t0; double c0; HP(int k, const char *nm) : k(k), t0(std::chrono::steady_clock::now()), c0(g_hpCalls ? *g_hpCalls : 0) { g_hpName[k] = nm; }
+    ~HP() { g_hp[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - ((g_hpCalls ? *g_hpCalls : 0) - c0); g_hpN[k]++; } };
+#define HPROF(k, nm) HP hp_##k(k, nm)
+#else
+#define HPROF(k, nm)
+#endif
 
 struct Children { int nChild = 0; int64_t child[3] = {-1, -1, -1}; };
 
@@ -55,12 +66,26 @@ void rsortByKey(std::vector<T> &v, KeyFn keyOf) {
     const size_t n = v.size();
     if (n < 2) return;
     static thread_local std::vector<std::pair<uint64_t, uint32_t>> kv;
+    static thread_local std::vector<uint64_t> k1;
     static thread_local std::vector<T> tmp;
     kv.resize(n);
-    for (size_t k = 0; k < n; k++) kv[k] = {keyOf(v[k]), (uint32_t) (n - 1 - k)};   // reversed position: plain pair order
-    std::sort(kv.begin(), kv.end());
+    uint64_t lo = ~0ull, hi = 0;
+    for (size_t k = 0; k < n; k++) {
+        const uint64_t key = keyOf(v[k]);
+        kv[k] = {key, (uint32_t) (n - 1 - k)};      // reversed position: plain pair order
+        lo = std::min(lo, key); hi = std::max(hi, key);
+    }
     tmp.resize(n);
-    for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - kv[k].second];
+    if (hi - lo < (1ull << 32) && n < (1ull << 31)) {
+        // the usual case (float criteria; (i,j) keys with one i): key and reversed position share one word
+        k1.resize(n);
+        for (size_t k = 0; k < n; k++) k1[k] = ((kv[k].first - lo) << 32) | kv[k].second;
+        std::sort(k1.begin(), k1.end());
+        for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - (uint32_t) k1[k]];
+    } else {
+        std::sort(kv.begin(), kv.end());
+        for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - kv[k].second];
+    }
     v.swap(tmp);
 }
 
@@ -88,6 +113,7 @@ public:
         freshVal.assign(maxnodes, 0);
         freshEpoch.assign(maxnodes, -1);
         wantEpoch.assign(maxnodes, -1);
+        hintedEpoch.assign(maxnodes, -1);
         up.resize(maxnodes);
         for (int64_t i = 0; i < maxnodes; i++) up[i] = i;
         hostThreads = opt.hostThreads > 0 ? opt.hostThreads : std::max(1, std::min(16, omp_get_num_procs()));
@@ -158,7 +184,7 @@ private:
     // fixed between two joins = one "epoch".
     int64_t epoch = 0, epochActive = 0;
     std::vector<P> freshVal;
-    std::vector<int64_t> freshEpoch, wantEpoch, leafGaps;
+    std::vector<int64_t> freshEpoch, wantEpoch, hintedEpoch, leafGaps;
     std::vector<int64_t> wantIds;
     std::vector<P> wantVals;
 
@@ -181,6 +207,7 @@ private:
     // ONE device call for everything queued so far: out-distance requests and pair requests
     void flush(int64_t nActive) {
         if (wantIds.empty() && reqI.empty()) return;
+        HPROF(12, "flush(host part)");
         wantVals.resize(wantIds.size());
         reqD.resize(reqI.size()); reqW.resize(reqI.size());
         check(timed([&] { return vft_eval_batch(ctx, wantIds.data(), (int64_t) wantIds.size(), nActive, totdiam, wantVals.data(),
@@ -310,7 +337,10 @@ private:
 
     // what getBestFromTopHits(iNode) will ask for (NJ.tcc:4267-4298)
     void hintList(int64_t nActive, int64_t iNode) {
+        HPROF(13, "hintList");
         if (iNode < 0 || parent[iNode] >= 0) return;
+        if (hintedEpoch[iNode] == epoch) return;         // already queued in this epoch (lists do not change within one)
+        hintedEpoch[iNode] = epoch;
         wantOut(iNode, nActive, /*evenIfNotStale*/true);
         for (const Hit &h : topHitsLists[iNode].hits) {
             int64_t j = activeAncestor(h.j);
@@ -359,6 +389,17 @@ private:
     void topHitNJSearch(int64_t nActive, Besthit &join);
     void getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin);
     void topHitJoin(int64_t newnode, int64_t nActive);
+    void refreshListsOnDevice(int64_t newnode, int64_t nActive, const std::vector<Besthit> &allhits);
+    std::vector<Besthit> thjCombined, thjUnique;          // scratch of topHitJoin
+    std::vector<int64_t> thjSlots;
+    // scratch of resetTopVisible
+    std::vector<int64_t> rtvTouched; int64_t rtvStamp = 0;
+    std::vector<std::vector<id_t>> rtvCandT, rtvWantT;
+    std::vector<id_t> rtvCand;
+    std::vector<Besthit> rtvVis;
+    std::vector<std::pair<uint64_t, uint32_t>> rtvKv;
+    std::vector<int64_t> rfNodes, rfOffset, rfOwnJ, rfAllJ, rfCount, rfOutJ;      // scratch of refreshListsOnDevice
+    std::vector<P> rfOwnDist, rfAllDist, rfOutDist;
     int64_t oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<Besthit> &out);
     void fastNJSearch(int64_t nActive, std::vector<Besthit> &besthits, Besthit &join);
     void setBestHitFull(int64_t node, int64_t nActive, Besthit &bestjoin, std::vector<Besthit> *allhits);
@@ -368,6 +409,7 @@ private:
 // number of *active* entries; entries [n, K) are the inactive sentinels in psort order.
 template<typename P>
 int64_t NJ<P>::oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<Besthit> &out) {
+    HPROF(10, "oneVsAll(host part)");
     std::vector<int64_t> js(K);
     std::vector<P> d(K), w(K), c(K);
     int64_t n = 0;
@@ -385,6 +427,7 @@ int64_t NJ<P>::oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<B
 // sortSaveBestHits, NJ.tcc:4535-4578
 template<typename P>
 void NJ<P>::sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int64_t nIn, int64_t nOut, bool sort) {
+    HPROF(8, "sortSaveBestHits");
     if (sort) sortByCriterion(besthits);
     if (nIn > (int64_t) besthits.size()) nIn = (int64_t) besthits.size();
     int64_t nSave = 0, jLast = -1;
@@ -433,6 +476,7 @@ void NJ<P>::transferBestHits(int64_t nActive, int64_t iNode, const std::vector<B
 template<typename P>
 void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out,
                                   std::vector<int64_t> &slots) {
+    HPROF(6, "uniqueBestHitsPrepare");
     uniqueCore(nActive, combined, out);
     slots.assign(out.size(), -1);
     for (size_t k = 0; k < out.size(); k++) {
@@ -447,7 +491,13 @@ template<typename P>
 void NJ<P>::uniqueCore(int64_t nActive, std::vector<Besthit> &combined, std::vector<Besthit> &out) {
     for (auto &h : combined) updateBestHit(nActive, h, false);
     {   // psort by (i,j), NJ.tcc:4797, :7309-7311; ids fit 31 bits, -1 sorts first
-        rsortByKey(combined, [](const Besthit &a) { return ((uint64_t) (uint32_t) ((int64_t) a.i + 1) << 32) | (uint32_t) ((int64_t) a.j + 1); });
+        // every valid entry of one list usually has the same i (the list's node): the (i,j) order is then the j order
+        int64_t firstI = -1;
+        bool uniformI = true;
+        for (const Besthit &h : combined)
+            if (h.i >= 0 && h.j >= 0) { if (firstI < 0) firstI = h.i; else if (h.i != firstI) { uniformI = false; break; } }
+        if (uniformI) rsortByKey(combined, [](const Besthit &a) { return (a.i < 0 || a.j < 0) ? (uint64_t) 0 : (uint64_t) a.j + 1; });
+        else rsortByKey(combined, [](const Besthit &a) { return ((uint64_t) (uint32_t) ((int64_t) a.i + 1) << 32) | (uint32_t) ((int64_t) a.j + 1); });
     }
     out.clear();
     out.reserve(combined.size());
@@ -466,6 +516,7 @@ void NJ<P>::uniqueCore(int64_t nActive, std::vector<Besthit> &combined, std::vec
 
 template<typename P>
 void NJ<P>::uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out, const std::vector<int64_t> &slots) {
+    HPROF(7, "uniqueBestHitsFinish");
     for (size_t k = 0; k < out.size(); k++) {
         Besthit &h = out[k];
         if (h.dist < 0.0) {                                      // :4826-4827
@@ -604,37 +655,95 @@ void NJ<P>::setAllLeafTopHits() {
     }
 }
 
-// resetTopVisible, NJ.tcc:4728-4784
+// resetTopVisible, NJ.tcc:4728-4784.  O(nActive) work, called every m/2 joins and after every refresh: the scans
+// run on the host threads.  The reference evaluates getVisible() for every live node in ascending order; the
+// only side effect of that loop is the lazy out-distance refresh of the nodes it touches (setCriterion,
+// :1092-1098), which does not depend on the order -- so the touched set is marked first, its stale members are
+// fetched in one device call and committed, and the criteria are then computed from read-only state.
 template<typename P>
 void NJ<P>::resetTopVisible(int64_t nActive) {
-    // pass 1: which nodes have a live visible hit (getVisible's tests, :546-553) + staleness hints
-    static thread_local std::vector<int64_t> cand;
-    cand.clear();
-    for (int64_t i = 0; i < maxnode; i++) {
-        if (parent[i] >= 0) continue;
-        const Hit &h = visible[i];
-        if (h.j < 0 || parent[h.j] >= 0) continue;
-        cand.push_back(i);
-        if (opt.prefetch) { wantOut(i, nActive); wantOut(h.j, nActive); }
-    }
-    flush(nActive);
-    // pass 2: criteria, in ascending node order = the order of visibleSorted[] in the reference
-    const size_t nVisible = cand.size();
-    static thread_local std::vector<Besthit> vis;
-    vis.resize(nVisible);
-    for (size_t k = 0; k < nVisible; k++) getVisible(nActive, cand[k], vis[k]);
-    // The reference allocates nActive slots (:4729), fills nVisible of them and psorts ALL of them
-    // (:4744); the unfilled tail is value-initialised (i=j=0, criterion 0) and takes part in the
-    // sort, and only the first nVisible sorted slots are read (:4761).  Reproduced literally, but
-    // only as much of the order as is consumed is materialised: (key, reversed position) pairs,
-    // partially sorted, extended on demand.
-    const size_t nAll = (size_t) std::max<int64_t>(nActive, (int64_t) nVisible);
-    static thread_local std::vector<std::pair<uint64_t, uint32_t>> kv;
-    kv.resize(nAll);
+    HPROF(1, "resetTopVisible");
+    const int nT = maxnode >= 4096 ? hostThreads : 1;
+    if ((int64_t) rtvTouched.size() < maxnodes) rtvTouched.assign(maxnodes, 0);
+    const int64_t stamp = ++rtvStamp;
+    std::vector<std::vector<id_t>> &candT = rtvCandT, &wantT = rtvWantT;
+    candT.resize(nT); wantT.resize(nT);
+    std::vector<id_t> &cand = rtvCand;
+    std::vector<Besthit> &vis = rtvVis;
+    std::vector<std::pair<uint64_t, uint32_t>> &kv = rtvKv;
+    bool needSequential = false;
+    size_t nVisible = 0, nAll = 0;
     const uint64_t zeroKey = orderKey((P) 0);
-    for (size_t k = 0; k < nAll; k++) kv[k] = {k < nVisible ? orderKey(vis[k].criterion) : zeroKey, (uint32_t) (nAll - 1 - k)};
+#pragma omp parallel num_threads(nT)
+    {
+        const int t = omp_get_thread_num(), nth = omp_get_num_threads();
+        const int64_t lo = maxnode * t / nth, hi = maxnode * (t + 1) / nth;
+        // pass 1: which nodes have a live visible hit (getVisible's tests, :546-553); mark what the loop touches
+        std::vector<id_t> &mine = candT[t];
+        mine.clear();
+        for (int64_t i = lo; i < hi; i++) {
+            if (parent[i] >= 0) continue;
+            const Hit &h = visible[i];
+            if (h.j < 0 || parent[h.j] >= 0) continue;
+            mine.push_back((id_t) i);
+            __atomic_store_n(&rtvTouched[i], stamp, __ATOMIC_RELAXED);
+            __atomic_store_n(&rtvTouched[h.j], stamp, __ATOMIC_RELAXED);
+        }
+#pragma omp barrier
+        // the touched nodes whose out-distance is stale and not in hand yet (owner computes: wantOut's state is per node)
+        std::vector<id_t> &w = wantT[t];
+        w.clear();
+        if (opt.prefetch)
+            for (int64_t i = lo; i < hi; i++)
+                if (rtvTouched[i] == stamp && parent[i] < 0 && nOutDistActive[i] != nActive && freshEpoch[i] != epoch
+                    && wantEpoch[i] != epoch && stale(i, nActive)) {
+                    wantEpoch[i] = epoch;
+                    w.push_back((id_t) i);
+                }
+#pragma omp barrier
+#pragma omp single
+        {
+            cand.clear();
+            for (int k = 0; k < nth; k++) cand.insert(cand.end(), candT[k].begin(), candT[k].end());   // ascending node order
+            for (int k = 0; k < nth; k++) for (id_t i : wantT[k]) wantIds.push_back(i);
+            flush(nActive);
+            nVisible = cand.size();
+            nAll = (size_t) std::max<int64_t>(nActive, (int64_t) nVisible);
+            vis.resize(nVisible);
+            kv.resize(nAll);
+        }   // implicit barrier
+        // commit what setCriterion would refresh (:1092-1098)
+        bool seq = false;
+        for (int64_t i = lo; i < hi; i++)
+            if (rtvTouched[i] == stamp && parent[i] < 0 && stale(i, nActive)) {
+                if (freshEpoch[i] == epoch && epochActive == nActive) { outDistances[i] = freshVal[i]; nOutDistActive[i] = nActive; }
+                else seq = true;
+            }
+        if (seq) {
+#pragma omp atomic write
+            needSequential = true;
+        }
+#pragma omp barrier
+#pragma omp single
+        {
+            if (needSequential)                         // prefetching off (or a value not in hand): one at a time, as the reference would
+                for (int64_t i = 0; i < maxnode; i++)
+                    if (rtvTouched[i] == stamp && parent[i] < 0 && stale(i, nActive)) setOutDistance(i, nActive);
+        }   // implicit barrier
+        // pass 2: criteria, in ascending node order = the order of visibleSorted[] in the reference (read-only now)
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < (int64_t) nVisible; k++) getVisible(nActive, cand[k], vis[k]);
+        // The reference allocates nActive slots (:4729), fills nVisible of them and psorts ALL of them
+        // (:4744); the unfilled tail is value-initialised (i=j=0, criterion 0) and takes part in the
+        // sort, and only the first nVisible sorted slots are read (:4761).  Reproduced literally, but
+        // only as much of the order as is consumed is materialised: (key, reversed position) pairs.
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < (int64_t) nAll; k++)
+            kv[k] = {(size_t) k < nVisible ? orderKey(vis[k].criterion) : zeroKey, (uint32_t) (nAll - 1 - k)};
+    }
     size_t sorted = std::min(nAll, 4 * topvisible.size() + 64);
-    std::partial_sort(kv.begin(), kv.begin() + sorted, kv.end());
+    if (sorted < nAll) std::nth_element(kv.begin(), kv.begin() + sorted, kv.end());
+    std::sort(kv.begin(), kv.begin() + sorted);
     static thread_local std::vector<int64_t> inTopVisible;
     static thread_local std::vector<int64_t> touched;
     if ((int64_t) inTopVisible.size() < maxnodes) inTopVisible.assign(maxnodes, -1);
@@ -658,6 +767,7 @@ void NJ<P>::resetTopVisible(int64_t nActive) {
 // updateTopVisible, NJ.tcc:4661-4711
 template<typename P>
 void NJ<P>::updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit) {
+    HPROF(2, "updateTopVisible");
     bool bIn = false;
     for (size_t k = 0; k < topvisible.size() && !bIn; k++) {
         int64_t iNode = topvisible[k];
@@ -690,6 +800,7 @@ void NJ<P>::updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit) {
 // updateVisible, NJ.tcc:4635-4658
 template<typename P>
 void NJ<P>::updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode) {
+    HPROF(3, "updateVisible(incl updateTopVisible)");
     if (opt.prefetch) {
         for (const Besthit &hit : tophitsNode) if (hit.i >= 0) hintVisible(nActive, hit.j);
         flushOut(nActive);
@@ -711,6 +822,7 @@ void NJ<P>::updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode) {
 // getBestFromTopHits, NJ.tcc:4267-4298
 template<typename P>
 void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin) {
+    HPROF(4, "getBestFromTopHits");
     TopHitsList &l = topHitsLists[iNode];
     if (opt.prefetch) { hintList(nActive, iNode); flush(nActive); }
     setOutDistance(iNode, nActive);                                      // :4276
@@ -729,6 +841,7 @@ void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin
 // topHitNJSearch, NJ.tcc:4137-4264
 template<typename P>
 void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
+    HPROF(5, "topHitNJSearch(total)");
     if (opt.prefetch) {
         for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
         // Speculation: guess the join from the values we already hold (stale out-distances rescaled,
@@ -810,14 +923,15 @@ void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
 // topHitJoin, NJ.tcc:4306-4533 (no 2nd-level lists: hitSource is always -1)
 template<typename P>
 void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
+    HPROF(11, "topHitJoin(total)");
     TopHitsList &lNew = topHitsLists[newnode];
     TopHitsList *lChild[2] = {&topHitsLists[child[newnode].child[0]], &topHitsLists[child[newnode].child[1]]};
     size_t n0 = lChild[0]->hits.size();
-    std::vector<Besthit> combinedList(n0 + lChild[1]->hits.size());
+    std::vector<Besthit> &combinedList = thjCombined, &uniqueList = thjUnique;      // scratch reused across joins
+    std::vector<int64_t> &uniqueSlots = thjSlots;
+    combinedList.resize(n0 + lChild[1]->hits.size());
     hitsToBestHits(lChild[0]->hits, child[newnode].child[0], combinedList.data());
     hitsToBestHits(lChild[1]->hits, child[newnode].child[1], combinedList.data() + n0);
-    std::vector<Besthit> uniqueList;
-    std::vector<int64_t> uniqueSlots;
     uniqueBestHitsPrepare(nActive, combinedList, uniqueList, uniqueSlots);
     if (opt.prefetch) {      // what updateTopVisible / updateVisible below can touch (a superset)
         for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
@@ -854,8 +968,16 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
             if (parent[i] < 0) { outDistances[i] = od[i]; nOutDistActive[i] = nActive; }
     }
     std::vector<Besthit> allhits;
-    oneVsAll(newnode, nActive, 2 * m, allhits);                          // :4470-4471 (top 2m is all that is read)
+    const int64_t nRealHits = oneVsAll(newnode, nActive, 2 * m, allhits);    // :4470-4471 (top 2m is all that is read)
     sortSaveBestHits(newnode, allhits, (int64_t) allhits.size(), m, false);   // :4472
+    if (opt.prefetch && nRealHits >= 2 * m) {
+        // The m list merges of :4477-4515 in ONE device pass (vft_tophits_merge): the host only resolves the
+        // active ancestors of the stored hits (it owns the tree) and packs the lists.
+        refreshListsOnDevice(newnode, nActive, allhits);
+        pairCache.clear();
+        resetTopVisible(nActive);                                        // :4517
+        return;
+    }
 
     // expand the lists of the top m hits, :4477-4515.  The m iterations are independent (they
     // read allhits and parent[], write only their own list), so their distance requests are
@@ -908,6 +1030,52 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     res->nPairPrefetchHit += hits;
     pairCache.clear();
     resetTopVisible(nActive);                                            // :4517
+}
+
+// The list-merging loop of a refresh (NJ.tcc:4477-4515) through vft_tophits_merge.  Every entry of allhits is a
+// real, active hit here (the caller checked), so transferBestHits has no ancestor to resolve on that side.
+template<typename P>
+void NJ<P>::refreshListsOnDevice(int64_t newnode, int64_t nActive, const std::vector<Besthit> &allhits) {
+    HPROF(9, "refreshListsOnDevice");
+    // (plain locals, captured by reference into the host-thread regions below)
+    std::vector<int64_t> &iNodes = rfNodes, &ownOffset = rfOffset, &ownJ = rfOwnJ, &allJ = rfAllJ, &outCount = rfCount, &outJ = rfOutJ;
+    std::vector<P> &ownDist = rfOwnDist, &allDist = rfAllDist, &outDist = rfOutDist;
+    iNodes.clear();
+    for (int64_t iHit = 0; iHit < m; iHit++) {                            // :4477-4482
+        if (allhits[iHit].i < 0) continue;
+        const int64_t iNode = allhits[iHit].j;
+        if (parent[iNode] >= 0) continue;
+        iNodes.push_back(iNode);
+    }
+    const int64_t nLists = (int64_t) iNodes.size(), nAvail = 2 * m;
+    ownOffset.assign(nLists + 1, 0);
+    for (int64_t l = 0; l < nLists; l++) ownOffset[l + 1] = ownOffset[l] + (int64_t) topHitsLists[iNodes[l]].hits.size();
+    ownJ.resize(ownOffset[nLists]); ownDist.resize(ownOffset[nLists]);
+    allJ.resize(nAvail); allDist.resize(nAvail);
+    for (int64_t k = 0; k < nAvail; k++) { allJ[k] = allhits[k].j; allDist[k] = allhits[k].dist; }
+#pragma omp parallel for schedule(static) num_threads(hostThreads)
+    for (int64_t l = 0; l < nLists; l++) {
+        const std::vector<Hit> &hits = topHitsLists[iNodes[l]].hits;
+        int64_t o = ownOffset[l];
+        for (const Hit &h : hits) {                                      // updateBestHit(.., false), :1626-1648
+            const int64_t j = activeAncestor(h.j);
+            ownJ[o] = j;
+            ownDist[o] = j == h.j ? h.dist : (P) -1e20;
+            o++;
+        }
+    }
+    outCount.resize(nLists); outJ.resize(nLists * m); outDist.resize(nLists * m);
+    check(timed([&] { return vft_tophits_merge(ctx, newnode, nActive, m, nLists, iNodes.data(), ownOffset.data(), ownJ.data(),
+                                               ownDist.data(), nAvail, allJ.data(), allDist.data(), outCount.data(), outJ.data(),
+                                               outDist.data()); }));
+#pragma omp parallel for schedule(static) num_threads(hostThreads)
+    for (int64_t l = 0; l < nLists; l++) {
+        TopHitsList &lst = topHitsLists[iNodes[l]];
+        lst.age = 0;
+        lst.hits.resize(outCount[l]);
+        for (int64_t k = 0; k < outCount[l]; k++) { lst.hits[k].j = (id_t) outJ[l * m + k]; lst.hits[k].dist = outDist[l * m + k]; }
+        visible[iNodes[l]] = lst.hits[0];                                // :4513
+    }
 }
 
 // setBestHit with the full allhits array (visible-set mode only, N tiny): NJ.tcc:3571-3639
@@ -1111,6 +1279,9 @@ template<typename P>
 int run(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, const uint8_t *codes, vft_nj_result *res) {
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
+#ifdef VFT_HOSTPROF
+    g_hpCalls = &res->secondsInCalls; for (int k = 0; k < 32; k++) { g_hp[k] = 0; g_hpN[k] = 0; }
+#endif
     NJ<P> nj(ctx, cfg, opt, res, codes);
     try {
         vft_timer_start(ctx);
@@ -1130,6 +1301,9 @@ int run(vft_ctx *ctx, const vft_config &cfg, const vft_nj_options &opt, const ui
     res->root = nj.root;
     res->maxnode = nj.maxnode;
     res->secondsTotal = std::chrono::duration<double>(clk::now() - t0).count();
+#ifdef VFT_HOSTPROF
+    for (int k = 0; k < 32; k++) if (g_hpN[k]) std::fprintf(stderr, "[hostprof] %-40s %9ld calls %8.1f ms  %7.2f us/call\n", g_hpName[k], g_hpN[k], 1e3 * g_hp[k], 1e6 * g_hp[k] / g_hpN[k]);
+#endif
     return VFT_OK;
 }
 
@@ -1165,14 +1339,21 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     res->deviceMsResident = res->secondsEndToEnd = res->secondsInCalls = 0;
     for (double &x : res->secondsHost) x = 0;
     auto e2e0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - e2e0).count(); };
     vft_ctx *ctx = nullptr;
     int rc = vft_ctx_create(cfg, &ctx);
     if (rc != VFT_OK) return rc;
+    const double tCreate = since();
     if (cfg->useMatrix) rc = vft_upload_tables(ctx, tables[0], tables[1], tables[2], tables[3]);
     if (rc == VFT_OK) rc = vft_upload_leaves(ctx, codes);
+    const double tUpload = since();
     if (rc == VFT_OK) rc = cfg->precision == 32 ? run<float>(ctx, *cfg, opt, codes, res) : run<double>(ctx, *cfg, opt, codes, res);
+    const double tRun = since();
     if (rc == VFT_OK) vft_get_counters(ctx, &res->counters);
     vft_ctx_destroy(ctx);
-    res->secondsEndToEnd = std::chrono::duration<double>(std::chrono::steady_clock::now() - e2e0).count();
+    res->secondsEndToEnd = since();
+    if (std::getenv("VFT_TIMING"))
+        std::fprintf(stderr, "[vft_nj_build] create %.1f ms, upload %.1f ms, run %.1f ms, destroy %.1f ms\n", 1e3 * tCreate,
+                     1e3 * (tUpload - tCreate), 1e3 * (tRun - tUpload), 1e3 * (res->secondsEndToEnd - tRun));
     return rc;
 }

@@ -36,6 +36,86 @@ static int cuda_fail(cudaError_t e, const char *what) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
 
+// ---- allocation cache -----------------------------------------------------------------------------
+// vft_nj_build creates and destroys a context per tree; cudaMalloc / cudaHostAlloc / cudaFree cost
+// milliseconds to hundreds of milliseconds each (cudaFree also synchronises the device).  Freed blocks
+// are therefore parked in a small process-wide cache (exact-size reuse, per device) instead of going
+// back to the driver: a caching allocator, nothing else -- contents are never reused, every context
+// re-initialises its buffers.  VFT_POOL_MB caps the parked device bytes (default 8192; 0 disables).
+#include <mutex>
+#include <unordered_map>
+namespace {
+enum { MEM_DEVICE = 0, MEM_PINNED = 1 };
+struct MemBlock { void *p; size_t bytes; int kind, device; };
+std::mutex g_memMu;
+std::unordered_map<void *, MemBlock> g_memLive;
+std::vector<MemBlock> g_memParked;
+size_t g_parkedBytes[2] = {0, 0};
+
+size_t pool_cap(int kind) {
+    static const long mb = [] { const char *e = std::getenv("VFT_POOL_MB"); return e ? std::atol(e) : 8192l; }();
+    return kind == MEM_DEVICE ? (size_t) mb << 20 : std::min<size_t>((size_t) mb << 20, (size_t) 512 << 20);
+}
+void raw_free(const MemBlock &b) { if (b.kind == MEM_DEVICE) cudaFree(b.p); else cudaFreeHost(b.p); }
+
+void mem_release_all() {
+    std::lock_guard<std::mutex> lk(g_memMu);
+    for (const MemBlock &b : g_memParked) raw_free(b);
+    g_memParked.clear();
+    g_parkedBytes[0] = g_parkedBytes[1] = 0;
+}
+
+cudaError_t mem_alloc(void **out, size_t bytes, int kind) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes == 0) bytes = 1;
+    {
+        std::lock_guard<std::mutex> lk(g_memMu);
+        for (size_t k = 0; k < g_memParked.size(); k++) {
+            const MemBlock b = g_memParked[k];
+            if (b.bytes == bytes && b.kind == kind && b.device == dev) {
+                g_memParked[k] = g_memParked.back(); g_memParked.pop_back();
+                g_parkedBytes[kind] -= bytes;
+                g_memLive[b.p] = b;
+                *out = b.p;
+                return cudaSuccess;
+            }
+        }
+    }
+    cudaError_t e = kind == MEM_DEVICE ? cudaMalloc(out, bytes) : cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) {                  // out of memory: give the parked blocks back and retry once
+        cudaGetLastError();
+        mem_release_all();
+        e = kind == MEM_DEVICE ? cudaMalloc(out, bytes) : cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_memMu);
+        g_memLive[*out] = MemBlock{*out, bytes, kind, dev};
+    }
+    return e;
+}
+
+void mem_free(void *p) {
+    if (!p) return;
+    MemBlock b;
+    {
+        std::lock_guard<std::mutex> lk(g_memMu);
+        auto it = g_memLive.find(p);
+        if (it == g_memLive.end()) return;
+        b = it->second;
+        g_memLive.erase(it);
+        if (g_parkedBytes[b.kind] + b.bytes <= pool_cap(b.kind) && g_memParked.size() < 256) {
+            g_memParked.push_back(b);
+            g_parkedBytes[b.kind] += b.bytes;
+            return;
+        }
+    }
+    raw_free(b);
+}
+}  // namespace
+
+extern "C" int vft_release_cached_memory(void) { mem_release_all(); return VFT_OK; }
+
 // =================================================================================================
 // kernels
 // =================================================================================================
@@ -54,17 +134,18 @@ template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
 k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
        int64_t n, int64_t nOutItems, int G, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
-       unsigned int *__restrict__ doneCount, volatile unsigned int *__restrict__ doneFlag, unsigned int seq) {
+       unsigned int *__restrict__ doneCount, P *__restrict__ hostOut) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
     const int64_t item = warp * G + lane;
-    const bool valid = lane < G && item < n;
+    const bool inRange = lane < G && item < n;
     // small lists travel in the kernel parameters (no PCIe read at kernel start), large ones are
-    // read from the mapped pinned buffer
-    const int64_t a = !valid ? -1 : (ia ? ia[item] : inl.a[item]), b = !valid ? -1 : (ib ? ib[item] : inl.b[item]);
+    // read from the mapped pinned buffer (or, for vft_tophits_merge, from device memory)
+    const int64_t a = !inRange ? -1 : (ia ? ia[item] : inl.a[item]), b = !inRange ? -1 : (ib ? ib[item] : inl.b[item]);
+    const bool valid = inRange && a >= 0;                // a < 0: empty slot (vft_tophits_merge), nothing is written
     const bool isOut = valid && item < nOutItems;
     const bool isSeq = valid && !isOut && !raw && a < s.nSeqs && b < s.nSeqs;
     P d = 0, w = 0;
@@ -83,6 +164,19 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
         else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
     }
     if (valid) { r0[item] = d; r1[item] = w; }
+    // Results go to DEVICE memory; the last CTA to finish copies both arrays to the mapped host buffer with
+    // wide, coalesced stores.  (One 4-byte store per item straight into host memory costs a PCIe
+    // transaction each -- several microseconds for a 250-item list, more than the distances themselves.)
+    if (hostOut == nullptr) return;
+    __shared__ bool amLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) amLast = atomicAdd(doneCount, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) { hostOut[k] = __ldcg(r0 + k); hostOut[n + k] = __ldcg(r1 + k); }
+    if (threadIdx.x == 0) *doneCount = 0;
 }
 
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
@@ -132,7 +226,7 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
 // setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
-k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam, P *__restrict__ out) {
+k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -147,7 +241,7 @@ k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double t
         P dd, ww;
         finish_dist<P>(den, top, dd, ww);
         const P v = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
-        out[j] = v; s.outDist[j] = v;
+        s.outDist[j] = v;
     }
 }
 
@@ -285,6 +379,133 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
     }
 }
 
+// ---- top-hits refresh on the device: vft_tophits_merge -------------------------------------------------
+// One CTA per list.  psort order (key ascending, ties in reverse input order) = ascending order of the
+// unique composite (key, n-1-inputIndex): a bitonic network over (uint64 key, uint32 tie) pairs in shared memory.
+constexpr int MRG_T = 256;
+constexpr int MRG_MAX = 4096;
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t *key, uint32_t *tie, int np2) {
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const uint64_t ka = key[lo], kb = key[hi];
+                const uint32_t ta = tie[lo], tb = tie[hi];
+                const bool aFirst = ka < kb || (ka == kb && ta < tb);
+                if (up ? !aFirst : aFirst) { key[lo] = kb; key[hi] = ka; tie[lo] = tb; tie[hi] = ta; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// transferBestHits(updateDistances=false) + the psort by (i,j) + dedupe of uniqueBestHits (NJ.tcc:4580-4613,
+// :4786-4822): writes the surviving candidates of list l (ascending j) and, for those without a distance,
+// a request slot for k_eval
+template<typename P>
+__global__ void __launch_bounds__(MRG_T)
+k_merge_prep(const int32_t *__restrict__ iNode, const int32_t *__restrict__ ownOffset, const int32_t *__restrict__ ownJ,
+             const P *__restrict__ ownDist, int nAvail, const int32_t *__restrict__ allJ, const P *__restrict__ allDist,
+             int newnode, int cap, int np2, int nSeqs, int32_t *__restrict__ uJ, P *__restrict__ uD, int32_t *__restrict__ reqA,
+             int32_t *__restrict__ reqB, int32_t *__restrict__ count, unsigned long long *__restrict__ acct) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *key = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *tie = reinterpret_cast<uint32_t *>(smem + (size_t) np2 * 8);
+    __shared__ int warpTot[MRG_T / 32];
+    __shared__ int total;
+    const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int iN = iNode[l], o0 = ownOffset[l], nOwn = ownOffset[l + 1] - o0, n = nOwn + nAvail;
+    for (int e = tid; e < np2; e += MRG_T) {
+        uint64_t k = ~0ull;
+        uint32_t t = 0xFFFFFFFFu;
+        if (e < n) {
+            const int j = e < nOwn ? ownJ[o0 + e] : allJ[e - nOwn];
+            k = (j >= 0 && j != iN) ? (uint64_t) (j + 1) : 0;                              // :1631-1637: no ancestor / self -> dropped
+            t = (uint32_t) (n - 1 - e);
+        }
+        key[e] = k; tie[e] = t;
+    }
+    block_bitonic_sort(key, tie, np2);
+    // first of each run of equal j survives (:4802-4821); block-wide compaction
+    const int per = max(1, np2 / MRG_T), t0 = tid * per;
+    int mine = 0;
+    for (int t = t0; t < t0 + per && t < n; t++) mine += (key[t] != 0 && (t == 0 || key[t - 1] != key[t])) ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warpTot[wid] = incl;
+    __syncthreads();
+    int base = incl - mine;
+    for (int w = 0; w < wid; w++) base += warpTot[w];
+    if (tid == MRG_T - 1) total = base + mine;
+    unsigned long long nSeq = 0, nProf = 0, bytesLeaf = 0, bytesInt = 0;
+    for (int t = t0; t < t0 + per && t < n; t++) {
+        if (key[t] != 0 && (t == 0 || key[t - 1] != key[t])) {
+            const int e = n - 1 - (int) tie[t], j = (int) key[t] - 1;
+            const P d = e < nOwn ? ownDist[o0 + e] : (iN == newnode ? allDist[e - nOwn] : (P) -1e20);   // :4601-4606
+            const size_t slot = (size_t) l * cap + base;
+            const bool need = d < (P) 0;                                                      // :4826
+            uJ[slot] = j; uD[slot] = d; reqA[slot] = need ? iN : -1; reqB[slot] = j;
+            if (need) { if (iN < nSeqs && j < nSeqs) nSeq++; else { nProf++; if (j < nSeqs) bytesLeaf++; else bytesInt++; } }
+            base++;
+        }
+    }
+    __syncthreads();
+    const int nu = total;
+    for (int t = nu + tid; t < cap; t += MRG_T) reqA[(size_t) l * cap + t] = -1;
+    if (tid == 0) count[l] = nu;
+    // accounting: warp-reduced, one atomic per warp and counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nSeq += __shfl_xor_sync(0xFFFFFFFFu, nSeq, o); nProf += __shfl_xor_sync(0xFFFFFFFFu, nProf, o);
+        bytesLeaf += __shfl_xor_sync(0xFFFFFFFFu, bytesLeaf, o); bytesInt += __shfl_xor_sync(0xFFFFFFFFu, bytesInt, o);
+    }
+    if (lane == 0) {
+        if (nSeq) atomicAdd(&acct[0], nSeq);
+        if (nProf) atomicAdd(&acct[1], nProf);
+        if (bytesLeaf + nSeq) atomicAdd(&acct[2], bytesLeaf + nSeq);
+        if (bytesInt) atomicAdd(&acct[3], bytesInt);
+    }
+}
+
+// the tail of uniqueBestHits (distances in, criterion from the fresh out-distance table, NJ.tcc:4823-4831,
+// :1099-1107) + sortSaveBestHits (psort by criterion, first m; NJ.tcc:4535-4578)
+template<typename P>
+__global__ void __launch_bounds__(MRG_T)
+k_merge_finish(Store<P> s, const int32_t *__restrict__ iNode, int64_t nActive, int m, int cap, int np2,
+               const int32_t *__restrict__ uJ, P *__restrict__ uD, const int32_t *__restrict__ reqA, const P *__restrict__ r0,
+               const int32_t *__restrict__ count, int32_t *__restrict__ outCount, int32_t *__restrict__ outJ, P *__restrict__ outDist) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *key = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *tie = reinterpret_cast<uint32_t *>(smem + (size_t) np2 * 8);
+    const int l = blockIdx.x, tid = threadIdx.x;
+    const int iN = iNode[l], cnt = count[l];
+    const double outI = (double) s.outDist[iN];
+    for (int t = tid; t < np2; t += MRG_T) {
+        uint64_t k = ~0ull;
+        uint32_t ti = 0xFFFFFFFFu;
+        if (t < cnt) {
+            const size_t slot = (size_t) l * cap + t;
+            const int j = uJ[slot];
+            P d = uD[slot];
+            if (reqA[slot] >= 0) { d = r0[slot]; uD[slot] = d; }
+            const P c = (P) xsub((double) d, xadd(outI, (double) s.outDist[j]) / (double) (nActive - 2));
+            k = order_key(c); ti = (uint32_t) (cnt - 1 - t);
+        }
+        key[t] = k; tie[t] = ti;
+    }
+    block_bitonic_sort(key, tie, np2);
+    const int nSave = min(m, cnt);                       // every j is distinct and != iNode here
+    for (int t = tid; t < nSave; t += MRG_T) {
+        const size_t src = (size_t) l * cap + (cnt - 1 - (int) tie[t]);
+        outJ[(size_t) l * m + t] = uJ[src]; outDist[(size_t) l * m + t] = uD[src];
+    }
+    if (tid == 0) outCount[l] = nSave;
+}
+
 // averageProfile (NJ.tcc:2067-2135) + profileDist(new,new) (NJ.tcc:3040-3043); ONE CTA:
 // positions in parallel, then thread 0 adds the per-position self-distance terms in order.
 template<typename P, int A, bool MATRIX, bool UPDATE>
@@ -360,9 +581,19 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // ordered sums over the positions (skipped positions hold +0.0, which is exact to add): 8 terms of each
+        // chain are fetched ahead of the 16 dependent additions
         double top = 0, denom = 0;
-        for (int64_t pos = 0; pos < s.L; pos++)
-            if (termW[pos] > 0) { denom = xadd(denom, termW[pos]); top = xadd(top, termT[pos]); }
+        for (int64_t pos = 0; pos < s.Lp; pos += 8) {
+            double w8[8], t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const double2 a = *reinterpret_cast<const double2 *>(termW + pos + k), b = *reinterpret_cast<const double2 *>(termT + pos + k);
+                w8[k] = a.x; w8[k + 1] = a.y; t8[k] = b.x; t8[k + 1] = b.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { denom = xadd(denom, w8[k]); top = xadd(top, t8[k]); }
+        }
         s.selfweight[oid] = (P) (denom > 0 ? denom : 0.01);
         s.selfdist[oid] = (P) (denom > 0 ? top / denom : 1.0);
         s.diameter[oid] = diameterOut;
@@ -401,73 +632,119 @@ k_outprofile_update(Store<P> s, int64_t o1, int64_t o2, int64_t nw, int64_t nAct
 }
 
 // outProfile, NJ.tcc:729-815.  The reference accumulates node after node (ascending id) into every
-// position; the order matters (P-typed sums), so the node loop stays sequential -- but its loads do
-// not have to be: ONE WARP per position, the 32 lanes fetch 32 consecutive nodes' (code, weight,
-// vector) for that position at once (and the next 32 while these are being added), then the values
-// are broadcast lane by lane, in node order, into the accumulators that every lane keeps identically.
-template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(128)
-k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    const int64_t pos = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-    if (pos >= s.L) return;
-    const double inweight = 1.0 / (double) n;                                              // :732
-    P wout = 0;
-    P f[A];
-#pragma unroll
-    for (int k = 0; k < A; k++) f[k] = 0;
+// position's weight and A frequencies; the sums are P-typed and therefore order dependent, so every
+// accumulator stays a sequential chain over the nodes -- but the L*A (+L) chains are independent, and
+// nothing forces the LOADS to be sequential.  Producer/consumer inside one CTA of 256 threads:
+//   - all threads fetch the next tile (64 nodes x PP positions: codes, weights, vectors; coalesced,
+//     thousands of loads in flight) into registers,
+//   - meanwhile the first PP*A threads, one per (position, state), run their chains over the current
+//     tile out of shared memory,
+//   - the fetched tile is stored to the other shared-memory buffer; one barrier per tile.
+// Time per tile ~ max(load latency, 64 dependent additions): close to the chain bound.
+constexpr int REB_T = 256, REB_TN = 64;
+template<int A> struct RebShape { static constexpr int PP = (A == 4) ? 32 : 8; };
+template<typename P, int A>
+__host__ __device__ inline size_t rebuild_smem_bytes() {
+    constexpr int PP = RebShape<A>::PP;
+    return (size_t) 2 * REB_TN * PP * A * sizeof(P) + (size_t) 2 * REB_TN * PP * sizeof(P) + (size_t) 2 * REB_TN * PP + 2 * REB_TN * 4
+           + (size_t) PP * A * sizeof(P);
+}
 
-    struct Item { uint32_t c; P w; bool vec; P v[A]; };
-    auto fetch = [&](int64_t in, Item &it) {
-        it.c = VFT_DEV_NOCODE; it.w = 0; it.vec = false;
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(REB_T)
+k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
+    constexpr int PP = RebShape<A>::PP, TN = REB_TN, NPAIR = TN * PP / REB_T;
+    extern __shared__ __align__(16) unsigned char smem[];
+    P *sV = reinterpret_cast<P *>(smem);                                   // [2][TN][PP][A]
+    P *sW = sV + 2 * TN * PP * A;                                          // [2][TN][PP]
+    P *fs = sW + 2 * TN * PP;                                              // [PP][A]
+    int *sId = reinterpret_cast<int *>(fs + PP * A);                       // [2][TN]
+    uint8_t *sC = reinterpret_cast<uint8_t *>(sId + 2 * TN);               // [2][TN][PP]
+    const int tid = threadIdx.x;
+    const int64_t pos0 = (int64_t) blockIdx.x * PP;
+    const int nTiles = (int) ((n + TN - 1) / TN);
+    const double inweight = 1.0 / (double) n;                              // :732
+    // consumer role
+    const bool chain = tid < PP * A;
+    const int k = tid % A, pl = (tid / A) % PP;
+    P wout = 0, f = 0;
+    // producer registers: NPAIR (node, position) pairs per thread
+    uint32_t rc[NPAIR]; P rw[NPAIR]; P rv[NPAIR][A];
+    auto fetch = [&](int tile, int buf) {
 #pragma unroll
-        for (int k = 0; k < A; k++) it.v[k] = 0;
-        if (in >= n) return;
-        const int64_t id = ids[in];
-        it.c = (uint32_t) s.codes[id * s.Lp + pos];
-        if (id < s.nSeqs) it.w = it.c != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
-        else {
-            const int64_t row = id - s.nSeqs;
-            it.w = s.weights[row * s.Lp + pos];
-            if (it.c == VFT_DEV_NOCODE && it.w > 0) {
-                it.vec = true;
-                const P *src = s.vecs + (row * s.Lp + pos) * A;
+        for (int q = 0; q < NPAIR; q++) {
+            const int e = q * REB_T + tid, u = e / PP, p = e % PP;
+            const int64_t iu = (int64_t) tile * TN + u, pos = pos0 + p;
+            rc[q] = VFT_DEV_NOCODE; rw[q] = 0;
 #pragma unroll
-                for (int k = 0; k < A; k++) it.v[k] = src[k];
-            }
-        }
-    };
-    Item cur, nxt;
-    fetch(lane, cur);
-    for (int64_t in0 = 0; in0 < n; in0 += 32) {
-        fetch(in0 + 32 + lane, nxt);                  // in flight while `cur` is consumed
-        const int cnt = (int) min((int64_t) 32, n - in0);
-        for (int u = 0; u < cnt; u++) {
-            const P w = __shfl_sync(full, cur.w, u);
-            wout = (P) xadd((double) wout, xmul((double) w, inweight));                    // :741
-            if (w > 0) {                                                                   // uniform
-                const uint32_t c = __shfl_sync(full, cur.c, u);
-                const bool vec = __shfl_sync(full, (int) cur.vec, u) != 0;
-                if (vec) {
-                    P fin[A];
-#pragma unroll
-                    for (int k = 0; k < A; k++) fin[k] = __shfl_sync(full, cur.v[k], u);
-                    add_to_freq<P, A, MATRIX>(s, f, (double) w, c, fin);                   // :771-774
-                } else {
-                    add_to_freq<P, A, MATRIX>(s, f, (double) w, c, nullptr);
+            for (int a = 0; a < A; a++) rv[q][a] = 0;
+            if (iu < n) {
+                const int64_t id = sId[buf * TN + u];
+                rc[q] = (uint32_t) s.codes[id * s.Lp + pos];
+                if (id < s.nSeqs) rw[q] = rc[q] != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+                else {
+                    const int64_t row = id - s.nSeqs;
+                    rw[q] = s.weights[row * s.Lp + pos];
+                    load_vec<P, A>(s.vecs + (row * s.Lp + pos) * A, rv[q]);
                 }
             }
         }
-        cur = nxt;
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < NPAIR; q++) {
+            const int e = q * REB_T + tid;                                 // = u * PP + p
+            sC[buf * TN * PP + e] = (uint8_t) rc[q];
+            sW[buf * TN * PP + e] = rw[q];
+#pragma unroll
+            for (int a = 0; a < A; a++) sV[((size_t) buf * TN * PP + e) * A + a] = rv[q][a];
+        }
+    };
+    if (tid < TN) sId[tid] = tid < n ? (int) ids[tid] : 0;
+    if (tid < TN) sId[TN + tid] = (int64_t) TN + tid < n ? (int) ids[TN + tid] : 0;
+    __syncthreads();
+    fetch(0, 0);
+    stash(0);
+    __syncthreads();
+    for (int t = 0; t < nTiles; t++) {
+        const int cur = t & 1;
+        if (t + 1 < nTiles) fetch(t + 1, cur ^ 1);                         // in flight during the chains below
+        int idNext = 0;
+        const bool haveId = t + 2 < nTiles && tid < TN;
+        if (haveId) { const int64_t iu = (int64_t) (t + 2) * TN + tid; idNext = iu < n ? (int) ids[iu] : 0; }
+        if (chain) {
+            const uint8_t *cC = sC + cur * TN * PP + pl;
+            const P *cW = sW + cur * TN * PP + pl;
+            const P *cV = sV + ((size_t) cur * TN * PP + pl) * A + k;
+#pragma unroll 8
+            for (int u = 0; u < TN; u++) {
+                const uint32_t c = cC[u * PP];
+                const P w = cW[u * PP];
+                wout = (P) xadd((double) wout, xmul((double) w, inweight));                // :741
+                if (w > 0) {                                                               // addToFreq, :821-833
+                    if (c == VFT_DEV_NOCODE) f = padd(f, pmul(cV[(size_t) u * PP * A], w));
+                    else if (MATRIX) f = padd(f, pmul(s.codeFreq[c * 20 + k], w));
+                    else if (c == (uint32_t) k) f = (P) xadd((double) f, (double) w);       // :831
+                }
+            }
+        }
+        if (t + 1 < nTiles) stash(cur ^ 1);
+        if (haveId) sId[cur * TN + tid] = idNext;
+        __syncthreads();
     }
-    if (wout <= 0) wout = (P) 1e-20;                                                       // :743-745
-    normalize_freq<P, A, MATRIX>(s, f);                                                    // :789-794
-    if (lane == 0) {
+    if (chain) fs[pl * A + k] = f;
+    __syncthreads();
+    const int64_t pos = pos0 + pl;
+    if (chain && k == 0 && pos < s.L) {
+        if (wout <= 0) wout = (P) 1e-20;                                                   // :743-745
+        P fa[A];
+#pragma unroll
+        for (int q = 0; q < A; q++) fa[q] = fs[pl * A + q];
+        normalize_freq<P, A, MATRIX>(s, fa);                                               // :789-794
         s.ow[pos] = wout;
 #pragma unroll
-        for (int k = 0; k < A; k++) s.ov[pos * A + k] = f[k];
-        if (MATRIX) code_dist_row<P, A, MATRIX>(s, f, s.ocd + pos * A);                    // :801-803
+        for (int q = 0; q < A; q++) s.ov[pos * A + q] = fa[q];
+        if (MATRIX) code_dist_row<P, A, MATRIX>(s, fa, s.ocd + pos * A);                   // :801-803
     }
 }
 
@@ -554,6 +831,9 @@ struct vft_ctx {
     int64_t *d_ids, *d_pi, *d_pj;              // staging for lists
     void *d_out1, *d_out2;
     int64_t listCap;
+    // vft_tophits_merge scratch
+    void *d_mrg; size_t mrgCap;
+    unsigned long long *d_acct;
     // pinned host
     void *h_in, *h_out;
     size_t hCap;
@@ -572,21 +852,23 @@ struct vft_ctx {
     // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
     cudaEvent_t tmr0, tmr1;
     bool profile;
-    struct Pending { cudaEvent_t a, b; int cls; };
+    struct Pending { cudaEvent_t a, b; int cls, kid; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> pool;
 };
 
 enum { CLS_DIST = 0, CLS_SELECT = 1, CLS_PROFILE = 2 };
+// finer split of the same timings: index into vft_counters.msKernel / nKernel (names: VFT_KERNEL_NAMES in the header)
+enum { K_EVAL_SMALL = 0, K_EVAL_LARGE, K_ONE_VS_ALL, K_OUT_DIST_ALL, K_SELECT, K_MERGE, K_AVERAGE, K_OUTPROFILE_UPDATE, K_REBUILD, K_LOGLK, K_POSTERIOR };
 
-static void prof_begin(vft_ctx *c, int cls) {
+static void prof_begin(vft_ctx *c, int cls, int kid) {
     if (!c->profile) return;
     vft_ctx::Pending p;
     for (cudaEvent_t *e : {&p.a, &p.b}) {
         if (c->pool.empty()) cudaEventCreate(e);
         else { *e = c->pool.back(); c->pool.pop_back(); }
     }
-    p.cls = cls;
+    p.cls = cls; p.kid = kid;
     cudaEventRecord(p.a, c->stream);
     c->pending.push_back(p);
 }
@@ -603,6 +885,7 @@ static void prof_resolve(vft_ctx *c) {
         if (p.cls == CLS_DIST) { c->cnt.msDist += ms; c->cnt.distLaunches++; }
         else if (p.cls == CLS_SELECT) c->cnt.msSelect += ms;
         else c->cnt.msProfile += ms;
+        c->cnt.msKernel[p.kid] += ms; c->cnt.nKernel[p.kid]++;
         c->pool.push_back(p.a); c->pool.push_back(p.b);
     }
     c->pending.clear();
@@ -645,9 +928,9 @@ extern "C" const char *vft_backend_name(void) { return "cuda-sm100a"; }
 static int ensure_lists(vft_ctx *c, int64_t n) {
     if (n <= c->listCap) return VFT_OK;
     int64_t cap = std::max<int64_t>(n, 2 * c->listCap);
-    cudaFree(c->d_ids); cudaFree(c->d_pi); cudaFree(c->d_pj); cudaFree(c->d_out1); cudaFree(c->d_out2);
-    CK(cudaMalloc(&c->d_ids, cap * 8)); CK(cudaMalloc(&c->d_pi, cap * 8)); CK(cudaMalloc(&c->d_pj, cap * 8));
-    CK(cudaMalloc(&c->d_out1, cap * 8)); CK(cudaMalloc(&c->d_out2, cap * 8));
+    mem_free(c->d_ids); mem_free(c->d_pi); mem_free(c->d_pj); mem_free(c->d_out1); mem_free(c->d_out2);
+    CK(mem_alloc((void **) &c->d_ids, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_pi, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_pj, cap * 8, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_out1, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_out2, cap * 8, MEM_DEVICE));
     c->listCap = cap;
     return VFT_OK;
 }
@@ -655,9 +938,9 @@ static int ensure_lists(vft_ctx *c, int64_t n) {
 static int ensure_pinned(vft_ctx *c, size_t bytes) {
     if (bytes <= c->hCap) return VFT_OK;
     size_t cap = std::max(bytes, 2 * c->hCap);
-    if (c->h_in) cudaFreeHost(c->h_in);
-    if (c->h_out) cudaFreeHost(c->h_out);
-    CK(cudaMallocHost(&c->h_in, cap)); CK(cudaMallocHost(&c->h_out, cap));
+    mem_free(c->h_in); mem_free(c->h_out);
+    c->h_in = c->h_out = nullptr; c->hCap = 0;
+    CK(mem_alloc(&c->h_in, cap, MEM_PINNED)); CK(mem_alloc(&c->h_out, cap, MEM_PINNED));
     c->hCap = cap;
     return VFT_OK;
 }
@@ -685,15 +968,15 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->tmr0)); CK(cudaEventCreate(&c->tmr1));
     const size_t ps = c->ps, Lp = (size_t) c->Lp, A = (size_t) c->A, N = (size_t) c->N, M = (size_t) c->M;
-    CK(cudaMalloc(&c->codes, M * Lp));
-    CK(cudaMalloc(&c->weights, N * Lp * ps));
-    CK(cudaMalloc(&c->vecs, N * Lp * A * ps));
-    CK(cudaMalloc(&c->ow, Lp * ps)); CK(cudaMalloc(&c->ov, Lp * A * ps)); CK(cudaMalloc(&c->ocd, Lp * A * ps));
-    CK(cudaMalloc(&c->diameter, M * ps)); CK(cudaMalloc(&c->selfdist, M * ps)); CK(cudaMalloc(&c->selfweight, M * ps));
-    CK(cudaMalloc(&c->outDist, M * ps)); CK(cudaMalloc(&c->active, M));
-    CK(cudaMalloc(&c->tables, 840 * ps));
-    CK(cudaMalloc(&c->d_dist, M * ps)); CK(cudaMalloc(&c->d_weight, M * ps)); CK(cudaMalloc(&c->d_crit, M * ps));
-    CK(cudaMalloc(&c->d_keys, M * 8));
+    CK(mem_alloc((void **) &c->codes, M * Lp, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->weights, N * Lp * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->vecs, N * Lp * A * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->ow, Lp * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->ov, Lp * A * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->ocd, Lp * A * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->diameter, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->selfdist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->selfweight, M * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->outDist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->active, M, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->tables, 840 * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_dist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_weight, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_crit, M * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_keys, M * 8, MEM_DEVICE));
     c->d_tkA = c->d_tkB = nullptr; c->d_tvA = c->d_tvB = nullptr; c->d_rec = nullptr;
     CK(cudaMemsetAsync(c->codes, VFT_NOCODE, M * Lp, c->stream));
     CK(cudaMemsetAsync(c->weights, 0, N * Lp * ps, c->stream));
@@ -705,12 +988,12 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->active, 0, M, c->stream));
     CK(cudaMemsetAsync(c->tables, 0, 840 * ps, c->stream));
     c->activeHost.assign(M, 0);
-    CK(cudaMalloc(&c->mlTables, 1300 * ps)); CK(cudaMalloc(&c->mlRates, 64 * ps)); CK(cudaMalloc(&c->mlRatecat, Lp * 4));
+    CK(mem_alloc((void **) &c->mlTables, 1300 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRates, 64 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRatecat, Lp * 4, MEM_DEVICE));
     CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
     c->hasTransmat = false; c->hasRates = false;
-    CK(cudaMalloc(&c->d_doneCount, 4));
+    CK(mem_alloc((void **) &c->d_doneCount, 4, MEM_DEVICE));
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
-    { void *f = nullptr; CK(cudaHostAlloc(&f, 64, cudaHostAllocMapped)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
+    { void *f = nullptr; CK(mem_alloc(&f, 64, MEM_PINNED)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
     c->seq = 0;
     int rc = ensure_lists(c, std::max<int64_t>(4096, c->M));
     // pinned request/response buffers sized once for the largest list the NJ driver produces
@@ -738,11 +1021,9 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_tkA, c->d_tkB,
                     c->d_tvA, c->d_tvB, c->d_rec, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
-    for (void *p : ptrs) if (p) cudaFree(p);
-    if (c->h_in) cudaFreeHost(c->h_in);
-    if (c->h_out) cudaFreeHost(c->h_out);
-    if (c->h_flag) cudaFreeHost((void *) c->h_flag);
-    if (c->d_doneCount) cudaFree(c->d_doneCount);
+    for (void *p : ptrs) mem_free(p);
+    mem_free(c->h_in); mem_free(c->h_out); mem_free((void *) c->h_flag);
+    mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
     cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
@@ -800,8 +1081,12 @@ extern "C" int vft_outprofile_rebuild(vft_ctx *c, const int64_t *ids, int64_t n)
     std::memcpy(c->h_in, ids, (size_t) n * 8);
     CK(cudaMemcpyAsync(c->d_ids, c->h_in, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
     c->cnt.h2dBytes += n * 8;
-#define CALL_REB(P, A_, MX) k_outprofile_rebuild<P, A_, MX><<<(unsigned) ((c->L + 3) / 4), 128, 0, c->stream>>>(make_store<P>(c), c->d_ids, n)
-    prof_begin(c, CLS_PROFILE);
+#define CALL_REB(P, A_, MX)                                                                                          \
+    do {                                                                                                             \
+        cudaFuncSetAttribute(k_outprofile_rebuild<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rebuild_smem_bytes<P, A_>()); \
+        k_outprofile_rebuild<P, A_, MX><<<(unsigned) ((c->L + RebShape<A_>::PP - 1) / RebShape<A_>::PP), REB_T, rebuild_smem_bytes<P, A_>(), c->stream>>>(make_store<P>(c), c->d_ids, n); \
+    } while (0)
+    prof_begin(c, CLS_PROFILE, K_REBUILD);
     VFT_DISPATCH(c, CALL_REB);
     prof_end(c);
     CK(cudaGetLastError());
@@ -815,7 +1100,7 @@ extern "C" int vft_outprofile_update(vft_ctx *c, int64_t old1, int64_t old2, int
         || old2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad argument");
 #define CALL_UPD(P, A_, MX) k_outprofile_update<P, A_, MX><<<(unsigned) ((c->L + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), old1, old2, newnode, nActiveOld)
-    prof_begin(c, CLS_PROFILE);
+    prof_begin(c, CLS_PROFILE, K_OUTPROFILE_UPDATE);
     VFT_DISPATCH(c, CALL_UPD);
     prof_end(c);
     CK(cudaGetLastError());
@@ -841,7 +1126,7 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
             k_average<P, A_, MX, false><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld); \
         }                                                                                                     \
     } while (0)
-    prof_begin(c, CLS_PROFILE);
+    prof_begin(c, CLS_PROFILE, K_AVERAGE);
     VFT_DISPATCH(c, CALL_AVG);
     prof_end(c);
     CK(cudaGetLastError());
@@ -916,23 +1201,29 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     const int G = pick_group(c, n);
     const int64_t warps = (n + G - 1) / G;
     const unsigned blocks = (unsigned) ((warps + 3) / 4);
-    void *r0 = c->h_out, *r1 = (char *) c->h_out + (size_t) n * 8;
+    rc = ensure_lists(c, n); if (rc) return rc;
+    void *r0 = c->d_out1, *r1 = c->d_out2;                    // device-side results; the kernel's last CTA copies them out
+    void *hr0 = c->h_out, *hr1 = (char *) c->h_out + (size_t) n * c->ps;
     const bool inlineItems = n <= INLINE_ITEMS;
     InlineItems inl;
     if (inlineItems) { std::memcpy(inl.a, ha, (size_t) n * 4); std::memcpy(inl.b, hb, (size_t) n * 4); }
-    const unsigned int seq = ++c->seq;
-#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : ha, inlineItems ? nullptr : hb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, c->h_flag, seq)
-    prof_begin(c, CLS_DIST);
+    const int32_t *qa = ha, *qb = hb;                         // mid-sized lists: read by the kernel from the mapped buffer
+    if (n > 4096) {                                           // big batches: one DMA into device staging
+        CK(cudaMemcpyAsync(c->d_pi, ha, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
+        qa = (const int32_t *) c->d_pi; qb = qa + n;
+    }
+#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hr0)
+    prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     VFT_DISPATCH(c, CALL_EVAL);
     prof_end(c);
     CK(cudaGetLastError());
     CK(sync_stream(c));
     c->cnt.launches++;
     c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += n * 2 * (int64_t) c->ps;
-    if (nOut) std::memcpy(outDist, r0, (size_t) nOut * c->ps);
+    if (nOut) std::memcpy(outDist, hr0, (size_t) nOut * c->ps);
     if (nPairs) {
-        std::memcpy(dist, (char *) r0 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
-        std::memcpy(weight, (char *) r1 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+        std::memcpy(dist, (char *) hr0 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+        std::memcpy(weight, (char *) hr1 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
     }
     return VFT_OK;
 }
@@ -953,11 +1244,12 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
     const int G = pick_group(c, n);
     const int64_t warps = (n + G - 1) / G;
-#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam, (P *) c->h_out)
-    prof_begin(c, CLS_DIST);
+#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam)
+    prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
     VFT_DISPATCH(c, CALL_ODA);
     prof_end(c);
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_out, c->outDist, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));   // one DMA instead of a PCIe write per lane
     CK(sync_stream(c));
     int64_t nAct = 0;
     for (int64_t i = 0; i < n; i++)
@@ -988,7 +1280,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     const int64_t warpsQ = (n + Gq - 1) / Gq;
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
 #define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-    prof_begin(c, CLS_DIST);
+    prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
     if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
     prof_end(c);
     CK(cudaGetLastError());
@@ -1003,7 +1295,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     int rc = ensure_pinned(c, (size_t) std::max<int64_t>(nRet, 1) * recSz); if (rc) return rc;
     if (nRet > 0) {
         const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12;
-        prof_begin(c, CLS_SELECT);
+        prof_begin(c, CLS_SELECT, K_SELECT);
         if (c->ps == 4) k_topk_select<float, 4><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
         else k_topk_select<double, 8><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->h_out);
         prof_end(c);
@@ -1026,6 +1318,101 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     c->cnt.profileOps += c->nActInternal;
     c->cnt.algoBytes += c->nActInternal * profile_bytes(c, c->N);
     c->cnt.algoBytes += profile_bytes(c, query);
+    return VFT_OK;
+}
+
+extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, int64_t m, int64_t nLists, const int64_t *iNode,
+                                 const int64_t *ownOffset, const int64_t *ownJ, const void *ownDist, int64_t nAvail,
+                                 const int64_t *allJ, const void *allDist, int64_t *outCount, int64_t *outJ, void *outDist) {
+    if (!c || !iNode || !ownOffset || !allJ || !allDist || !outCount || !outJ || !outDist || nLists < 0 || m < 1 || nAvail < 0 || nActive < 3)
+        return fail(VFT_EINVAL, "bad argument");
+    if (nLists == 0) return VFT_OK;
+    int64_t maxOwn = 0;
+    for (int64_t l = 0; l < nLists; l++) {
+        if (iNode[l] < 0 || iNode[l] >= c->maxnode || !c->activeHost[iNode[l]] || ownOffset[l + 1] < ownOffset[l]) return fail(VFT_EINVAL, "bad list");
+        maxOwn = std::max(maxOwn, ownOffset[l + 1] - ownOffset[l]);
+    }
+    const int64_t total = ownOffset[nLists], cap = maxOwn + nAvail;
+    if (total > 0 && (!ownJ || !ownDist)) return fail(VFT_EINVAL, "null argument");
+    int np2 = 32;
+    while (np2 < cap) np2 <<= 1;
+    if (np2 > MRG_MAX) return fail(VFT_EINVAL, "candidate lists longer than 4096 entries are not supported");
+    const size_t ps = c->ps;
+    // request: int32 iNode[nLists] | ownOffset[nLists+1] | ownJ[total] | allJ[nAvail] | (8-aligned) P ownDist[total] | allDist[nAvail]
+    const size_t nInts = (size_t) nLists + (size_t) nLists + 1 + (size_t) total + (size_t) nAvail;
+    const size_t offP = (nInts * 4 + 7) & ~(size_t) 7;
+    const size_t inBytes = offP + ((size_t) total + (size_t) nAvail) * ps;
+    // response: int32 count[nLists] | j[nLists*m] | (8-aligned) P dist[nLists*m]
+    const size_t offOD = (((size_t) nLists + (size_t) nLists * m) * 4 + 7) & ~(size_t) 7;
+    const size_t outBytes = offOD + (size_t) nLists * m * ps + 32;
+    int rc = ensure_pinned(c, std::max(inBytes, outBytes)); if (rc) return rc;
+    int32_t *hi = (int32_t *) c->h_in;
+    int32_t *hNode = hi, *hOff = hNode + nLists, *hOwnJ = hOff + nLists + 1, *hAllJ = hOwnJ + total;
+    for (int64_t l = 0; l < nLists; l++) hNode[l] = (int32_t) iNode[l];
+    for (int64_t l = 0; l <= nLists; l++) hOff[l] = (int32_t) ownOffset[l];
+    for (int64_t k = 0; k < total; k++) {
+        if (ownJ[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        hOwnJ[k] = ownJ[k] < 0 ? -1 : (int32_t) ownJ[k];
+    }
+    for (int64_t k = 0; k < nAvail; k++) {
+        if (allJ[k] < 0 || allJ[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        hAllJ[k] = (int32_t) allJ[k];
+    }
+    char *hP = (char *) c->h_in + offP;
+    std::memcpy(hP, ownDist ? ownDist : allDist, (size_t) total * ps);
+    std::memcpy(hP + (size_t) total * ps, allDist, (size_t) nAvail * ps);
+    // device scratch per slot: uJ, reqA, reqB (int32), uD, r0, r1 (P); + count[nLists]
+    const size_t slots = (size_t) nLists * cap;
+    const size_t need = slots * (12 + 3 * ps) + (size_t) nLists * 4 + 64;
+    if (need > c->mrgCap) {
+        mem_free(c->d_mrg);
+        c->d_mrg = nullptr; c->mrgCap = 0;
+        CK(mem_alloc((void **) &c->d_mrg, need * 2, MEM_DEVICE));
+        c->mrgCap = need * 2;
+    }
+    if (!c->d_acct) { CK(mem_alloc((void **) &c->d_acct, 32, MEM_DEVICE)); }
+    CK(cudaMemsetAsync(c->d_acct, 0, 32, c->stream));
+    char *dm = (char *) c->d_mrg;
+    void *uD = dm, *r0 = dm + slots * ps, *r1 = dm + 2 * slots * ps;                      // P arrays first (8-byte aligned)
+    int32_t *uJ = (int32_t *) (dm + 3 * slots * ps), *reqA = uJ + slots, *reqB = reqA + slots, *cnt = reqB + slots;
+    const size_t smemSort = (size_t) np2 * 12;
+    int32_t *hoCount = (int32_t *) c->h_out, *hoJ = hoCount + nLists;
+    void *hoD = (char *) c->h_out + offOD;
+    const int G = pick_group(c, (int64_t) slots);
+    const int64_t warps = ((int64_t) slots + G - 1) / G;
+    const unsigned evalBlocks = (unsigned) ((warps + 3) / 4);
+    InlineItems inl;
+    inl.a[0] = 0;
+#define CALL_MERGE(P, A_, MX)                                                                                     \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(k_merge_prep<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_MAX * 12);         \
+        cudaFuncSetAttribute(k_merge_finish<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_MAX * 12);       \
+        prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
+        k_merge_prep<P><<<(unsigned) nLists, MRG_T, smemSort, c->stream>>>(hNode, hOff, hOwnJ, (const P *) hP, (int) nAvail, hAllJ, \
+            (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ, (P *) uD, reqA, reqB, cnt, c->d_acct); \
+        prof_end(c);                                                                                              \
+        prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
+        k_eval<P, A_, MX><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA, reqB, (int64_t) slots, 0, G, 0, nActive, 0.0, (P *) r0, (P *) r1, c->d_doneCount, (P *) nullptr); \
+        prof_end(c);                                                                                              \
+        prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
+        k_merge_finish<P><<<(unsigned) nLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode, nActive, (int) m, (int) cap, np2, uJ, (P *) uD, reqA, (const P *) r0, cnt, hoCount, hoJ, (P *) hoD); \
+        prof_end(c);                                                                                              \
+    } while (0)
+    VFT_DISPATCH(c, CALL_MERGE);
+    CK(cudaGetLastError());
+    unsigned long long acct[4];
+    CK(cudaMemcpyAsync(acct, c->d_acct, 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(sync_stream(c));
+    c->cnt.launches += 3;
+    for (int64_t l = 0; l < nLists; l++) {
+        outCount[l] = hoCount[l];
+        for (int64_t k = 0; k < hoCount[l]; k++) outJ[l * m + k] = hoJ[l * m + k];
+        std::memcpy((char *) outDist + (size_t) l * m * ps, (char *) hoD + (size_t) l * m * ps, (size_t) hoCount[l] * ps);
+        c->cnt.algoBytes += profile_bytes(c, iNode[l]);                                  // a list shares its query
+    }
+    c->cnt.seqOps += (int64_t) acct[0]; c->cnt.profileOps += (int64_t) acct[1];
+    c->cnt.algoBytes += (int64_t) acct[2] * c->L + (int64_t) acct[3] * profile_bytes(c, c->N);
+    c->cnt.h2dBytes += (int64_t) inBytes; c->cnt.d2hBytes += (int64_t) outBytes;
     return VFT_OK;
 }
 
@@ -1104,7 +1491,7 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pair_loglk<P, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         k_pair_loglk<P, A_><<<blocks, 128, smem, c->stream>>>(make_store<P>(c), make_model<P>(c), ha, hb, hl, n, outLk, outSite); \
     } while (0)
-    prof_begin(c, CLS_DIST);
+    prof_begin(c, CLS_DIST, K_LOGLK);
     if (c->cfg.precision == 32) { if (c->A == 4) CALL_LK(float, 4); else CALL_LK(float, 20); }
     else { if (c->A == 4) CALL_LK(double, 4); else CALL_LK(double, 20); }
     prof_end(c);
@@ -1123,7 +1510,7 @@ extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, in
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     const unsigned blocks = (unsigned) ((c->Lp + 127) / 128);
 #define CALL_POST(P, A_) k_posterior<P, A_><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), make_model<P>(c), out_id, id1, id2, len1, len2)
-    prof_begin(c, CLS_PROFILE);
+    prof_begin(c, CLS_PROFILE, K_POSTERIOR);
     if (c->cfg.precision == 32) { if (c->A == 4) CALL_POST(float, 4); else CALL_POST(float, 20); }
     else { if (c->A == 4) CALL_POST(double, 4); else CALL_POST(double, 20); }
     prof_end(c);

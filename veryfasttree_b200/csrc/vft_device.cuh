@@ -636,12 +636,12 @@ __device__ __forceinline__ P out_distance_finish(const Store<P> &s, int64_t iNod
 
 // orderable keys: ascending unsigned order == ascending floating order
 __device__ __forceinline__ uint64_t order_key(float x) {
-    uint32_t u = __float_as_uint(x);
+    uint32_t u = __float_as_uint(__fadd_rn(x, 0.0f));          // -0.0 -> +0.0: the reference compares values, not bits
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     return (uint64_t) u;
 }
 __device__ __forceinline__ uint64_t order_key(double x) {
-    uint64_t u = (uint64_t) __double_as_longlong(x);
+    uint64_t u = (uint64_t) __double_as_longlong(__dadd_rn(x, 0.0));
     return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
 }
 
