@@ -131,7 +131,8 @@ def flatten(o, pfx=""):
 
 
 @pytest.mark.parametrize("prec", [32, 64])
-@pytest.mark.parametrize("kind,n,L,joins", [("nt", 700, 333, 300), ("aa", 400, 207, 150), ("nt", 5000, 200, 600)])
+@pytest.mark.parametrize("kind,n,L,joins", [("nt", 700, 333, 300), ("aa", 400, 207, 150), ("nt", 5000, 200, 600),
+                                            ("aa", 300, 610, 120), ("nt", 400, 1100, 150)])   # long rows: the CTA-per-pair kernel
 def test_cuda_bit_exact_vs_oracle(glib, olib, kind, n, L, joins, prec):
     chars = synth.make_alignment(n, L, kind, seed=100 + n)
     chars[::17, ::5] = ord("-")           # ragged gaps, also in nt

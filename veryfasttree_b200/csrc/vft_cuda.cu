@@ -179,6 +179,51 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
     if (threadIdx.x == 0) *doneCount = 0;
 }
 
+// The same request list, ONE CTA PER ITEM (the per-join lists of long alignments: a few hundred pairs of
+// ~100 KB each cannot fill the machine with one warp per pair, and one warp walking 40+ chunks is latency
+// bound).  The CTA's warps split the chunks of the pair, write the per-position terms into one full-length
+// row in shared memory, and one lane adds the row in position order.  Leaf x leaf pairs take the same
+// path: with unit weights profileDist's terms ARE seqDist's (NJ.tcc:1601-1624), only the no-overlap
+// weight differs (0 instead of 0.01).
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(256)
+k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
+            int64_t n, int64_t nOutItems, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
+            unsigned int *__restrict__ doneCount, P *__restrict__ hostOut) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int64_t item = blockIdx.x;
+    const int64_t a = ia ? ia[item] : inl.a[item], b = ib ? ib[item] : inl.b[item];
+    if (a >= 0) {
+        const bool isOut = item < nOutItems;
+        const bool isSeq = !isOut && !raw && a < s.nSeqs && b < s.nSeqs;
+        double den, top;
+        group_profile_dist<P, A, MATRIX, true>(s, a, isOut ? (int64_t) -1 : b, 1u, 1, smemRaw, den, top, (int) (threadIdx.x >> 5),
+                                               (int) (blockDim.x >> 5));
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            cta_ordered_sum<P, A, MATRIX>(s, smemRaw, den, top);
+            if (threadIdx.x == 0) {
+                P dd, ww, d, w = 0;
+                finish_dist<P>(den, top, dd, ww);
+                if (isOut) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
+                else if (isSeq) { d = (P) xadd((double) dd, 0.0); w = den > 0 ? ww : (P) 0; }     // :1621-1622, :1122
+                else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
+                r0[item] = d; r1[item] = w;
+            }
+        }
+    }
+    if (hostOut == nullptr) return;
+    __shared__ bool amLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) amLast = atomicAdd(doneCount, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) { hostOut[k] = __ldcg(r0 + k); hostOut[n + k] = __ldcg(r1 + k); }
+    if (threadIdx.x == 0) *doneCount = 0;
+}
+
 // setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
@@ -510,16 +555,17 @@ k_merge_finish(Store<P> s, const int32_t *__restrict__ iNode, int64_t nActive, i
 // positions in parallel, then thread 0 adds the per-position self-distance terms in order.
 template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
-k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld) {
+k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
+          double *__restrict__ gTerms, unsigned int *__restrict__ doneCount) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double *termW = reinterpret_cast<double *>(smem);            // [Lp] w*w
-    double *termT = termW + s.Lp;                                // [Lp] w*w*piece
+    double *termW = gTerms;                                      // [Lp] w*w          (global: the CTAs split the positions)
+    double *termT = gTerms + s.Lp;                               // [Lp] w*w*piece
     const View<P, A> p1 = make_view<P, A>(s, id1), p2 = make_view<P, A>(s, id2);
     const int64_t row = oid - s.nSeqs;
     uint8_t *oc = s.codes + oid * s.Lp;
     P *ow = s.weights + row * s.Lp;
     P *ov = s.vecs + row * s.Lp * A;
-    for (int64_t pos = threadIdx.x; pos < s.Lp; pos += blockDim.x) {
+    for (int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; pos < s.Lp; pos += (int64_t) gridDim.x * blockDim.x) {
         double tw = 0, tt = 0;
         if (pos < s.L) {
             const uint32_t c1 = p1.codes[pos], c2 = p2.codes[pos];
@@ -579,8 +625,19 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
         }
         termW[pos] = tw; termT[pos] = tt;
     }
+    // the last CTA to finish adds the self-distance terms in position order
+    __shared__ bool amLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) amLast = atomicAdd(doneCount, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    double *sT = reinterpret_cast<double *>(smem);               // [2*Lp] staged copy of both term arrays
+    for (int64_t k = threadIdx.x; k < 2 * s.Lp; k += blockDim.x) sT[k] = __ldcg(gTerms + k);
     __syncthreads();
     if (threadIdx.x == 0) {
+        *doneCount = 0;
         // ordered sums over the positions (skipped positions hold +0.0, which is exact to add): 8 terms of each
         // chain are fetched ahead of the 16 dependent additions
         double top = 0, denom = 0;
@@ -588,7 +645,7 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
             double w8[8], t8[8];
 #pragma unroll
             for (int k = 0; k < 8; k += 2) {
-                const double2 a = *reinterpret_cast<const double2 *>(termW + pos + k), b = *reinterpret_cast<const double2 *>(termT + pos + k);
+                const double2 a = *reinterpret_cast<const double2 *>(sT + pos + k), b = *reinterpret_cast<const double2 *>(sT + s.Lp + pos + k);
                 w8[k] = a.x; w8[k + 1] = a.y; t8[k] = b.x; t8[k + 1] = b.y;
             }
 #pragma unroll
@@ -832,7 +889,9 @@ struct vft_ctx {
     void *d_out1, *d_out2;
     int64_t listCap;
     // vft_tophits_merge scratch
+    double *d_terms;                           // [2*Lp] self-distance terms of k_average
     void *d_mrg; size_t mrgCap;
+    bool wideOk;
     unsigned long long *d_acct;
     // pinned host
     void *h_in, *h_out;
@@ -992,6 +1051,7 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
     c->hasTransmat = false; c->hasRates = false;
     CK(mem_alloc((void **) &c->d_doneCount, 4, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_terms, 2 * Lp * 8, MEM_DEVICE));
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
     { void *f = nullptr; CK(mem_alloc(&f, 64, MEM_PINNED)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
     c->seq = 0;
@@ -1007,6 +1067,9 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
         cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
         cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
         VFT_DISPATCH(c, SET_SMEM);
+#define SET_SMEM_WIDE(P, A_, MX) do { const size_t w = wide_smem_bytes<P, A_, MX>(c->Lp); c->wideOk = w <= 200 * 1024; \
+        if (c->wideOk && w > 48 * 1024) cudaFuncSetAttribute(k_eval_wide<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) w); } while (0)
+        VFT_DISPATCH(c, SET_SMEM_WIDE);
     }
     cudaFuncSetAttribute(k_topk_select<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     cudaFuncSetAttribute(k_topk_select<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
@@ -1023,7 +1086,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
                     c->d_tvA, c->d_tvB, c->d_rec, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
     mem_free(c->h_in); mem_free(c->h_out); mem_free((void *) c->h_flag);
-    mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct);
+    mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
     cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
@@ -1115,15 +1178,18 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
     if (update && nActiveOld < 2) return fail(VFT_EINVAL, "bad nActiveOld");
     if (bionjWeight < 0) bionjWeight = 0.5;
     const size_t smem = (size_t) c->Lp * 16;
-    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the single-CTA average kernel");
+    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the average kernel's term buffer");
+    // short alignments: one CTA (no cross-CTA hand-off); long ones: 64 positions per CTA, the last CTA adds the terms
+    const int AVG_T = c->Lp <= 512 ? 256 : 64;
+    const unsigned avgBlocks = c->Lp <= 512 ? 1u : (unsigned) ((c->Lp + AVG_T - 1) / AVG_T);
 #define CALL_AVG(P, A_, MX)                                                                                   \
     do {                                                                                                      \
         if (update) {                                                                                         \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, true><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld); \
+            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount); \
         } else {                                                                                              \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, false><<<1, 256, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld); \
+            k_average<P, A_, MX, false><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount); \
         }                                                                                                     \
     } while (0)
     prof_begin(c, CLS_PROFILE, K_AVERAGE);
@@ -1213,8 +1279,12 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         qa = (const int32_t *) c->d_pi; qb = qa + n;
     }
 #define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hr0)
+    // long alignments, lists that cannot fill the machine with a warp per pair: a CTA per pair
+    const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
+    const int wideThreads = n <= 160 ? 256 : 128;
+#define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hr0)
     prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
-    VFT_DISPATCH(c, CALL_EVAL);
+    if (wide) { VFT_DISPATCH(c, CALL_EVAL_WIDE); } else { VFT_DISPATCH(c, CALL_EVAL); }
     prof_end(c);
     CK(cudaGetLastError());
     CK(sync_stream(c));

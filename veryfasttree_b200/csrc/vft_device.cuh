@@ -380,9 +380,13 @@ __device__ __forceinline__ void load_vec(const P *__restrict__ src, P *v) {
     }
 }
 
-template<typename P, int A, bool MATRIX>
+// WIDE variant (one pair per CTA, the mid-sized lists of long alignments): the calling warp evaluates the chunks
+// chunk0, chunk0+chunkStep, ... of ONE pair into a full-length term row (T, W: [Lp rounded up to C] each) and does
+// not accumulate; the caller adds the row in order once every warp of the CTA is done (cta_ordered_sum).
+template<typename P, int A, bool MATRIX, bool WIDE = false>
 __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t myA, int64_t myB, unsigned mask, int rows,
-                                                   unsigned char *smw, double &denomOut, double &topOut) {
+                                                   unsigned char *smw, double &denomOut, double &topOut,
+                                                   int chunk0 = 0, int chunkStep = 1) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     constexpr int PPL = TileShape<A, MATRIX>::PPL, C = TileShape<A, MATRIX>::C;
@@ -390,8 +394,9 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
     constexpr bool VCOND = MATRIX;                     // matrix mode: vectors (or codeFreq rows / table entries) are fetched once codes and weights are known
     constexpr int TS = C + 2;                          // row strides: 16-byte aligned rows, conflict-free 128-bit row reads
     constexpr int WS = sizeof(P) == 4 ? C + 4 : C + 2;
-    double *T = reinterpret_cast<double *>(smw);       // [rows][TS]
-    P *W = reinterpret_cast<P *>(smw + (size_t) rows * TS * 8);   // [rows][WS]; w1*w2 is a P product: exact in P
+    const int nChunksAll = (int) ((s.Lp + C - 1) / C);
+    double *T = reinterpret_cast<double *>(smw);       // [rows][TS]  (WIDE: [nChunksAll*C])
+    P *W = reinterpret_cast<P *>(smw + (WIDE ? (size_t) nChunksAll * C * 8 : (size_t) rows * TS * 8));   // [rows][WS]; w1*w2 is a P product: exact in P
     const int nItems = __popc(mask);                   // <= rows <= R (caller's contract)
     denomOut = 0; topOut = 0;
     if (nItems == 0) return;
@@ -399,7 +404,7 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
     const int srcLane = lane < nItems ? __fns(mask, 0, lane + 1) : 0;
     const int rowA = (int) __shfl_sync(full, myA, srcLane), rowB = (int) __shfl_sync(full, myB, srcLane);
     const uint32_t Lp = (uint32_t) s.Lp, nSeqs = (uint32_t) s.nSeqs;
-    const int nChunks = (int) ((Lp + C - 1) / C);
+    const int nChunks = WIDE ? (nChunksAll - chunk0 + chunkStep - 1) / chunkStep : nChunksAll;   // chunks this warp evaluates
     P eig[MATRIX ? A : 1];
     if constexpr (MATRIX) {
 #pragma unroll
@@ -428,7 +433,7 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
         Unit u;
         u.k = k; u.c = c;
         u.na = __shfl_sync(full, rowA, k); u.nb = __shfl_sync(full, rowB, k);
-        u.pos = (uint32_t) c * C + lane * PPL;
+        u.pos = (uint32_t) (WIDE ? chunk0 + c * chunkStep : c) * C + lane * PPL;
         u.in = u.pos < Lp;                             // Lp is a multiple of 32 >= PPL: a lane's PPL positions are all in or all out
         return u;
     };
@@ -540,8 +545,8 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
             }
             tt[i] = on ? xmul((double) wt[i], pc) : 0.0;
         }
-        double *tr = T + u.k * TS + lane * PPL;
-        P *wr = W + u.k * WS + lane * PPL;
+        double *tr = WIDE ? T + u.pos : T + u.k * TS + lane * PPL;
+        P *wr = WIDE ? W + u.pos : W + u.k * WS + lane * PPL;
         if constexpr (PPL == 4) {
             *reinterpret_cast<double2 *>(tr) = make_double2(tt[0], tt[1]);
             *reinterpret_cast<double2 *>(tr + 2) = make_double2(tt[2], tt[3]);
@@ -552,7 +557,7 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
             for (int i = 0; i < PPL; i++) { tr[i] = tt[i]; wr[i] = wt[i]; }
         }
         // end of a chunk: every row holds its C terms -> ordered accumulation, one lane per pair
-        if (u.k + 1 == nItems) {
+        if (!WIDE && u.k + 1 == nItems) {
             __syncwarp();
             if (lane < nItems) {
                 const double *trow = T + lane * TS;
@@ -573,6 +578,7 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
     };
 
     const int U = nChunks * nItems;
+    if (U <= 0) return;
     // Two register buffers (X, Y) alternate between "being computed" and "being loaded": the loop is
     // unrolled by two so that no buffer is ever copied.  Matrix mode adds a second, earlier stage for the
     // codes + weights (a few registers, rotated).
@@ -601,10 +607,40 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
         if constexpr (VCOND) { uY = uZ; cwY = cwZ; }
         else if (u + 3 < U) { uY = nextUnit(uX); loadA(uY, cwY, qY); }
     }
+    if (WIDE) return;
     // hand each item's sums back to the lane that owns it
     const int rank = __popc(mask & ((1u << lane) - 1u));
     denomOut = __shfl_sync(full, den, rank);
     topOut = __shfl_sync(full, top, rank);
+}
+
+// shared memory of the WIDE variant: one full-length term row per CTA
+template<typename P, int A, bool MATRIX>
+__host__ __device__ inline size_t wide_smem_bytes(int64_t Lp) {
+    constexpr int C = TileShape<A, MATRIX>::C;
+    const size_t cols = (size_t) ((Lp + C - 1) / C) * C;
+    return cols * (8 + sizeof(P));
+}
+
+// the ordered accumulation of a full-length term row by ONE lane (call with a full warp; lane 0 returns the sums)
+template<typename P, int A, bool MATRIX>
+__device__ __forceinline__ void cta_ordered_sum(const Store<P> &s, const unsigned char *smw, double &denomOut, double &topOut) {
+    constexpr int C = TileShape<A, MATRIX>::C;
+    const int cols = (int) ((s.Lp + C - 1) / C) * C;
+    const double *T = reinterpret_cast<const double *>(smw);
+    const P *W = reinterpret_cast<const P *>(smw + (size_t) cols * 8);
+    double den = 0, top = 0;
+    if ((threadIdx.x & 31) == 0) {
+        for (int j = 0; j < cols; j += 8) {
+            double t8[8]; P w8[8];
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) { const double2 t = *reinterpret_cast<const double2 *>(T + j + q); t8[q] = t.x; t8[q + 1] = t.y; }
+            load_vec<P, 8>(W + j, w8);
+#pragma unroll
+            for (int q = 0; q < 8; q++) { den = xadd(den, (double) w8[q]); top = xadd(top, t8[q]); }
+        }
+    }
+    denomOut = den; topOut = top;
 }
 
 // profileDist's tail, NJ.tcc:1187-1188
