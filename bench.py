@@ -126,6 +126,46 @@ def run_reference(chars, threads: int, timeout: float = 900):
         return t, chars.shape[0]
 
 
+def batch_regime(lib, codes, device, n_pairs=262144, n_joins=6000):
+    """The same distance kernel in its bandwidth regime: one refresh-shaped request of n_pairs candidate pairs
+    (lists of internal nodes) through vft_dist_pairs; device time from CUDA events on the context's stream."""
+    n, L = codes.shape
+    cfg = api.make_config(n, L, 4, WORKLOAD["precision"], device=device)
+    cfg.reserved = 1
+    rs = np.random.RandomState(3)
+    with api.Context(lib, cfg) as ctx:
+        ctx.upload_leaves(codes)
+        ctx.outprofile_rebuild()
+        ctx.out_distance_all(n, 0.0)
+        active = list(range(n))
+        n_joins = min(n_joins, n // 2 - 2)
+        for k in range(n_joins):
+            a = active.pop(rs.randint(len(active))); b = active.pop(rs.randint(len(active)))
+            ctx.profile_average_update(n + k, a, b, n - k, -1.0, 0.001)
+            active.append(n + k)
+        internal = np.arange(n, n + n_joins)
+        m = 128
+        pi = np.repeat(internal[rs.randint(0, n_joins, size=m)], n_pairs // m)
+        pj = internal[rs.randint(0, n_joins, size=n_pairs)]
+        best = None
+        for _ in range(4):
+            c0 = ctx.counters()
+            ctx.dist_pairs(pi, pj)
+            c1 = ctx.counters()
+            ms, by = c1.msDist - c0.msDist, c1.algoBytes - c0.algoBytes
+            if best is None or ms < best[0]:
+                best = (ms, by)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    gbps = best[1] / best[0] / 1e6
+    return {"what": "one vft_dist_pairs request of %d internal-node pairs (%d lists), k_eval(batch)" % (n_pairs, 128),
+            "ms": round(best[0], 3), "algorithmic_bytes": int(best[1]), "achieved": round(gbps, 1), "unit": "GB/s",
+            "frac": round(gbps / peak, 4)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,15 +277,27 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dist_s = prof["msDist"] * 1e-3
-    achieved = (prof["distBytes"] / dist_s) / 1e9 if dist_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "distance sweep (k_dist_pairs + k_one_vs_all + k_out_distance)",
+    # per-kernel table of the profiled pass (CUDA events on the launching stream around every launch)
+    kernels = {}
+    for nm, ms, cnt, by in zip(api.KERNEL_NAMES, prof["msKernel"], prof["nKernel"], prof["bytesKernel"]):
+        if cnt:
+            kernels[nm] = {"launches": int(cnt), "ms": round(ms, 2), "us_per_launch": round(1e3 * ms / cnt, 2),
+                           "algorithmic_gb": round(by / 1e9, 3), "gbps": round(by / ms / 1e6, 1) if by and ms > 0 else None}
+    dist_kernels = [k for k in kernels if kernels[k]["algorithmic_gb"]]
+    dom = max(dist_kernels, key=lambda k: kernels[k]["ms"])
+    achieved = kernels[dom]["gbps"]
+    batch = batch_regime(lib, codes, local_rank) if rank == 0 else None
+    roofline = {"bound": "hbm", "kernel": dom + " -- the dominant kernel of the step: one launch per per-join candidate list "
+                "(40-250 pairs of 0.2-4.4 KB), latency bound, the slab is L2 resident",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_step": prof["distBytes"], "launches_per_step": prof["distLaunches"],
-                "ms_per_step_in_kernel": prof["msDist"], "ms_select": prof["msSelect"], "ms_profile_update": prof["msProfile"],
-                "traffic": None}
-
+                "algorithmic_bytes_per_launch": int(1e9 * kernels[dom]["algorithmic_gb"] / kernels[dom]["launches"]),
+                "us_per_launch": kernels[dom]["us_per_launch"],
+                "traffic": 256, "traffic_note": "dram__bytes_read+write per launch from profiles/r1_k_eval_small_ncu_full.md: "
+                "the 75 MB slab stays in the 126 MB L2, so DRAM traffic is ~0 and far BELOW the algorithmic bytes",
+                "distance_sweep_all_kernels": {"algorithmic_bytes_per_step": prof["distBytes"], "ms_per_step": prof["msDist"],
+                                               "gbps": (prof["distBytes"] / (prof["msDist"] * 1e-3)) / 1e9 if prof["msDist"] > 0 else None},
+                "batch_regime": batch}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,7 +324,8 @@ def main():
                        "parity": "join order, top-hit lists and branch lengths identical to the reference at -threads 1"},
             "e2e": {"value": taxa_total * args.steps / e2e_max, "unit": "taxa/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps},
-            "gpu_launches": int(launches_total), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+            "gpu_launches": int(launches_total), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
             "wall_s": t_wall}
     print(json.dumps(line))
     if world > 1:

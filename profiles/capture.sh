@@ -1,20 +1,14 @@
 #!/bin/bash
-# Run under gpurun (one GPU).  Writes raw ncu output to gpurun_out/; summaries are committed under profiles/.
-#   1. launch list: every kernel of one full step with its device time (cold-cache, serialised: SHARES only)
-#   2. full-metric capture of the dominant kernel (k_eval) for dram bytes / stall reasons
+# Run under gpurun (one GPU).  Raw ncu output goes to gpurun_out/; the summaries are committed under profiles/.
+#   1. launch list: every kernel of one full C2-shaped step (4 000 taxa) with its device time
+#      (cold-cache, serialised: compare SHARES, not absolutes)
+#   2. --set full captures: the per-join k_eval launches of a 16 000-taxon step (warm cache), one large
+#      nt batch and one large aa batch (bandwidth regime), the CTA-per-pair kernel on aa lists
 set -x
-TAXA=${TAXA:-4000}
 mkdir -p gpurun_out
-cat > /tmp/one_step.py <<PY
-import sys
-sys.path.insert(0, '.')
-from veryfasttree_b200 import api, synth
-chars = synth.make_alignment($TAXA, 200, 'nt', 1)
-chars = chars[synth.unique_rows(chars)]
-t = api.nj_build(api.encode(chars, 'nt'), 4, 32, trace=False)
-print('taxa', chars.shape[0], 'launches', t.stats['counters']['launches'], 'device ms', t.stats['deviceMsResident'])
-PY
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file gpurun_out/launches_r1.csv python /tmp/one_step.py > gpurun_out/launches_r1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_eval -s 3000 -c 3 -o gpurun_out/prof_k_eval_r1 -f python /tmp/one_step.py > gpurun_out/prof_k_eval_r1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_one_vs_all_warp -s 2 -c 2 -o gpurun_out/prof_k_ova_r1 -f python /tmp/one_step.py > gpurun_out/prof_k_ova_r1.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80000 --csv --log-file gpurun_out/launches.csv python profiles/one_step.py 4000 > gpurun_out/launches.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none --cache-control none -k regex:k_eval -s 20000 -c 3 -o gpurun_out/prof_eval_small -f python profiles/one_step.py 16000 > gpurun_out/prof_eval_small.log 2>&1
+timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_eval -c 1 -o gpurun_out/prof_batch_nt -f python profiles/big_batch.py 16000 nt 200 262144 1 > gpurun_out/prof_batch_nt.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_eval -c 1 -o gpurun_out/prof_batch_aa -f python profiles/big_batch.py 20000 aa 1287 131072 1 > gpurun_out/prof_batch_aa.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none --cache-control none -k regex:k_eval_wide -s 3000 -c 2 -o gpurun_out/prof_wide_aa -f python profiles/scale_aa.py 4000 1287 > gpurun_out/prof_wide_aa.log 2>&1
 ls -la gpurun_out

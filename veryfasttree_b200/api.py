@@ -32,7 +32,7 @@ class VftCounters(C.Structure):
                 ("profileAvgOps", C.c_int64), ("launches", C.c_int64), ("algoBytes", C.c_int64),
                 ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64), ("msDist", C.c_double), ("msSelect", C.c_double),
                 ("msProfile", C.c_double), ("distLaunches", C.c_int64), ("distBytes", C.c_int64),
-                ("msKernel", C.c_double * 12), ("nKernel", C.c_int64 * 12)]
+                ("msKernel", C.c_double * 12), ("nKernel", C.c_int64 * 12), ("bytesKernel", C.c_int64 * 12)]
 
 
 KERNEL_NAMES = ["k_eval(list<=384)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
@@ -372,7 +372,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
     lib.check(rc, "vft_nj_build")
     stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:25]}
     stats["secondsHost"] = [float(x) for x in res.secondsHost]
-    stats.update({"counters": {k: (list(getattr(res.counters, k)) if k in ("msKernel", "nKernel") else getattr(res.counters, k))
+    stats.update({"counters": {k: (list(getattr(res.counters, k)) if k in ("msKernel", "nKernel", "bytesKernel") else getattr(res.counters, k))
                                for k, _ in VftCounters._fields_}})
     return NJTree(n, precision, parent, n_child, child, bl, res.root, res.maxnode, res.m,
                   joins, lth, stats)

@@ -920,6 +920,12 @@ enum { CLS_DIST = 0, CLS_SELECT = 1, CLS_PROFILE = 2 };
 // finer split of the same timings: index into vft_counters.msKernel / nKernel (names: VFT_KERNEL_NAMES in the header)
 enum { K_EVAL_SMALL = 0, K_EVAL_LARGE, K_ONE_VS_ALL, K_OUT_DIST_ALL, K_SELECT, K_MERGE, K_AVERAGE, K_OUTPROFILE_UPDATE, K_REBUILD, K_LOGLK, K_POSTERIOR };
 
+// attributes the algorithmic bytes accounted inside a scope to one kernel (vft_counters.bytesKernel)
+struct BytesScope {
+    vft_ctx *c; int kid; int64_t b0;
+    BytesScope(vft_ctx *c, int kid);
+    ~BytesScope();
+};
 static void prof_begin(vft_ctx *c, int cls, int kid) {
     if (!c->profile) return;
     vft_ctx::Pending p;
@@ -954,6 +960,9 @@ static cudaError_t sync_stream(vft_ctx *c) {
     if (e == cudaSuccess) prof_resolve(c);
     return e;
 }
+
+BytesScope::BytesScope(vft_ctx *c, int kid) : c(c), kid(kid), b0(c->cnt.algoBytes) {}
+BytesScope::~BytesScope() { c->cnt.bytesKernel[kid] += c->cnt.algoBytes - b0; }
 
 template<typename P>
 static Store<P> make_store(vft_ctx *c) {
@@ -1247,6 +1256,7 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         return fail(VFT_EINVAL, "null argument");
     const int64_t n = nOut + nPairs;
     if (n == 0) return VFT_OK;
+    BytesScope bytesScope(c, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     int rc = ensure_pinned(c, (size_t) n * 16); if (rc) return rc;
     int32_t *ha = (int32_t *) c->h_in, *hb = ha + n;
     const bool raw = (flags & VFT_PAIRS_PROFILE_RAW) != 0;
@@ -1311,6 +1321,7 @@ extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, 
 extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam, void *outDist, int64_t maxnode) {
     if (!c || !outDist || maxnode < c->maxnode) return fail(VFT_EINVAL, "bad argument");
     const int64_t n = c->maxnode;
+    BytesScope bytesScope(c, K_OUT_DIST_ALL);
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
     const int G = pick_group(c, n);
     const int64_t warps = (n + G - 1) / G;
@@ -1344,6 +1355,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     if (!c || !j_out || !dist || !weight || !criterion || !nOut) return fail(VFT_EINVAL, "null argument");
     if (query < 0 || query >= c->maxnode || !c->activeHost[query]) return fail(VFT_EINVAL, "query must be an active node");
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
+    BytesScope bytesScope(c, K_ONE_VS_ALL);
     const int64_t n = c->maxnode;
     if (K > SEL_MAXK) return fail(VFT_EINVAL, "K larger than 4096 is not supported");
     const int Gq = pick_group(c, n);
@@ -1397,6 +1409,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
     if (!c || !iNode || !ownOffset || !allJ || !allDist || !outCount || !outJ || !outDist || nLists < 0 || m < 1 || nAvail < 0 || nActive < 3)
         return fail(VFT_EINVAL, "bad argument");
     if (nLists == 0) return VFT_OK;
+    BytesScope bytesScope(c, K_EVAL_LARGE);
     int64_t maxOwn = 0;
     for (int64_t l = 0; l < nLists; l++) {
         if (iNode[l] < 0 || iNode[l] >= c->maxnode || !c->activeHost[iNode[l]] || ownOffset[l + 1] < ownOffset[l]) return fail(VFT_EINVAL, "bad list");
@@ -1542,6 +1555,7 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     if (n == 0) return VFT_OK;
+    BytesScope bytesScope(c, K_LOGLK);
     const size_t need = (size_t) n * 24 + (siteLk ? (size_t) n * c->L * 8 : 0);
     int rc = ensure_pinned(c, need); if (rc) return rc;
     int32_t *ha = (int32_t *) c->h_in, *hb = ha + n;
