@@ -1284,19 +1284,25 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     InlineItems inl;
     if (inlineItems) { std::memcpy(inl.a, ha, (size_t) n * 4); std::memcpy(inl.b, hb, (size_t) n * 4); }
     const int32_t *qa = ha, *qb = hb;                         // mid-sized lists: read by the kernel from the mapped buffer
-    if (n > 4096) {                                           // big batches: one DMA into device staging
+    const bool dma = n > 4096;                                // big batches: requests and results travel by DMA
+    if (dma) {
         CK(cudaMemcpyAsync(c->d_pi, ha, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream));
         qa = (const int32_t *) c->d_pi; qb = qa + n;
     }
-#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hr0)
+    void *hostOut = dma ? nullptr : hr0;
+#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut)
     // long alignments, lists that cannot fill the machine with a warp per pair: a CTA per pair
     const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
     const int wideThreads = n <= 160 ? 256 : 128;
-#define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hr0)
+#define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut)
     prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     if (wide) { VFT_DISPATCH(c, CALL_EVAL_WIDE); } else { VFT_DISPATCH(c, CALL_EVAL); }
     prof_end(c);
     CK(cudaGetLastError());
+    if (dma) {
+        CK(cudaMemcpyAsync(hr0, r0, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(hr1, r1, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(sync_stream(c));
     c->cnt.launches++;
     c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += n * 2 * (int64_t) c->ps;
