@@ -172,6 +172,28 @@ public:
         check(vft_dist_one_vs_all(ctx.get(), query, nActive, K, j, dist, weight, criterion, &n));
         return n;
     }
+    // the m list merges of a top-hits refresh, NJ.tcc:4477-4515 (own lists with their active ancestors resolved)
+    void topHitsMerge(int64_t newnode, int64_t nActive, int64_t m, int64_t nLists, const int64_t *iNode, const int64_t *ownOffset,
+                      const int64_t *ownJ, const numeric_t *ownDist, int64_t nAvail, const int64_t *allJ, const numeric_t *allDist,
+                      int64_t *outCount, int64_t *outJ, numeric_t *outDist) {
+        check(vft_tophits_merge(ctx.get(), newnode, nActive, m, nLists, iNode, ownOffset, ownJ, ownDist, nAvail, allJ, allDist, outCount,
+                                outJ, outDist));
+    }
+    // likelihood phase: TransitionMatrix tables + Rates, pairLogLk (NJ.tcc:1192), posteriorProfile (NJ.tcc:2137)
+    void uploadTransmat(const numeric_t *codeFreq, const numeric_t *eigenval, const numeric_t *eigeninv, const numeric_t *eigeninvT,
+                        const numeric_t *statinv) {
+        check(vft_upload_transmat(ctx.get(), codeFreq, eigenval, eigeninv, eigeninvT, statinv));
+    }
+    void syncRates(const numeric_t *rates, int64_t nRateCats, const int64_t *ratecat, double MLMinRelBranchLength,
+                   double MLMinBranchLength, int fastexpLevel) {
+        check(vft_sync_rates(ctx.get(), rates, nRateCats, ratecat, MLMinRelBranchLength, MLMinBranchLength, fastexpLevel));
+    }
+    void pairLogLkBatch(const int64_t *i, const int64_t *j, const double *length, int64_t n, double *loglk, double *siteLk = nullptr) {
+        check(vft_pair_loglk_batch(ctx.get(), i, j, length, n, loglk, siteLk));
+    }
+    void posteriorProfile(int64_t out, int64_t id1, int64_t id2, double len1, double len2) {
+        check(vft_posterior_profile(ctx.get(), out, id1, id2, len1, len2));
+    }
 
 private:
     std::shared_ptr<vft_ctx> ctx;        // copies of the policy object share one device context
