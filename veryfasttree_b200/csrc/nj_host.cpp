@@ -188,7 +188,9 @@ private:
     std::vector<int64_t> wantIds;
     std::vector<P> wantVals;
 
-    void newEpoch(int64_t nActive) { epoch++; epochActive = nActive; pairCache.clear(); }
+    int64_t hintGen = 0;             // generation of the pair cache: a list is hinted at most once per generation
+    void clearPairs() { pairCache.clear(); hintGen++; }
+    void newEpoch(int64_t nActive) { epoch++; epochActive = nActive; clearPairs(); }
 
     bool stale(int64_t i, int64_t nActive) const {       // trigger of NJ.tcc:1092-1098
         int64_t nDiffAllow = opt.tophitsMult > 0 ? (int64_t) (nActive * opt.staleOutLimit) : 0;
@@ -339,8 +341,8 @@ private:
     void hintList(int64_t nActive, int64_t iNode) {
         HPROF(13, "hintList");
         if (iNode < 0 || parent[iNode] >= 0) return;
-        if (hintedEpoch[iNode] == epoch) return;         // already queued in this epoch (lists do not change within one)
-        hintedEpoch[iNode] = epoch;
+        if (hintedEpoch[iNode] == hintGen) return;       // already queued since the pair cache was last cleared
+        hintedEpoch[iNode] = hintGen;
         wantOut(iNode, nActive, /*evenIfNotStale*/true);
         for (const Hit &h : topHitsLists[iNode].hits) {
             int64_t j = activeAncestor(h.j);
@@ -387,6 +389,7 @@ private:
     void updateTopVisible(int64_t nActive, int64_t iIn, const Hit &hit);
     void updateVisible(int64_t nActive, std::vector<Besthit> &tophitsNode);
     void topHitNJSearch(int64_t nActive, Besthit &join);
+    void speculateSearch(int64_t nActive);
     void getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin);
     void topHitJoin(int64_t newnode, int64_t nActive);
     void refreshListsOnDevice(int64_t newnode, int64_t nActive, const std::vector<Besthit> &allhits);
@@ -437,6 +440,7 @@ void NJ<P>::sortSaveBestHits(int64_t iNode, std::vector<Besthit> &besthits, int6
         if (j != iNode && j != jLast && j >= 0) { nSave++; jLast = j; }
     }
     TopHitsList &l = topHitsLists[iNode];
+    hintedEpoch[iNode] = -1;                         // the list changes: hints issued for the old one do not cover it
     l.hits.resize(nSave);
     int64_t iSave = 0;
     jLast = -1;
@@ -614,7 +618,7 @@ void NJ<P>::setAllLeafTopHits() {
                 sortSaveBestHits(closeNode, besthitsNeighbor, 2 * m, m, true);                            // :3991
             }
         }
-        pairCache.clear();
+        clearPairs();
     }
 
     for (int64_t i = 0; i < nSeqs; i++) visible[i] = topHitsLists[i].hits[0];       // :4037-4044
@@ -838,34 +842,43 @@ void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin
     }
 }
 
+// Hints for topHitNJSearch (queued, not flushed): the out-distances its scan over the top-visible set can refresh,
+// and -- speculation -- what the hill-climb over the two top-hit lists of the likely join will ask for.  The join
+// is guessed from the values already held (stale out-distances rescaled, no refresh).  Only a hint: the exact
+// search decides, and fetches whatever the guess did not cover.  Called a second time from topHitJoin, whose one
+// device call then usually covers the NEXT search as well (the next join almost never involves the node just
+// created), so that a join costs one synchronous round trip instead of two.
+template<typename P>
+void NJ<P>::speculateSearch(int64_t nActive) {
+    for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
+    int64_t g1 = -1, g2 = -1, g3 = -1;
+    double c1 = 1e300, c2 = 1e300, c3 = 1e300;
+    for (int64_t iNode : topvisible) {
+        if (iNode < 0 || parent[iNode] >= 0) continue;
+        const Hit &h = visible[iNode];
+        if (h.j < 0 || parent[h.j] >= 0) continue;
+        double outI = outDistances[iNode], outJ = outDistances[h.j];
+        if (nOutDistActive[iNode] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[iNode] - 1);
+        if (nOutDistActive[h.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[h.j] - 1);
+        double c = h.dist - (outI + outJ) / (double) (nActive - 2);
+        if (c < c1) { c3 = c2; g3 = g2; c2 = c1; g2 = g1; c1 = c; g1 = iNode; }
+        else if (c < c2) { c3 = c2; g3 = g2; c2 = c; g2 = iNode; }
+        else if (c < c3) { c3 = c; g3 = iNode; }
+    }
+    for (int64_t g : {g1, g2, g3}) {
+        if (g < 0) continue;
+        const int64_t gj = visible[g].j;
+        hintList(nActive, g); hintList(nActive, gj);
+        wantPair(g, gj);
+    }
+}
+
 // topHitNJSearch, NJ.tcc:4137-4264
 template<typename P>
 void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
     HPROF(5, "topHitNJSearch(total)");
     if (opt.prefetch) {
-        for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
-        // Speculation: guess the join from the values we already hold (stale out-distances rescaled,
-        // no refresh) and queue what the hill-climb over its two top-hit lists and the join itself
-        // will ask for, so that the whole search usually costs ONE device call.  Only a hint: the
-        // exact search below decides, and fetches whatever the guess did not cover.
-        int64_t g1 = -1, g2 = -1;
-        double c1 = 1e300, c2 = 1e300;
-        for (int64_t iNode : topvisible) {
-            if (iNode < 0 || parent[iNode] >= 0) continue;
-            const Hit &h = visible[iNode];
-            if (h.j < 0 || parent[h.j] >= 0) continue;
-            double outI = outDistances[iNode], outJ = outDistances[h.j];
-            if (nOutDistActive[iNode] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[iNode] - 1);
-            if (nOutDistActive[h.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[h.j] - 1);
-            double c = h.dist - (outI + outJ) / (double) (nActive - 2);
-            if (c < c1) { c2 = c1; g2 = g1; c1 = c; g1 = iNode; } else if (c < c2) { c2 = c; g2 = iNode; }
-        }
-        for (int64_t g : {g1, g2}) {
-            if (g < 0) continue;
-            const int64_t gj = visible[g].j;
-            hintList(nActive, g); hintList(nActive, gj);
-            wantPair(g, gj);
-        }
+        speculateSearch(nActive);
         flush(nActive);
     }
     int64_t nCandidate = 0, iNodeBestCandidate = -1;
@@ -936,6 +949,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     if (opt.prefetch) {      // what updateTopVisible / updateVisible below can touch (a superset)
         for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
         for (const Besthit &h : uniqueList) hintVisible(nActive, h.j);
+        speculateSearch(nActive);                    // ... and what the NEXT join search will most likely ask for
     }
     flush(nActive);
     uniqueBestHitsFinish(nActive, uniqueList, uniqueSlots);
@@ -974,7 +988,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         // The m list merges of :4477-4515 in ONE device pass (vft_tophits_merge): the host only resolves the
         // active ancestors of the stored hits (it owns the tree) and packs the lists.
         refreshListsOnDevice(newnode, nActive, allhits);
-        pairCache.clear();
+        clearPairs();
         resetTopVisible(nActive);                                        // :4517
         return;
     }
@@ -1028,7 +1042,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         visible[wk.iNode] = topHitsLists[wk.iNode].hits[0];
     }
     res->nPairPrefetchHit += hits;
-    pairCache.clear();
+    clearPairs();
     resetTopVisible(nActive);                                            // :4517
 }
 
@@ -1072,6 +1086,7 @@ void NJ<P>::refreshListsOnDevice(int64_t newnode, int64_t nActive, const std::ve
     for (int64_t l = 0; l < nLists; l++) {
         TopHitsList &lst = topHitsLists[iNodes[l]];
         lst.age = 0;
+        hintedEpoch[iNodes[l]] = -1;
         lst.hits.resize(outCount[l]);
         for (int64_t k = 0; k < outCount[l]; k++) { lst.hits[k].j = (id_t) outJ[l * m + k]; lst.hits[k].dist = outDist[l * m + k]; }
         visible[iNodes[l]] = lst.hits[0];                                // :4513
