@@ -227,7 +227,7 @@ typedef struct vft_counters {
     int64_t nKernel[12];
     int64_t bytesKernel[12];  /* algorithmic bytes of the distance kernels, always counted */
 } vft_counters;
-#define VFT_KERNEL_NAMES "k_eval(list<=384)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", \
+#define VFT_KERNEL_NAMES "k_eval(inline list)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", \
                          "k_merge_prep+finish", "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", \
                          "k_posterior", "-"
 #define VFT_CFG_PROFILE 1    /* vft_config.reserved bit: time every kernel with CUDA events */

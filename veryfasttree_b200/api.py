@@ -35,7 +35,7 @@ class VftCounters(C.Structure):
                 ("msKernel", C.c_double * 12), ("nKernel", C.c_int64 * 12), ("bytesKernel", C.c_int64 * 12)]
 
 
-KERNEL_NAMES = ["k_eval(list<=384)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
+KERNEL_NAMES = ["k_eval(inline list)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
                 "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", "k_posterior", "-"]
 
 

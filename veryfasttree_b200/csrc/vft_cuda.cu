@@ -127,8 +127,8 @@ extern "C" int vft_release_cached_memory(void) { mem_release_all(); return VFT_O
 // per-join lists (latency), larger for the refresh batches (throughput).
 // ia/ib/r0/r1 live in pinned host memory mapped into the device address space (zero-copy): a
 // request costs one launch and one stream synchronisation, no separate memcpy.
-constexpr int INLINE_ITEMS = 384;
-struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 3 KB of kernel parameters
+constexpr int INLINE_ITEMS = 896;
+struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 7 KB of kernel parameters
 
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
