@@ -201,6 +201,24 @@ int  vft_pair_loglk_batch(vft_ctx *ctx, const int64_t *i, const int64_t *j, cons
    the parent of id1,id2 at distances len1,len2 */
 int  vft_posterior_profile(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2, double len1, double len2);
 
+/* one tree LEVEL of recomputeMLProfiles (NJ.tcc:3508-3542) in one launch: n independent posteriorProfile items */
+int  vft_posterior_profile_batch(vft_ctx *ctx, int64_t n, const int64_t *out_id, const int64_t *id1, const int64_t *id2,
+                                 const double *len1, const double *len2);
+/* the configuration the context was created with; *hasTransmat = a transition matrix is loaded (else Jukes-Cantor) */
+int  vft_get_config(vft_ctx *ctx, vft_config *out, int32_t *hasTransmat);
+
+/* -- whole-tree likelihood sweeps: recomputeMLProfiles (NJ.tcc:3508-3542) + treeLogLk
+      (NJ.tcc:5114-5259) as LEVEL-SYNCHRONOUS batches over the entry points above (veryfasttree_b200/csrc/ml_host.cpp):
+      one vft_posterior_profile_batch per tree level, one vft_pair_loglk_batch for all internal nodes, the terms
+      added in the reference's post-order.  nChild[maxnode], child[maxnode*3], branchlength[maxnode] (numeric_t) as in
+      vft_nj_result.  recomputeProfiles != 0: rebuild every 2-child internal profile bottom-up first.  The root's own
+      profile row is used as scratch for the posterior of its first two children (NJ.tcc:5143-5146).
+      leafCodes[nSeqs*nPos]: needed only for the Jukes-Cantor gap correction (NJ.tcc:5231-5257), may be NULL
+      otherwise.  siteLoglk: NULL or [nPos]. */
+int  vft_tree_loglk(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                    const void *branchlength, int32_t recomputeProfiles, const uint8_t *leafCodes, double *loglk,
+                    double *siteLoglk);
+
 /* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
       vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
 int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);

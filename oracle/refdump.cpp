@@ -102,6 +102,7 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
     Alignment aln(options, in, lg);
     aln.readAlignment();
     std::vector<std::string> seqs = aln.seqs;
+    std::vector<std::string> seqsTree = aln.seqs;      // the NeighbourJoining ctor consumes its sequences
     int64_t N = (int64_t) seqs.size(), L = aln.nPos, A = options.nCodes;
     typedef AVX256Operations<P> op_t;
     typedef NeighbourJoining<P, AVX256Operations> NJ;
@@ -184,6 +185,35 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
     put("ml.lk.len", 'd', {(int64_t) pl.size()}, pl.data());
     put("ml.lk.loglk", 'd', {(int64_t) ll.size()}, ll.data());
     put("ml.lk.site", 'd', {3, L}, site.data());
+
+    // whole-tree sweeps on the NJ tree of the same alignment: recomputeMLProfiles (NJ.tcc:3516-3542) + treeLogLk
+    // (NJ.tcc:5114-5259), with the same rates
+    {
+        std::unique_ptr<DiskMemory> e1, e2;
+        NJ nj2(options, lg, progress, seqsTree, L, cons, dmat, transmat, e1, e2);
+        nj2.fastNJ();
+        nj2.rates.reset(nCat, L);
+        for (int64_t c = 0; c < nCat; c++) nj2.rates.rates[c] = (P) rv[c];
+        for (int64_t i = 0; i < L; i++) nj2.rates.ratecat[i] = (i * 7 + i / 3) % nCat;
+        nj2.recomputeMLProfiles();
+        std::vector<double> siteLk(L, 0.0);
+        double lk = nj2.treeLogLk(siteLk.data());
+        double lkNoSite = nj2.treeLogLk(nullptr);
+        std::vector<int64_t> nch(nj2.maxnode), ch(nj2.maxnode * 3, -1), par(nj2.maxnode);
+        std::vector<P> bl(nj2.maxnode);
+        for (int64_t i = 0; i < nj2.maxnode; i++) {
+            nch[i] = nj2.child[i].nChild; par[i] = nj2.parent[i]; bl[i] = nj2.branchlength[i];
+            for (int k = 0; k < nj2.child[i].nChild; k++) ch[i * 3 + k] = nj2.child[i].child[k];
+        }
+        putq("ml.tree.root", {nj2.root});
+        putq("ml.tree.nChild", nch); putq("ml.tree.child", ch, {nj2.maxnode, 3}); putq("ml.tree.parent", par);
+        putv<P>("ml.tree.branchlength", bl);
+        double lks[2] = {lk, lkNoSite};
+        put("ml.tree.loglk", 'd', {2}, lks);
+        put("ml.tree.site", 'd', {L}, siteLk.data());
+        Dumper<P> DT(nj2);
+        DT.profile("ml.tree.lastnode", nj2.profiles[nj2.root - 1]);
+    }
     return 0;
 }
 

@@ -224,4 +224,28 @@ def replay_ml(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision:
             if libm_free:
                 if not bits_equal(site, dump["ml.lk.site"]): bad.append("ml.lk.site")
             elif not np.allclose(site, dump["ml.lk.site"], rtol=stol, atol=0): bad.append("ml.lk.site~")
+        # whole-tree sweeps: recomputeMLProfiles + treeLogLk of the reference on its own NJ tree (level-synchronous here)
+        if "ml.tree.loglk" in dump:
+            root = int(dump["ml.tree.root"][0])
+            n_child = dump["ml.tree.nChild"]; child = dump["ml.tree.child"]; bl = dump["ml.tree.branchlength"]
+            want_lk = dump["ml.tree.loglk"]
+            tol = 1e-5 if precision == 32 else 1e-12
+            lk_site, site_lk = ctx.tree_loglk(root, n_child, child, bl, recompute=True, leaf_codes=codes, site=True)
+            lk_plain, _ = ctx.tree_loglk(root, n_child, child, bl, recompute=False, leaf_codes=codes, site=False)
+            for nm, got, want in (("ml.tree.loglk(site)", lk_site, want_lk[0]), ("ml.tree.loglk", lk_plain, want_lk[1])):
+                r = abs(got - want) / max(1e-300, abs(want))
+                rel = max(rel, r)
+                if exact_log:
+                    if got != want: bad.append(nm)
+                elif r > tol: bad.append("%s rel=%g" % (nm, r))
+            want_site = dump["ml.tree.site"]
+            if exact_log:
+                if not bits_equal(site_lk, want_site): bad.append("ml.tree.site")
+            elif not np.allclose(site_lk, want_site, rtol=10 * tol, atol=10 * tol): bad.append("ml.tree.site~")
+            w, cd, v = ctx.get_profile(root - 1)             # the last 2-child node rebuilt by the level-synchronous sweep
+            if not np.array_equal(cd, dump["ml.tree.lastnode.codes"]): bad.append("ml.tree.lastnode.codes")
+            ptol = 2e-5 if precision == 32 else 1e-11
+            if not np.allclose(w, dump["ml.tree.lastnode.weights"], rtol=ptol, atol=ptol): bad.append("ml.tree.lastnode.weights")
+            if not np.allclose(v.reshape(dump["ml.tree.lastnode.vectors"].shape), dump["ml.tree.lastnode.vectors"], rtol=ptol, atol=ptol):
+                bad.append("ml.tree.lastnode.vectors")
     return bad, rel

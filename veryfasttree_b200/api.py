@@ -67,6 +67,7 @@ ABI_SYMBOLS = [
     "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
     "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
     "vft_dist_one_vs_all_range", "vft_tophits_merge", "vft_release_cached_memory",
+    "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk",
 ]
 
 
@@ -108,6 +109,9 @@ class Lib:
         d.vft_dist_one_vs_all.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_dist_one_vs_all_range.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64)]
         d.vft_get_profile.argtypes = [vp, i64, vp, vp, vp]
+        if hasattr(d, "vft_tree_loglk"):
+            d.vft_posterior_profile_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+            d.vft_tree_loglk.argtypes = [vp, i64, i64, vp, vp, vp, i32, vp, C.POINTER(dbl), vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -279,6 +283,19 @@ class Context:
                                                       _ptr(own_dist), len(all_j), _ptr(all_j), _ptr(all_dist),
                                                       _ptr(cnt), _ptr(oj), _ptr(od)), "vft_tophits_merge")
         return cnt, oj, od
+
+    def tree_loglk(self, root, n_child, child, branchlength, recompute=True, leaf_codes=None, site=False):
+        """vft_tree_loglk: (loglk, siteLoglk or None)."""
+        n_child = np.ascontiguousarray(n_child, dtype=np.int32)
+        child = np.ascontiguousarray(child, dtype=np.int64)
+        bl = np.ascontiguousarray(branchlength, dtype=self.dt)
+        lk = C.c_double()
+        sl = np.zeros(self.cfg.nPos, dtype=np.float64) if site else None
+        lc = np.ascontiguousarray(leaf_codes, dtype=np.uint8) if leaf_codes is not None else None
+        self.lib.check(self.lib.dll.vft_tree_loglk(self.h, int(root), len(n_child), _ptr(n_child), _ptr(child), _ptr(bl),
+                                                   1 if recompute else 0, _ptr(lc) if lc is not None else None, C.byref(lk),
+                                                   _ptr(sl) if sl is not None else None), "vft_tree_loglk")
+        return lk.value, sl
 
     def get_profile(self, node):
         L, A = self.cfg.nPos, self.cfg.nCodes

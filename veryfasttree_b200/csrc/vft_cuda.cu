@@ -824,8 +824,13 @@ k_pair_loglk(Store<P> s, MLModel<P> m, const int32_t *__restrict__ ia, const int
 // JC pSame/pDiff vectors) are built once per CTA in shared memory
 template<typename P, int A>
 __global__ void __launch_bounds__(128)
-k_posterior(Store<P> s, MLModel<P> m, int64_t oid, int64_t id1, int64_t id2, double len1, double len2) {
+k_posterior(Store<P> s, MLModel<P> m, int64_t oid, int64_t id1, int64_t id2, double len1, double len2,
+            const int32_t *__restrict__ items, const double *__restrict__ lens) {
     __shared__ __align__(16) unsigned char tab[2 * 64 * 20 * 8];
+    if (items != nullptr) {          // batched (one tree level): item blockIdx.y = (out, id1, id2), (len1, len2)
+        oid = items[3 * blockIdx.y]; id1 = items[3 * blockIdx.y + 1]; id2 = items[3 * blockIdx.y + 2];
+        len1 = lens[2 * blockIdx.y]; len2 = lens[2 * blockIdx.y + 1];
+    }
     if (len1 < m.MLMinBranchLength) len1 = m.MLMinBranchLength;                            // :2139-2144
     if (len2 < m.MLMinBranchLength) len2 = m.MLMinBranchLength;
     P *ee1 = reinterpret_cast<P *>(tab), *ee2 = reinterpret_cast<P *>(tab + 64 * 20 * 8);
@@ -1599,7 +1604,7 @@ extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, in
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     const unsigned blocks = (unsigned) ((c->Lp + 127) / 128);
-#define CALL_POST(P, A_) k_posterior<P, A_><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), make_model<P>(c), out_id, id1, id2, len1, len2)
+#define CALL_POST(P, A_) k_posterior<P, A_><<<blocks, 128, 0, c->stream>>>(make_store<P>(c), make_model<P>(c), out_id, id1, id2, len1, len2, nullptr, nullptr)
     prof_begin(c, CLS_PROFILE, K_POSTERIOR);
     if (c->cfg.precision == 32) { if (c->A == 4) CALL_POST(float, 4); else CALL_POST(float, 20); }
     else { if (c->A == 4) CALL_POST(double, 4); else CALL_POST(double, 20); }
@@ -1609,6 +1614,53 @@ extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, in
     if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
     return VFT_OK;            // asynchronous
+}
+
+extern "C" int vft_posterior_profile_batch(vft_ctx *c, int64_t n, const int64_t *out_id, const int64_t *id1, const int64_t *id2,
+                                           const double *len1, const double *len2) {
+    if (!c || n < 0 || (n > 0 && (!out_id || !id1 || !id2 || !len1 || !len2))) return fail(VFT_EINVAL, "null argument");
+    if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
+    if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
+    const int64_t CH = 32768;                                  // grid.y limit is 65535
+    for (int64_t k0 = 0; k0 < n; k0 += CH) {
+        const int64_t m = std::min(CH, n - k0);
+        int rc = ensure_pinned(c, (size_t) m * 32); if (rc) return rc;
+        rc = ensure_lists(c, m * 4); if (rc) return rc;
+        int32_t *hi = (int32_t *) c->h_in;
+        double *hl = (double *) ((char *) c->h_in + (size_t) m * 16);
+        for (int64_t k = 0; k < m; k++) {
+            const int64_t o = out_id[k0 + k], a = id1[k0 + k], b = id2[k0 + k];
+            if (o < c->N || o >= c->M || a < 0 || b < 0 || a >= c->M || b >= c->M) return fail(VFT_EINVAL, "bad node id");
+            hi[3 * k] = (int32_t) o; hi[3 * k + 1] = (int32_t) a; hi[3 * k + 2] = (int32_t) b;
+            hl[2 * k] = len1[k0 + k]; hl[2 * k + 1] = len2[k0 + k];
+        }
+        // one DMA for the items, then one launch for the whole level
+        CK(cudaMemcpyAsync(c->d_pi, c->h_in, (size_t) m * 32, cudaMemcpyHostToDevice, c->stream));
+        const int32_t *dItems = (const int32_t *) c->d_pi;
+        const double *dLens = (const double *) ((const char *) c->d_pi + (size_t) m * 16);
+        const dim3 grid((unsigned) ((c->Lp + 127) / 128), (unsigned) m);
+#define CALL_POSTB(P, A_) k_posterior<P, A_><<<grid, 128, 0, c->stream>>>(make_store<P>(c), make_model<P>(c), 0, 0, 0, 0.0, 0.0, dItems, dLens)
+        prof_begin(c, CLS_PROFILE, K_POSTERIOR);
+        if (c->cfg.precision == 32) { if (c->A == 4) CALL_POSTB(float, 4); else CALL_POSTB(float, 20); }
+        else { if (c->A == 4) CALL_POSTB(double, 4); else CALL_POSTB(double, 20); }
+        prof_end(c);
+        CK(cudaGetLastError());
+        CK(sync_stream(c));                                   // h_in is reused
+        c->cnt.launches++;
+        for (int64_t k = 0; k < m; k++) {
+            const int64_t o = out_id[k0 + k];
+            if (!c->activeHost[o]) { c->activeHost[o] = 1; c->nActInternal++; }
+            if (o >= c->maxnode) c->maxnode = o + 1;
+        }
+    }
+    return VFT_OK;
+}
+
+extern "C" int vft_get_config(vft_ctx *c, vft_config *out, int32_t *hasTransmat) {
+    if (!c || !out) return fail(VFT_EINVAL, "null argument");
+    *out = c->cfg;
+    if (hasTransmat) *hasTransmat = c->hasTransmat ? 1 : 0;
+    return VFT_OK;
 }
 
 extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *codes, void *vectors) {
