@@ -26,6 +26,14 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# One rank per GPU shares the host cores with the other ranks: the driver's host-thread regions must not
+# oversubscribe them (spinning OpenMP workers of several ranks on the same cores cost 5x), and NCCL's banner must
+# not land on stdout next to the JSON line.  Both are read when the libraries load, so they are set first.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_WAIT_POLICY"] = "PASSIVE"
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 import re
 import subprocess
 import sys
@@ -175,6 +183,17 @@ def main():
     ap.add_argument("--taxa", type=int, default=WORKLOAD["n"], help="override the workload size (debug only)")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the JSON: anything a library prints on fd 1 meanwhile (NCCL's version banner)
+    # is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        print(json.dumps(line), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,14 +204,14 @@ def main():
             return 0
         chars = make_workload(1, args.taxa)
         if not os.path.exists(REF_BIN):
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/VeryFastTree was not built (no /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/VeryFastTree was not built (no /root/reference at build time)"})
             return 0
         times = []
         threads = best_thread_count(host_cores)
         for it in range(args.warmup + args.steps):
             t, nu = run_reference(chars, threads)
             if t is None:
-                print(json.dumps({"impl": "reference", "unavailable": "reference binary failed to run"}))
+                emit({"impl": "reference", "unavailable": "reference binary failed to run"})
                 return 0
             if it >= args.warmup:
                 times.append(t)
@@ -208,7 +227,7 @@ def main():
                                  "sample": "the full workload, %d timed runs of the unmodified reference binary; threads = fastest of a 1..%d sweep on a 3000-taxon sample" % (len(times), host_cores)},
                 "e2e": {"value": value, "unit": "taxa/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -217,6 +236,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = api.load()
+    # host threads of the driver's list-processing regions: this rank's share of the cores
+    host_threads = max(1, min(16, host_cores // max(1, world)))
 
     chars = make_workload(1 + rank, args.taxa)
     codes = api.encode(chars, WORKLOAD["kind"])
@@ -232,7 +253,8 @@ def main():
     def one_step(profile=False):
         flush.fill_(1)                       # L2 flush between iterations
         torch.cuda.synchronize()
-        return api.nj_build(codes, 4, WORKLOAD["precision"], lib=lib, device=local_rank, trace=False, profile=profile)
+        return api.nj_build(codes, 4, WORKLOAD["precision"], lib=lib, device=local_rank, trace=False, profile=profile,
+                            host_threads=host_threads)
 
     for _ in range(args.warmup):
         one_step()
@@ -319,7 +341,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "taxa_per_gpu": int(n_unique), "columns": WORKLOAD["pos"],
-                       "parallelism": "replicas x%d" % args.gpus, "l2": "flushed between steps (256 MiB write)",
+                       "parallelism": "replicas x%d" % args.gpus, "host_threads_per_rank": host_threads,
+                       "l2": "flushed between steps (256 MiB write)",
                        "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)",
                        "parity": "join order, top-hit lists and branch lengths identical to the reference at -threads 1"},
             "e2e": {"value": taxa_total * args.steps / e2e_max, "unit": "taxa/s", "h2d_bytes_per_step": h2d // args.steps,
@@ -327,9 +350,9 @@ def main():
             "gpu_launches": int(launches_total), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "wall_s": t_wall}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    emit(line)
     return 0
 
 

@@ -212,3 +212,15 @@ def test_cuda_likelihood_matches_reference(glib, name, prec, lvl):
     chars, kind, model = replay.ml_case_chars(name)
     bad, rel = replay.replay_ml(glib, dump, chars, kind, prec, exact_log=False)
     assert bad == [], (bad, rel)
+
+
+def test_second_device_and_host_threads(glib):
+    """A context on device 1 (when there is one): every entry point binds the calling thread to the context's device,
+    and the host-thread regions of the driver make no device call of their own (bench.py --gpus N, rank > 0)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    chars, kind = replay.golden_case("nt1000")
+    want = open(os.path.join(replay.GOLDEN, "nt1000_f32.nj.tree")).read().strip()
+    tree = api.nj_build(api.encode(chars, kind), 4, 32, lib=glib, device=1, host_threads=8)
+    assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want

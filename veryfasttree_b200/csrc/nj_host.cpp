@@ -216,7 +216,7 @@ private:
                              reqI.data(), reqJ.data(), (int64_t) reqI.size(), VFT_PAIRS_JOIN, reqD.data(), reqW.data()); }));
         for (size_t k = 0; k < wantIds.size(); k++) { freshVal[wantIds[k]] = wantVals[k]; freshEpoch[wantIds[k]] = epoch; }
         for (size_t k = 0; k < reqI.size(); k++)
-            if (reqCached[k]) pairCache[pkey(reqI[k], reqJ[k])] = DW{reqD[k], reqW[k]};
+            if (reqCached[k]) pairCache.put(pkey(reqI[k], reqJ[k]), DW{reqD[k], reqW[k]});
         wantIds.clear();
         reqI.clear(); reqJ.clear(); reqCached.clear();
     }
@@ -241,7 +241,39 @@ private:
 
     // ---- pair distance service (distance half of setDistCriterion, NJ.tcc:1115-1122) -----------
     struct DW { P dist, weight; };
-    std::unordered_map<uint64_t, DW> pairCache;
+    // (i,j) -> distance of the current out-profile epoch: open addressing, cleared in O(1) by a generation stamp
+    struct PairCache {
+        struct Slot { uint64_t key; int64_t gen; DW val; };
+        std::vector<Slot> tab = std::vector<Slot>(1 << 12, Slot{0, -1, DW{0, 0}});
+        int64_t gen = 0;
+        size_t used = 0;
+        static size_t hash(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; return (size_t) k; }
+        void clear() { gen++; used = 0; }
+        DW *find(uint64_t key) {
+            const size_t mask = tab.size() - 1;
+            for (size_t h = hash(key) & mask;; h = (h + 1) & mask) {
+                Slot &s = tab[h];
+                if (s.gen != gen) return nullptr;
+                if (s.key == key) return &s.val;
+            }
+        }
+        void put(uint64_t key, DW v) {
+            if (2 * (used + 1) > tab.size()) grow();
+            const size_t mask = tab.size() - 1;
+            for (size_t h = hash(key) & mask;; h = (h + 1) & mask) {
+                Slot &s = tab[h];
+                if (s.gen != gen) { s.key = key; s.gen = gen; s.val = v; used++; return; }
+                if (s.key == key) { s.val = v; return; }
+            }
+        }
+        void grow() {
+            std::vector<Slot> old;
+            old.swap(tab);
+            tab.assign(old.size() * 2, Slot{0, -1, DW{0, 0}});
+            used = 0;
+            for (const Slot &s : old) if (s.gen == gen) put(s.key, s.val);
+        }
+    } pairCache;
     std::vector<int64_t> reqI, reqJ;
     std::vector<P> reqD, reqW;        // results of the last flush, by request slot
 
@@ -252,8 +284,8 @@ private:
     // hint for a pair looked up later through pairDist() (small, sporadic lists)
     void wantPair(int64_t i, int64_t j) {
         if (!opt.prefetch) return;
-        if (pairCache.find(pkey(i, j)) != pairCache.end()) return;
-        pairCache[pkey(i, j)] = DW{0, -1};          // weight -1 marks "requested"
+        if (pairCache.find(pkey(i, j)) != nullptr) return;
+        pairCache.put(pkey(i, j), DW{0, -1});       // weight -1 marks "requested"
         reqI.push_back(i); reqJ.push_back(j); reqCached.push_back(1);
     }
 
@@ -266,8 +298,8 @@ private:
     }
 
     DW pairDist(int64_t i, int64_t j) {
-        auto it = pairCache.find(pkey(i, j));
-        if (it != pairCache.end() && it->second.weight >= 0) { res->nPairPrefetchHit++; return it->second; }
+        const DW *it = pairCache.find(pkey(i, j));
+        if (it != nullptr && it->weight >= 0) { res->nPairPrefetchHit++; return *it; }
         DW r;
         check(timed([&] { return vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight); }));
         res->nPairSingleFetch++;
@@ -678,6 +710,8 @@ void NJ<P>::resetTopVisible(int64_t nActive) {
     bool needSequential = false;
     size_t nVisible = 0, nAll = 0;
     const uint64_t zeroKey = orderKey((P) 0);
+    // Device calls (and the exceptions they can raise) stay on the calling thread, outside the parallel regions:
+    // the context is bound to that thread's CUDA device.
 #pragma omp parallel num_threads(nT)
     {
         const int t = omp_get_thread_num(), nth = omp_get_num_threads();
@@ -704,18 +738,19 @@ void NJ<P>::resetTopVisible(int64_t nActive) {
                     wantEpoch[i] = epoch;
                     w.push_back((id_t) i);
                 }
-#pragma omp barrier
-#pragma omp single
-        {
-            cand.clear();
-            for (int k = 0; k < nth; k++) cand.insert(cand.end(), candT[k].begin(), candT[k].end());   // ascending node order
-            for (int k = 0; k < nth; k++) for (id_t i : wantT[k]) wantIds.push_back(i);
-            flush(nActive);
-            nVisible = cand.size();
-            nAll = (size_t) std::max<int64_t>(nActive, (int64_t) nVisible);
-            vis.resize(nVisible);
-            kv.resize(nAll);
-        }   // implicit barrier
+    }
+    cand.clear();
+    for (int k = 0; k < (int) candT.size(); k++) cand.insert(cand.end(), candT[k].begin(), candT[k].end());   // ascending node order
+    for (int k = 0; k < (int) wantT.size(); k++) for (id_t i : wantT[k]) wantIds.push_back(i);
+    flush(nActive);
+    nVisible = cand.size();
+    nAll = (size_t) std::max<int64_t>(nActive, (int64_t) nVisible);
+    vis.resize(nVisible);
+    kv.resize(nAll);
+#pragma omp parallel num_threads(nT)
+    {
+        const int t = omp_get_thread_num(), nth = omp_get_num_threads();
+        const int64_t lo = maxnode * t / nth, hi = maxnode * (t + 1) / nth;
         // commit what setCriterion would refresh (:1092-1098)
         bool seq = false;
         for (int64_t i = lo; i < hi; i++)
@@ -727,13 +762,12 @@ void NJ<P>::resetTopVisible(int64_t nActive) {
 #pragma omp atomic write
             needSequential = true;
         }
-#pragma omp barrier
-#pragma omp single
-        {
-            if (needSequential)                         // prefetching off (or a value not in hand): one at a time, as the reference would
-                for (int64_t i = 0; i < maxnode; i++)
-                    if (rtvTouched[i] == stamp && parent[i] < 0 && stale(i, nActive)) setOutDistance(i, nActive);
-        }   // implicit barrier
+    }
+    if (needSequential)                             // prefetching off (or a value not in hand): one at a time, as the reference would
+        for (int64_t i = 0; i < maxnode; i++)
+            if (rtvTouched[i] == stamp && parent[i] < 0 && stale(i, nActive)) setOutDistance(i, nActive);
+#pragma omp parallel num_threads(nT)
+    {
         // pass 2: criteria, in ascending node order = the order of visibleSorted[] in the reference (read-only now)
 #pragma omp for schedule(static)
         for (int64_t k = 0; k < (int64_t) nVisible; k++) getVisible(nActive, cand[k], vis[k]);

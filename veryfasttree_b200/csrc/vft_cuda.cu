@@ -960,6 +960,11 @@ static void prof_resolve(vft_ctx *c) {
     }
     c->pending.clear();
 }
+// the calling thread may be a host-pool thread that never selected the context's device
+static inline void bind_device(vft_ctx *c) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != c->cfg.device) cudaSetDevice(c->cfg.device);
+}
 static cudaError_t sync_stream(vft_ctx *c) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) prof_resolve(c);
@@ -1094,6 +1099,7 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
 
 extern "C" int vft_ctx_destroy(vft_ctx *c) {
     if (!c) return VFT_OK;
+    bind_device(c);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_tkA, c->d_tkB,
@@ -1112,6 +1118,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
 extern "C" int vft_upload_tables(vft_ctx *c, const void *distances, const void *eigenval, const void *eigentot,
                                  const void *codeFreq) {
     if (!c || !distances || !eigenval || !eigentot || !codeFreq) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     const size_t ps = c->ps;
     char *h = (char *) c->h_in;
     std::memcpy(h, distances, 400 * ps); std::memcpy(h + 400 * ps, eigenval, 20 * ps);
@@ -1123,6 +1130,7 @@ extern "C" int vft_upload_tables(vft_ctx *c, const void *distances, const void *
 
 extern "C" int vft_upload_leaves(vft_ctx *c, const uint8_t *codes) {
     if (!c || !codes) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     // clamp unknowns to NOCODE on the way (NJ.tcc:449-452) into the padded rows
     std::vector<uint8_t> padded((size_t) c->N * c->Lp, VFT_NOCODE);
     for (int64_t i = 0; i < c->N; i++)
@@ -1147,6 +1155,7 @@ extern "C" int vft_upload_leaves(vft_ctx *c, const uint8_t *codes) {
 
 extern "C" int vft_outprofile_rebuild(vft_ctx *c, const int64_t *ids, int64_t n) {
     if (!c) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     std::vector<int64_t> own;
     if (!ids) {
         for (int64_t i = 0; i < c->maxnode; i++) if (c->activeHost[i]) own.push_back(i);
@@ -1176,6 +1185,7 @@ extern "C" int vft_outprofile_update(vft_ctx *c, int64_t old1, int64_t old2, int
     if (!c || nActiveOld < 2 || newnode < c->N || newnode >= c->maxnode || old1 < 0 || old2 < 0 || old1 >= c->maxnode
         || old2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad argument");
+    bind_device(c);
 #define CALL_UPD(P, A_, MX) k_outprofile_update<P, A_, MX><<<(unsigned) ((c->L + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), old1, old2, newnode, nActiveOld)
     prof_begin(c, CLS_PROFILE, K_OUTPROFILE_UPDATE);
     VFT_DISPATCH(c, CALL_UPD);
@@ -1189,6 +1199,7 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
                           int64_t nActiveOld, bool update) {
     if (!c || out_id < c->N || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad node id");
+    bind_device(c);
     if (update && nActiveOld < 2) return fail(VFT_EINVAL, "bad nActiveOld");
     if (bionjWeight < 0) bionjWeight = 0.5;
     const size_t smem = (size_t) c->Lp * 16;
@@ -1230,6 +1241,7 @@ extern "C" int vft_profile_average_update(vft_ctx *c, int64_t out_id, int64_t id
 
 extern "C" int vft_get_self(vft_ctx *c, int64_t id, double *selfdist, double *selfweight) {
     if (!c || id < 0 || id >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+    bind_device(c);
     char buf[16];
     CK(cudaMemcpyAsync(buf, (char *) c->selfdist + id * c->ps, c->ps, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(buf + 8, (char *) c->selfweight + id * c->ps, c->ps, cudaMemcpyDeviceToHost, c->stream));
@@ -1257,6 +1269,7 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
                               void *outDist, const int64_t *pi, const int64_t *pj, int64_t nPairs, int32_t flags,
                               void *dist, void *weight) {
     if (!c) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     if ((nOut > 0 && (!out_ids || !outDist)) || (nPairs > 0 && (!pi || !pj || !dist || !weight)) || nOut < 0 || nPairs < 0)
         return fail(VFT_EINVAL, "null argument");
     const int64_t n = nOut + nPairs;
@@ -1331,6 +1344,7 @@ extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, 
 
 extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam, void *outDist, int64_t maxnode) {
     if (!c || !outDist || maxnode < c->maxnode) return fail(VFT_EINVAL, "bad argument");
+    bind_device(c);
     const int64_t n = c->maxnode;
     BytesScope bytesScope(c, K_OUT_DIST_ALL);
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
@@ -1364,6 +1378,7 @@ extern "C" int vft_dist_one_vs_all(vft_ctx *c, int64_t query, int64_t nActive, i
 extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nActive, int64_t K, int64_t jBegin, int64_t jEnd,
                                          int64_t *j_out, void *dist, void *weight, void *criterion, int64_t *nOut) {
     if (!c || !j_out || !dist || !weight || !criterion || !nOut) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     if (query < 0 || query >= c->maxnode || !c->activeHost[query]) return fail(VFT_EINVAL, "query must be an active node");
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
     BytesScope bytesScope(c, K_ONE_VS_ALL);
@@ -1419,6 +1434,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
                                  const int64_t *allJ, const void *allDist, int64_t *outCount, int64_t *outJ, void *outDist) {
     if (!c || !iNode || !ownOffset || !allJ || !allDist || !outCount || !outJ || !outDist || nLists < 0 || m < 1 || nAvail < 0 || nActive < 3)
         return fail(VFT_EINVAL, "bad argument");
+    bind_device(c);
     if (nLists == 0) return VFT_OK;
     BytesScope bytesScope(c, K_EVAL_LARGE);
     int64_t maxOwn = 0;
@@ -1526,6 +1542,7 @@ static MLModel<P> make_model(vft_ctx *c) {
 extern "C" int vft_upload_transmat(vft_ctx *c, const void *codeFreq, const void *eigenval, const void *eigeninv,
                                    const void *eigeninvT, const void *statinv) {
     if (!c) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     c->hasTransmat = codeFreq != nullptr;
     if (!codeFreq) return VFT_OK;
     if (!eigenval || !eigeninv || !statinv) return fail(VFT_EINVAL, "null argument");
@@ -1547,6 +1564,7 @@ extern "C" int vft_sync_rates(vft_ctx *c, const void *rates, int64_t nRateCats, 
                               double MLMinRelBranchLength, double MLMinBranchLength, int32_t fastexpLevel) {
     if (!c || !rates || !ratecat || nRateCats < 1 || nRateCats > 64 || fastexpLevel < 0 || fastexpLevel > 3)
         return fail(VFT_EINVAL, "bad argument");
+    bind_device(c);
     std::vector<int32_t> rc((size_t) c->Lp, 0);
     for (int64_t i = 0; i < c->L; i++) {
         if (ratecat[i] < 0 || ratecat[i] >= nRateCats) return fail(VFT_EINVAL, "bad rate category");
@@ -1563,6 +1581,7 @@ extern "C" int vft_sync_rates(vft_ctx *c, const void *rates, int64_t nRateCats, 
 extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t *pj, const double *length, int64_t n,
                                     double *loglk, double *siteLk) {
     if (!c || (n > 0 && (!pi || !pj || !length || !loglk))) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     if (n == 0) return VFT_OK;
@@ -1601,6 +1620,7 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
 extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double len1, double len2) {
     if (!c || out_id < c->N || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode)
         return fail(VFT_EINVAL, "bad node id");
+    bind_device(c);
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     const unsigned blocks = (unsigned) ((c->Lp + 127) / 128);
@@ -1619,6 +1639,7 @@ extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, in
 extern "C" int vft_posterior_profile_batch(vft_ctx *c, int64_t n, const int64_t *out_id, const int64_t *id1, const int64_t *id2,
                                            const double *len1, const double *len2) {
     if (!c || n < 0 || (n > 0 && (!out_id || !id1 || !id2 || !len1 || !len2))) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
     if (!c->hasTransmat && c->A != 4) return fail(VFT_EINVAL, "Jukes-Cantor needs nCodes == 4");
     const int64_t CH = 32768;                                  // grid.y limit is 65535
@@ -1665,6 +1686,7 @@ extern "C" int vft_get_config(vft_ctx *c, vft_config *out, int32_t *hasTransmat)
 
 extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *codes, void *vectors) {
     if (!c || id < -1 || id >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+    bind_device(c);
     const size_t ps = c->ps, L = (size_t) c->L, Lp = (size_t) c->Lp, A = (size_t) c->A;
     CK(sync_stream(c));
     if (id < 0) {
@@ -1691,6 +1713,7 @@ extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *c
 
 extern "C" int vft_get_counters(vft_ctx *c, vft_counters *out) {
     if (!c || !out) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     CK(sync_stream(c));
     c->cnt.distBytes = c->cnt.algoBytes;      // only the distance kernels account algorithmic bytes
     *out = c->cnt;
@@ -1699,12 +1722,14 @@ extern "C" int vft_get_counters(vft_ctx *c, vft_counters *out) {
 
 extern "C" int vft_timer_start(vft_ctx *c) {
     if (!c) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     CK(cudaEventRecord(c->tmr0, c->stream));
     return VFT_OK;
 }
 
 extern "C" int vft_timer_stop(vft_ctx *c, double *ms) {
     if (!c || !ms) return fail(VFT_EINVAL, "null argument");
+    bind_device(c);
     CK(cudaEventRecord(c->tmr1, c->stream));
     CK(cudaEventSynchronize(c->tmr1));
     float f = 0;
