@@ -5,15 +5,18 @@
 //   weights  P     [N][Lp]         internal nodes only (row = id - N)
 //   vecs     P     [N][Lp][A]      internal nodes only, dense (unused where the code is known)
 //   out-profile ow[Lp], ov[Lp][A], ocd[Lp][A]; per-node scalars diameter/selfdist/selfweight/outDist/active
-// Lp = nPos rounded up to 32: code rows are read with 128-bit loads and a warp covers 32 positions.
+// Lp = nPos rounded up to 32; rows are 16-byte aligned and read with 128-bit loads.
 //
-// Kernels (one thread accumulates one pair, see vft_device.cuh for why):
-//   k_dist_pairs      candidate lists           (transferBestHits / uniqueBestHits / getBestFromTopHits)
-//   k_one_vs_all      query vs every active node + criterion -> 64-bit sort keys   (setBestHit)
-//   k_topk_*          chunked bitonic sort + merge tree: the K best in the reference's psort order
-//   k_out_distance    profileDist(node, out-profile) + the setOutDistance algebra
-//   k_average         averageProfile + self distance of the new node
-//   k_outprofile_*    updateOutProfile / outProfile + setCodeDist
+// Kernels (the ordered accumulation they share is in vft_device.cuh):
+//   k_eval / k_eval_wide  candidate lists + lazy out-distances (transferBestHits / uniqueBestHits / getBestFromTopHits):
+//                         up to R pairs per warp, or one CTA per pair for the per-join lists of long alignments
+//   k_one_vs_all_*        query vs every active node + criterion -> 64-bit sort keys   (setBestHit)
+//   k_topk_select         radix select + bitonic sort: the K best in the reference's psort order
+//   k_merge_prep/finish   the m list merges of a top-hits refresh (vft_tophits_merge)
+//   k_out_distance_all    profileDist(node, out-profile) + the setOutDistance algebra, every active node
+//   k_average             averageProfile (+ fused updateOutProfile) + self distance of the new node
+//   k_outprofile_*        updateOutProfile / outProfile + setCodeDist
+//   k_pair_loglk, k_posterior   pairLogLk / posteriorProfile (vft_ml.cuh), one tree level per launch
 // There is no CPU fallback: without a usable device vft_ctx_create returns VFT_ENODEVICE.
 #include "../../include/vft_b200.h"
 #include "vft_device.cuh"
@@ -887,9 +890,6 @@ struct vft_ctx {
     void *codes, *weights, *vecs, *ow, *ov, *ocd, *diameter, *selfdist, *selfweight, *outDist, *active, *tables;
     void *d_dist, *d_weight, *d_crit;          // [M] one-vs-all scratch
     uint64_t *d_keys;                          // [M]
-    uint64_t *d_tkA, *d_tkB;                   // top-k ping-pong
-    uint32_t *d_tvA, *d_tvB;
-    void *d_rec;                               // [SORT_N] Rec
     int64_t *d_ids, *d_pi, *d_pj;              // staging for lists
     void *d_out1, *d_out2;
     int64_t listCap;
@@ -909,9 +909,7 @@ struct vft_ctx {
     bool hasTransmat, hasRates;
     int nRateCats, fastexp;
     double MLMinRel, MLMinBr;
-    unsigned int seq;
     unsigned int *d_doneCount;
-    volatile unsigned int *h_flag;
     vft_counters cnt;
     // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
     cudaEvent_t tmr0, tmr1;
@@ -1055,7 +1053,6 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(mem_alloc((void **) &c->tables, 840 * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_dist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_weight, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_crit, M * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_keys, M * 8, MEM_DEVICE));
-    c->d_tkA = c->d_tkB = nullptr; c->d_tvA = c->d_tvB = nullptr; c->d_rec = nullptr;
     CK(cudaMemsetAsync(c->codes, VFT_NOCODE, M * Lp, c->stream));
     CK(cudaMemsetAsync(c->weights, 0, N * Lp * ps, c->stream));
     CK(cudaMemsetAsync(c->ow, 0, Lp * ps, c->stream));
@@ -1072,8 +1069,6 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(mem_alloc((void **) &c->d_doneCount, 4, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_terms, 2 * Lp * 8, MEM_DEVICE));
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
-    { void *f = nullptr; CK(mem_alloc(&f, 64, MEM_PINNED)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
-    c->seq = 0;
     int rc = ensure_lists(c, std::max<int64_t>(4096, c->M));
     // pinned request/response buffers sized once for the largest list the NJ driver produces
     // (m lists of 2m pairs at a refresh, m = sqrt(N); every active node in the all-node sweeps)
@@ -1102,10 +1097,9 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     bind_device(c);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
-                    c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_tkA, c->d_tkB,
-                    c->d_tvA, c->d_tvB, c->d_rec, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
+                    c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
-    mem_free(c->h_in); mem_free(c->h_out); mem_free((void *) c->h_flag);
+    mem_free(c->h_in); mem_free(c->h_out);
     mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);

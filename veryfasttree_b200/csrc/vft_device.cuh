@@ -6,8 +6,8 @@
 // what makes the top-hit indices identical to the reference rather than merely close: the
 // criterion has many exact and near ties, and the order of the double-precision accumulation
 // over positions decides them.  Consequences for the kernel design:
-//   - a pair's distance is accumulated by ONE thread, positions in ascending order (the
-//     per-position work is cheap; parallelism comes from the thousands of pairs in a batch);
+//   - a pair's distance is accumulated by ONE lane, positions in ascending order; parallelism
+//     comes from running the chains of many pairs side by side (group_profile_dist);
 //   - mul and add are kept separate (__dmul_rn/__dadd_rn, __fmul_rn/__fadd_rn; the file is also
 //     compiled with -fmad=false);
 //   - the P-typed 20-wide dot products reproduce the lane order of AVX256Operations.tcc.
