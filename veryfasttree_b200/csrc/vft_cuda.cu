@@ -321,10 +321,10 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
     uint32_t *sv = reinterpret_cast<uint32_t *>(smem + 32 * 256 * 4 + SEL_MAXK * 8);   // [SEL_MAXK] node ids
     __shared__ uint64_t prefKey, maskKey;
     __shared__ uint32_t prefIdx, maskIdx;
-    __shared__ unsigned int need, cnt;
+    __shared__ unsigned int need, cnt, allTies;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int PASSES = KEYBYTES + 4;
-    if (tid == 0) { prefKey = 0; maskKey = 0; prefIdx = 0; maskIdx = 0; need = (unsigned) K; cnt = 0; }
+    if (tid == 0) { prefKey = 0; maskKey = 0; prefIdx = 0; maskIdx = 0; need = (unsigned) K; cnt = 0; allTies = 0; }
     __syncthreads();
     for (int p = 0; p < PASSES; p++) {
         for (int t = tid; t < 32 * 256; t += SEL_T) hist[t] = 0;
@@ -383,9 +383,13 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
                 need = want - cum;
                 if (onKey) { prefKey |= (uint64_t) d << shift; maskKey |= (uint64_t) 0xFFu << shift; }
                 else { prefIdx |= (uint32_t) d << shift; maskIdx |= 0xFFu << shift; }
+                // last key pass: the bin holds exactly the elements that tie with the K-th criterion.  If all of them
+                // are needed (the usual case: no tie is cut) the four index passes have nothing left to decide.
+                if (p == KEYBYTES - 1 && want - cum == loc[b]) { allTies = 1; prefIdx = 0xFFFFFFFFu; }
             }
         }
         __syncthreads();
+        if (allTies) break;
     }
     // the K-th composite is (prefKey, prefIdx): select everything <= it
     const uint64_t tk = prefKey;
