@@ -133,8 +133,10 @@ extern "C" int vft_release_cached_memory(void) { mem_release_all(); return VFT_O
 constexpr int INLINE_ITEMS = 896;
 struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 7 KB of kernel parameters
 
-template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(128)
+// DENSE = the throughput build for batches (fp32: capped at 128 registers -> 16 warps/SM, a few bytes of spill);
+// the per-join lists (one item per warp, latency bound) use the uncapped build.
+template<typename P, int A, bool MATRIX, bool DENSE>
+__global__ void __launch_bounds__(128, (DENSE && sizeof(P) == 4) ? 4 : 2)
 k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
        int64_t n, int64_t nOutItems, int G, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
        unsigned int *__restrict__ doneCount, P *__restrict__ hostOut) {
@@ -246,7 +248,7 @@ k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
 
 // setBestHit for an INTERNAL query: every distance is a profileDist; each warp owns G node slots
 template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, sizeof(P) == 4 ? 4 : 2)
 k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd, int G,
                   P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -273,7 +275,7 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
 
 // setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist
 template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, sizeof(P) == 4 ? 4 : 2)
 k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
@@ -565,8 +567,9 @@ __global__ void __launch_bounds__(256)
 k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
           double *__restrict__ gTerms, unsigned int *__restrict__ doneCount) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double *termW = gTerms;                                      // [Lp] w*w          (global: the CTAs split the positions)
-    double *termT = gTerms + s.Lp;                               // [Lp] w*w*piece
+    const bool single = gridDim.x == 1;                          // short alignments: one CTA, the terms never leave shared memory
+    double *termW = single ? reinterpret_cast<double *>(smem) : gTerms;   // [Lp] w*w   (global when the CTAs split the positions)
+    double *termT = termW + s.Lp;                                // [Lp] w*w*piece
     const View<P, A> p1 = make_view<P, A>(s, id1), p2 = make_view<P, A>(s, id2);
     const int64_t row = oid - s.nSeqs;
     uint8_t *oc = s.codes + oid * s.Lp;
@@ -633,18 +636,20 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
         termW[pos] = tw; termT[pos] = tt;
     }
     // the last CTA to finish adds the self-distance terms in position order
-    __shared__ bool amLast;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) amLast = atomicAdd(doneCount, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!amLast) return;
-    __threadfence();
-    double *sT = reinterpret_cast<double *>(smem);               // [2*Lp] staged copy of both term arrays
-    for (int64_t k = threadIdx.x; k < 2 * s.Lp; k += blockDim.x) sT[k] = __ldcg(gTerms + k);
+    double *sT = reinterpret_cast<double *>(smem);               // [2*Lp] both term arrays
+    if (!single) {
+        __shared__ bool amLast;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) amLast = atomicAdd(doneCount, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!amLast) return;
+        __threadfence();
+        for (int64_t k = threadIdx.x; k < 2 * s.Lp; k += blockDim.x) sT[k] = __ldcg(gTerms + k);
+        if (threadIdx.x == 0) *doneCount = 0;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        *doneCount = 0;
         // ordered sums over the positions (skipped positions hold +0.0, which is exact to add): 8 terms of each
         // chain are fetched ahead of the 16 dependent additions
         double top = 0, denom = 0;
@@ -1081,7 +1086,8 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     {
         // the grouped distance kernels use up to 4 warps x R rows of the [R][C] term tile
 #define SET_SMEM(P, A_, MX) do { const int need = (int) (4 * group_smem_bytes<P, A_, MX>(TileShape<A_, MX>::R)); \
-        cudaFuncSetAttribute(k_eval<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+        cudaFuncSetAttribute(k_eval<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+        cudaFuncSetAttribute(k_eval<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
         cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
         cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
         VFT_DISPATCH(c, SET_SMEM);
@@ -1306,7 +1312,9 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         qa = (const int32_t *) c->d_pi; qb = qa + n;
     }
     void *hostOut = dma ? nullptr : hr0;
-#define CALL_EVAL(P, A_, MX) k_eval<P, A_, MX><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut)
+#define EVAL_ARGS(P) make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, G, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut
+#define CALL_EVAL(P, A_, MX) do { if (G > 1) k_eval<P, A_, MX, true><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(EVAL_ARGS(P)); \
+        else k_eval<P, A_, MX, false><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(EVAL_ARGS(P)); } while (0)
     // long alignments, lists that cannot fill the machine with a warp per pair: a CTA per pair
     const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
     const int wideThreads = n <= 160 ? 256 : 128;
@@ -1500,7 +1508,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
             (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ, (P *) uD, reqA, reqB, cnt, c->d_acct); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
-        k_eval<P, A_, MX><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA, reqB, (int64_t) slots, 0, G, 0, nActive, 0.0, (P *) r0, (P *) r1, c->d_doneCount, (P *) nullptr); \
+        k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA, reqB, (int64_t) slots, 0, G, 0, nActive, 0.0, (P *) r0, (P *) r1, c->d_doneCount, (P *) nullptr); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
         k_merge_finish<P><<<(unsigned) nLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode, nActive, (int) m, (int) cap, np2, uJ, (P *) uD, reqA, (const P *) r0, cnt, hoCount, hoJ, (P *) hoD); \
