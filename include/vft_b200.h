@@ -219,6 +219,16 @@ int  vft_tree_loglk(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *
                     const void *branchlength, int32_t recomputeProfiles, const uint8_t *leafCodes, double *loglk,
                     double *siteLoglk);
 
+/* setMLRates (NJ.tcc:5429-5488): the CAT approximation.  nRateCats candidate rates evenly spaced in log from 1/n to n
+   (MLSiteRates, :5366-5377); for each, every site at that rate: recomputeMLProfiles + treeLogLk with per-site
+   log-likelihoods (MLSiteLikelihoodsByRate, :5381-5408) -- nRateCats level-synchronous whole-tree sweeps; then the
+   best category per site under the Gamma(3,1/3) prior, rates rescaled to average 1, profiles rebuilt.  Leaves the
+   context with the chosen rates loaded (as vft_sync_rates).  rates[nRateCats] (numeric_t), ratecat[nPos];
+   siteLoglk: NULL or [nRateCats*nPos].  The three scalars as in vft_sync_rates. */
+int  vft_set_ml_rates(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                      const void *branchlength, int64_t nRateCats, double MLMinRelBranchLength, double MLMinBranchLength,
+                      int32_t fastexpLevel, const uint8_t *leafCodes, void *rates, int64_t *ratecat, double *siteLoglk);
+
 /* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
       vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
 int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);

@@ -213,6 +213,14 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
         put("ml.tree.site", 'd', {L}, siteLk.data());
         Dumper<P> DT(nj2);
         DT.profile("ml.tree.lastnode", nj2.profiles[nj2.root - 1]);
+        // setMLRates (NJ.tcc:5429-5488) with 6 candidate rates on the same tree
+        options.nRateCats = 6;
+        nj2.setMLRates();
+        std::vector<P> r6(nj2.rates.rates.begin(), nj2.rates.rates.end());
+        std::vector<int64_t> rc6(nj2.rates.ratecat.begin(), nj2.rates.ratecat.end());
+        putv<P>("ml.cat.rates", r6); putq("ml.cat.ratecat", rc6);
+        double lkCat = nj2.treeLogLk(nullptr);
+        put("ml.cat.loglk", 'd', {1}, &lkCat);
     }
     return 0;
 }

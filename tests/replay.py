@@ -248,4 +248,23 @@ def replay_ml(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision:
             if not np.allclose(w, dump["ml.tree.lastnode.weights"], rtol=ptol, atol=ptol): bad.append("ml.tree.lastnode.weights")
             if not np.allclose(v.reshape(dump["ml.tree.lastnode.vectors"].shape), dump["ml.tree.lastnode.vectors"], rtol=ptol, atol=ptol):
                 bad.append("ml.tree.lastnode.vectors")
+            # setMLRates: 6 whole-tree sweeps + the per-site category choice; then the tree likelihood under the chosen rates
+            if "ml.cat.rates" in dump:
+                want_r, want_c = dump["ml.cat.rates"], dump["ml.cat.ratecat"]
+                got_r, got_c, _ = ctx.set_ml_rates(root, n_child, child, bl, len(want_r), float(dump["ml.minlen"][0]),
+                                                   float(dump["ml.minlen"][1]), lvl, leaf_codes=codes)
+                lk_cat, _ = ctx.tree_loglk(root, n_child, child, bl, recompute=False, leaf_codes=codes)
+                # a near-tie between two categories may flip under the GPU's libm: the categories must agree where the
+                # CPU double is used, and almost everywhere otherwise
+                if exact_log:
+                    if not np.array_equal(got_c, want_c): bad.append("ml.cat.ratecat")
+                    if not bits_equal(got_r, want_r): bad.append("ml.cat.rates")
+                    if lk_cat != float(dump["ml.cat.loglk"][0]): bad.append("ml.cat.loglk")
+                else:
+                    if np.mean(got_c != want_c) > 0.02: bad.append("ml.cat.ratecat~")
+                    if np.array_equal(got_c, want_c):
+                        if not np.allclose(got_r, want_r, rtol=10 * tol, atol=0): bad.append("ml.cat.rates~")
+                        r = abs(lk_cat - float(dump["ml.cat.loglk"][0])) / abs(float(dump["ml.cat.loglk"][0]))
+                        rel = max(rel, r)
+                        if r > tol: bad.append("ml.cat.loglk rel=%g" % r)
     return bad, rel

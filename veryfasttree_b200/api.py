@@ -67,7 +67,7 @@ ABI_SYMBOLS = [
     "vft_timer_start", "vft_timer_stop", "vft_eval_batch", "vft_profile_average_update",
     "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
     "vft_dist_one_vs_all_range", "vft_tophits_merge", "vft_release_cached_memory",
-    "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk",
+    "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk", "vft_set_ml_rates",
 ]
 
 
@@ -112,6 +112,7 @@ class Lib:
         if hasattr(d, "vft_tree_loglk"):
             d.vft_posterior_profile_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp]
             d.vft_tree_loglk.argtypes = [vp, i64, i64, vp, vp, vp, i32, vp, C.POINTER(dbl), vp]
+            d.vft_set_ml_rates.argtypes = [vp, i64, i64, vp, vp, vp, i64, dbl, dbl, i32, vp, vp, vp, vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -296,6 +297,20 @@ class Context:
                                                    1 if recompute else 0, _ptr(lc) if lc is not None else None, C.byref(lk),
                                                    _ptr(sl) if sl is not None else None), "vft_tree_loglk")
         return lk.value, sl
+
+    def set_ml_rates(self, root, n_child, child, branchlength, n_rate_cats, min_rel, min_br, fastexp, leaf_codes=None):
+        """vft_set_ml_rates: (rates[nRateCats], ratecat[nPos], siteLoglk[nRateCats, nPos])."""
+        n_child = np.ascontiguousarray(n_child, dtype=np.int32)
+        child = np.ascontiguousarray(child, dtype=np.int64)
+        bl = np.ascontiguousarray(branchlength, dtype=self.dt)
+        rates = np.zeros(n_rate_cats, dtype=self.dt)
+        ratecat = np.zeros(self.cfg.nPos, dtype=np.int64)
+        site = np.zeros((n_rate_cats, self.cfg.nPos), dtype=np.float64)
+        lc = np.ascontiguousarray(leaf_codes, dtype=np.uint8) if leaf_codes is not None else None
+        self.lib.check(self.lib.dll.vft_set_ml_rates(self.h, int(root), len(n_child), _ptr(n_child), _ptr(child), _ptr(bl), int(n_rate_cats),
+                                                     float(min_rel), float(min_br), int(fastexp), _ptr(lc) if lc is not None else None,
+                                                     _ptr(rates), _ptr(ratecat), _ptr(site)), "vft_set_ml_rates")
+        return rates, ratecat, site
 
     def get_profile(self, node):
         L, A = self.cfg.nPos, self.cfg.nCodes

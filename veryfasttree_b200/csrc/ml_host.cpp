@@ -21,50 +21,63 @@ namespace {
 
 constexpr double LkUnderflow = 1.0e-4, LkUnderflowInv = 1.0e4, LogLkUnderflow = 9.21034037197618;   // Constants.h:13-15
 
+// post-order of the reference: children in index order, a node after its children (traversePostorder, NJ.tcc:3342-3377)
+int post_order(int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child, std::vector<int64_t> &order) {
+    order.clear();
+    order.reserve((size_t) maxnode);
+    std::vector<std::pair<int64_t, int>> st;
+    st.push_back({root, 0});
+    while (!st.empty()) {
+        auto &top = st.back();
+        if (top.second < nChild[top.first]) {
+            const int64_t c = child[3 * top.first + top.second++];
+            if (c < 0 || c >= maxnode) return VFT_EINVAL;
+            st.push_back({c, 0});
+        } else { order.push_back(top.first); st.pop_back(); }
+    }
+    return VFT_OK;
+}
+
+// recomputeMLProfiles, NJ.tcc:3508-3542: every 2-child node = posterior of its children; one launch per tree level
+template<typename P>
+int recompute_profiles(vft_ctx *ctx, const std::vector<int64_t> &order, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                       const P *bl) {
+    // height above the leaves; level h depends only on levels < h
+    std::vector<int32_t> height((size_t) maxnode, 0);
+    int32_t H = 0;
+    for (int64_t node : order) {
+        int32_t h = 0;
+        for (int k = 0; k < nChild[node]; k++) h = std::max(h, height[child[3 * node + k]] + 1);
+        height[node] = h; H = std::max(H, h);
+    }
+    std::vector<std::vector<int64_t>> levels((size_t) H + 1);
+    for (int64_t node : order) if (nChild[node] == 2) levels[height[node]].push_back(node);   // :3508-3514
+    std::vector<int64_t> o, a, b;
+    std::vector<double> l1, l2;
+    for (int32_t h = 1; h <= H; h++) {
+        const auto &lv = levels[h];
+        if (lv.empty()) continue;
+        o.assign(lv.begin(), lv.end()); a.resize(lv.size()); b.resize(lv.size()); l1.resize(lv.size()); l2.resize(lv.size());
+        for (size_t k = 0; k < lv.size(); k++) {
+            a[k] = child[3 * lv[k]]; b[k] = child[3 * lv[k] + 1];
+            l1[k] = (double) bl[a[k]]; l2[k] = (double) bl[b[k]];
+        }
+        int rc = vft_posterior_profile_batch(ctx, (int64_t) lv.size(), o.data(), a.data(), b.data(), l1.data(), l2.data());
+        if (rc != VFT_OK) return rc;
+    }
+    return VFT_OK;
+}
+
 template<typename P>
 int tree_loglk(vft_ctx *ctx, const vft_config &cfg, bool jukesCantor, int64_t root, int64_t maxnode, const int32_t *nChild,
                const int64_t *child, const P *bl, bool recompute, const uint8_t *leafCodes, double *loglkOut, double *siteLoglk) {
     const int64_t N = cfg.nSeqs, L = cfg.nPos;
     if (N < 2) { *loglkOut = 0.0; return VFT_OK; }                                          // NJ.tcc:5161-5163
-    // post-order of the reference: children in index order, a node after its children (traversePostorder)
     std::vector<int64_t> order;
-    order.reserve((size_t) maxnode);
-    {
-        std::vector<std::pair<int64_t, int>> st;
-        st.push_back({root, 0});
-        while (!st.empty()) {
-            auto &top = st.back();
-            if (top.second < nChild[top.first]) {
-                const int64_t c = child[3 * top.first + top.second++];
-                if (c < 0 || c >= maxnode) return VFT_EINVAL;
-                st.push_back({c, 0});
-            } else { order.push_back(top.first); st.pop_back(); }
-        }
-    }
+    if (post_order(root, maxnode, nChild, child, order) != VFT_OK) return VFT_EINVAL;
     if (recompute) {
-        // height above the leaves; level h depends only on levels < h
-        std::vector<int32_t> height((size_t) maxnode, 0);
-        int32_t H = 0;
-        for (int64_t node : order) {
-            int32_t h = 0;
-            for (int k = 0; k < nChild[node]; k++) h = std::max(h, height[child[3 * node + k]] + 1);
-            height[node] = h; H = std::max(H, h);
-        }
-        std::vector<std::vector<int64_t>> levels((size_t) H + 1);
-        for (int64_t node : order) if (nChild[node] == 2) levels[height[node]].push_back(node);   // :3508-3514
-        std::vector<int64_t> o, a, b;
-        std::vector<double> l1, l2;
-        for (int32_t h = 1; h <= H; h++) {
-            const auto &lv = levels[h];
-            if (lv.empty()) continue;
-            o.assign(lv.begin(), lv.end()); a.resize(lv.size()); b.resize(lv.size()); l1.resize(lv.size()); l2.resize(lv.size());
-            for (size_t k = 0; k < lv.size(); k++) {
-                a[k] = child[3 * lv[k]]; b[k] = child[3 * lv[k] + 1];
-                l1[k] = (double) bl[a[k]]; l2[k] = (double) bl[b[k]];
-            }
-            int rc = vft_posterior_profile_batch(ctx, (int64_t) lv.size(), o.data(), a.data(), b.data(), l1.data(), l2.data());
-            if (rc != VFT_OK) return rc;
-        }
+        int rc = recompute_profiles<P>(ctx, order, maxnode, nChild, child, bl);
+        if (rc != VFT_OK) return rc;
     }
     // the pairLogLk terms, in post-order; the root's second term needs the posterior of its first two children
     std::vector<int64_t> pi, pj;
@@ -125,6 +138,59 @@ int tree_loglk(vft_ctx *ctx, const vft_config &cfg, bool jukesCantor, int64_t ro
     return VFT_OK;
 }
 
+// setMLRates, NJ.tcc:5429-5488 (+ MLSiteRates :5366-5377, MLSiteLikelihoodsByRate :5381-5408): nRateCats whole-tree
+// sweeps, one per candidate rate, then the per-site choice with the Gamma(3,1/3) prior
+template<typename P>
+int set_ml_rates(vft_ctx *ctx, const vft_config &cfg, bool jukesCantor, int64_t root, int64_t maxnode, const int32_t *nChild,
+                 const int64_t *child, const P *bl, int64_t nRateCats, double minRel, double minBr, int32_t fastexp,
+                 const uint8_t *leafCodes, P *ratesOut, int64_t *ratecatOut, double *siteLoglkOut) {
+    const int64_t L = cfg.nPos;
+    std::vector<int64_t> order;
+    if (post_order(root, maxnode, nChild, child, order) != VFT_OK) return VFT_EINVAL;
+    std::vector<int64_t> zeros((size_t) L, 0);
+    P one = (P) 1.0;
+    int rc = vft_sync_rates(ctx, &one, 1, zeros.data(), minRel, minBr, fastexp);              // rates.reset(1, nPos), :5431
+    if (rc != VFT_OK) return rc;
+    if (nRateCats == 1) {                                                                       // :5433-5436
+        ratesOut[0] = one;
+        for (int64_t i = 0; i < L; i++) ratecatOut[i] = 0;
+        return recompute_profiles<P>(ctx, order, maxnode, nChild, child, bl);
+    }
+    std::vector<P> rates((size_t) nRateCats);                                                   // MLSiteRates, :5366-5377
+    {
+        const double logNCat = std::log((double) nRateCats), logMinRate = -logNCat, logMaxRate = logNCat;
+        const double logd = (logMaxRate - logMinRate) / (double) (nRateCats - 1);
+        for (int64_t i = 0; i < nRateCats; i++) rates[i] = (P) std::exp(logMinRate + logd * (double) i);
+    }
+    std::vector<double> own;
+    double *site = siteLoglkOut;
+    if (!site) { own.resize((size_t) (nRateCats * L)); site = own.data(); }
+    for (int64_t iRate = 0; iRate < nRateCats; iRate++) {                                       // MLSiteLikelihoodsByRate, :5389-5404
+        rc = vft_sync_rates(ctx, &rates[iRate], 1, zeros.data(), minRel, minBr, fastexp);
+        if (rc != VFT_OK) return rc;
+        double lk;
+        rc = tree_loglk<P>(ctx, cfg, jukesCantor, root, maxnode, nChild, child, bl, /*recompute*/true, leafCodes, &lk, site + L * iRate);
+        if (rc != VFT_OK) return rc;
+    }
+    double sumRates = 0;                                                                        // :5449-5470
+    for (int64_t iPos = 0; iPos < L; iPos++) {
+        int64_t iBest = -1;
+        double dBest = -1e20;
+        for (int64_t iRate = 0; iRate < nRateCats; iRate++) {
+            const double v = site[L * iRate + iPos] + 2.0 * std::log(rates[iRate]) - 3.0 * rates[iRate];
+            if (v > dBest) { iBest = iRate; dBest = v; }
+        }
+        ratecatOut[iPos] = iBest;
+        sumRates += rates[iBest];
+    }
+    const double avgRate = sumRates / L;                                                        // :5473-5476
+    for (int64_t iRate = 0; iRate < nRateCats; iRate++) rates[iRate] /= avgRate;
+    for (int64_t iRate = 0; iRate < nRateCats; iRate++) ratesOut[iRate] = rates[iRate];
+    rc = vft_sync_rates(ctx, rates.data(), nRateCats, ratecatOut, minRel, minBr, fastexp);       // :5479
+    if (rc != VFT_OK) return rc;
+    return recompute_profiles<P>(ctx, order, maxnode, nChild, child, bl);                       // :5482
+}
+
 }  // namespace
 
 extern "C" int vft_tree_loglk(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
@@ -141,4 +207,21 @@ extern "C" int vft_tree_loglk(vft_ctx *ctx, int64_t root, int64_t maxnode, const
                                  leafCodes, loglk, siteLoglk);
     return tree_loglk<double>(ctx, cfg, !hasTransmat, root, maxnode, nChild, child, (const double *) branchlength, recomputeProfiles != 0,
                               leafCodes, loglk, siteLoglk);
+}
+
+extern "C" int vft_set_ml_rates(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                                const void *branchlength, int64_t nRateCats, double MLMinRelBranchLength, double MLMinBranchLength,
+                                int32_t fastexpLevel, const uint8_t *leafCodes, void *rates, int64_t *ratecat, double *siteLoglk) {
+    if (!ctx || !nChild || !child || !branchlength || !rates || !ratecat || root < 0 || root >= maxnode || nRateCats < 1 || nRateCats > 64)
+        return VFT_EINVAL;
+    vft_config cfg;
+    int32_t hasTransmat = 0;
+    int rc = vft_get_config(ctx, &cfg, &hasTransmat);
+    if (rc != VFT_OK) return rc;
+    if (maxnode > 2 * cfg.nSeqs) return VFT_EINVAL;
+    if (cfg.precision == 32)
+        return set_ml_rates<float>(ctx, cfg, !hasTransmat, root, maxnode, nChild, child, (const float *) branchlength, nRateCats,
+                                   MLMinRelBranchLength, MLMinBranchLength, fastexpLevel, leafCodes, (float *) rates, ratecat, siteLoglk);
+    return set_ml_rates<double>(ctx, cfg, !hasTransmat, root, maxnode, nChild, child, (const double *) branchlength, nRateCats,
+                                MLMinRelBranchLength, MLMinBranchLength, fastexpLevel, leafCodes, (double *) rates, ratecat, siteLoglk);
 }
