@@ -61,6 +61,10 @@ typedef struct vft_config {
     int32_t device;             /* CUDA ordinal                                               */
     int32_t reserved;
     double  fPostTotalTolerance;/* Options.fPostTotalTolerance (Constants.h:37-38)            */
+    int64_t nScratch;           /* extra dense profile rows, ids 2*nSeqs .. 2*nSeqs+nScratch-1: the
+                                   temporaries of the ML phase (the reference's stack Profiles AB, CD, ...
+                                   of MLQuartetOptimize NJ.tcc:1670-1745 and its upProfiles[], :3382-3434).
+                                   Valid only as arguments of the likelihood entry points.  0 for NJ. */
 } vft_config;
 
 /* -- life cycle: replaces CudaOperations() ctor / configCuda (CudaOperations.cu:169-175) ---- */
@@ -229,9 +233,70 @@ int  vft_set_ml_rates(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t
                       const void *branchlength, int64_t nRateCats, double MLMinRelBranchLength, double MLMinBranchLength,
                       int32_t fastexpLevel, const uint8_t *leafCodes, void *rates, int64_t *ratecat, double *siteLoglk);
 
+/* -- branch-length optimisation and ML NNI quartets as LOCK-STEP batches
+      (veryfasttree_b200/csrc/ml_opt.cpp).  The reference optimises one branch at a time -- Brent's minimiser
+      (onedimenmin / brent, NJ.tcc:7024-7190) asks for one pairLogLk per iteration -- and parallelises over OpenMP
+      sections / tree partitions.  Here the n items of a call advance together: each round is ONE
+      vft_posterior_profile_batch plus ONE vft_pair_loglk_batch carrying the pending request of every item.  Each
+      item performs exactly the reference's `-threads 1` sequence of operations; the items of one call must be
+      independent (no item reads a profile row another one writes).  Temporaries (the reference's stack Profiles)
+      live in the scratch rows of vft_config.nScratch. ------------------------------------------------------------ */
+typedef struct vft_ml_options {
+    double  MLMinBranchLength;           /* Constants.h:30-31 (5e-4 float / 5e-9 double); must match vft_sync_rates */
+    double  MLFTolBranchLength;          /* Constants.h:27-28 (0.001): Brent's fractional tolerance                 */
+    double  MLMinBranchLengthTolerance;  /* Constants.h:24-25 (1e-4 / 1e-9): Brent's absolute tolerance             */
+    double  closeLogLkLimit;             /* Constants.h:40 (5.0): star test and give-up thresholds of the NNI       */
+    int32_t mlAccuracy;                  /* Options.h:62 (1): -mlacc; >= 2 always runs that many full rounds        */
+    int32_t fastNNI;                     /* 1: star-topology test after the internal branch (NJ.tcc:1689-1698), as the
+                                            reference's serial branch of MLQuartetNNI applies it (:4905-4918 -- at
+                                            `-threads 1` it does so whatever its bFast argument says); 0: never, as
+                                            in its OpenMP-sections branch (:4925-4951)                              */
+} vft_ml_options;
+typedef struct vft_ml_stats {            /* how the work of a call was batched */
+    int64_t rounds;                      /* lock-step rounds                                 */
+    int64_t loglkCalls, loglkItems;      /* vft_pair_loglk_batch calls / (pair,length) items */
+    int64_t posteriorCalls, posteriorItems;
+} vft_ml_stats;
+void vft_ml_default_options(int32_t precision, vft_ml_options *opt);
+
+/* MLPairOptimize (NJ.tcc:1790-1803) for n pairs: length[k] in = the starting guess (>= MLMinBranchLength), out = the
+   optimum in [MLMinBranchLength, 6]; loglk[k] = pairLogLk there.  stats may be NULL. */
+int  vft_ml_pair_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *idA, const int64_t *idB,
+                                double *length, double *loglk, vft_ml_stats *stats);
+/* MLQuartetNNI (NJ.tcc:4885-5004) for n quartets, each through MLQuartetOptimize (NJ.tcc:1650-1788) of up to three
+   topologies per round: ids[4n] = profiles A,B,C,D (setupABCD order, NJ.tcc:1942-1974; D may be a scratch row holding
+   an up-profile); len[5n] numeric_t in/out in the order A,B,C,D,internal; criteria[3n] (in: the caller's previous
+   values, kept where a topology is not evaluated; out: log-likelihoods of AB|CD, AC|BD, AD|BC); choice[n] 0/1/2;
+   starTest[n] (may be NULL) = 1 where the star test ended the item early (then only len[internal] is updated, as in
+   the reference).  Uses scratch rows firstScratchRow .. firstScratchRow+3n-1.  No topological constraints. */
+int  vft_ml_quartet_nni_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
+                              double *criteria, int32_t *choice, int32_t *starTest, int64_t firstScratchRow,
+                              vft_ml_stats *stats);
+/* The per-node body of optimizeAllBranchLengths (NJ.tcc:5044-5058) for n nodes: ids[3n] = the three profiles that
+   meet at the node (child, child, up-profile -- or the three children of the root), len[3n] numeric_t in/out; two
+   sweeps, each branch optimised against the posterior of the other two.  Scratch rows firstScratchRow .. +n-1. */
+int  vft_ml_star_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
+                                int64_t firstScratchRow, vft_ml_stats *stats);
+/* optimizeAllBranchLengths (NJ.tcc:5006-5112) over a whole tree (arrays as in vft_tree_loglk; branchlength in/out;
+   the node profiles must be current, e.g. after vft_tree_loglk(recomputeProfiles=1), and are kept current).
+   VFT_ML_SCHEDULE_REFERENCE: the reference's post-order at `-threads 1`, up-profiles built lazily down the path from
+     the root (getUpProfile, NJ.tcc:3382-3434) -- identical branch lengths; needs depth+2 scratch rows.
+   VFT_ML_SCHEDULE_LEVELS: all nodes of one tree level in lock-step (up-profiles of the whole tree first, top-down);
+     a node sees the state left by the previous LEVEL instead of by the previously visited node, the same kind of
+     difference the reference's own tree-partitioned OpenMP mode has (NJ.tcc:5086-5107); needs one scratch row per
+     internal node plus at least one more (the more, the wider the batches). */
+#define VFT_ML_SCHEDULE_REFERENCE 0
+#define VFT_ML_SCHEDULE_LEVELS    1
+int  vft_ml_optimize_branch_lengths(vft_ctx *ctx, const vft_ml_options *opt, int64_t root, int64_t maxnode,
+                                    const int32_t *nChild, const int64_t *child, void *branchlength, int32_t schedule,
+                                    vft_ml_stats *stats);
+
 /* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
       vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
 int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);
+/* the counterpart: a dense profile written into an internal-node or scratch row (a profile the caller
+   built itself, e.g. an up-profile it holds on the host); same three arrays */
+int  vft_put_profile(vft_ctx *ctx, int64_t id, const void *weights, const uint8_t *codes, const void *vectors);
 
 /* running totals of work done through this context (feeds roofline accounting, Debug.h:12-15) */
 typedef struct vft_counters {

@@ -221,6 +221,99 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
         putv<P>("ml.cat.rates", r6); putq("ml.cat.ratecat", rc6);
         double lkCat = nj2.treeLogLk(nullptr);
         put("ml.cat.loglk", 'd', {1}, &lkCat);
+
+        // ---- SURVEY 8a rows a15-a17 under the CAT rates just chosen: MLPairOptimize (NJ.tcc:1790), MLQuartetNNI
+        //      (:4885; MLQuartetOptimize :1650, onedimenmin :7024, brent :7098), the per-node body of
+        //      optimizeAllBranchLengths (:5044-5058) and the whole sweep (:5006-5112); all by the reference itself
+        typedef typename NJ::Profile Profile;
+        options.MLFTolBranchLength = sizeof(P) == 8 ? Constants::MLFTolBranchLengthDouble : Constants::MLFTolBranchLengthFloat;
+        options.MLMinBranchLengthTolerance = sizeof(P) == 8 ? Constants::MLMinBranchLengthToleranceDouble : Constants::MLMinBranchLengthToleranceFloat;
+        double optScalars[4] = {options.MLMinBranchLength, options.MLFTolBranchLength, options.MLMinBranchLengthTolerance, Constants::closeLogLkLimit};
+        put("ml.opt.scalars", 'd', {4}, optScalars);
+        putq("ml.opt.flags", {(int64_t) options.mlAccuracy, (int64_t) options.fastNNI});
+        const int64_t M2 = nj2.maxnode;
+        {
+            std::vector<int64_t> pa, pb;
+            std::vector<double> l0, l1, lk;
+            for (int64_t k = 0; k < 10; k++) {
+                int64_t a = (k * 3) % N, b = k % 2 ? N + (k * 5) % (M2 - 1 - N) : (k * 7 + 4) % N;
+                if (a == b) b = (b + 1) % N;
+                double len = k == 0 ? options.MLMinBranchLength : k == 1 ? 1.5 * options.MLMinBranchLength : k == 2 ? 4.0 : 0.03 + 0.09 * (double) k;
+                pa.push_back(a); pb.push_back(b); l0.push_back(len);
+                lk.push_back(nj2.MLPairOptimize(nj2.profiles[a], nj2.profiles[b], &len));
+                l1.push_back(len);
+            }
+            putq("ml.opt.pair.a", pa); putq("ml.opt.pair.b", pb);
+            put("ml.opt.pair.len0", 'd', {(int64_t) l0.size()}, l0.data());
+            put("ml.opt.pair.len1", 'd', {(int64_t) l1.size()}, l1.data());
+            put("ml.opt.pair.loglk", 'd', {(int64_t) lk.size()}, lk.data());
+        }
+        {
+            std::vector<std::unique_ptr<Profile>> upProfiles(nj2.maxnodes);
+            std::vector<int64_t> qids, qnode, qchoice;
+            std::vector<P> qlen0, qlen1;
+            std::vector<double> qcrit;
+            int64_t nQ = 0;
+            for (int64_t node = N; node < M2; node++) {
+                if (node == nj2.root || nj2.child[node].nChild != 2) continue;
+                Profile *p4[4];
+                int64_t abcd[4];
+                nj2.setupABCD(node, p4, upProfiles.data(), abcd, true);
+                DT.profile("ml.opt.q" + std::to_string(nQ) + ".D", *p4[3]);
+                for (int fast = 1; fast >= 0; fast--) {
+                    P len[5] = {nj2.branchlength[abcd[0]], nj2.branchlength[abcd[1]], nj2.branchlength[abcd[2]], nj2.branchlength[abcd[3]], nj2.branchlength[node]};
+                    double crit[3] = {0.0, 0.0, 0.0};
+                    for (int i = 0; i < 5; i++) qlen0.push_back(len[i]);
+                    int choice = (int) nj2.MLQuartetNNI(p4, crit, len, fast != 0);
+                    for (int i = 0; i < 5; i++) qlen1.push_back(len[i]);
+                    for (int i = 0; i < 3; i++) qcrit.push_back(crit[i]);
+                    qchoice.push_back(choice);
+                }
+                for (int i = 0; i < 4; i++) qids.push_back(abcd[i]);
+                qnode.push_back(node);
+                nQ++;
+            }
+            putq("ml.opt.q.node", qnode); putq("ml.opt.q.ids", qids, {nQ, 4}); putq("ml.opt.q.choice", qchoice, {nQ, 2});
+            putv<P>("ml.opt.q.len0", qlen0, {nQ, 2, 5}); putv<P>("ml.opt.q.len1", qlen1, {nQ, 2, 5});
+            put("ml.opt.q.criteria", 'd', {nQ, 2, 3}, qcrit.data());
+            putq("ml.opt.q.nStar", {(int64_t) options.debug.nStarTests});
+            // the per-node body of traverseOptimizeAllBranchLengths on a few nodes (state untouched: local lengths)
+            std::vector<int64_t> snode, sids;
+            std::vector<P> slen0, slen1;
+            int64_t nS = 0;
+            for (int64_t node = N; node < M2; node += 3) {
+                const int64_t nChild = nj2.child[node].nChild;
+                if (nChild < 2) continue;
+                int64_t nodes[3] = {nj2.child[node].child[0], nj2.child[node].child[1], nChild == 3 ? nj2.child[node].child[2] : node};
+                Profile *p3[3] = {&nj2.profiles[nodes[0]], &nj2.profiles[nodes[1]],
+                                  nChild == 3 ? &nj2.profiles[nodes[2]] : nj2.getUpProfile(upProfiles.data(), node, true)};
+                DT.profile("ml.opt.s" + std::to_string(nS) + ".U", *p3[2]);
+                P bl3[3] = {nj2.branchlength[nodes[0]], nj2.branchlength[nodes[1]], nj2.branchlength[nodes[2]]};
+                for (int i = 0; i < 3; i++) slen0.push_back(bl3[i]);
+                for (int iter = 0; iter < 2; iter++)
+                    for (int i = 0; i < 3; i++) {
+                        int b1 = (i + 1) % 3, b2 = (i + 2) % 3;
+                        Profile pB(L, nj2.nCons);
+                        nj2.posteriorProfile(pB, *p3[b1], *p3[b2], bl3[b1], bl3[b2]);
+                        double len = bl3[i];
+                        if (len < options.MLMinBranchLength) len = options.MLMinBranchLength;
+                        nj2.MLPairOptimize(*p3[i], pB, &len);
+                        bl3[i] = len;
+                    }
+                for (int i = 0; i < 3; i++) { slen1.push_back(bl3[i]); sids.push_back(nodes[i]); }
+                snode.push_back(node);
+                nS++;
+            }
+            putq("ml.opt.s.node", snode); putq("ml.opt.s.ids", sids, {nS, 3});
+            putv<P>("ml.opt.s.len0", slen0, {nS, 3}); putv<P>("ml.opt.s.len1", slen1, {nS, 3});
+        }
+        // the whole sweep, then the tree likelihood with the new lengths
+        nj2.optimizeAllBranchLengths();
+        std::vector<P> blOpt(M2);
+        for (int64_t i = 0; i < M2; i++) blOpt[i] = nj2.branchlength[i];
+        putv<P>("ml.opt.tree.branchlength", blOpt);
+        double lkOpt = nj2.treeLogLk(nullptr);
+        put("ml.opt.tree.loglk", 'd', {1}, &lkOpt);
     }
     return 0;
 }

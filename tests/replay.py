@@ -268,3 +268,132 @@ def replay_ml(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision:
                         rel = max(rel, r)
                         if r > tol: bad.append("ml.cat.loglk rel=%g" % r)
     return bad, rel
+
+
+def replay_ml_opt(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: int, exact: bool, device: int = 0):
+    """Replays the a15-a17 section of oracle/refdump.cpp's "ml" script -- the reference's own MLPairOptimize,
+    MLQuartetNNI (MLQuartetOptimize / onedimenmin / brent), the per-node body of optimizeAllBranchLengths and the whole
+    sweep -- through the lock-step batch entry points.  `exact` (the CPU double of the ABI: same libm): every length,
+    criterion, choice and the final tree bit-identical.  Otherwise (the device: exp/log differ in the last bits, which
+    can move a Brent iterate) lengths within Brent's own fractional tolerance and log-likelihoods within the
+    north_star tolerance.  Returns (list of mismatches, info dict)."""
+    bad, info = [], {}
+    N, L, A = [int(x) for x in dump["shape"]]
+    codes = api.encode(chars, kind)
+    lvl = int(dump["ml.fastexp"][0])
+    has_tm = bool(dump["ml.hasTransmat"][0])
+    q_ids = dump["ml.opt.q.ids"]; nQ = len(q_ids)
+    s_ids = dump["ml.opt.s.ids"]; nS = len(s_ids)
+    n_scratch = nQ + 3 * nQ + 2 * nS + N + 8
+    cfg = api.make_config(N, L, A, precision, use_matrix=False, reduction=1, device=device, n_scratch=n_scratch)
+    dt = api.np_dtype(precision)
+    lk_tol = 1e-5 if precision == 32 else 1e-10
+    len_rtol = 5e-3                      # Brent's fractional tolerance is 1e-3 (Constants.h:27-28)
+
+    def cmp_len(name, got, want, floor):
+        if exact:
+            if not bits_equal(np.asarray(got, dtype=want.dtype).reshape(want.shape), want): bad.append(name)
+        elif not np.allclose(got.reshape(want.shape), want, rtol=len_rtol, atol=2 * floor): bad.append(name + "~")
+
+    def cmp_lk(name, got, want):
+        got = np.asarray(got, dtype=np.float64).reshape(np.shape(want)); want = np.asarray(want, dtype=np.float64)
+        if exact:
+            if not bits_equal(got, want): bad.append(name)
+        else:
+            rel = float(np.max(np.abs(got - want) / np.maximum(1e-300, np.abs(want))))
+            info[name] = rel
+            if rel > lk_tol: bad.append("%s rel=%g" % (name, rel))
+
+    with api.Context(lib, cfg) as ctx:
+        ctx.upload_leaves(codes)
+        d = lib.dll
+        if has_tm:
+            arrs = [np.ascontiguousarray(dump[k], dtype=dt) for k in ("ml.codeFreq", "ml.eigenval", "ml.eigeninv", "ml.eigeninvT", "ml.statinv")]
+            lib.check(d.vft_upload_transmat(ctx.h, *[api._ptr(a) for a in arrs]), "vft_upload_transmat")
+        else:
+            lib.check(d.vft_upload_transmat(ctx.h, None, None, None, None, None), "vft_upload_transmat")
+        rates = np.ascontiguousarray(dump["ml.cat.rates"], dtype=dt)
+        ratecat = np.ascontiguousarray(dump["ml.cat.ratecat"], dtype=np.int64)
+        lib.check(d.vft_sync_rates(ctx.h, api._ptr(rates), len(rates), api._ptr(ratecat), float(dump["ml.minlen"][0]),
+                                   float(dump["ml.minlen"][1]), lvl), "vft_sync_rates")
+        root = int(dump["ml.tree.root"][0])
+        n_child = dump["ml.tree.nChild"]; child = dump["ml.tree.child"]; bl = np.ascontiguousarray(dump["ml.tree.branchlength"], dtype=dt)
+        lk0, _ = ctx.tree_loglk(root, n_child, child, bl, recompute=True, leaf_codes=codes)      # profiles under the CAT rates
+        cmp_lk("ml.cat.loglk", lk0, dump["ml.cat.loglk"][0])
+        sc = dump["ml.opt.scalars"]; fl = dump["ml.opt.flags"]
+        minlen = float(sc[0])
+        opt = ctx.ml_options(MLMinBranchLength=minlen, MLFTolBranchLength=float(sc[1]), MLMinBranchLengthTolerance=float(sc[2]),
+                             closeLogLkLimit=float(sc[3]), mlAccuracy=int(fl[0]), fastNNI=int(fl[1]))
+        # MLPairOptimize
+        ln, lk, st = ctx.ml_pair_optimize(opt, dump["ml.opt.pair.a"], dump["ml.opt.pair.b"], dump["ml.opt.pair.len0"])
+        cmp_len("ml.opt.pair.len1", ln, dump["ml.opt.pair.len1"], minlen)
+        cmp_lk("ml.opt.pair.loglk", lk, dump["ml.opt.pair.loglk"])
+        info["pair.stats"] = st
+        # MLQuartetNNI: D (an up-profile, or a root sibling) goes into a scratch row; all quartets in one call
+        base = 2 * N
+        ids = np.array(q_ids, dtype=np.int64)
+        for k in range(nQ):
+            ctx.put_profile(base + k, dump["ml.opt.q%d.D.weights" % k], dump["ml.opt.q%d.D.codes" % k], dump["ml.opt.q%d.D.vectors" % k])
+            ids[k, 3] = base + k
+        # (the reference's serial branch ignores bFast, NJ.tcc:4905-4918: its two dumps per quartet are the same run)
+        first = None
+        for fi in (0, 1):
+            opt.fastNNI = 1
+            ln, crit, choice, star, st = ctx.ml_quartet_nni(opt, ids, dump["ml.opt.q.len0"][:, fi, :], base + nQ)
+            first = first or (ln, crit, choice, star)
+            want_choice = dump["ml.opt.q.choice"][:, fi]; want_crit = dump["ml.opt.q.criteria"][:, fi, :]
+            info["quartet.stats"] = st
+            info["quartet.star"] = int(star.sum())
+            if exact:
+                if not np.array_equal(choice, want_choice): bad.append("ml.opt.q.choice[%d]" % fi)
+                cmp_len("ml.opt.q.len1[%d]" % fi, ln, dump["ml.opt.q.len1"][:, fi, :], minlen)
+                if not bits_equal(crit, np.ascontiguousarray(want_crit)): bad.append("ml.opt.q.criteria[%d]" % fi)
+                if not np.array_equal(star != 0, want_crit[:, 1] < -1e19): bad.append("ml.opt.q.star[%d]" % fi)
+            else:
+                # a choice may only differ where the two best criteria are within the log-likelihood tolerance of each other
+                for k in np.nonzero(choice != want_choice)[0]:
+                    c = np.sort(want_crit[k])[::-1]
+                    if abs(c[0] - c[1]) > 10 * lk_tol * abs(c[0]): bad.append("ml.opt.q.choice[%d][%d]" % (fi, k))
+                same = choice == want_choice
+                real = want_crit > -1e19
+                rel = np.abs(crit - want_crit)[real & same[:, None]] / np.abs(want_crit[real & same[:, None]])
+                info["quartet.crit.rel"] = float(rel.max()) if rel.size else 0.0
+                if rel.size and rel.max() > 10 * lk_tol: bad.append("ml.opt.q.criteria[%d] rel=%g" % (fi, rel.max()))
+                if not np.array_equal(star != 0, want_crit[:, 1] < -1e19): bad.append("ml.opt.q.star[%d]" % fi)
+                if not np.allclose(ln[same], dump["ml.opt.q.len1"][:, fi, :][same], rtol=len_rtol, atol=2 * minlen): bad.append("ml.opt.q.len1[%d]~" % fi)
+        # without the star test (the reference's sections branch): items the test did not stop are the same computation
+        opt.fastNNI = 0
+        ln, crit, choice, star, st = ctx.ml_quartet_nni(opt, ids, dump["ml.opt.q.len0"][:, 0, :], base + nQ)
+        keep = first[3] == 0
+        if star.any() or (crit < -1e19).any(): bad.append("fastNNI=0 ran a star test")
+        if not (bits_equal(ln[keep], first[0][keep]) and bits_equal(crit[keep], first[1][keep]) and np.array_equal(choice[keep], first[2][keep])):
+            bad.append("fastNNI=0 differs where no star test fired")
+        opt.fastNNI = int(fl[1])
+        # the per-node body of optimizeAllBranchLengths
+        sbase = base + 4 * nQ
+        sid = np.array(s_ids, dtype=np.int64)
+        for k in range(nS):
+            ctx.put_profile(sbase + k, dump["ml.opt.s%d.U.weights" % k], dump["ml.opt.s%d.U.codes" % k], dump["ml.opt.s%d.U.vectors" % k])
+            sid[k, 2] = sbase + k
+        ln, st = ctx.ml_star_optimize(opt, sid, dump["ml.opt.s.len0"], sbase + nS)
+        cmp_len("ml.opt.s.len1", ln, dump["ml.opt.s.len1"], minlen)
+        info["star.stats"] = st
+        # the whole sweep in the reference's order, then the tree likelihood with the new lengths
+        bl1, st = ctx.ml_optimize_branch_lengths(opt, root, n_child, child, bl, schedule=0)
+        info["tree.stats.reference"] = st
+        cmp_len("ml.opt.tree.branchlength", bl1, np.ascontiguousarray(dump["ml.opt.tree.branchlength"], dtype=dt), minlen)
+        lk1, _ = ctx.tree_loglk(root, n_child, child, bl1, recompute=False, leaf_codes=codes)
+        cmp_lk("ml.opt.tree.loglk", lk1, dump["ml.opt.tree.loglk"][0])
+        # the level-synchronous schedule from the same start: a different (Jacobi-style) visiting order, so not the same
+        # lengths -- but it must improve the likelihood about as much as the reference's sweep does
+        lk0b, _ = ctx.tree_loglk(root, n_child, child, bl, recompute=True, leaf_codes=codes)
+        bl2, st = ctx.ml_optimize_branch_lengths(opt, root, n_child, child, bl, schedule=1)
+        info["tree.stats.levels"] = st
+        lk2, _ = ctx.tree_loglk(root, n_child, child, bl2, recompute=False, leaf_codes=codes)
+        lk2r, _ = ctx.tree_loglk(root, n_child, child, bl2, recompute=True, leaf_codes=codes)
+        want1 = float(dump["ml.opt.tree.loglk"][0])
+        info["tree.loglk"] = {"start": lk0b, "reference": want1, "levels": lk2}
+        if abs(lk2 - lk2r) > 10 * lk_tol * abs(lk2r): bad.append("levels: profiles not current after the sweep")
+        if not (lk2 > lk0b): bad.append("levels: likelihood did not improve")
+        if (want1 - lk2) > 0.25 * (want1 - lk0b) + 1e-6 * abs(want1): bad.append("levels: gain %.4f vs reference %.4f" % (lk2 - lk0b, want1 - lk0b))
+    return bad, info

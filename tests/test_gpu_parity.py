@@ -214,6 +214,21 @@ def test_cuda_likelihood_matches_reference(glib, name, prec, lvl):
     assert bad == [], (bad, rel)
 
 
+@pytest.mark.parametrize("name,prec,lvl", ML_PARAMS)
+def test_cuda_ml_optimizers_match_reference(glib, name, prec, lvl):
+    """SURVEY 8a rows a15-a17 on the device: MLPairOptimize, MLQuartetNNI (MLQuartetOptimize / onedimenmin / brent), the
+    per-node body of optimizeAllBranchLengths and the whole sweep as lock-step batches over k_pair_loglk / k_posterior,
+    vs the reference's own functions (tests/golden/*.mldump.bin).  The device's exp/log differ from libm in the last
+    bits, which can move a Brent iterate: optimised lengths within 5x Brent's own fractional tolerance (1e-3),
+    log-likelihoods within the north_star tolerance (1e-5 fp32 / 1e-10 fp64 relative), NNI choices identical except
+    between criteria closer than that tolerance."""
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d_e%d.mldump.bin" % (name, prec, lvl)))
+    chars, kind, model = replay.ml_case_chars(name)
+    bad, info = replay.replay_ml_opt(glib, dump, chars, kind, prec, exact=False)
+    print(info)
+    assert bad == [], (bad, info)
+
+
 def test_second_device_and_host_threads(glib):
     """A context on device 1 (when there is one): every entry point binds the calling thread to the context's device,
     and the host-thread regions of the driver make no device call of their own (bench.py --gpus N, rank > 0)."""

@@ -117,3 +117,18 @@ def test_oracle_likelihood_matches_reference(olib, name, prec, lvl):
     chars, kind, model = replay.ml_case_chars(name)
     bad, rel = replay.replay_ml(olib, dump, chars, kind, prec, exact_log=True)
     assert bad == [] and rel == 0.0
+
+
+@pytest.mark.parametrize("name,prec,lvl", ML_PARAMS)
+def test_oracle_ml_optimizers_match_reference(olib, name, prec, lvl):
+    """SURVEY 8a rows a15-a17 -- MLPairOptimize (NJ.tcc:1790), MLQuartetNNI (:4885) through MLQuartetOptimize (:1650),
+    onedimenmin (:7024) and brent (:7098), the per-node body of optimizeAllBranchLengths (:5044) and the whole sweep
+    (:5006) -- as lock-step batches (csrc/ml_opt.cpp) over the CPU double of the ABI vs the reference's own functions:
+    every optimised length, log-likelihood, NNI choice and the final tree bit-identical."""
+    dump = replay.read_refdump(os.path.join(replay.GOLDEN, "%s_f%d_e%d.mldump.bin" % (name, prec, lvl)))
+    chars, kind, model = replay.ml_case_chars(name)
+    bad, info = replay.replay_ml_opt(olib, dump, chars, kind, prec, exact=True)
+    assert bad == [], (bad, info)
+    # the batching itself: all quartets advance together, so a call makes far fewer device calls than evaluations
+    st = info["quartet.stats"]
+    assert st["loglkItems"] > 8 * st["loglkCalls"]

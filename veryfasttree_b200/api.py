@@ -24,7 +24,8 @@ CODES_AA = "ARNDCQEGHILKMFPSTWYV"      # /root/reference/src/Constants.h:50
 class VftConfig(C.Structure):
     _fields_ = [("nSeqs", C.c_int64), ("nPos", C.c_int64), ("nCodes", C.c_int32),
                 ("precision", C.c_int32), ("useMatrix", C.c_int32), ("reduction", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32), ("fPostTotalTolerance", C.c_double)]
+                ("device", C.c_int32), ("reserved", C.c_int32), ("fPostTotalTolerance", C.c_double),
+                ("nScratch", C.c_int64)]
 
 
 class VftCounters(C.Structure):
@@ -37,6 +38,20 @@ class VftCounters(C.Structure):
 
 KERNEL_NAMES = ["k_eval(inline list)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
                 "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", "k_posterior", "-"]
+
+
+class VftMlOptions(C.Structure):
+    _fields_ = [("MLMinBranchLength", C.c_double), ("MLFTolBranchLength", C.c_double),
+                ("MLMinBranchLengthTolerance", C.c_double), ("closeLogLkLimit", C.c_double),
+                ("mlAccuracy", C.c_int32), ("fastNNI", C.c_int32)]
+
+
+class VftMlStats(C.Structure):
+    _fields_ = [("rounds", C.c_int64), ("loglkCalls", C.c_int64), ("loglkItems", C.c_int64),
+                ("posteriorCalls", C.c_int64), ("posteriorItems", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class VftNjOptions(C.Structure):
@@ -68,6 +83,8 @@ ABI_SYMBOLS = [
     "vft_upload_transmat", "vft_sync_rates", "vft_pair_loglk_batch", "vft_posterior_profile",
     "vft_dist_one_vs_all_range", "vft_tophits_merge", "vft_release_cached_memory",
     "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk", "vft_set_ml_rates",
+    "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
+    "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths",
 ]
 
 
@@ -113,6 +130,15 @@ class Lib:
             d.vft_posterior_profile_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp]
             d.vft_tree_loglk.argtypes = [vp, i64, i64, vp, vp, vp, i32, vp, C.POINTER(dbl), vp]
             d.vft_set_ml_rates.argtypes = [vp, i64, i64, vp, vp, vp, i64, dbl, dbl, i32, vp, vp, vp, vp]
+        if hasattr(d, "vft_ml_quartet_nni_batch"):
+            mo, ms = C.POINTER(VftMlOptions), C.POINTER(VftMlStats)
+            d.vft_put_profile.argtypes = [vp, i64, vp, vp, vp]
+            d.vft_ml_default_options.argtypes = [i32, mo]
+            d.vft_ml_default_options.restype = None
+            d.vft_ml_pair_optimize_batch.argtypes = [vp, mo, i64, vp, vp, vp, vp, ms]
+            d.vft_ml_quartet_nni_batch.argtypes = [vp, mo, i64, vp, vp, vp, vp, vp, i64, ms]
+            d.vft_ml_star_optimize_batch.argtypes = [vp, mo, i64, vp, vp, i64, ms]
+            d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -166,9 +192,9 @@ def np_dtype(precision: int):
     return np.float32 if precision == 32 else np.float64
 
 
-def make_config(n_seqs, n_pos, n_codes, precision, use_matrix=False, reduction=1, device=0) -> VftConfig:
+def make_config(n_seqs, n_pos, n_codes, precision, use_matrix=False, reduction=1, device=0, n_scratch=0) -> VftConfig:
     tol = 1.0e-10 if precision == 32 else 1.0e-20     # Constants.h:37-38
-    return VftConfig(n_seqs, n_pos, n_codes, precision, int(use_matrix), reduction, device, 0, tol)
+    return VftConfig(n_seqs, n_pos, n_codes, precision, int(use_matrix), reduction, device, 0, tol, n_scratch)
 
 
 class Context:
@@ -319,6 +345,61 @@ class Context:
         v = np.empty((L, A), dtype=self.dt)
         self.lib.check(self.lib.dll.vft_get_profile(self.h, node, _ptr(w), _ptr(cd), _ptr(v)), "vft_get_profile")
         return w, cd, v
+
+    def put_profile(self, node, weights, codes, vectors):
+        w = np.ascontiguousarray(weights, dtype=self.dt)
+        cd = np.ascontiguousarray(codes, dtype=np.uint8)
+        v = np.ascontiguousarray(vectors, dtype=self.dt)
+        self.lib.check(self.lib.dll.vft_put_profile(self.h, int(node), _ptr(w), _ptr(cd), _ptr(v)), "vft_put_profile")
+
+    # ---- branch-length optimisation / ML NNI quartets (lock-step batches, csrc/ml_opt.cpp) ----
+    def ml_options(self, **kw) -> VftMlOptions:
+        o = VftMlOptions()
+        self.lib.dll.vft_ml_default_options(self.cfg.precision, C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def ml_pair_optimize(self, opt, id_a, id_b, length):
+        """vft_ml_pair_optimize_batch: (length[n], loglk[n], stats)."""
+        a = np.ascontiguousarray(id_a, dtype=np.int64); b = np.ascontiguousarray(id_b, dtype=np.int64)
+        ln = np.array(length, dtype=np.float64); lk = np.zeros(len(a), dtype=np.float64)
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_pair_optimize_batch(self.h, C.byref(opt), len(a), _ptr(a), _ptr(b), _ptr(ln), _ptr(lk),
+                                                               C.byref(st)), "vft_ml_pair_optimize_batch")
+        return ln, lk, st.as_dict()
+
+    def ml_quartet_nni(self, opt, ids, length, first_scratch_row, criteria=None):
+        """vft_ml_quartet_nni_batch: (len[n,5], criteria[n,3], choice[n], star[n], stats)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1, 4)
+        n = len(ids)
+        ln = np.array(length, dtype=self.dt).reshape(n, 5)
+        crit = np.zeros((n, 3), dtype=np.float64) if criteria is None else np.array(criteria, dtype=np.float64).reshape(n, 3)
+        choice = np.zeros(n, dtype=np.int32); star = np.zeros(n, dtype=np.int32)
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_quartet_nni_batch(self.h, C.byref(opt), n, _ptr(ids), _ptr(ln), _ptr(crit), _ptr(choice),
+                                                             _ptr(star), int(first_scratch_row), C.byref(st)), "vft_ml_quartet_nni_batch")
+        return ln, crit, choice, star, st.as_dict()
+
+    def ml_star_optimize(self, opt, ids, length, first_scratch_row):
+        """vft_ml_star_optimize_batch: (len[n,3], stats)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1, 3)
+        n = len(ids)
+        ln = np.array(length, dtype=self.dt).reshape(n, 3)
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_star_optimize_batch(self.h, C.byref(opt), n, _ptr(ids), _ptr(ln), int(first_scratch_row),
+                                                               C.byref(st)), "vft_ml_star_optimize_batch")
+        return ln, st.as_dict()
+
+    def ml_optimize_branch_lengths(self, opt, root, n_child, child, branchlength, schedule=0):
+        """vft_ml_optimize_branch_lengths: (branchlength[maxnode], stats)."""
+        n_child = np.ascontiguousarray(n_child, dtype=np.int32)
+        child = np.ascontiguousarray(child, dtype=np.int64)
+        bl = np.array(branchlength, dtype=self.dt)
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_optimize_branch_lengths(self.h, C.byref(opt), int(root), len(n_child), _ptr(n_child), _ptr(child),
+                                                                   _ptr(bl), int(schedule), C.byref(st)), "vft_ml_optimize_branch_lengths")
+        return bl, st.as_dict()
 
     def counters(self) -> VftCounters:
         c = VftCounters()

@@ -100,18 +100,26 @@ int tree_loglk(vft_ctx *ctx, const vft_config &cfg, bool jukesCantor, int64_t ro
     if (!siteLoglk) {
         int rc = vft_pair_loglk_batch(ctx, pi.data(), pj.data(), pl.data(), nTerms, term.data(), nullptr);
         if (rc != VFT_OK) return rc;
-        for (int64_t k = 0; k < nTerms; k++) loglk += term[k];                              // :5126, :5148, :5196
+        // each node's contribution is summed on its own first (traverseTreeLogLk returns it, :5116-5157), so the two
+        // terms of the 3-child root -- the last two -- are added to each other before they join the total (:5196)
+        const int64_t nPlain = nChild[root] == 3 ? nTerms - 2 : nTerms;
+        for (int64_t k = 0; k < nPlain; k++) loglk += term[k];
+        if (nPlain < nTerms) loglk += term[nPlain] + term[nPlain + 1];
     } else {
         std::vector<double> siteLk((size_t) L, 1.0);                                        // :5168-5175
         for (int64_t i = 0; i < L; i++) siteLoglk[i] = 0.0;
         const int64_t CH = std::max<int64_t>(1, std::min<int64_t>(nTerms, (int64_t) (64 << 20) / (8 * L)));
         std::vector<double> rows((size_t) CH * L);
+        double rootFirst = 0.0;
         for (int64_t k0 = 0; k0 < nTerms; k0 += CH) {
             const int64_t m = std::min(CH, nTerms - k0);
             int rc = vft_pair_loglk_batch(ctx, pi.data() + k0, pj.data() + k0, pl.data() + k0, m, term.data() + k0, rows.data());
             if (rc != VFT_OK) return rc;
             for (int64_t k = 0; k < m; k++) {
-                loglk += term[k0 + k];
+                // (the root's two terms are added to each other first, as traverseTreeLogLk does)
+                if (nChild[root] == 3 && k0 + k == nTerms - 2) rootFirst = term[k0 + k];
+                else if (nChild[root] == 3 && k0 + k == nTerms - 1) loglk += rootFirst + term[k0 + k];
+                else loglk += term[k0 + k];
                 const double *r = rows.data() + k * L;
                 for (int64_t i = 0; i < L; i++) siteLk[i] *= r[i];                          // pairLogLk's site_likelihoods[i] *= lkAB
                 if (pi[k0 + k] != root)                                                     // :5127-5135 (not after the root's second term)

@@ -871,7 +871,7 @@ k_posterior(Store<P> s, MLModel<P> m, int64_t oid, int64_t id1, int64_t id2, dou
     s.codes[oid * s.Lp + pos] = (uint8_t) cOut;
 #pragma unroll
     for (int k = 0; k < A; k++) s.vecs[(row * s.Lp + pos) * A + k] = f[k];
-    if (pos == 0) s.active[oid] = 1;
+    if (pos == 0 && oid < 2 * s.nSeqs) s.active[oid] = 1;              // scratch rows have no per-node state
 }
 
 // leaves: selfweight = nPos - nGaps (NJ.tcc:249-252), active, padding of the code rows
@@ -893,6 +893,7 @@ struct vft_ctx {
     vft_config cfg;
     int A;
     int64_t N, M, L, Lp, maxnode;
+    int64_t S = 0;                 // scratch profile rows (cfg.nScratch): ids M .. M+S-1, likelihood entry points only
     size_t ps;
     cudaStream_t stream;
     // device
@@ -1052,18 +1053,21 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     c->profile = (cfg->reserved & VFT_CFG_PROFILE) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->tmr0)); CK(cudaEventCreate(&c->tmr1));
-    const size_t ps = c->ps, Lp = (size_t) c->Lp, A = (size_t) c->A, N = (size_t) c->N, M = (size_t) c->M;
-    CK(mem_alloc((void **) &c->codes, M * Lp, MEM_DEVICE));
-    CK(mem_alloc((void **) &c->weights, N * Lp * ps, MEM_DEVICE));
-    CK(mem_alloc((void **) &c->vecs, N * Lp * A * ps, MEM_DEVICE));
+    if (cfg->nScratch < 0 || 2 * cfg->nSeqs + cfg->nScratch >= 0x7FFF0000ll) return fail(VFT_EINVAL, "bad nScratch");
+    c->S = cfg->nScratch;
+    const size_t ps = c->ps, Lp = (size_t) c->Lp, A = (size_t) c->A, N = (size_t) c->N, M = (size_t) c->M, S = (size_t) c->S;
+    // the scratch rows (ids M .. M+S-1) extend the three profile arrays; the per-node NJ arrays stay [M]
+    CK(mem_alloc((void **) &c->codes, (M + S) * Lp, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->weights, (N + S) * Lp * ps, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->vecs, (N + S) * Lp * A * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->ow, Lp * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->ov, Lp * A * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->ocd, Lp * A * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->diameter, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->selfdist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->selfweight, M * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->outDist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->active, M, MEM_DEVICE));
     CK(mem_alloc((void **) &c->tables, 840 * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_dist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_weight, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_crit, M * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_keys, M * 8, MEM_DEVICE));
-    CK(cudaMemsetAsync(c->codes, VFT_NOCODE, M * Lp, c->stream));
-    CK(cudaMemsetAsync(c->weights, 0, N * Lp * ps, c->stream));
+    CK(cudaMemsetAsync(c->codes, VFT_NOCODE, (M + S) * Lp, c->stream));
+    CK(cudaMemsetAsync(c->weights, 0, (N + S) * Lp * ps, c->stream));
     CK(cudaMemsetAsync(c->ow, 0, Lp * ps, c->stream));
     CK(cudaMemsetAsync(c->ov, 0, Lp * A * ps, c->stream));
     CK(cudaMemsetAsync(c->ocd, 0, Lp * A * ps, c->stream));
@@ -1584,6 +1588,15 @@ extern "C" int vft_sync_rates(vft_ctx *c, const void *rates, int64_t nRateCats, 
     return VFT_OK;
 }
 
+// ids the likelihood entry points may read / write: tree nodes, plus the scratch rows of cfg.nScratch
+static inline bool ml_readable(const vft_ctx *c, int64_t id) { return id >= 0 && (id < c->maxnode || (id >= c->M && id < c->M + c->S)); }
+static inline bool ml_writable(const vft_ctx *c, int64_t id) { return id >= c->N && id < c->M + c->S; }
+static inline void ml_written(vft_ctx *c, int64_t id) {
+    if (id >= c->M) return;
+    if (!c->activeHost[id]) { c->activeHost[id] = 1; c->nActInternal++; }
+    if (id >= c->maxnode) c->maxnode = id + 1;
+}
+
 extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t *pj, const double *length, int64_t n,
                                     double *loglk, double *siteLk) {
     if (!c || (n > 0 && (!pi || !pj || !length || !loglk))) return fail(VFT_EINVAL, "null argument");
@@ -1597,7 +1610,7 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
     int32_t *ha = (int32_t *) c->h_in, *hb = ha + n;
     double *hl = (double *) ((char *) c->h_in + (size_t) n * 8);
     for (int64_t k = 0; k < n; k++) {
-        if (pi[k] < 0 || pj[k] < 0 || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        if (!ml_readable(c, pi[k]) || !ml_readable(c, pj[k])) return fail(VFT_EINVAL, "bad node id");
         ha[k] = (int32_t) pi[k]; hb[k] = (int32_t) pj[k]; hl[k] = length[k];
         c->cnt.algoBytes += profile_bytes(c, pi[k]) + profile_bytes(c, pj[k]) + c->L * 4;
     }
@@ -1624,7 +1637,7 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
 }
 
 extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double len1, double len2) {
-    if (!c || out_id < c->N || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode)
+    if (!c || !ml_writable(c, out_id) || !ml_readable(c, id1) || !ml_readable(c, id2))
         return fail(VFT_EINVAL, "bad node id");
     bind_device(c);
     if (!c->hasRates) return fail(VFT_EINVAL, "vft_sync_rates has not been called");
@@ -1637,8 +1650,7 @@ extern "C" int vft_posterior_profile(vft_ctx *c, int64_t out_id, int64_t id1, in
     prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;
-    if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
-    if (out_id >= c->maxnode) c->maxnode = out_id + 1;
+    ml_written(c, out_id);
     return VFT_OK;            // asynchronous
 }
 
@@ -1657,7 +1669,7 @@ extern "C" int vft_posterior_profile_batch(vft_ctx *c, int64_t n, const int64_t 
         double *hl = (double *) ((char *) c->h_in + (size_t) m * 16);
         for (int64_t k = 0; k < m; k++) {
             const int64_t o = out_id[k0 + k], a = id1[k0 + k], b = id2[k0 + k];
-            if (o < c->N || o >= c->M || a < 0 || b < 0 || a >= c->M || b >= c->M) return fail(VFT_EINVAL, "bad node id");
+            if (!ml_writable(c, o) || a < 0 || b < 0 || a >= c->M + c->S || b >= c->M + c->S) return fail(VFT_EINVAL, "bad node id");
             hi[3 * k] = (int32_t) o; hi[3 * k + 1] = (int32_t) a; hi[3 * k + 2] = (int32_t) b;
             hl[2 * k] = len1[k0 + k]; hl[2 * k + 1] = len2[k0 + k];
         }
@@ -1674,11 +1686,7 @@ extern "C" int vft_posterior_profile_batch(vft_ctx *c, int64_t n, const int64_t 
         CK(cudaGetLastError());
         CK(sync_stream(c));                                   // h_in is reused
         c->cnt.launches++;
-        for (int64_t k = 0; k < m; k++) {
-            const int64_t o = out_id[k0 + k];
-            if (!c->activeHost[o]) { c->activeHost[o] = 1; c->nActInternal++; }
-            if (o >= c->maxnode) c->maxnode = o + 1;
-        }
+        for (int64_t k = 0; k < m; k++) ml_written(c, out_id[k0 + k]);
     }
     return VFT_OK;
 }
@@ -1691,7 +1699,7 @@ extern "C" int vft_get_config(vft_ctx *c, vft_config *out, int32_t *hasTransmat)
 }
 
 extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *codes, void *vectors) {
-    if (!c || id < -1 || id >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+    if (!c || id < -1 || !(id == -1 || ml_readable(c, id))) return fail(VFT_EINVAL, "bad node id");
     bind_device(c);
     const size_t ps = c->ps, L = (size_t) c->L, Lp = (size_t) c->Lp, A = (size_t) c->A;
     CK(sync_stream(c));
@@ -1714,6 +1722,20 @@ extern "C" int vft_get_profile(vft_ctx *c, int64_t id, void *weights, uint8_t *c
         if (weights) CK(cudaMemcpy(weights, (char *) c->weights + row * Lp * ps, L * ps, cudaMemcpyDeviceToHost));
         if (vectors) CK(cudaMemcpy(vectors, (char *) c->vecs + row * Lp * A * ps, L * A * ps, cudaMemcpyDeviceToHost));
     }
+    return VFT_OK;
+}
+
+// a dense profile written from the host into an internal-node or scratch row (the counterpart of vft_get_profile)
+extern "C" int vft_put_profile(vft_ctx *c, int64_t id, const void *weights, const uint8_t *codes, const void *vectors) {
+    if (!c || !weights || !codes || !vectors) return fail(VFT_EINVAL, "null argument");
+    if (!ml_writable(c, id)) return fail(VFT_EINVAL, "bad node id");
+    bind_device(c);
+    const size_t ps = c->ps, L = (size_t) c->L, Lp = (size_t) c->Lp, A = (size_t) c->A, row = (size_t) (id - c->N);
+    CK(sync_stream(c));
+    CK(cudaMemcpy((char *) c->codes + (size_t) id * Lp, codes, L, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char *) c->weights + row * Lp * ps, weights, L * ps, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char *) c->vecs + row * Lp * A * ps, vectors, L * A * ps, cudaMemcpyHostToDevice));
+    ml_written(c, id);
     return VFT_OK;
 }
 
