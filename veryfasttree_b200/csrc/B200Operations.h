@@ -132,9 +132,11 @@ public:
     // ---- 2. the batched surface: one method per replaced loop -----------------------------------
     // Bound to a device context by the NeighbourJoining constructor (after seqsToProfiles):
     //   operations.attach(nSeqs, nPos, options.nCodes, options.useMatrix, options.fPostTotalTolerance)
-    void attach(int64_t nSeqs, int64_t nPos, int nCodes, bool useMatrix, double fPostTotalTolerance, int device = 0) {
+    // nScratch: extra profile rows for the temporaries of the ML phase (stack Profiles of MLQuartetOptimize, upProfiles[])
+    void attach(int64_t nSeqs, int64_t nPos, int nCodes, bool useMatrix, double fPostTotalTolerance, int device = 0, int64_t nScratch = 0) {
         vft_config cfg;
         std::memset(&cfg, 0, sizeof cfg);
+        cfg.nScratch = nScratch;
         cfg.nSeqs = nSeqs; cfg.nPos = nPos; cfg.nCodes = nCodes;
         cfg.precision = (int32_t) (8 * sizeof(Precision));
         cfg.useMatrix = useMatrix ? 1 : 0;
@@ -193,6 +195,41 @@ public:
     }
     void posteriorProfile(int64_t out, int64_t id1, int64_t id2, double len1, double len2) {
         check(vft_posterior_profile(ctx.get(), out, id1, id2, len1, len2));
+    }
+    void posteriorProfileBatch(int64_t n, const int64_t *out, const int64_t *id1, const int64_t *id2, const double *len1, const double *len2) {
+        check(vft_posterior_profile_batch(ctx.get(), n, out, id1, id2, len1, len2));                               // one tree level, NJ.tcc:3508-3542
+    }
+    // whole-tree sweeps: recomputeMLProfiles + treeLogLk (NJ.tcc:3508-3542, :5114-5259), setMLRates (NJ.tcc:5429-5488)
+    double treeLogLk(int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child, const numeric_t *branchlength,
+                     bool recomputeProfiles, const uint8_t *leafCodes = nullptr, double *siteLoglk = nullptr) {
+        double lk = 0;
+        check(vft_tree_loglk(ctx.get(), root, maxnode, nChild, child, branchlength, recomputeProfiles ? 1 : 0, leafCodes, &lk, siteLoglk));
+        return lk;
+    }
+    void setMLRates(int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child, const numeric_t *branchlength,
+                    int64_t nRateCats, double MLMinRelBranchLength, double MLMinBranchLength, int fastexpLevel, const uint8_t *leafCodes,
+                    numeric_t *rates, int64_t *ratecat) {
+        check(vft_set_ml_rates(ctx.get(), root, maxnode, nChild, child, branchlength, nRateCats, MLMinRelBranchLength, MLMinBranchLength,
+                               fastexpLevel, leafCodes, rates, ratecat, nullptr));
+    }
+    // branch-length optimisation and ML NNI quartets as lock-step batches (csrc/ml_opt.cpp): MLPairOptimize (NJ.tcc:1790),
+    // MLQuartetNNI (NJ.tcc:4885) over MLQuartetOptimize / onedimenmin / brent, the per-node body of
+    // optimizeAllBranchLengths (NJ.tcc:5044-5058) and the whole sweep (NJ.tcc:5006-5112).  Needs a context created with
+    // scratch rows (attach(..., nScratch)).
+    void mlPairOptimizeBatch(const vft_ml_options &opt, int64_t n, const int64_t *idA, const int64_t *idB, double *length, double *loglk) {
+        check(vft_ml_pair_optimize_batch(ctx.get(), &opt, n, idA, idB, length, loglk, nullptr));
+    }
+    void mlQuartetNNIBatch(const vft_ml_options &opt, int64_t n, const int64_t *ids, numeric_t *len, double *criteria, int32_t *choice,
+                           int32_t *starTest, int64_t firstScratchRow) {
+        check(vft_ml_quartet_nni_batch(ctx.get(), &opt, n, ids, len, criteria, choice, starTest, firstScratchRow, nullptr));
+    }
+    void mlStarOptimizeBatch(const vft_ml_options &opt, int64_t n, const int64_t *ids, numeric_t *len, int64_t firstScratchRow) {
+        check(vft_ml_star_optimize_batch(ctx.get(), &opt, n, ids, len, firstScratchRow, nullptr));
+    }
+    void mlOptimizeBranchLengths(const vft_ml_options &opt, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                                 numeric_t *branchlength, bool referenceOrder) {
+        check(vft_ml_optimize_branch_lengths(ctx.get(), &opt, root, maxnode, nChild, child, branchlength,
+                                             referenceOrder ? VFT_ML_SCHEDULE_REFERENCE : VFT_ML_SCHEDULE_LEVELS, nullptr));
     }
 
 private:

@@ -60,29 +60,56 @@ inline uint64_t orderKey(float x) { if (x == 0) x = 0; uint32_t u; std::memcpy(&
 inline uint64_t orderKey(double x) { if (x == 0) x = 0; uint64_t u; std::memcpy(&u, &x, 8); return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull); }
 
 // psort order for an array of records with an integer key: key ascending, ties by input position
-// DESCENDING.  Sorts 16-byte (key, position) pairs and permutes once; scratch is per thread.
+// DESCENDING.  The usual case -- float criteria, or (i,j) keys with one i: the keys span less than 2^32 -- is a stable
+// LSD radix sort (8-bit digits, digits shared by every key skipped) of the records taken in REVERSED input order, which
+// leaves equal keys in reverse input order; lists here are a few hundred entries, where this is ~4x cheaper than a
+// comparison sort.  Scratch is per thread.
 template<class T, class KeyFn>
 void rsortByKey(std::vector<T> &v, KeyFn keyOf) {
     const size_t n = v.size();
     if (n < 2) return;
     static thread_local std::vector<std::pair<uint64_t, uint32_t>> kv;
-    static thread_local std::vector<uint64_t> k1;
+    static thread_local std::vector<uint64_t> k1, k2;
     static thread_local std::vector<T> tmp;
-    kv.resize(n);
+    k1.resize(n);
     uint64_t lo = ~0ull, hi = 0;
     for (size_t k = 0; k < n; k++) {
         const uint64_t key = keyOf(v[k]);
-        kv[k] = {key, (uint32_t) (n - 1 - k)};      // reversed position: plain pair order
+        k1[k] = key;
         lo = std::min(lo, key); hi = std::max(hi, key);
     }
     tmp.resize(n);
     if (hi - lo < (1ull << 32) && n < (1ull << 31)) {
-        // the usual case (float criteria; (i,j) keys with one i): key and reversed position share one word
-        k1.resize(n);
-        for (size_t k = 0; k < n; k++) k1[k] = ((kv[k].first - lo) << 32) | kv[k].second;
-        std::sort(k1.begin(), k1.end());
-        for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - (uint32_t) k1[k]];
+        // word r = (key - lo) << 32 | source position, for the sources in reversed order
+        k2.resize(n);
+        for (size_t r = 0; r < n; r++) { const size_t src = n - 1 - r; k2[r] = ((k1[src] - lo) << 32) | (uint32_t) src; }
+        if (n <= 32) {
+            // tiny lists: insertion sort on the key half only (stable)
+            for (size_t a = 1; a < n; a++) {
+                const uint64_t x = k2[a];
+                size_t c = a;
+                while (c > 0 && (k2[c - 1] >> 32) > (x >> 32)) { k2[c] = k2[c - 1]; c--; }
+                k2[c] = x;
+            }
+            for (size_t k = 0; k < n; k++) tmp[k] = v[(uint32_t) k2[k]];
+            v.swap(tmp);
+            return;
+        }
+        uint64_t *src = k2.data(), *dst = k1.data();
+        const uint64_t span = hi - lo;
+        for (int shift = 32; shift < 64 && (span >> (shift - 32)) != 0; shift += 8) {
+            uint32_t count[256] = {0};
+            for (size_t k = 0; k < n; k++) count[(src[k] >> shift) & 255]++;
+            if (count[(src[0] >> shift) & 255] == n) continue;          // every key has this digit
+            uint32_t sum = 0;
+            for (int d = 0; d < 256; d++) { const uint32_t c = count[d]; count[d] = sum; sum += c; }
+            for (size_t k = 0; k < n; k++) dst[count[(src[k] >> shift) & 255]++] = src[k];
+            std::swap(src, dst);
+        }
+        for (size_t k = 0; k < n; k++) tmp[k] = v[(uint32_t) src[k]];
     } else {
+        kv.resize(n);
+        for (size_t k = 0; k < n; k++) kv[k] = {k1[k], (uint32_t) (n - 1 - k)};      // reversed position: plain pair order
         std::sort(kv.begin(), kv.end());
         for (size_t k = 0; k < n; k++) tmp[k] = v[n - 1 - kv[k].second];
     }

@@ -817,19 +817,22 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
     }
 }
 
-// pairLogLk (NJ.tcc:1192-1447): one warp per (pair, length) item
+// pairLogLk (NJ.tcc:1192-1447): W warps per (pair, length) item, 8 / W items per CTA.  W = 1 for whole-tree batches
+// (treeLogLk: one item per internal node); the lock-step Brent rounds of ml_opt.cpp carry tens to hundreds of items, far
+// fewer than the machine has warps, and get up to 8 warps each.
 template<typename P, int A>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_pair_loglk(Store<P> s, MLModel<P> m, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
-             const double *__restrict__ len, int64_t n, double *__restrict__ loglk, double *__restrict__ siteLk) {
+             const double *__restrict__ len, int64_t n, double *__restrict__ loglk, double *__restrict__ siteLk, int W, int tableBytes) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    const int64_t item = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-    const size_t perWarp = (size_t) s.Lp * 8 + 64 * 20 * 8;
-    unsigned char *mine = smemRaw + (threadIdx.x >> 5) * perWarp;
-    if (item >= n) return;
-    const double v = pair_loglk_warp<P, A>(s, m, ia[item], ib[item], len[item], reinterpret_cast<double *>(mine),
-                                           mine + (size_t) s.Lp * 8, siteLk ? siteLk + item * s.L : nullptr);
-    if ((threadIdx.x & 31) == 0) loglk[item] = v;
+    const int nT = 32 * W, perCta = 8 / W, local = threadIdx.x / nT, tid = threadIdx.x - local * nT;
+    const int64_t item = blockIdx.x * (int64_t) perCta + local;
+    const size_t perItem = (size_t) s.Lp * 8 + (size_t) tableBytes;
+    unsigned char *mine = smemRaw + local * perItem;
+    const bool valid = item < n;
+    pair_loglk_group<P, A>(s, m, valid, valid ? ia[item] : 0, valid ? ib[item] : 0, valid ? len[item] : 0.0,
+                           reinterpret_cast<double *>(mine), mine + (size_t) s.Lp * 8, valid && siteLk ? siteLk + item * s.L : nullptr,
+                           tid, nT, valid ? loglk + item : nullptr);
 }
 
 // posteriorProfile (NJ.tcc:2137-2447): one thread per position; the two expEigenRates tables (or the
@@ -1615,14 +1618,20 @@ extern "C" int vft_pair_loglk_batch(vft_ctx *c, const int64_t *pi, const int64_t
         c->cnt.algoBytes += profile_bytes(c, pi[k]) + profile_bytes(c, pj[k]) + c->L * 4;
     }
     double *outLk = (double *) c->h_out, *outSite = siteLk ? outLk + n : nullptr;
-    const size_t perWarp = (size_t) c->Lp * 8 + 64 * 20 * 8;
-    const size_t smem = 4 * perWarp;
-    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-warp likelihood buffers");
-    const unsigned blocks = (unsigned) ((n + 3) / 4);
+    // warps per item: as many as keep ~16 warps per SM busy, at most 8 (one CTA per item)
+    int W = 1;
+    while (W < 8 && n * (2 * W) <= 148 * 16) W *= 2;
+    const int tableBytes = (int) (((c->hasTransmat ? (size_t) c->nRateCats * c->A * c->ps : (size_t) c->nRateCats * 16) + 15) / 16 * 16);
+    const size_t perItem = (size_t) c->Lp * 8 + (size_t) tableBytes;
+    while (W < 8 && (size_t) (8 / W) * perItem > 100 * 1024) W *= 2;      // long alignments: fewer items per CTA, two CTAs per SM
+    const int perCta = 8 / W;
+    const size_t smem = (size_t) perCta * perItem;
+    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-item likelihood buffers");
+    const unsigned blocks = (unsigned) ((n + perCta - 1) / perCta);
 #define CALL_LK(P, A_)                                                                                          \
     do {                                                                                                        \
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pair_loglk<P, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-        k_pair_loglk<P, A_><<<blocks, 128, smem, c->stream>>>(make_store<P>(c), make_model<P>(c), ha, hb, hl, n, outLk, outSite); \
+        k_pair_loglk<P, A_><<<blocks, 256, smem, c->stream>>>(make_store<P>(c), make_model<P>(c), ha, hb, hl, n, outLk, outSite, W, tableBytes); \
     } while (0)
     prof_begin(c, CLS_DIST, K_LOGLK);
     if (c->cfg.precision == 32) { if (c->A == 4) CALL_LK(float, 4); else CALL_LK(float, 20); }

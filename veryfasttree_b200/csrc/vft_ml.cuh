@@ -145,38 +145,53 @@ __device__ __forceinline__ double site_lk(const Store<P> &s, const MLModel<P> &m
     return (double) vec_mul3_sum<P, A>(ee, fA, fB, s.reduction);                           // :1359
 }
 
-// pairLogLk, NJ.tcc:1192-1447, by one warp.  sm: [Lp] doubles (per-site lkAB), then the tables.
+// pairLogLk, NJ.tcc:1192-1447, by the nT threads (1, 2, 4 or 8 warps) that share one (pair, length) item; every thread of
+// the CTA calls this (the barriers are CTA-wide), `valid` = the group has an item.  sm: [Lp] doubles (per-site lkAB), then
+// the group's exp(eigenvalue x rate x length) table.  The per-site values are computed by all threads; the product over
+// the sites is the reference's own sequential chain (double products with the 1e-4 / 1e4 rescale, whose rounding depends
+// on the order), run by the group's first thread over register-prefetched blocks of 8 terms.
 template<typename P, int A>
-__device__ __forceinline__ double pair_loglk_warp(const Store<P> &s, const MLModel<P> &m, int64_t i, int64_t j, double length,
-                                                  double *termL, void *tableRaw, double *siteOut) {
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void pair_loglk_group(const Store<P> &s, const MLModel<P> &m, bool valid, int64_t i, int64_t j, double length,
+                                                 double *termL, void *tableRaw, double *siteOut, int tid, int nT, double *out) {
     P *expeigen = reinterpret_cast<P *>(tableRaw);
     double *pSame = reinterpret_cast<double *>(tableRaw), *pDiff = pSame + m.nRateCats;
-    if (m.codeFreq) exp_eigen_rates<P, A>(m, length, expeigen, lane, 32);
-    else jc_tables<P>(m, length, pSame, pDiff, lane, 32);
-    __syncwarp();
-    const View<P, A> p1 = make_view<P, A>(s, i), p2 = make_view<P, A>(s, j);
-    for (int64_t pos = lane; pos < s.Lp; pos += 32) {
-        const double v = pos < s.L ? site_lk<P, A>(s, m, p1, p2, pos, expeigen, pSame, pDiff) : 1.0;
-        termL[pos] = v;
-        if (siteOut && pos < s.L) siteOut[pos] = v;
+    if (valid) {
+        if (m.codeFreq) exp_eigen_rates<P, A>(m, length, expeigen, tid, nT);
+        else jc_tables<P>(m, length, pSame, pDiff, tid, nT);
     }
-    __syncwarp();
-    double loglk = 0.0;
-    if (lane == 0) {
-        const double LkUnderflow = 1.0e-4, LkUnderflowInv = 1.0e4, LogLkUnderflow = 9.21034037197618;   // Constants.h:13-15
-        double lk = 1.0;
-        const bool up = m.codeFreq != nullptr;          // the JC branch has no upward rescale (:1259-1262)
-        for (int64_t pos = 0; pos < s.L; pos++) {
-            lk = xmul(lk, termL[pos]);
-            while (lk < LkUnderflow) { lk = xmul(lk, LkUnderflowInv); loglk = xsub(loglk, LogLkUnderflow); }
-            if (up) while (lk > LkUnderflowInv) { lk = xmul(lk, LkUnderflow); loglk = xadd(loglk, LogLkUnderflow); }
+    __syncthreads();
+    if (valid) {
+        const View<P, A> p1 = make_view<P, A>(s, i), p2 = make_view<P, A>(s, j);
+        for (int64_t pos = tid; pos < s.Lp; pos += nT) {
+            const double v = pos < s.L ? site_lk<P, A>(s, m, p1, p2, pos, expeigen, pSame, pDiff) : 1.0;
+            termL[pos] = v;
+            if (siteOut && pos < s.L) siteOut[pos] = v;
         }
-        loglk = xadd(loglk, log(lk));                                                      // :1444
     }
-    __syncwarp();
-    return __shfl_sync(full, loglk, 0);
+    __syncthreads();
+    if (valid && tid == 0) {
+        const double LkUnderflow = 1.0e-4, LkUnderflowInv = 1.0e4, LogLkUnderflow = 9.21034037197618;   // Constants.h:13-15
+        double lk = 1.0, loglk = 0.0;
+        const bool up = m.codeFreq != nullptr;          // the JC branch has no upward rescale (:1259-1262)
+        const double2 *t2 = reinterpret_cast<const double2 *>(termL);
+        // (Two branch-free variants of this chain -- the rescale as a select, and as predicated multiplies decided on the
+        // high word -- were measured SLOWER on the B200 than this literal form with one guarding test per site: 177 / 194 ms
+        // against 123 ms per sweep of profiles/ml_opt.py.)
+        for (int64_t p0 = 0; p0 < s.Lp; p0 += 8) {      // Lp is a multiple of 32; the padding holds 1.0 (exact, no rescale)
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const double2 x = t2[(p0 >> 1) + q]; t[2 * q] = x.x; t[2 * q + 1] = x.y; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                lk = xmul(lk, t[q]);
+                if (lk < LkUnderflow || (up && lk > LkUnderflowInv)) {
+                    while (lk < LkUnderflow && lk > 0.0) { lk = xmul(lk, LkUnderflowInv); loglk = xsub(loglk, LogLkUnderflow); }
+                    if (up) while (lk > LkUnderflowInv) { lk = xmul(lk, LkUnderflow); loglk = xadd(loglk, LogLkUnderflow); }
+                }
+            }
+        }
+        *out = xadd(loglk, log(lk));                                                       // :1444
+    }
 }
 
 // posteriorProfile for one position, NJ.tcc:2176-2261 (JC) / :2266-2334 (nt matrix) / :2340-2429 (aa, exactML)
