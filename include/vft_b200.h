@@ -272,6 +272,12 @@ int  vft_ml_pair_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t
 int  vft_ml_quartet_nni_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
                               double *criteria, int32_t *choice, int32_t *starTest, int64_t firstScratchRow,
                               vft_ml_stats *stats);
+/* chooseNNI (NJ.tcc:4836-4852), the minimum-evolution counterpart: for n quartets ids[4n] = A,B,C,D (node ids), the six
+   profile distances of each (correctedPairDistances, NJ.tcc:1460-1488: bare profileDist, Options.pseudoWeight prior,
+   logCorrect NJ.tcc:322-330 when logdist) evaluated as ONE vft_dist_pairs batch; criteria[3n] = d(AB)+d(CD), d(AC)+d(BD),
+   d(AD)+d(BC) (lower is better), choice[n] 0/1/2 with the reference's tie rules.  No topological constraints. */
+int  vft_choose_nni_batch(vft_ctx *ctx, int64_t n, const int64_t *ids, double pseudoWeight, int32_t logdist,
+                          double *criteria, int32_t *choice);
 /* The per-node body of optimizeAllBranchLengths (NJ.tcc:5044-5058) for n nodes: ids[3n] = the three profiles that
    meet at the node (child, child, up-profile -- or the three children of the root), len[3n] numeric_t in/out; two
    sweeps, each branch optimised against the posterior of the other two.  Scratch rows firstScratchRow .. +n-1. */

@@ -499,6 +499,32 @@ static int run(const std::string &fasta, bool aa, bool tophitsOnly) {
         }
         putq("join.i", pi); putq("join.j", pj); putv<P>("join.dist", dd); putv<P>("join.weight", ww);
     }
+    // chooseNNI (NJ.tcc:4836-4852) over quartets of active nodes: default options, then with a pseudo-count prior and
+    // without the log correction
+    {
+        typedef typename NeighbourJoining<P, AVX256Operations>::Profile Profile;
+        std::vector<int64_t> q;
+        for (size_t x = 0; x + 3 < active.size() && x < 24; x++) {
+            q.push_back(active[x]); q.push_back(active[active.size() - 1 - x]); q.push_back(active[(x * 7 + 2) % active.size()]); q.push_back(active[(x * 3 + 5) % active.size()]);
+        }
+        const int64_t nq = (int64_t) q.size() / 4;
+        for (int variant = 0; variant < 3; variant++) {
+            options.pseudoWeight = variant == 1 ? 1.0 : 0.0;
+            options.logdist = variant != 2;
+            std::vector<double> crit;
+            std::vector<int64_t> ch;
+            for (int64_t k = 0; k < nq; k++) {
+                Profile *p4[4] = {&nj.profiles[q[4 * k]], &nj.profiles[q[4 * k + 1]], &nj.profiles[q[4 * k + 2]], &nj.profiles[q[4 * k + 3]]};
+                double c[3];
+                ch.push_back((int64_t) nj.chooseNNI(p4, c));
+                crit.insert(crit.end(), c, c + 3);
+            }
+            put("nni" + std::to_string(variant) + ".criteria", 'd', {nq, 3}, crit.data());
+            putq("nni" + std::to_string(variant) + ".choice", ch);
+        }
+        options.pseudoWeight = 0.0; options.logdist = true;
+        putq("nni.ids", q, {nq, 4});
+    }
     // full out-profile rebuild over the active set (outProfile, NJ.tcc:729-815)
     {
         typedef typename NeighbourJoining<P, AVX256Operations>::Profile Profile;

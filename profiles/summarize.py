@@ -87,7 +87,20 @@ def launch_list():
     return agg, tot
 
 
+def ml():
+    """k_pair_loglk in its two regimes (profiles/capture_ml.sh)."""
+    summarize(os.path.join(RAW, "prof_loglk_round.ncu-rep"), "Round 1 -- `ncu --set full` of `k_pair_loglk<float,20>` inside a lock-step Brent round (aa 4 000 x 1287, JTT, ~70-130 items x 8 warps, warm L2)",
+              "ncu --set full --import-source on --clock-control none --cache-control none -k regex:k_pair_loglk -s 600 -c 2 -o gpurun_out/prof_loglk_round python profiles/ml_opt.py 4000 1287 0",
+              "Reading: one round of csrc/ml_opt.cpp = the pending pairLogLk of every live branch optimisation: ~70-130 (pair, length) items, one CTA of 8 warps each (W = 8), so at most one CTA per SM on half of the SMs.  The 256 threads compute the 1287 per-site likelihoods in 5-6 strides (20-state dot products with the exp(eigenvalue x rate x length) table in shared memory), then the CTA's first thread runs the reference's sequential product over the sites -- double multiplies with the 1e-4 / 1e4 rescale, whose rounding depends on the order, so it cannot be split (DSETP + BRA + DMUL = the top stall samples).  The launch is LATENCY bound: `sm__cycles_elapsed.max` is one CTA's critical path, issue slots ~14 % busy on the SMs in use, DRAM traffic ~0 (the 4 000 profiles = 436 MB are mostly L2 hits between rounds).  Before the W-warps-per-item change the same round took 156 us (one warp per item).  What bounds a sweep is the number of rounds on the tree's critical path (height x 6 Brent minimisations), ~1 500 per sweep here.", "%s_k_pair_loglk_round_ncu_full.md" % TAG)
+    summarize(os.path.join(RAW, "prof_loglk_tree.ncu-rep"), "Round 1 -- `ncu --set full` of `k_pair_loglk<float,20>` on a whole-tree batch (treeLogLk, aa 20 000 x 1287: 19 999 items, one warp each)",
+              "ncu --set full --import-source on --clock-control none -k regex:k_pair_loglk -c 2 -o gpurun_out/prof_loglk_tree python profiles/ml_sweep.py 20000 1287",
+              "Reading: all pairLogLk terms of treeLogLk in one launch: 19 999 items x 2 profiles x 109 KB = 4.38 GB algorithmic, W = 1 (8 items per CTA, 86 KB of shared memory: two CTAs = 16 warps per SM).  Live CUDA-event time without the profiler: 2.66 ms = 1.65 TB/s = 26 % of the measured 6.45 TB/s HBM peak (was 5.7 ms with 4 items per CTA and a 10 KB table per warp).  DRAM traffic 2.2 GB: half the algorithmic bytes (leaf profiles are 1 byte per site; vectors are fetched only where a site has no known code).  Limiter: each warp's lane 0 runs the 1287-step sequential product while the other 31 lanes idle (DSETP/BRA/DMUL chain), and 16 warps per SM cannot hide it; next step is to give the product chains of several items to the lanes of one warp (transpose through shared memory, as the distance kernels do for their ordered sums).", "%s_k_pair_loglk_tree_ncu_full.md" % TAG)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "ml":
+        ml()
+        sys.exit(0)
     launch_list()
     summarize(os.path.join(RAW, "prof_eval_small.ncu-rep"), "Round 1 -- `ncu --set full` of the dominant kernel: `k_eval<float,4,false>`, per-join request lists (16 000 taxa, warm L2)",
               "ncu --set full --import-source on --clock-control none --cache-control none -k regex:k_eval -s 20000 -c 3 -o gpurun_out/prof_eval_small python profiles/one_step.py 16000",

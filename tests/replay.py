@@ -143,6 +143,11 @@ def replay(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: in
         d, wt = ctx.dist_pairs(dump["join.i"], dump["join.j"], flags=0)
         cmp("join.dist", d)
         cmp("join.weight", wt)
+        if "nni.ids" in dump:        # chooseNNI (NJ.tcc:4836-4852): defaults / pseudo-count prior / no log correction
+            for variant, (pw, logd) in enumerate(((0.0, True), (1.0, True), (0.0, False))):
+                crit, choice = ctx.choose_nni(dump["nni.ids"], pw, logd)
+                cmp("nni%d.criteria" % variant, crit)
+                cmp("nni%d.choice" % variant, choice.astype(np.int64))
         ctx.outprofile_rebuild()
         w, cd, v = ctx.get_profile(-1)
         cmp("rebuild.outprofile.weights", w)

@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "vft_dist_one_vs_all_range", "vft_tophits_merge", "vft_release_cached_memory",
     "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk", "vft_set_ml_rates",
     "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
-    "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths",
+    "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
 ]
 
 
@@ -139,6 +139,7 @@ class Lib:
             d.vft_ml_quartet_nni_batch.argtypes = [vp, mo, i64, vp, vp, vp, vp, vp, i64, ms]
             d.vft_ml_star_optimize_batch.argtypes = [vp, mo, i64, vp, vp, i64, ms]
             d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
+            d.vft_choose_nni_batch.argtypes = [vp, i64, vp, dbl, i32, vp, vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -380,6 +381,14 @@ class Context:
         self.lib.check(self.lib.dll.vft_ml_quartet_nni_batch(self.h, C.byref(opt), n, _ptr(ids), _ptr(ln), _ptr(crit), _ptr(choice),
                                                              _ptr(star), int(first_scratch_row), C.byref(st)), "vft_ml_quartet_nni_batch")
         return ln, crit, choice, star, st.as_dict()
+
+    def choose_nni(self, ids, pseudo_weight=0.0, logdist=True):
+        """vft_choose_nni_batch: (criteria[n,3], choice[n])."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1, 4)
+        crit = np.zeros((len(ids), 3), dtype=np.float64); choice = np.zeros(len(ids), dtype=np.int32)
+        self.lib.check(self.lib.dll.vft_choose_nni_batch(self.h, len(ids), _ptr(ids), float(pseudo_weight), 1 if logdist else 0,
+                                                         _ptr(crit), _ptr(choice)), "vft_choose_nni_batch")
+        return crit, choice
 
     def ml_star_optimize(self, opt, ids, length, first_scratch_row):
         """vft_ml_star_optimize_batch: (len[n,3], stats)."""

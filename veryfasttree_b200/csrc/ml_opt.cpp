@@ -599,6 +599,59 @@ extern "C" int vft_ml_quartet_nni_batch(vft_ctx *ctx, const vft_ml_options *opt,
     return rc;
 }
 
+// chooseNNI, NJ.tcc:4836-4852: the minimum-evolution counterpart of MLQuartetNNI.  The six profile distances of every
+// quartet (correctedPairDistances, NJ.tcc:1460-1488) are ONE vft_dist_pairs call for the whole batch; the pseudo-count
+// prior, the log correction (logCorrect, NJ.tcc:322-330) and the three-way comparison are scalar work on the results.
+extern "C" int vft_choose_nni_batch(vft_ctx *ctx, int64_t n, const int64_t *ids, double pseudoWeight, int32_t logdist,
+                                    double *criteria, int32_t *choice) {
+    vft_config cfg;
+    if (!ctx || n < 0 || (n > 0 && (!ids || !criteria || !choice)) || vft_get_config(ctx, &cfg, nullptr) != VFT_OK) return VFT_EINVAL;
+    if (n == 0) return VFT_OK;
+    const bool single = cfg.precision == 32;
+    std::vector<int64_t> pi((size_t) (6 * n)), pj((size_t) (6 * n));
+    for (int64_t k = 0; k < n; k++)
+        for (int h = 0, i = 0; i < 4; i++)
+            for (int j = i + 1; j < 4; j++, h++) { pi[(size_t) (6 * k + h)] = ids[4 * k + i]; pj[(size_t) (6 * k + h)] = ids[4 * k + j]; }   // qAB qAC qAD qBC qBD qCD
+    std::vector<double> raw((size_t) (12 * n));                  // room for 6n distances + 6n weights of either precision
+    void *dist = raw.data(), *weight = (char *) raw.data() + (size_t) (6 * n) * (single ? 4 : 8);
+    const int rc = vft_dist_pairs(ctx, pi.data(), pj.data(), 6 * n, VFT_PAIRS_PROFILE_RAW, dist, weight);
+    if (rc != VFT_OK) return rc;
+    const bool jukesCantor = cfg.nCodes == 4 && !cfg.useMatrix;
+    for (int64_t k = 0; k < n; k++) {
+        double d[6];
+        for (int h = 0; h < 6; h++) d[h] = rdP(dist, 6 * k + h, single);
+        if (pseudoWeight > 0) {                                  // :1472-1484
+            double dTop = 0, dBottom = 0;
+            for (int h = 0; h < 6; h++) {
+                // hit.dist * hit.weight is a numeric_t product
+                const double prod = single ? (double) (((const float *) dist)[6 * k + h] * ((const float *) weight)[6 * k + h])
+                                           : ((const double *) dist)[6 * k + h] * ((const double *) weight)[6 * k + h];
+                dTop += prod;
+                dBottom += rdP(weight, 6 * k + h, single);
+            }
+            const double prior = dBottom > 0.01 ? dTop / dBottom : 3.0;
+            for (int h = 0; h < 6; h++) {
+                const double w = rdP(weight, 6 * k + h, single);
+                d[h] = (d[h] * w + prior * pseudoWeight) / (w + pseudoWeight);
+            }
+        }
+        if (logdist)                                             // logCorrect, :322-330
+            for (int h = 0; h < 6; h++) {
+                const double maxscore = 3.0;
+                double x = d[h];
+                if (jukesCantor) x = x < 0.74 ? -0.75 * std::log(1.0 - x * 4.0 / 3.0) : maxscore;
+                else x = x < 0.99 ? -1.3 * std::log(1.0 - x) : maxscore;
+                d[h] = x < maxscore ? x : maxscore;
+            }
+        double *c = criteria + 3 * k;
+        c[0] = d[0] + d[5]; c[1] = d[1] + d[4]; c[2] = d[2] + d[3];        // AB+CD, AC+BD, AD+BC (:4843-4845)
+        choice[k] = 0;
+        if (c[1] < c[0] && c[1] <= c[2]) choice[k] = 1;
+        else if (c[2] < c[0] && c[2] <= c[1]) choice[k] = 2;
+    }
+    return VFT_OK;
+}
+
 extern "C" int vft_ml_star_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
                                           int64_t firstScratchRow, vft_ml_stats *stats) {
     Opt o; vft_config cfg;
