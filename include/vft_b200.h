@@ -109,6 +109,25 @@ int  vft_profile_average_update(vft_ctx *ctx, int64_t out_id, int64_t id1, int64
                                 double bionjWeight, double diameter_out, int64_t nActiveOld);
 int  vft_get_self(vft_ctx *ctx, int64_t id, double *selfdist, double *selfweight);
 
+/* -- speculative join: the NEXT join's device work launched ahead of the host's decision ------------------------------
+   The join loop is a dependency chain (search -> averageProfile -> distances of the new node -> bookkeeping -> search):
+   the device idles while the host decides and the host idles while the device computes.  The caller's guess of the next
+   join is right ~95 % of the time, so it may launch that join early, asynchronously, with NOTHING committed:
+     launch : profile out_id (must be the next free id) = average of id1,id2 as vft_profile_average_update would build
+              it; the updated out-profile goes to a shadow copy; then bare profileDist(out_id, pair_j[k]) (NJ.tcc:1167-1190,
+              no diameter correction) and bare profileDist(out_ids[k], NEW out-profile) (out_ids may contain out_id).
+              Raw values because the corrections (NJ.tcc:1120, :1046-1052) need diameter[out_id] / totdiam, which the
+              host only knows once the join is decided; the caller finishes them in the same arithmetic.
+     take   : the guess was right -- commits what vft_profile_average_update commits (per-node state, the out-profile:
+              a pointer swap) and returns the results; self2 = {selfdist, selfweight} of the new node (numeric_t).
+     discard: the guess was wrong -- nothing to undo.
+   Any other entry point may be called between launch and take/discard; it sees the uncommitted state. */
+int  vft_spec_join_launch(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight, int64_t nActiveOld,
+                          const int64_t *pair_j, int64_t nPairs, const int64_t *out_ids, int64_t nOut);
+int  vft_spec_join_take(vft_ctx *ctx, double diameter_out, void *pairDist, void *pairWeight, void *outDist,
+                        void *outWeight, void *self2);
+int  vft_spec_join_discard(vft_ctx *ctx);
+
 /* -- out-distances: setOutDistance (NJ.tcc:1012-1053) --------------------------------------- */
 /* fresh value for each ids[k] at this nActive/totdiam against the current out-profile.
    Pure: does not touch the context's own out-distance table (the caller decides what to commit,
@@ -379,6 +398,7 @@ typedef struct vft_nj_result {
     int64_t root, maxnode, m;
     int64_t nSeeds, nCloseUsed, nRefreshTopHits, nVisibleUpdate, nHillBetter;
     int64_t nOutPrefetchHit, nOutSingleFetch, nPairPrefetchHit, nPairSingleFetch, nDeviceCalls;
+    int64_t nSpecHit, nSpecMiss;/* speculative joins (vft_spec_join_*) that were taken / dropped */
     double  secondsLeafTopHits, secondsJoins, secondsTotal;
     double  deviceMsResident;   /* vft_timer around ctor tail + fastNJ: leaves already in HBM  */
     double  secondsEndToEnd;    /* host clock around everything incl. context + upload + result */

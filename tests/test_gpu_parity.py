@@ -229,6 +229,17 @@ def test_cuda_ml_optimizers_match_reference(glib, name, prec, lvl):
     assert bad == [], (bad, info)
 
 
+def test_speculative_join_on_device(glib, monkeypatch):
+    """vft_spec_join_* on the device (shadow out-profile, raw distances, state commit): with the speculative path on, the
+    1000-taxon tree is still the reference's, byte for byte."""
+    monkeypatch.setenv("VFT_SPECULATION", "1")
+    chars, kind = replay.golden_case("nt1000")
+    want = open(os.path.join(replay.GOLDEN, "nt1000_f32.nj.tree")).read().strip()
+    tree = api.nj_build(api.encode(chars, kind), 4, 32, lib=glib)
+    assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+    assert tree.stats["nSpecHit"] > 500
+
+
 def test_second_device_and_host_threads(glib):
     """A context on device 1 (when there is one): every entry point binds the calling thread to the context's device,
     and the host-thread regions of the driver make no device call of their own (bench.py --gpus N, rank > 0)."""

@@ -132,3 +132,20 @@ def test_oracle_ml_optimizers_match_reference(olib, name, prec, lvl):
     # the batching itself: all quartets advance together, so a call makes far fewer device calls than evaluations
     st = info["quartet.stats"]
     assert st["loglkItems"] > 8 * st["loglkCalls"]
+
+
+@pytest.mark.parametrize("name,prec", [("nt1000", 32), ("aa300", 32), ("c1", 64)])
+def test_speculative_join_is_only_a_hint(olib, name, prec, monkeypatch):
+    """The speculative-join path (vft_spec_join_launch / _take / _discard: the guessed NEXT join computed ahead, raw
+    distances finished on the host in the reference's arithmetic) must leave the tree byte-identical to the reference's,
+    whether a guess is taken or dropped."""
+    monkeypatch.setenv("VFT_SPECULATION", "1")
+    chars, kind = replay.golden_case(name)
+    tables = None
+    if kind == "aa":
+        z = np.load(os.path.join(replay.GOLDEN, "blosum45_f%d.npz" % prec))
+        tables = [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=olib, tables=tables)
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
+    assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+    assert tree.stats["nSpecHit"] > 0.5 * (chars.shape[0] - 3) and tree.stats["nSpecMiss"] > 0

@@ -69,6 +69,7 @@ class VftNjResult(C.Structure):
                 ("nVisibleUpdate", C.c_int64), ("nHillBetter", C.c_int64),
                 ("nOutPrefetchHit", C.c_int64), ("nOutSingleFetch", C.c_int64),
                 ("nPairPrefetchHit", C.c_int64), ("nPairSingleFetch", C.c_int64), ("nDeviceCalls", C.c_int64),
+                ("nSpecHit", C.c_int64), ("nSpecMiss", C.c_int64),
                 ("secondsLeafTopHits", C.c_double), ("secondsJoins", C.c_double), ("secondsTotal", C.c_double),
                 ("deviceMsResident", C.c_double), ("secondsEndToEnd", C.c_double), ("secondsInCalls", C.c_double), ("secondsHost", C.c_double * 8),
                 ("counters", VftCounters)]
@@ -85,6 +86,7 @@ ABI_SYMBOLS = [
     "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk", "vft_set_ml_rates",
     "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
+    "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard",
 ]
 
 
@@ -492,7 +494,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
         tptr = C.cast(arr, C.c_void_p)
     rc = lib.dll.vft_nj_build(C.byref(cfg), C.byref(opt), _ptr(codes), tptr, C.byref(res))
     lib.check(rc, "vft_nj_build")
-    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:25]}
+    stats = {k: getattr(res, k) for k, _ in VftNjResult._fields_[9:27]}
     stats["secondsHost"] = [float(x) for x in res.secondsHost]
     stats.update({"counters": {k: (list(getattr(res.counters, k)) if k in ("msKernel", "nKernel", "bytesKernel") else getattr(res.counters, k))
                                for k, _ in VftCounters._fields_}})

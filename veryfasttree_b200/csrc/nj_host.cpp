@@ -144,12 +144,20 @@ public:
         up.resize(maxnodes);
         for (int64_t i = 0; i < maxnodes; i++) up[i] = i;
         hostThreads = opt.hostThreads > 0 ? opt.hostThreads : std::max(1, std::min(16, omp_get_num_procs()));
+        // EXPERIMENTAL, off unless VFT_SPECULATION=1: bit-identical trees and a 98 % hit rate, but measured SLOWER on the
+        // B200 (C2 1.68 s vs 1.26 s; 100k x 1287 aa 30.6 s vs 26.5 s): each speculated join costs three more launches of
+        // host API time, and the hints for the search after next still need their own synchronous call.  It pays only
+        // once those go out asynchronously too.
+        specEnabled = opt.prefetch && std::getenv("VFT_SPECULATION") != nullptr && std::getenv("VFT_SPECULATION")[0] == '1';
+        selfdistH.assign(maxnodes, 0); selfweightH.assign(maxnodes, 0); selfKnown.assign(maxnodes, 0);
+        specSeenP.assign(maxnodes, 0); specSeenO.assign(maxnodes, 0);
         // nGaps(i) = nPos - selfweight[i] (NJ.tcc:249-252, :3762): gap/unknown columns of leaf i
         leafGaps.assign(nSeqs, 0);
         for (int64_t i = 0; i < nSeqs; i++) {
             int64_t g = 0;
             for (int64_t p = 0; p < nPos; p++) g += codes[i * nPos + p] >= cfg.nCodes;
             leafGaps[i] = g;
+            selfweightH[i] = (P) (nPos - g); selfdistH[i] = 0; selfKnown[i] = 1;      // NJ.tcc:249-252
         }
     }
 
@@ -462,6 +470,28 @@ private:
     std::vector<std::pair<uint64_t, uint32_t>> rtvKv;
     std::vector<int64_t> rfNodes, rfOffset, rfOwnJ, rfAllJ, rfCount, rfOutJ;      // scratch of refreshListsOnDevice
     std::vector<P> rfOwnDist, rfAllDist, rfOutDist;
+    // ---- speculative next join (vft_spec_join_*) ---------------------------------------------------------------
+    // While the host finishes join t (list bookkeeping, the next search), the device already computes join t+1 as
+    // guessed by speculateSearch -- the new profile, the updated out-profile (shadow copy) and the raw distances the
+    // next topHitJoin will ask for.  If the search then picks that very pair (~95 %), the values are finished here in
+    // the reference's arithmetic (diameter correction NJ.tcc:1120, setOutDistance NJ.tcc:1046-1052) and injected
+    // into the pair / out-distance services, exactly as if they had been fetched; otherwise they are dropped.  Like
+    // every prefetch in this file it is only a hint: the decisions never depend on it.
+    struct Spec {
+        bool valid = false;
+        int64_t g = -1, gj = -1, out = -1, nActiveNext = 0, refreshes = 0;
+        std::vector<int64_t> pairJ, outIds;
+    } spec;
+    bool specEnabled = false;
+    int64_t guessG = -1, guessGj = -1;                    // the last guess of speculateSearch
+    int64_t nActiveOutProfileReset = 0;
+    std::vector<P> selfdistH, selfweightH;                // host mirror of the device's self distances (needed to finish raw out-distances)
+    std::vector<char> selfKnown;
+    std::vector<int64_t> specSeenP, specSeenO; int64_t specStamp = 0;
+    std::vector<P> specPD, specPW, specOD, specOW;
+    void specLaunch(int64_t nActiveNext);
+    bool specTake(int64_t i, int64_t j, int64_t newnode, int64_t nActive);
+    void specInject(int64_t newnode, int64_t nActive);
     int64_t oneVsAll(int64_t query, int64_t nActive, int64_t K, std::vector<Besthit> &out);
     void fastNJSearch(int64_t nActive, std::vector<Besthit> &besthits, Besthit &join);
     void setBestHitFull(int64_t node, int64_t nActive, Besthit &bestjoin, std::vector<Besthit> *allhits);
@@ -544,7 +574,10 @@ void NJ<P>::uniqueBestHitsPrepare(int64_t nActive, std::vector<Besthit> &combine
     slots.assign(out.size(), -1);
     for (size_t k = 0; k < out.size(); k++) {
         const Besthit &h = out[k];
-        if (h.dist < 0.0) slots[k] = slotPair(h.i, h.j);
+        if (h.dist < 0.0) {
+            const DW *have = pairCache.find(pkey(h.i, h.j));                 // a speculated join left it there (specInject)
+            slots[k] = (have != nullptr && have->weight >= 0) ? -2 : slotPair(h.i, h.j);
+        }
         hintCriterion(nActive, h.i, h.j);
     }
 }
@@ -584,7 +617,7 @@ void NJ<P>::uniqueBestHitsFinish(int64_t nActive, std::vector<Besthit> &out, con
         Besthit &h = out[k];
         if (h.dist < 0.0) {                                      // :4826-4827
             if (slots[k] >= 0) { h.dist = reqD[slots[k]]; h.weight = reqW[slots[k]]; res->nPairPrefetchHit++; setCriterion(nActive, h); }
-            else setDistCriterion(nActive, h);
+            else setDistCriterion(nActive, h);                           // -2: from the pair cache; -1: fetched on demand
         } else setCriterion(nActive, h);
     }
 }
@@ -926,6 +959,7 @@ void NJ<P>::speculateSearch(int64_t nActive) {
         double c = h.dist - (outI + outJ) / (double) (nActive - 2);
         if (c < c1) { c1 = c; g1 = iNode; }
     }
+    guessG = g1; guessGj = g1 >= 0 ? (int64_t) visible[g1].j : -1;
     for (int64_t g : {g1}) {
         if (g < 0) continue;
         const int64_t gj = visible[g].j;
@@ -1012,6 +1046,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         speculateSearch(nActive);                    // (covers the top-visible set)                    // ... and what the NEXT join search will most likely ask for
     }
     flush(nActive);
+    if (specEnabled) specLaunch(nActive);           // the device starts on the NEXT join while the host finishes this one
     uniqueBestHitsFinish(nActive, uniqueList, uniqueSlots);
     int64_t nUnique = (int64_t) uniqueList.size();
     lChild[0]->hits.clear(); lChild[0]->hits.shrink_to_fit();
@@ -1034,6 +1069,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     // ---- refresh, NJ.tcc:4439-4517 ------------------------------------------------------------
     Section secRefresh(this, 5);
     res->nRefreshTopHits++;
+    if (spec.valid) { spec.valid = false; check(vft_spec_join_discard(ctx)); }      // a refresh rewrites the lists the guess was built from
     lNew.age = 0;
     {   // every out-distance up to date, :4451-4464
         std::vector<P> od(maxnodes);
@@ -1201,6 +1237,91 @@ void NJ<P>::fastNJSearch(int64_t nActive, std::vector<Besthit> &besthits, Besthi
     } while (changed);
 }
 
+// Launch the guessed next join (g, gj) -> row maxnode, with the distances topHitJoin will ask for: the new node against
+// the active ancestors of both children's top hits (uniqueBestHits, NJ.tcc:4786-4833: every one of them is recomputed,
+// the parent changed), and the out-distances setCriterion / updateVisible / updateTopVisible can refresh at the next
+// nActive (the new node's own, the candidates', their visible partners', the top-visible set's).  A superset is harmless.
+template<typename P>
+void NJ<P>::specLaunch(int64_t nActiveNext) {
+    spec.valid = false;
+    const int64_t g = guessG, gj = guessGj;
+    if (g < 0 || gj < 0 || g == gj || parent[g] >= 0 || parent[gj] >= 0 || nActiveNext <= 3 || maxnode >= maxnodes - 1) return;
+    {   // the next join must not be one that rebuilds the out-profile from scratch (NJ.tcc:3012-3033)
+        const int64_t changed = nActiveOutProfileReset - (nActiveNext - 1);
+        if (changed >= opt.nResetOutProfile && changed >= opt.fResetOutProfile * nActiveOutProfileReset) return;
+    }
+    const int64_t R = maxnode, nAfter = nActiveNext - 1;
+    const int64_t stampP = ++specStamp;
+    spec.pairJ.clear(); spec.outIds.clear();
+    auto wantOutNext = [&](int64_t i) {
+        if (i < 0 || parent[i] >= 0 || i == g || i == gj || specSeenO[i] == stampP) return;
+        specSeenO[i] = stampP;
+        if (!selfKnown[i]) return;
+        int64_t nDiffAllow = opt.tophitsMult > 0 ? (int64_t) (nAfter * opt.staleOutLimit) : 0;
+        if (nOutDistActive[i] - nAfter > nDiffAllow) spec.outIds.push_back(i);
+    };
+    spec.outIds.push_back(R);
+    for (int64_t c : {g, gj})
+        for (const Hit &h : topHitsLists[c].hits) {
+            const int64_t j = activeAncestor(h.j);
+            if (j < 0 || j == g || j == gj || specSeenP[j] == stampP) continue;
+            specSeenP[j] = stampP;
+            spec.pairJ.push_back(j);
+            wantOutNext(j);
+            wantOutNext(visible[j].j);
+        }
+    for (int64_t iNode : topvisible) {
+        if (iNode < 0 || parent[iNode] >= 0) continue;
+        wantOutNext(iNode);
+        wantOutNext(visible[iNode].j);
+    }
+    if (spec.pairJ.empty() || spec.pairJ.size() + spec.outIds.size() > 4096) return;
+    check(timed([&] { return vft_spec_join_launch(ctx, R, std::min(g, gj), std::max(g, gj), opt.bionj ? 0.5 : -1.0, nActiveNext, spec.pairJ.data(),
+                                                  (int64_t) spec.pairJ.size(), spec.outIds.data(), (int64_t) spec.outIds.size()); }));
+    spec.valid = true; spec.g = g; spec.gj = gj; spec.out = R; spec.nActiveNext = nActiveNext; spec.refreshes = res->nRefreshTopHits;
+}
+
+// The search picked (i, j) at nActive: if that is the speculated pair, commit it on the device and fetch the raw results
+template<typename P>
+bool NJ<P>::specTake(int64_t i, int64_t j, int64_t newnode, int64_t nActive) {
+    if (!((i == spec.g && j == spec.gj) || (i == spec.gj && j == spec.g)) || newnode != spec.out || nActive != spec.nActiveNext) return false;
+    specPD.resize(spec.pairJ.size()); specPW.resize(spec.pairJ.size());
+    specOD.resize(spec.outIds.size()); specOW.resize(spec.outIds.size());
+    P self2[2];
+    check(timed([&] { return vft_spec_join_take(ctx, (double) diameter[newnode], specPD.data(), specPW.data(), specOD.data(), specOW.data(), self2); }));
+    selfdistH[newnode] = self2[0]; selfweightH[newnode] = self2[1]; selfKnown[newnode] = 1;
+    spec.valid = false;
+    return true;
+}
+
+// After newEpoch(nActive): hand the speculated values to the pair and out-distance services of this epoch
+template<typename P>
+void NJ<P>::specInject(int64_t newnode, int64_t nActive) {
+    for (size_t k = 0; k < spec.pairJ.size(); k++) {
+        const int64_t j = spec.pairJ[k];
+        P d = specPD[k] - (P) (diameter[newnode] + diameter[j]);                             // NJ.tcc:1120, numeric_t arithmetic
+        d = (P) ((double) d + 0.0);                                                          // :1122 (no constraints)
+        pairCache.put(pkey(newnode, j), DW{d, specPW[k]});
+    }
+    const P pN = (P) nActive, pN1 = (P) (nActive - 1);
+    for (size_t k = 0; k < spec.outIds.size(); k++) {
+        const int64_t i = spec.outIds[k];
+        const P ddist = specOD[k], dweight = specOW[k];
+        // setOutDistance's algebra, NJ.tcc:1046-1052, operand types as in the reference
+        const P t1 = ddist * dweight;
+        const P t2 = t1 * pN;
+        const P t3 = selfweightH[i] * selfdistH[i];
+        const P t4 = t2 - t3;
+        const double top = (double) (P) (pN1 * t4);
+        const P b1 = dweight * pN;
+        const double bottom = (double) (P) (b1 - selfweightH[i]);
+        const double pd = top / bottom;
+        const P dn = diameter[i] * pN1;
+        freshVal[i] = (P) (bottom > 0.01 ? pd - (double) dn - (totdiam - (double) diameter[i]) : 3.0);
+        freshEpoch[i] = epoch;
+    }
+}
+
 // fastNJ, NJ.tcc:2796-3155
 template<typename P>
 void NJ<P>::fastNJ() {
@@ -1242,7 +1363,7 @@ void NJ<P>::fastNJ() {
     auto t1 = clk::now();
     res->secondsLeafTopHits = std::chrono::duration<double>(t1 - t0).count();
 
-    int64_t nActiveOutProfileReset = nSeqs;
+    nActiveOutProfileReset = nSeqs;
     for (int64_t nActive = nSeqs; nActive > 3; nActive--) {
         Besthit join;
         {
@@ -1293,8 +1414,17 @@ void NJ<P>::fastNJ() {
                                     + bionjWeight * (1 - bionjWeight) * varIJ);
         // averageProfile (:3008, + the self-distance of :3040-3043) and the out-profile (:3012-3037)
         int64_t changedActiveOutProfile = nActiveOutProfileReset - (nActive - 1);
-        if (changedActiveOutProfile >= opt.nResetOutProfile
-            && changedActiveOutProfile >= opt.fResetOutProfile * nActiveOutProfileReset) {
+        const bool rebuildOut = changedActiveOutProfile >= opt.nResetOutProfile
+                                && changedActiveOutProfile >= opt.fResetOutProfile * nActiveOutProfileReset;
+        bool taken = false;
+        if (spec.valid) {
+            if (!rebuildOut) taken = specTake(join.i, join.j, newnode, nActive);
+            if (!taken) { spec.valid = false; check(vft_spec_join_discard(ctx)); res->nSpecMiss++; }
+        }
+        if (taken) {
+            totdiam += (P) ((P) (diameter[newnode] - diameter[join.i]) - diameter[join.j]);
+            res->nSpecHit++;
+        } else if (rebuildOut) {
             check(timed([&] { return vft_profile_average(ctx, newnode, join.i, join.j, opt.bionj ? bionjWeight : -1.0,
                                                          (double) diameter[newnode]); }));
             totdiam = 0;
@@ -1307,6 +1437,12 @@ void NJ<P>::fastNJ() {
             totdiam += (P) ((P) (diameter[newnode] - diameter[join.i]) - diameter[join.j]);
         }
         newEpoch(nActive - 1);
+        if (taken) specInject(newnode, nActive - 1);
+        else if (specEnabled) {                     // the self distance of a node joined the ordinary way: fetched (rare)
+            double sd = 0, sw = 0;
+            check(timed([&] { return vft_get_self(ctx, newnode, &sd, &sw); }));
+            selfdistH[newnode] = (P) sd; selfweightH[newnode] = (P) sw; selfKnown[newnode] = 1;
+        }
 
         if (m > 0) {
             Section sec(this, 4);
@@ -1410,6 +1546,7 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     res->root = -1; res->maxnode = 0; res->m = 0;
     res->nSeeds = res->nCloseUsed = res->nRefreshTopHits = res->nVisibleUpdate = res->nHillBetter = 0;
     res->nOutPrefetchHit = res->nOutSingleFetch = res->nPairPrefetchHit = res->nPairSingleFetch = res->nDeviceCalls = 0;
+    res->nSpecHit = res->nSpecMiss = 0;
     res->secondsLeafTopHits = res->secondsJoins = res->secondsTotal = 0;
     res->deviceMsResident = res->secondsEndToEnd = res->secondsInCalls = 0;
     for (double &x : res->secondsHost) x = 0;

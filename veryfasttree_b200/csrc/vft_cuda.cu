@@ -131,6 +131,7 @@ extern "C" int vft_release_cached_memory(void) { mem_release_all(); return VFT_O
 // ia/ib/r0/r1 live in pinned host memory mapped into the device address space (zero-copy): a
 // request costs one launch and one stream synchronisation, no separate memcpy.
 constexpr int INLINE_ITEMS = 896;
+constexpr size_t SPEC_MAX = 4096;                                     // items of one speculative join request
 struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 7 KB of kernel parameters
 
 // DENSE = the throughput build for batches (fp32: capped at 128 registers -> 16 warps/SM, a few bytes of spill);
@@ -165,8 +166,8 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
     if (isProf) {
         P dd, ww;
         finish_dist<P>(den, top, dd, ww);
-        if (isOut) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
-        else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
+        if (isOut && !raw) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
+        else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }      // raw out item: bare profileDist(node, out-profile)
     }
     if (valid) { r0[item] = d; r1[item] = w; }
     // Results go to DEVICE memory; the last CTA to finish copies both arrays to the mapped host buffer with
@@ -210,7 +211,7 @@ k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *
             if (threadIdx.x == 0) {
                 P dd, ww, d, w = 0;
                 finish_dist<P>(den, top, dd, ww);
-                if (isOut) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
+                if (isOut && !raw) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
                 else if (isSeq) { d = (P) xadd((double) dd, 0.0); w = den > 0 ? ww : (P) 0; }     // :1621-1622, :1122
                 else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
                 r0[item] = d; r1[item] = w;
@@ -565,7 +566,9 @@ k_merge_finish(Store<P> s, const int32_t *__restrict__ iNode, int64_t nActive, i
 template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
 k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
-          double *__restrict__ gTerms, unsigned int *__restrict__ doneCount) {
+          double *__restrict__ gTerms, unsigned int *__restrict__ doneCount, P *dOw, P *dOv, P *dOcd, P *specSelf) {
+    // dOw/dOv/dOcd: where the UPDATEd out-profile goes (the live arrays, or the shadow copy of a speculative join);
+    // specSelf != nullptr: speculative -- the self distance goes there and no per-node state is committed
     extern __shared__ __align__(16) unsigned char smem[];
     const bool single = gridDim.x == 1;                          // short alignments: one CTA, the terms never leave shared memory
     double *termW = single ? reinterpret_cast<double *>(smem) : gTerms;   // [Lp] w*w   (global when the CTAs split the positions)
@@ -612,7 +615,7 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
                 const double newMult = xsub(xsub(xadd(originalMult, (double) wo), (double) w1), (double) w2);   // :963
                 P wout = (P) (newMult / (double) (nActiveOld - 1));                        // :964
                 if (wout <= 0) wout = (P) 1e-20;
-                s.ow[pos] = wout;
+                dOw[pos] = wout;
 #pragma unroll
                 for (int k = 0; k < A; k++) g[k] = (P) xmul((double) g[k], originalMult);  // :969-971
                 if (w1 > 0) add_to_freq<P, A, MATRIX>(s, g, (double) (-w1), c1, (c1 == VFT_DEV_NOCODE && p1.v) ? p1.v + pos * A : nullptr);
@@ -620,8 +623,8 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
                 if (wo > 0) add_to_freq<P, A, MATRIX>(s, g, (double) wo, co, hasVec ? f : nullptr);
                 normalize_freq<P, A, MATRIX>(s, g);                                        // :984
 #pragma unroll
-                for (int k = 0; k < A; k++) s.ov[pos * A + k] = g[k];
-                if (MATRIX) code_dist_row<P, A, MATRIX>(s, g, s.ocd + pos * A);            // :1001-1003
+                for (int k = 0; k < A; k++) dOv[pos * A + k] = g[k];
+                if (MATRIX) code_dist_row<P, A, MATRIX>(s, g, dOcd + pos * A);             // :1001-1003
             }
             if (wo > 0) {                                       // self-distance term, profileDist(out,out)
                 const double wt = (double) pmul(wo, wo);
@@ -663,11 +666,21 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
 #pragma unroll
             for (int k = 0; k < 8; k++) { denom = xadd(denom, w8[k]); top = xadd(top, t8[k]); }
         }
-        s.selfweight[oid] = (P) (denom > 0 ? denom : 0.01);
-        s.selfdist[oid] = (P) (denom > 0 ? top / denom : 1.0);
+        const P sw = (P) (denom > 0 ? denom : 0.01), sd = (P) (denom > 0 ? top / denom : 1.0);
+        if (specSelf) { specSelf[0] = sd; specSelf[1] = sw; return; }
+        s.selfweight[oid] = sw;
+        s.selfdist[oid] = sd;
         s.diameter[oid] = diameterOut;
         s.active[id1] = 0; s.active[id2] = 0; s.active[oid] = 1;
     }
+}
+
+// a speculative join that turned out right: its per-node state becomes real (vft_spec_join_take)
+template<typename P>
+__global__ void k_spec_commit(Store<P> s, int64_t oid, int64_t id1, int64_t id2, P diameterOut, const P *__restrict__ specSelf) {
+    s.selfdist[oid] = specSelf[0]; s.selfweight[oid] = specSelf[1];
+    s.diameter[oid] = diameterOut;
+    s.active[id1] = 0; s.active[id2] = 0; s.active[oid] = 1;
 }
 
 // updateOutProfile, NJ.tcc:943-1010: one thread per position
@@ -715,7 +728,7 @@ template<int A> struct RebShape { static constexpr int PP = (A == 4) ? 32 : 8; }
 template<typename P, int A>
 __host__ __device__ inline size_t rebuild_smem_bytes() {
     constexpr int PP = RebShape<A>::PP;
-    return (size_t) 2 * REB_TN * PP * A * sizeof(P) + (size_t) 2 * REB_TN * PP * sizeof(P) + (size_t) 2 * REB_TN * PP + 2 * REB_TN * 4
+    return (size_t) 2 * REB_TN * PP * A * sizeof(P) + (size_t) 2 * REB_TN * PP * sizeof(double) + 2 * REB_TN * 4
            + (size_t) PP * A * sizeof(P);
 }
 
@@ -724,11 +737,10 @@ __global__ void __launch_bounds__(REB_T)
 k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
     constexpr int PP = RebShape<A>::PP, TN = REB_TN, NPAIR = TN * PP / REB_T;
     extern __shared__ __align__(16) unsigned char smem[];
-    P *sV = reinterpret_cast<P *>(smem);                                   // [2][TN][PP][A]
-    P *sW = sV + 2 * TN * PP * A;                                          // [2][TN][PP]
-    P *fs = sW + 2 * TN * PP;                                              // [PP][A]
+    double *sW = reinterpret_cast<double *>(smem);                         // [2][TN][PP]     weight * inweight, the addend of :741
+    P *sV = reinterpret_cast<P *>(sW + 2 * TN * PP);                       // [2][TN][PP][A]  the addend of every (position, state) chain
+    P *fs = sV + 2 * TN * PP * A;                                          // [PP][A]
     int *sId = reinterpret_cast<int *>(fs + PP * A);                       // [2][TN]
-    uint8_t *sC = reinterpret_cast<uint8_t *>(sId + 2 * TN);               // [2][TN][PP]
     const int tid = threadIdx.x;
     const int64_t pos0 = (int64_t) blockIdx.x * PP;
     const int nTiles = (int) ((n + TN - 1) / TN);
@@ -759,14 +771,27 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
             }
         }
     };
+    // The producers also do everything of addToFreq (:821-833) that does not depend on the running sums: what reaches
+    // shared memory is, per (node, position), the double addend of the weight chain and the A addends of the frequency
+    // chains -- v*w, codeFreq[code]*w, or w at the node's own code; +0 where the reference adds nothing (x + 0 is exact).
+    // The consumer chains are then one dependent addition per node, no branch, no lookup.
     auto stash = [&](int buf) {
 #pragma unroll
         for (int q = 0; q < NPAIR; q++) {
             const int e = q * REB_T + tid;                                 // = u * PP + p
-            sC[buf * TN * PP + e] = (uint8_t) rc[q];
-            sW[buf * TN * PP + e] = rw[q];
+            const P w = rw[q];
+            const uint32_t c = rc[q];
+            sW[buf * TN * PP + e] = xmul((double) w, inweight);
 #pragma unroll
-            for (int a = 0; a < A; a++) sV[((size_t) buf * TN * PP + e) * A + a] = rv[q][a];
+            for (int a = 0; a < A; a++) {
+                P add = 0;
+                if (w > 0) {
+                    if (c == VFT_DEV_NOCODE) add = pmul(rv[q][a], w);
+                    else if (MATRIX) add = pmul(s.codeFreq[c * 20 + a], w);
+                    else if (c == (uint32_t) a) add = w;
+                }
+                sV[((size_t) buf * TN * PP + e) * A + a] = add;
+            }
         }
     };
     if (tid < TN) sId[tid] = tid < n ? (int) ids[tid] : 0;
@@ -782,19 +807,14 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
         const bool haveId = t + 2 < nTiles && tid < TN;
         if (haveId) { const int64_t iu = (int64_t) (t + 2) * TN + tid; idNext = iu < n ? (int) ids[iu] : 0; }
         if (chain) {
-            const uint8_t *cC = sC + cur * TN * PP + pl;
-            const P *cW = sW + cur * TN * PP + pl;
+            const double *cW = sW + cur * TN * PP + pl;
             const P *cV = sV + ((size_t) cur * TN * PP + pl) * A + k;
-#pragma unroll 8
+#pragma unroll 16
             for (int u = 0; u < TN; u++) {
-                const uint32_t c = cC[u * PP];
-                const P w = cW[u * PP];
-                wout = (P) xadd((double) wout, xmul((double) w, inweight));                // :741
-                if (w > 0) {                                                               // addToFreq, :821-833
-                    if (c == VFT_DEV_NOCODE) f = padd(f, pmul(cV[(size_t) u * PP * A], w));
-                    else if (MATRIX) f = padd(f, pmul(s.codeFreq[c * 20 + k], w));
-                    else if (c == (uint32_t) k) f = (P) xadd((double) f, (double) w);       // :831
-                }
+                wout = (P) xadd((double) wout, cW[u * PP]);                                // :741
+                // addToFreq, :821-833.  At a known code without a matrix the reference adds in double and narrows (:831);
+                // with a 53-bit intermediate that is the same value as the P addition (2p+2 <= 53 for p = 24; P = double trivially)
+                f = padd(f, cV[(size_t) u * PP * A]);
             }
         }
         if (t + 1 < nTiles) stash(cur ^ 1);
@@ -923,6 +943,12 @@ struct vft_ctx {
     int nRateCats, fastexp;
     double MLMinRel, MLMinBr;
     unsigned int *d_doneCount;
+    // speculative join (vft_spec_join_*): shadow out-profile, its own result buffers, completion event
+    void *ow2 = nullptr, *ov2 = nullptr, *ocd2 = nullptr, *d_specR0 = nullptr, *d_specR1 = nullptr, *d_specSelf = nullptr;
+    void *h_specIn = nullptr, *h_specOut = nullptr;
+    cudaEvent_t specDone = nullptr;
+    bool specPending = false;
+    int64_t specOut = -1, specId1 = -1, specId2 = -1, specNPairs = 0, specNOut = 0, specBytes = 0;
     vft_counters cnt;
     // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
     cudaEvent_t tmr0, tmr1;
@@ -1083,6 +1109,11 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
     c->hasTransmat = false; c->hasRates = false;
     CK(mem_alloc((void **) &c->d_doneCount, 4, MEM_DEVICE));
+    CK(mem_alloc(&c->ow2, Lp * ps, MEM_DEVICE)); CK(mem_alloc(&c->ov2, Lp * A * ps, MEM_DEVICE)); CK(mem_alloc(&c->ocd2, Lp * A * ps, MEM_DEVICE));
+    CK(cudaMemsetAsync(c->ow2, 0, Lp * ps, c->stream)); CK(cudaMemsetAsync(c->ov2, 0, Lp * A * ps, c->stream)); CK(cudaMemsetAsync(c->ocd2, 0, Lp * A * ps, c->stream));
+    CK(mem_alloc(&c->d_specR0, SPEC_MAX * ps, MEM_DEVICE)); CK(mem_alloc(&c->d_specR1, SPEC_MAX * ps, MEM_DEVICE)); CK(mem_alloc(&c->d_specSelf, 2 * ps, MEM_DEVICE));
+    CK(mem_alloc(&c->h_specIn, SPEC_MAX * 8, MEM_PINNED)); CK(mem_alloc(&c->h_specOut, 2 * SPEC_MAX * ps + 16, MEM_PINNED));
+    CK(cudaEventCreateWithFlags(&c->specDone, cudaEventDisableTiming));
     CK(mem_alloc((void **) &c->d_terms, 2 * Lp * 8, MEM_DEVICE));
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
     int rc = ensure_lists(c, std::max<int64_t>(4096, c->M));
@@ -1118,6 +1149,8 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     for (void *p : ptrs) mem_free(p);
     mem_free(c->h_in); mem_free(c->h_out);
     mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms);
+    for (void *q : {c->ow2, c->ov2, c->ocd2, c->d_specR0, c->d_specR1, c->d_specSelf, c->h_specIn, c->h_specOut}) mem_free(q);
+    if (c->specDone) cudaEventDestroy(c->specDone);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
     cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
@@ -1222,10 +1255,10 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
     do {                                                                                                      \
         if (update) {                                                                                         \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount); \
+            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr); \
         } else {                                                                                              \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, false><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount); \
+            k_average<P, A_, MX, false><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr); \
         }                                                                                                     \
     } while (0)
     prof_begin(c, CLS_PROFILE, K_AVERAGE);
@@ -1342,6 +1375,111 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         std::memcpy(dist, (char *) hr0 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
         std::memcpy(weight, (char *) hr1 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
     }
+    return VFT_OK;
+}
+
+// ---- speculative join ---------------------------------------------------------------------------------------------
+// The join loop is a chain: search -> average the pair -> distances of the new node to its candidates -> bookkeeping ->
+// search ...; the device idles while the host decides and the host idles while the device computes.  The caller's guess
+// of the NEXT join is right ~95 % of the time (nj_host.cpp), so the next join's device work is launched ahead,
+// asynchronously and WITHOUT committing anything: the new profile goes into the next free row, the updated out-profile
+// into a shadow copy, every distance comes back raw (bare profileDist: the diameter / out-distance algebra needs host
+// scalars that are not known yet and is finished by the caller in the same arithmetic).  take() makes it real (state
+// kernel + pointer swap), discard() forgets it; a wrong guess costs nothing but the idle device time it used.
+extern "C" int vft_spec_join_launch(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight, int64_t nActiveOld,
+                                    const int64_t *pair_j, int64_t nPairs, const int64_t *out_ids, int64_t nOut) {
+    if (!c || nPairs < 0 || nOut < 0 || (nPairs > 0 && !pair_j) || (nOut > 0 && !out_ids)) return fail(VFT_EINVAL, "null argument");
+    const int64_t n = nOut + nPairs;
+    if (n < 1 || (size_t) n > SPEC_MAX) return fail(VFT_EINVAL, "speculative request too large");
+    if (out_id != c->maxnode || out_id >= c->M || id1 < 0 || id2 < 0 || id1 >= c->maxnode || id2 >= c->maxnode || id1 == id2
+        || !c->activeHost[id1] || !c->activeHost[id2] || nActiveOld < 3)
+        return fail(VFT_EINVAL, "bad speculative join");
+    bind_device(c);
+    c->specPending = false;
+    if (bionjWeight < 0) bionjWeight = 0.5;
+    const size_t smemAvg = (size_t) c->Lp * 16;
+    if (smemAvg > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the average kernel's term buffer");
+    int32_t *ha = (int32_t *) c->h_specIn, *hb = ha + n;
+    int64_t bytes = profile_bytes(c, out_id);
+    for (int64_t k = 0; k < nOut; k++) {
+        if (out_ids[k] < 0 || (out_ids[k] >= c->maxnode && out_ids[k] != out_id)) return fail(VFT_EINVAL, "bad node id");
+        ha[k] = (int32_t) out_ids[k]; hb[k] = -1;
+        bytes += profile_bytes(c, out_ids[k]);
+    }
+    if (nOut) bytes += profile_bytes(c, -1);
+    for (int64_t k = 0; k < nPairs; k++) {
+        if (pair_j[k] < 0 || pair_j[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        ha[nOut + k] = (int32_t) out_id; hb[nOut + k] = (int32_t) pair_j[k];
+        bytes += profile_bytes(c, pair_j[k]);
+    }
+    const int AVG_T = c->Lp <= 512 ? 256 : 64;
+    const unsigned avgBlocks = c->Lp <= 512 ? 1u : (unsigned) ((c->Lp + AVG_T - 1) / AVG_T);
+#define CALL_SPEC_AVG(P, A_, MX)                                                                              \
+    do {                                                                                                      \
+        if (smemAvg > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemAvg); \
+        k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smemAvg, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) 0, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow2, (P *) c->ov2, (P *) c->ocd2, (P *) c->d_specSelf); \
+    } while (0)
+    prof_begin(c, CLS_PROFILE, K_AVERAGE);
+    VFT_DISPATCH(c, CALL_SPEC_AVG);
+    prof_end(c);
+    CK(cudaGetLastError());
+    // the distances, against the SHADOW out-profile, all raw
+    const int G = pick_group(c, n);
+    const int64_t warps = (n + G - 1) / G;
+    const unsigned blocks = (unsigned) ((warps + 3) / 4);
+    const bool inlineItems = n <= INLINE_ITEMS;
+    InlineItems inl;
+    if (inlineItems) { std::memcpy(inl.a, ha, (size_t) n * 4); std::memcpy(inl.b, hb, (size_t) n * 4); }
+    const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
+    const int wideThreads = n <= 160 ? 256 : 128;
+#define SPEC_STORE(P) ([&] { Store<P> st = make_store<P>(c); st.ow = (P *) c->ow2; st.ov = (P *) c->ov2; st.ocd = c->cfg.useMatrix ? (P *) c->ocd2 : nullptr; return st; }())
+#define SPEC_ARGS(P) SPEC_STORE(P), inl, inlineItems ? nullptr : ha, inlineItems ? nullptr : hb, n, nOut
+#define CALL_SPEC_EVAL(P, A_, MX) do { if (wide) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(SPEC_ARGS(P), 1, nActiveOld - 1, 0.0, (P *) c->d_specR0, (P *) c->d_specR1, c->d_doneCount, (P *) c->h_specOut); \
+        else if (G > 1) k_eval<P, A_, MX, true><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(SPEC_ARGS(P), G, 1, nActiveOld - 1, 0.0, (P *) c->d_specR0, (P *) c->d_specR1, c->d_doneCount, (P *) c->h_specOut); \
+        else k_eval<P, A_, MX, false><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(SPEC_ARGS(P), G, 1, nActiveOld - 1, 0.0, (P *) c->d_specR0, (P *) c->d_specR1, c->d_doneCount, (P *) c->h_specOut); } while (0)
+    prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
+    VFT_DISPATCH(c, CALL_SPEC_EVAL);
+    prof_end(c);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync((char *) c->h_specOut + (size_t) 2 * n * c->ps, c->d_specSelf, 2 * c->ps, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->specDone, c->stream));
+    c->cnt.launches += 2;
+    c->specPending = true; c->specOut = out_id; c->specId1 = id1; c->specId2 = id2; c->specNPairs = nPairs; c->specNOut = nOut; c->specBytes = bytes;
+    return VFT_OK;            // asynchronous
+}
+
+// The guess was right: (id1, id2) are joined into specOut.  pairDist/pairWeight[nPairs] = bare profileDist(out, pair_j[k]);
+// outDist/outWeight[nOut] = bare profileDist(out_ids[k], NEW out-profile); self2 = {selfdist, selfweight} of the new node.
+extern "C" int vft_spec_join_take(vft_ctx *c, double diameter_out, void *pairDist, void *pairWeight, void *outDist, void *outWeight,
+                                  void *self2) {
+    if (!c || !c->specPending) return fail(VFT_EINVAL, "no speculative join pending");
+    bind_device(c);
+    CK(cudaEventSynchronize(c->specDone));
+    c->specPending = false;
+    const int64_t out_id = c->specOut, id1 = c->specId1, id2 = c->specId2, nOut = c->specNOut, nPairs = c->specNPairs, n = nOut + nPairs;
+    if (c->cfg.precision == 32) k_spec_commit<float><<<1, 1, 0, c->stream>>>(make_store<float>(c), out_id, id1, id2, (float) diameter_out, (const float *) c->d_specSelf);
+    else k_spec_commit<double><<<1, 1, 0, c->stream>>>(make_store<double>(c), out_id, id1, id2, diameter_out, (const double *) c->d_specSelf);
+    CK(cudaGetLastError());
+    std::swap(c->ow, c->ow2); std::swap(c->ov, c->ov2); std::swap(c->ocd, c->ocd2);
+    c->cnt.launches++; c->cnt.profileAvgOps++; c->cnt.profileOps += 1 + n; c->cnt.outprofileOps += nOut;
+    c->cnt.algoBytes += c->specBytes; c->cnt.bytesKernel[n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE] += c->specBytes;
+    c->cnt.h2dBytes += n * 8; c->cnt.d2hBytes += (n * 2 + 2) * (int64_t) c->ps;
+    for (int64_t ch : {id1, id2})
+        if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
+    if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
+    if (out_id >= c->maxnode) c->maxnode = out_id + 1;
+    const char *h0 = (const char *) c->h_specOut, *h1 = h0 + (size_t) n * c->ps;
+    if (nOut && outDist) std::memcpy(outDist, h0, (size_t) nOut * c->ps);
+    if (nOut && outWeight) std::memcpy(outWeight, h1, (size_t) nOut * c->ps);
+    if (nPairs && pairDist) std::memcpy(pairDist, h0 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+    if (nPairs && pairWeight) std::memcpy(pairWeight, h1 + (size_t) nOut * c->ps, (size_t) nPairs * c->ps);
+    if (self2) std::memcpy(self2, h0 + (size_t) 2 * n * c->ps, 2 * c->ps);
+    return VFT_OK;
+}
+
+extern "C" int vft_spec_join_discard(vft_ctx *c) {
+    if (!c) return fail(VFT_EINVAL, "null argument");
+    c->specPending = false;      // the kernels may still run; nothing they wrote is live
     return VFT_OK;
 }
 
