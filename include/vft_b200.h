@@ -147,7 +147,8 @@ int  vft_out_distance_all(vft_ctx *ctx, int64_t nActive, double totdiam, void *o
    out-distance state that setCriterion needs. */
 #define VFT_PAIRS_JOIN        0   /* setDistCriterion semantics as described above            */
 #define VFT_PAIRS_PROFILE_RAW 1   /* bare profileDist (NJ.tcc:1167-1190): no leaf shortcut, no
-                                     diameter correction -- the calls at NJ.tcc:3125-3127, :2945 */
+                                     diameter correction -- the calls at NJ.tcc:3125-3127, :2945;
+                                     j == -1 stands for the out-profile (BIONJ, NJ.tcc:2945-2946) */
 int  vft_dist_pairs(vft_ctx *ctx, const int64_t *i, const int64_t *j, int64_t n, int32_t flags,
                     void *dist, void *weight);
 
@@ -372,7 +373,7 @@ typedef struct vft_nj_options {
     double  staleOutLimit;      /* Options.h:36  (0.01) */
     double  fResetOutProfile;   /* Options.h:38  (0.02) */
     int32_t nResetOutProfile;   /* Options.h:40  (200)  */
-    int32_t bionj;              /* Options.h:18  (0)    */
+    int32_t bionj;              /* Options.h:18  (0): BIONJ-weighted joins, NJ.tcc:2921-2966 */
     int32_t prefetch;           /* 1 = batch the lazily refreshed out-distances / pair distances
                                    ahead of the host loops (default); 0 = fetch one at a time
                                    (same results, used by the tests to prove the prefetch is only

@@ -4,6 +4,7 @@ where /root/reference exists; `make -C oracle ref` first).
   *.refdump.bin   kernel-level vectors from the reference's own templates (oracle/refdump.cpp)
   *.tophits.bin   leaf top-hit lists from the reference's own setAllLeafTopHits
   *.mldump.bin    pairLogLk / posteriorProfile of the reference (refdump "ml" mode: JC, GTR, JTT; CAT rates)
+  *.bionj.tree    the same with -bionj (BIONJ-weighted joins, NJ.tcc:2921-2966)
   *.nj.tree       the `NJ` line of the reference binary's -log (tree after the metric phase),
                   run with -threads 1 -ext AVX2 [-nt] [-double-precision] -noml -nni 0 -spr 0 -nosupport
   blosum45_f{32,64}.npz   the BLOSUM45 tables as the reference hands them to its kernels
@@ -30,11 +31,14 @@ TOPHITS_CASES = ["c1", "aa300"]
 TREE_CASES = ["nt60", "aa60", "c1", "nt1000", "aa300"]
 
 
-def ref_tree(fasta, kind, prec, threads=1):
+BIONJ_CASES = ["nt60", "aa60", "c1", "aa300"]
+
+
+def ref_tree(fasta, kind, prec, threads=1, bionj=False):
     with tempfile.TemporaryDirectory() as td:
         log = os.path.join(td, "log")
         args = [replay.REF_BIN] + (["-nt"] if kind == "nt" else []) + (["-double-precision"] if prec == 64 else [])
-        args += ["-ext", "AVX2", "-threads", str(threads), "-noml", "-nni", "0", "-spr", "0", "-nosupport", "-log", log, fasta]
+        args += (["-bionj"] if bionj else []) + ["-ext", "AVX2", "-threads", str(threads), "-noml", "-nni", "0", "-spr", "0", "-nosupport", "-log", log, fasta]
         subprocess.run(args, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
         for line in open(log):
             if line.startswith("NJ\t"):
@@ -58,6 +62,9 @@ def main():
                 if name in TREE_CASES:
                     with open(os.path.join(HERE, "%s_f%d.nj.tree" % (name, prec)), "w") as f:
                         f.write(ref_tree(fasta, kind, prec) + "\n")
+                if name in BIONJ_CASES:
+                    with open(os.path.join(HERE, "%s_f%d.bionj.tree" % (name, prec)), "w") as f:
+                        f.write(ref_tree(fasta, kind, prec, bionj=True) + "\n")
                 print("golden", name, prec)
         for name, (n, L, kind, seed, model, combos) in replay.ML_CASES.items():
             chars, kind, model = replay.ml_case_chars(name)

@@ -229,6 +229,15 @@ def test_cuda_ml_optimizers_match_reference(glib, name, prec, lvl):
     assert bad == [], (bad, info)
 
 
+@pytest.mark.parametrize("name,prec", [("c1", 32), ("aa300", 32), ("aa60", 64)])
+def test_bionj_tree_identical_to_reference_on_device(glib, name, prec):
+    """-bionj on the device: bare profileDist against the out-profile (vft_dist_pairs RAW with j = -1), weighted
+    k_average; the reference's -bionj tree byte for byte."""
+    from test_oracle_golden import _bionj_tree
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.bionj.tree" % (name, prec))).read().strip()
+    assert _bionj_tree(glib, name, prec) == want
+
+
 def test_speculative_join_on_device(glib, monkeypatch):
     """vft_spec_join_* on the device (shadow out-profile, raw distances, state commit): with the speculative path on, the
     1000-taxon tree is still the reference's, byte for byte."""

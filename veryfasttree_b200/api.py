@@ -463,7 +463,7 @@ class NJTree:
 
 def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | None = None,
              tables=None, device: int = 0, prefetch: bool = True, trace: bool = True,
-             reduction: int = 1, profile: bool = False, host_threads: int = 0) -> NJTree:
+             reduction: int = 1, profile: bool = False, host_threads: int = 0, bionj: bool = False) -> NJTree:
     """The metric phase (NJ ctor tail + fastNJ) through vft_nj_build with HOST buffers."""
     lib = lib or load()
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -475,6 +475,7 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
     lib.dll.vft_nj_default_options(C.byref(opt))
     opt.prefetch = int(prefetch)
     opt.hostThreads = host_threads
+    opt.bionj = int(bionj)
     M = 2 * n
     parent = np.full(M, -1, dtype=np.int64)
     n_child = np.zeros(M, dtype=np.int32)

@@ -148,7 +148,7 @@ public:
         // B200 (C2 1.68 s vs 1.26 s; 100k x 1287 aa 30.6 s vs 26.5 s): each speculated join costs three more launches of
         // host API time, and the hints for the search after next still need their own synchronous call.  It pays only
         // once those go out asynchronously too.
-        specEnabled = opt.prefetch && std::getenv("VFT_SPECULATION") != nullptr && std::getenv("VFT_SPECULATION")[0] == '1';
+        specEnabled = opt.prefetch && !opt.bionj && std::getenv("VFT_SPECULATION") != nullptr && std::getenv("VFT_SPECULATION")[0] == '1';
         selfdistH.assign(maxnodes, 0); selfweightH.assign(maxnodes, 0); selfKnown.assign(maxnodes, 0);
         specSeenP.assign(maxnodes, 0); specSeenO.assign(maxnodes, 0);
         // nGaps(i) = nPos - selfweight[i] (NJ.tcc:249-252, :3762): gap/unknown columns of leaf i
@@ -1405,7 +1405,32 @@ void NJ<P>::fastNJ() {
         double bionjWeight = 0.5;
         double varIJ = rawIJ - varDiameter[join.i] - varDiameter[join.j];
         if (opt.bionj && join.weight > 0.01 && varIJ > 0.001) {
-            throw DeviceError{VFT_EINVAL};       // BIONJ weighting (NJ.tcc:2921-2992) not built yet
+            // BIONJ weighting, NJ.tcc:2921-2966 (Gascuel 1997, eq. 9, with the variances read off the out-profile):
+            // bare profileDist of both children against the CURRENT out-profile, then scalar algebra in the
+            // reference's operand types (numeric_t products, double quotients)
+            const int64_t bi[2] = {join.i, join.j}, bo[2] = {-1, -1};
+            P od[2], ow[2];
+            check(timed([&] { return vft_dist_pairs(ctx, bi, bo, 2, VFT_PAIRS_PROFILE_RAW, od, ow); }));
+            P sdw[2], sww[2];
+            for (int k = 0; k < 2; k++) {
+                if (!selfKnown[bi[k]]) {
+                    double sd = 0, sw = 0;
+                    check(timed([&] { return vft_get_self(ctx, bi[k], &sd, &sw); }));
+                    selfdistH[bi[k]] = (P) sd; selfweightH[bi[k]] = (P) sw; selfKnown[bi[k]] = 1;
+                }
+                sdw[k] = selfdistH[bi[k]]; sww[k] = selfweightH[bi[k]];
+            }
+            const P pN = (P) nActive;
+            const double varIWeight = (P) ((P) ((P) (pN * ow[0]) - sww[0]) - join.weight);
+            const double varJWeight = (P) ((P) ((P) (pN * ow[1]) - sww[1]) - join.weight);
+            const double varITop = (double) (P) ((P) ((P) (od[0] * ow[0]) * pN) - (P) (sdw[0] * sww[0])) - rawIJ * (double) join.weight;
+            const double varJTop = (double) (P) ((P) ((P) (od[1] * ow[1]) * pN) - (P) (sdw[1] * sww[1])) - rawIJ * (double) join.weight;
+            const double deltaProfileVarOut = (double) (nActive - 2) * (varJTop / varJWeight - varITop / varIWeight);
+            const double deltaVarDiam = (P) ((P) (nActive - 2) * (P) (varDiameter[join.i] - varDiameter[join.j]));
+            if (varJWeight > 0.01 && varIWeight > 0.01)
+                bionjWeight = 0.5 + (deltaProfileVarOut + deltaVarDiam) / ((double) (2 * (nActive - 2)) * varIJ);
+            if (bionjWeight < 0) bionjWeight = 0;
+            if (bionjWeight > 1) bionjWeight = 1;
         }
         // :3003-3007: double * (P+P) ...
         diameter[newnode] = (P) (bionjWeight * (P) (branchlength[join.i] + diameter[join.i])
@@ -1540,7 +1565,6 @@ extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in,
     if (cfg->nSeqs >= (int64_t) 1 << 30) return VFT_EINVAL;
     vft_nj_options opt;
     if (opt_in) opt = *opt_in; else vft_nj_default_options(&opt);
-    if (opt.bionj) return VFT_EINVAL;
     if (cfg->useMatrix && !tables) return VFT_EINVAL;
     // zero the output counters, keep the caller's buffers
     res->root = -1; res->maxnode = 0; res->m = 0;

@@ -1350,7 +1350,8 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     if (nOut) { c->cnt.algoBytes += profile_bytes(c, -1); c->cnt.profileOps += nOut; c->cnt.outprofileOps += nOut; }
     int64_t lastQuery = -2;
     for (int64_t k = 0; k < nPairs; k++) {
-        if (pi[k] < 0 || pj[k] < 0 || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
+        // j == -1 with VFT_PAIRS_PROFILE_RAW: the out-profile (bare profileDist(i, outprofile), NJ.tcc:2945-2946)
+        if (pi[k] < 0 || (pj[k] < 0 && !(raw && pj[k] == -1)) || pi[k] >= c->maxnode || pj[k] >= c->maxnode) return fail(VFT_EINVAL, "bad node id");
         ha[nOut + k] = (int32_t) pi[k]; hb[nOut + k] = (int32_t) pj[k];
         if (!raw && pi[k] < c->N && pj[k] < c->N) { c->cnt.seqOps++; c->cnt.algoBytes += c->L; }
         else { c->cnt.profileOps++; c->cnt.algoBytes += profile_bytes(c, pj[k]); }
