@@ -484,6 +484,7 @@ private:
     } spec;
     bool specEnabled = false;
     int64_t guessG = -1, guessGj = -1;                    // the last guess of speculateSearch
+    bool searchHinted = false;                            // topHitJoin already ran speculateSearch for the coming search
     int64_t nActiveOutProfileReset = 0;
     std::vector<P> selfdistH, selfweightH;                // host mirror of the device's self distances (needed to finish raw out-distances)
     std::vector<char> selfKnown;
@@ -759,6 +760,7 @@ void NJ<P>::setAllLeafTopHits() {
 template<typename P>
 void NJ<P>::resetTopVisible(int64_t nActive) {
     HPROF(1, "resetTopVisible");
+    searchHinted = false;                              // a new top-visible set: the next search hints for itself
     const int nT = maxnode >= 4096 ? hostThreads : 1;
     if ((int64_t) rtvTouched.size() < maxnodes) rtvTouched.assign(maxnodes, 0);
     const int64_t stamp = ++rtvStamp;
@@ -944,19 +946,22 @@ void NJ<P>::getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin
 // created), so that a join costs one synchronous round trip instead of two.
 template<typename P>
 void NJ<P>::speculateSearch(int64_t nActive) {
-    for (int64_t iNode : topvisible) hintVisible(nActive, iNode);
+    HPROF(15, "speculateSearch");
     // one guess is enough: measured on 8 000 taxa, guessing the best three instead of the best one saves 1.5 % of the
-    // device calls and costs two more list scans per join
+    // device calls and costs two more list scans per join.  One pass over the top-visible set: the out-distance hints
+    // of hintVisible and the approximate criterion of the guess read the same entries.
     int64_t g1 = -1;
     double c1 = 1e300;
+    const double invN2 = 1.0 / (double) (nActive - 2);          // (a hint: need not round like the reference's division)
     for (int64_t iNode : topvisible) {
         if (iNode < 0 || parent[iNode] >= 0) continue;
         const Hit &h = visible[iNode];
         if (h.j < 0 || parent[h.j] >= 0) continue;
+        wantOut(iNode, nActive); wantOut(h.j, nActive);          // = hintVisible(nActive, iNode)
         double outI = outDistances[iNode], outJ = outDistances[h.j];
         if (nOutDistActive[iNode] != nActive) outI *= (nActive - 1) / (double) (nOutDistActive[iNode] - 1);
         if (nOutDistActive[h.j] != nActive) outJ *= (nActive - 1) / (double) (nOutDistActive[h.j] - 1);
-        double c = h.dist - (outI + outJ) / (double) (nActive - 2);
+        const double c = h.dist - (outI + outJ) * invN2;
         if (c < c1) { c1 = c; g1 = iNode; }
     }
     guessG = g1; guessGj = g1 >= 0 ? (int64_t) visible[g1].j : -1;
@@ -973,11 +978,15 @@ template<typename P>
 void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
     HPROF(5, "topHitNJSearch(total)");
     if (opt.prefetch) {
-        speculateSearch(nActive);
+        // topHitJoin has usually hinted this very search already (same epoch, same top-visible set); what its list
+        // bookkeeping changed since is fetched on demand by the scan below (counted in nOutSingleFetch)
+        if (!searchHinted) speculateSearch(nActive);
+        searchHinted = false;
         flush(nActive);
     }
     int64_t nCandidate = 0, iNodeBestCandidate = -1;
     double dBestCriterion = 1e20;
+    HPROF(16, "topHitNJSearch(scan of the top-visible set)");
     for (size_t k = 0; k < topvisible.size(); k++) {
         int64_t iNode = topvisible[k];
         Besthit v;
@@ -1043,7 +1052,7 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
     uniqueBestHitsPrepare(nActive, combinedList, uniqueList, uniqueSlots);
     if (opt.prefetch) {      // what updateTopVisible / updateVisible below can touch (a superset)
         for (const Besthit &h : uniqueList) hintVisible(nActive, h.j);
-        speculateSearch(nActive);                    // (covers the top-visible set)                    // ... and what the NEXT join search will most likely ask for
+        speculateSearch(nActive); searchHinted = true;   // (covers the top-visible set)                    // ... and what the NEXT join search will most likely ask for
     }
     flush(nActive);
     if (specEnabled) specLaunch(nActive);           // the device starts on the NEXT join while the host finishes this one
