@@ -317,6 +317,16 @@ int  vft_ml_optimize_branch_lengths(vft_ctx *ctx, const vft_ml_options *opt, int
                                     const int32_t *nChild, const int64_t *child, void *branchlength, int32_t schedule,
                                     vft_ml_stats *stats);
 
+/* -- SH-like local supports: SHSupport (NJ.tcc:1126-1165) for n quartets against ONE set of resampled
+      columns (resampleColumns, NJ.tcc:705-716; col[nBootstrap*nPos] comes from the caller's RNG).  Per quartet: loglk[3] of the
+      three topologies and their per-site likelihoods siteLk[3][nPos] as MLQuartetLogLk leaves them (NJ.tcc:5410-5427; the
+      siteLk output of vft_pair_loglk_batch multiplied up by the caller).  Every resample is one ordered gather-sum over the
+      columns for each topology (3 000 independent chains per quartet at the default 1 000 resamples); the logarithms are taken
+      on the host with the reference's libm, so the supports are bit-identical.  support[n] = fraction of resamples in which the
+      best topology's margin falls below the observed one. */
+int  vft_sh_support_batch(vft_ctx *ctx, int64_t n, int64_t nBootstrap, const int64_t *col, const double *loglk,
+                          const double *siteLk, double *support);
+
 /* -- introspection for tests: a node's dense profile (weights[nPos], codes[nPos],
       vectors[nPos*nCodes], zero where the reference stores no vector); id==-1 => out-profile -- */
 int  vft_get_profile(vft_ctx *ctx, int64_t id, void *weights, uint8_t *codes, void *vectors);

@@ -525,6 +525,37 @@ static int run(const std::string &fasta, bool aa, bool tophitsOnly) {
         options.pseudoWeight = 0.0; options.logdist = true;
         putq("nni.ids", q, {nq, 4});
     }
+    // SHSupport (NJ.tcc:1126-1165) with the reference's own resampled columns (resampleColumns, NJ.tcc:705-716): synthetic
+    // per-site likelihoods for the three topologies of a few quartets -- near-ties, a clear winner, a losing first topology
+    {
+        options.nBootstrap = 200;
+        std::vector<int64_t> col;
+        nj.resampleColumns(col);
+        const int64_t nq = 12;
+        std::vector<double> lk3(nq * 3), sl(nq * 3 * L), sup(nq);
+        uint64_t st = 0x9E3779B97F4A7C15ull;
+        auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double) (st >> 11) / 9007199254740992.0; };
+        for (int64_t q = 0; q < nq; q++) {
+            const double tilt = q % 4 == 0 ? 0.0 : q % 4 == 1 ? 0.004 : q % 4 == 2 ? 0.05 : -0.01;
+            for (int t = 0; t < 3; t++) {
+                double sum = 0;
+                for (int64_t i = 0; i < L; i++) {
+                    const double base = 0.02 + 0.9 * rnd();
+                    const double v = base * (1.0 + (t == 0 ? tilt : 0.0) * (rnd() - 0.3)) * (0.97 + 0.06 * rnd());
+                    sl[(q * 3 + t) * L + i] = v;
+                    sum += std::log(v);
+                }
+                lk3[q * 3 + t] = sum;
+            }
+            std::vector<double> sv(sl.begin() + q * 3 * L, sl.begin() + (q + 1) * 3 * L);
+            sup[q] = nj.SHSupport(col, &lk3[q * 3], sv);
+        }
+        putq("sh.col", col, {(int64_t) options.nBootstrap, L});
+        put("sh.loglk", 'd', {nq, 3}, lk3.data());
+        put("sh.siteLk", 'd', {nq, 3, L}, sl.data());
+        put("sh.support", 'd', {nq}, sup.data());
+        options.nBootstrap = 1000;
+    }
     // full out-profile rebuild over the active set (outProfile, NJ.tcc:729-815)
     {
         typedef typename NeighbourJoining<P, AVX256Operations>::Profile Profile;

@@ -148,6 +148,8 @@ def replay(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precision: in
                 crit, choice = ctx.choose_nni(dump["nni.ids"], pw, logd)
                 cmp("nni%d.criteria" % variant, crit)
                 cmp("nni%d.choice" % variant, choice.astype(np.int64))
+        if "sh.col" in dump:         # SHSupport (NJ.tcc:1126-1165) against the reference's own resampled columns
+            cmp("sh.support", ctx.sh_support(dump["sh.col"], dump["sh.loglk"], dump["sh.siteLk"]))
         ctx.outprofile_rebuild()
         w, cd, v = ctx.get_profile(-1)
         cmp("rebuild.outprofile.weights", w)

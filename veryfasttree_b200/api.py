@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "vft_posterior_profile_batch", "vft_get_config", "vft_tree_loglk", "vft_set_ml_rates",
     "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
-    "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard",
+    "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
 ]
 
 
@@ -142,6 +142,7 @@ class Lib:
             d.vft_ml_star_optimize_batch.argtypes = [vp, mo, i64, vp, vp, i64, ms]
             d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
             d.vft_choose_nni_batch.argtypes = [vp, i64, vp, dbl, i32, vp, vp]
+            d.vft_sh_support_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
@@ -391,6 +392,16 @@ class Context:
         self.lib.check(self.lib.dll.vft_choose_nni_batch(self.h, len(ids), _ptr(ids), float(pseudo_weight), 1 if logdist else 0,
                                                          _ptr(crit), _ptr(choice)), "vft_choose_nni_batch")
         return crit, choice
+
+    def sh_support(self, col, loglk, site_lk):
+        """vft_sh_support_batch: support[n] for col[nBoot, nPos], loglk[n, 3], site_lk[n, 3, nPos]."""
+        col = np.ascontiguousarray(col, dtype=np.int64); loglk = np.ascontiguousarray(loglk, dtype=np.float64)
+        site_lk = np.ascontiguousarray(site_lk, dtype=np.float64)
+        n = loglk.shape[0]
+        out = np.zeros(n, dtype=np.float64)
+        self.lib.check(self.lib.dll.vft_sh_support_batch(self.h, n, col.shape[0], _ptr(col), _ptr(loglk), _ptr(site_lk), _ptr(out)),
+                       "vft_sh_support_batch")
+        return out
 
     def ml_star_optimize(self, opt, ids, length, first_scratch_row):
         """vft_ml_star_optimize_batch: (len[n,3], stats)."""

@@ -907,6 +907,38 @@ k_posterior(Store<P> s, MLModel<P> m, int64_t oid, int64_t id1, int64_t id2, dou
     if (pos == 0 && oid < 2 * s.nSeqs) s.active[oid] = 1;              // scratch rows have no per-node state
 }
 
+// SHSupport, NJ.tcc:1126-1165: one thread per (quartet, resample); the quartet's 3 x nPos site log-likelihoods sit in shared
+// memory, the resampled columns are read transposed ([column][resample]: coalesced).  The three sums of a resample are ordered
+// chains over the columns, as in the reference; the vote is an integer.
+__global__ void __launch_bounds__(256)
+k_sh_support(const double *__restrict__ siteLogLk, const double *__restrict__ loglk, const int32_t *__restrict__ colT, int64_t nPos,
+             int64_t nBoot, unsigned int *__restrict__ votes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *sl = reinterpret_cast<double *>(smem);                     // [3][nPos]
+    const int64_t q = blockIdx.y;
+    for (int64_t t = threadIdx.x; t < 3 * nPos; t += blockDim.x) sl[t] = siteLogLk[q * 3 * nPos + t];
+    __syncthreads();
+    const int64_t iBoot = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    bool vote = false;
+    if (iBoot < nBoot) {
+        const double l0 = loglk[3 * q], l1 = loglk[3 * q + 1], l2 = loglk[3 * q + 2];
+        const double d1 = xsub(l0, l1), d2 = xsub(l0, l2), delta = d1 < d2 ? d1 : d2;
+        double r0 = -l0, r1 = -l1, r2 = -l2;
+        for (int64_t j = 0; j < nPos; j++) {
+            const int pos = colT[j * nBoot + iBoot];
+            r0 = xadd(r0, sl[pos]); r1 = xadd(r1, sl[nPos + pos]); r2 = xadd(r2, sl[2 * nPos + pos]);
+        }
+        const double r[3] = {r0, r1, r2};
+        int best = 0;
+        if (r[1] > r[best]) best = 1;
+        if (r[2] > r[best]) best = 2;
+        const double a = xsub(r[best], r[(best + 1) % 3]), b = xsub(r[best], r[(best + 2) % 3]);
+        vote = (a < b ? a : b) < delta;
+    }
+    const unsigned int n = __syncthreads_count(vote);
+    if (threadIdx.x == 0 && n) atomicAdd(&votes[q], n);
+}
+
 // leaves: selfweight = nPos - nGaps (NJ.tcc:249-252), active, padding of the code rows
 template<typename P>
 __global__ void k_init_leaves(Store<P> s) {
@@ -1915,6 +1947,52 @@ extern "C" int vft_put_profile(vft_ctx *c, int64_t id, const void *weights, cons
     CK(cudaMemcpy((char *) c->vecs + row * Lp * A * ps, vectors, L * A * ps, cudaMemcpyHostToDevice));
     ml_written(c, id);
     return VFT_OK;
+}
+
+extern "C" int vft_sh_support_batch(vft_ctx *c, int64_t n, int64_t nBootstrap, const int64_t *col, const double *loglk,
+                                    const double *siteLk, double *support) {
+    if (!c || n < 0 || nBootstrap < 1 || (n > 0 && (!col || !loglk || !siteLk || !support))) return fail(VFT_EINVAL, "bad argument");
+    if (n == 0) return VFT_OK;
+    bind_device(c);
+    const int64_t L = c->L;
+    const size_t smem = (size_t) 3 * L * 8;
+    if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the per-quartet site table");
+    // the resampled columns, transposed to [column][resample] and narrowed; the logarithms with the host's libm (NJ.tcc:1134-1136)
+    std::vector<int32_t> colT((size_t) (L * nBootstrap));
+    for (int64_t b = 0; b < nBootstrap; b++)
+        for (int64_t j = 0; j < L; j++) {
+            const int64_t p = col[b * L + j];
+            if (p < 0 || p >= L) return fail(VFT_EINVAL, "bad column index");
+            colT[(size_t) (j * nBootstrap + b)] = (int32_t) p;
+        }
+    const int64_t CH = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t) (256 << 20) / (24 * L)));     // quartets per launch
+    void *dCol = nullptr, *dSl = nullptr, *dLk = nullptr, *dVotes = nullptr;
+    CK(mem_alloc(&dCol, colT.size() * 4, MEM_DEVICE)); CK(mem_alloc(&dSl, (size_t) CH * 3 * L * 8, MEM_DEVICE));
+    CK(mem_alloc(&dLk, (size_t) CH * 24, MEM_DEVICE)); CK(mem_alloc(&dVotes, (size_t) CH * 4, MEM_DEVICE));
+    CK(cudaMemcpyAsync(dCol, colT.data(), colT.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_sh_support, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    std::vector<double> sl((size_t) CH * 3 * L);
+    std::vector<unsigned int> votes((size_t) CH);
+    int rc = VFT_OK;
+    for (int64_t q0 = 0; q0 < n && rc == VFT_OK; q0 += CH) {
+        const int64_t m = std::min(CH, n - q0);
+        for (int64_t k = 0; k < m * 3 * L; k++) sl[(size_t) k] = std::log(siteLk[q0 * 3 * L + k]);
+        cudaError_t e = cudaMemcpyAsync(dSl, sl.data(), (size_t) m * 3 * L * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dLk, loglk + 3 * q0, (size_t) m * 24, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dVotes, 0, (size_t) m * 4, c->stream);
+        if (e == cudaSuccess) {
+            const dim3 grid((unsigned) ((nBootstrap + 255) / 256), (unsigned) m);
+            k_sh_support<<<grid, 256, smem, c->stream>>>((const double *) dSl, (const double *) dLk, (const int32_t *) dCol, L, nBootstrap, (unsigned int *) dVotes);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(votes.data(), dVotes, (size_t) m * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = sync_stream(c);
+        if (e != cudaSuccess) { std::snprintf(g_err, sizeof g_err, "CUDA error: %s", cudaGetErrorString(e)); rc = VFT_ECUDA; break; }
+        c->cnt.launches++;
+        for (int64_t k = 0; k < m; k++) support[q0 + k] = (double) votes[(size_t) k] / (double) nBootstrap;         // :1164
+    }
+    mem_free(dCol); mem_free(dSl); mem_free(dLk); mem_free(dVotes);
+    return rc;
 }
 
 extern "C" int vft_get_counters(vft_ctx *c, vft_counters *out) {
