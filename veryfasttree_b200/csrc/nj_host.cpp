@@ -136,13 +136,13 @@ public:
         diameter.assign(maxnodes, 0);
         varDiameter.assign(maxnodes, 0);
         outDistances.assign(maxnodes, 0);
-        nOutDistActive.assign(maxnodes, nSeqs * 10);
+        nOutDistActive.assign(maxnodes, (int32_t) std::min<int64_t>(nSeqs * 10, 2000000000));      // "never computed": stale at any nActive
         freshVal.assign(maxnodes, 0);
         freshEpoch.assign(maxnodes, -1);
         wantEpoch.assign(maxnodes, -1);
         hintedEpoch.assign(maxnodes, -1);
         up.resize(maxnodes);
-        for (int64_t i = 0; i < maxnodes; i++) up[i] = i;
+        for (int64_t i = 0; i < maxnodes; i++) up[i] = (int32_t) i;
         hostThreads = opt.hostThreads > 0 ? opt.hostThreads : std::max(1, std::min(16, omp_get_num_procs()));
         // EXPERIMENTAL, off unless VFT_SPECULATION=1: bit-identical trees and a 98 % hit rate, but measured SLOWER on the
         // B200 (C2 1.68 s vs 1.26 s; 100k x 1287 aa 30.6 s vs 26.5 s): each speculated join costs three more launches of
@@ -186,7 +186,7 @@ private:
     vft_nj_result *res;
     int64_t nSeqs, nPos, maxnodes;
     std::vector<P> diameter, varDiameter, outDistances;
-    std::vector<int64_t> nOutDistActive;
+    std::vector<int32_t> nOutDistActive;     // (32-bit like the node ids: the per-join scans are bound by cache misses on these arrays)
     double totdiam = 0;
 
     // top-hits state, NJ.h:225-248
@@ -219,7 +219,8 @@ private:
     // fixed between two joins = one "epoch".
     int64_t epoch = 0, epochActive = 0;
     std::vector<P> freshVal;
-    std::vector<int64_t> freshEpoch, wantEpoch, hintedEpoch, leafGaps;
+    std::vector<int32_t> freshEpoch, wantEpoch, hintedEpoch;
+    std::vector<int64_t> leafGaps;
     std::vector<int64_t> wantIds;
     std::vector<P> wantVals;
 
@@ -378,7 +379,7 @@ private:
     // activeAncestor, NJ.tcc:536-544: the root of the subtree that contains i.  Same answer as
     // walking parent[], but over a union-find shortcut array with path halving (the walk can be
     // hundreds of levels deep on ladder-like trees); halving is skipped inside host-thread regions.
-    std::vector<int64_t> up;
+    std::vector<int32_t> up;
     int64_t activeAncestor(int64_t i) {
         if (i < 0) return i;
         if (omp_in_parallel()) { while (up[i] != i) i = up[i]; return i; }
