@@ -17,7 +17,7 @@
 // REVERSE input order".  rsort() below reproduces exactly that.
 //
 // Not supported (rejected with VFT_EINVAL, documented in DESIGN.md): -fastest / 2nd-level top
-// hits, topological constraints, -slow.
+// hits, topological constraints, -slow.  -bionj is supported (BIONJ weights, NJ.tcc:2921-2966).
 #include "../../include/vft_b200.h"
 
 #include <algorithm>

@@ -16,7 +16,12 @@
 //   k_out_distance_all    profileDist(node, out-profile) + the setOutDistance algebra, every active node
 //   k_average             averageProfile (+ fused updateOutProfile) + self distance of the new node
 //   k_outprofile_*        updateOutProfile / outProfile + setCodeDist
-//   k_pair_loglk, k_posterior   pairLogLk / posteriorProfile (vft_ml.cuh), one tree level per launch
+//   k_pair_loglk, k_posterior   pairLogLk / posteriorProfile (vft_ml.cuh): one tree level, or one lock-step round of the
+//                         branch-length / NNI optimisers (ml_opt.cpp), per launch; 1-8 warps per (pair, length) item
+//   k_sh_support          SHSupport: ordered gather-sums over resampled columns, one thread per (quartet, resample)
+//   k_spec_commit         state commit of a speculative join (vft_spec_join_*: k_average into a shadow out-profile +
+//                         k_eval in raw mode, launched ahead of the host's decision)
+// Scratch profile rows (cfg.nScratch, ids 2N ...) extend codes / weights / vecs for the temporaries of the ML phase.
 // There is no CPU fallback: without a usable device vft_ctx_create returns VFT_ENODEVICE.
 #include "../../include/vft_b200.h"
 #include "vft_device.cuh"
