@@ -170,3 +170,31 @@ def test_bionj_tree_identical_to_reference(olib, name, prec):
     plain = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
     assert _bionj_tree(olib, name, prec) == want
     assert want != plain          # the option does change the tree: the golden is not vacuous
+
+
+def test_new_entry_points_validate_their_arguments(olib):
+    """Scratch rows, speculative join, SHSupport, the lock-step optimisers: bad ids / sizes are errors, not crashes."""
+    import ctypes as C
+    chars, kind = replay.golden_case("nt60")
+    codes = api.encode(chars, kind)
+    N, L = codes.shape
+    cfg = api.make_config(N, L, 4, 32, n_scratch=4)
+    with api.Context(olib, cfg) as ctx:
+        ctx.upload_leaves(codes)
+        d = olib.dll
+        w = np.ones(L, dtype=np.float32); cd = np.full(L, 127, dtype=np.uint8); v = np.zeros((L, 4), dtype=np.float32)
+        assert d.vft_put_profile(ctx.h, 2 * N + 4, api._ptr(w), api._ptr(cd), api._ptr(v)) == -1      # past the scratch rows
+        assert d.vft_put_profile(ctx.h, 3, api._ptr(w), api._ptr(cd), api._ptr(v)) == -1              # a leaf row
+        assert d.vft_put_profile(ctx.h, 2 * N + 3, api._ptr(w), api._ptr(cd), api._ptr(v)) == 0
+        ids = np.array([0, 1], dtype=np.int64)
+        assert d.vft_spec_join_launch(ctx.h, N + 5, 0, 1, -1.0, N, api._ptr(ids), 2, None, 0) == -1   # not the next free row
+        assert d.vft_spec_join_launch(ctx.h, N, 0, 0, -1.0, N, api._ptr(ids), 2, None, 0) == -1       # a node with itself
+        assert d.vft_spec_join_take(ctx.h, 0.0, None, None, None, None, None) == -1                   # nothing pending
+        assert d.vft_spec_join_launch(ctx.h, N, 2, 3, -1.0, N, api._ptr(ids), 2, None, 0) == 0
+        assert d.vft_spec_join_discard(ctx.h) == 0
+        col = np.full((5, L), L, dtype=np.int64)                                                     # column index out of range
+        lk = np.zeros((1, 3)); sl = np.ones((1, 3, L)); out = np.zeros(1)
+        assert d.vft_sh_support_batch(ctx.h, 1, 5, api._ptr(col), api._ptr(lk), api._ptr(sl), api._ptr(out)) == -1
+        crit = np.zeros(3); ch = np.zeros(1, dtype=np.int32)
+        bad = np.array([0, 1, 2, 10 * N], dtype=np.int64)
+        assert d.vft_choose_nni_batch(ctx.h, 1, api._ptr(bad), 0.0, 1, api._ptr(crit), api._ptr(ch)) == -1

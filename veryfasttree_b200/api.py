@@ -143,6 +143,9 @@ class Lib:
             d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
             d.vft_choose_nni_batch.argtypes = [vp, i64, vp, dbl, i32, vp, vp]
             d.vft_sh_support_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+            d.vft_spec_join_launch.argtypes = [vp, i64, i64, i64, dbl, i64, vp, i64, vp, i64]
+            d.vft_spec_join_take.argtypes = [vp, dbl, vp, vp, vp, vp, vp]
+            d.vft_spec_join_discard.argtypes = [vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
