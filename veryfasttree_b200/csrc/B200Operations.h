@@ -226,6 +226,13 @@ public:
     void mlStarOptimizeBatch(const vft_ml_options &opt, int64_t n, const int64_t *ids, numeric_t *len, int64_t firstScratchRow) {
         check(vft_ml_star_optimize_batch(ctx.get(), &opt, n, ids, len, firstScratchRow, nullptr));
     }
+    // chooseNNI (NJ.tcc:4836-4852) and SHSupport (NJ.tcc:1126-1165) for sets of independent quartets / splits
+    void chooseNNIBatch(int64_t n, const int64_t *ids, double pseudoWeight, bool logdist, double *criteria, int32_t *choice) {
+        check(vft_choose_nni_batch(ctx.get(), n, ids, pseudoWeight, logdist ? 1 : 0, criteria, choice));
+    }
+    void shSupportBatch(int64_t n, int64_t nBootstrap, const int64_t *col, const double *loglk, const double *siteLk, double *support) {
+        check(vft_sh_support_batch(ctx.get(), n, nBootstrap, col, loglk, siteLk, support));
+    }
     void mlOptimizeBranchLengths(const vft_ml_options &opt, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
                                  numeric_t *branchlength, bool referenceOrder) {
         check(vft_ml_optimize_branch_lengths(ctx.get(), &opt, root, maxnode, nChild, child, branchlength,
