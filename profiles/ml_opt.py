@@ -57,6 +57,44 @@ with api.Context(lib, cfg) as ctx:
             lk, _ = ctx.tree_loglk(tree.root, n_child, child, bl, recompute=False)
             print('   setMLRates(%d categories): %.3f s, LogLk = %.3f' % (n_cat, time.time() - t0, lk), flush=True)
 
+    # MLQuartetNNI throughput: one quartet per internal node -- A, B = its children, C = its sibling,
+    # D = the parent's sibling (or another child of the root): read-only node profiles, temporaries in scratch rows, so
+    # any set of quartets is a valid batch.  (The real NNI round passes the parent's up-profile as D; same cost.)
+    par = np.full(M, -1, dtype=np.int64)
+    for nd in range(M):
+        for k in range(n_child[nd]):
+            par[child[nd, k]] = nd
+    def sib(x):
+        p = par[x]
+        return [c for c in child[p, :n_child[p]] if c != x]
+    quartets, lens = [], []
+    for nd in range(N, M):
+        if nd == tree.root or n_child[nd] != 2 or par[nd] < 0:
+            continue
+        p = par[nd]
+        c = sib(nd)[0]
+        d_ = sib(p)[0] if p != tree.root else sib(nd)[-1]
+        if d_ == c:
+            continue
+        a, b = child[nd, 0], child[nd, 1]
+        quartets.append([a, b, c, d_]); lens.append([bl[a], bl[b], bl[c], bl[d_], bl[nd]])
+    quartets = np.array(quartets, dtype=np.int64); lens = np.array(lens, dtype=dt)
+    CH = (2 * N) // 3                                          # three scratch rows per quartet
+    tot = dict(rounds=0, loglkItems=0, loglkCalls=0, posteriorItems=0, posteriorCalls=0)
+    n_star = n_swap = 0
+    c0 = ctx.counters()
+    t0 = time.time()
+    for q0 in range(0, len(quartets), CH):
+        ln, crit, choice, star, st = ctx.ml_quartet_nni(opt, quartets[q0:q0 + CH], lens[q0:q0 + CH], 2 * N)
+        for k in tot: tot[k] += st[k]
+        n_star += int(star.sum()); n_swap += int((choice != 0).sum())
+    dtq = time.time() - t0
+    c1 = ctx.counters()
+    print('MLQuartetNNI: %d quartets in %.3f s = %.1f us per quartet (%d per call); %d star tests, %d would swap; %d lock-step rounds, %d pairLogLk items in %d calls (%.0f per call), %d posteriors'
+          % (len(quartets), dtq, 1e6 * dtq / len(quartets), CH, n_star, n_swap, tot['rounds'], tot['loglkItems'], tot['loglkCalls'], tot['loglkItems'] / max(1, tot['loglkCalls']), tot['posteriorItems']), flush=True)
+    for nm, a, b, x, y in zip(api.KERNEL_NAMES, list(c1.msKernel), list(c0.msKernel), list(c1.nKernel), list(c0.nKernel)):
+        if x - y:
+            print('   %-22s %6d launches %9.2f ms' % (nm, x - y, a - b))
 if ref_threads > 0 and os.path.exists(replay.REF_BIN):
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, 'a.fa')
