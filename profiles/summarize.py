@@ -97,7 +97,20 @@ def ml():
               "Reading: all pairLogLk terms of treeLogLk in one launch: 19 999 items x 2 profiles x 109 KB = 4.38 GB algorithmic, W = 1 (8 items per CTA, 86 KB of shared memory: two CTAs = 16 warps per SM).  Live CUDA-event time without the profiler: 2.66 ms = 1.65 TB/s = 26 % of the measured 6.45 TB/s HBM peak (was 5.7 ms with 4 items per CTA and a 10 KB table per warp).  DRAM traffic 2.2 GB: half the algorithmic bytes (leaf profiles are 1 byte per site; vectors are fetched only where a site has no known code).  Limiter: each warp's lane 0 runs the 1287-step sequential product while the other 31 lanes idle (DSETP/BRA/DMUL chain), and 16 warps per SM cannot hide it; next step is to give the product chains of several items to the lanes of one warp (transpose through shared memory, as the distance kernels do for their ordered sums).", "%s_k_pair_loglk_tree_ncu_full.md" % TAG)
 
 
+def late():
+    """k_posterior on one tree level and the rebuilt k_outprofile_rebuild (captured late in the round)."""
+    summarize(os.path.join(RAW, "prof_posterior.ncu-rep"), "Round 1 -- `ncu --set full` of `k_posterior<float,20>` on one tree level of recomputeMLProfiles (aa 20 000 x 1287, JTT: 1 721 parents, grid 11 x 1 721)",
+              "ncu --set full --import-source on --clock-control none -k regex:k_posterior -s 3 -c 1 -o gpurun_out/prof_posterior python profiles/ml_sweep.py 20000 1287",
+              "Reading: one thread per site, grid.y = the parents of the level.  Per site the kernel does the reference's three 20 x 20 matrix-vector products (two rotations by exp(eigenvalue x rate x length) into the eigenbasis of the parent, one back through eigeninv: ~2.4 kFLOP) in separately rounded FMUL + FADD -- 63 % of the instruction stream, FMA pipe 32 % busy, issue slots 49 % busy at 4 CTAs of 128 threads per SM (106 registers).  340 MB read + 167 MB written for 1 721 x 3 profiles of 109 KB = 563 MB algorithmic: every byte moves once.  The kernel is ISSUE bound (non-fused multiply-adds are the price of the reference's rounding), with LDG latency (30 % of the stall samples: the 20-float vectors are read per thread, 80-byte stride) as the second limiter; the whole 29-level sweep takes 6.9 ms for 6.6 GB = 0.95 TB/s.", "%s_k_posterior_ncu_full.md" % TAG)
+    summarize(os.path.join(RAW, "prof_rebuild.ncu-rep"), "Round 1 -- `ncu --set full` of `k_outprofile_rebuild<float,4,false>` (16 000 x 200 nt, ~15 800 active nodes, cold)",
+              "ncu --set full --import-source on --clock-control none -k regex:k_outprofile_rebuild -s 2 -c 1 -o gpurun_out/prof_rebuild python profiles/one_step.py 16000",
+              "Reading: 7 CTAs (32 positions each) of 256 threads: the machine is empty by construction -- the reference's out-profile is a P-typed running sum over the nodes in id order (NJ.tcc:741, :771), one sequential chain per (position, state), 16 k links long.  After this round's change the producers (all 256 threads) turn every (node, position) into ready-made addends and the 128 chain threads do one dependent addition per node: live time 0.56 ms per rebuild (1.07 ms before), i.e. ~67 cycles per link, of which the weight chain's float -> double -> float round trip (F2F + DADD + F2F, 7.6 % of the instructions are conversions) is the longest dependency.  The 1.28 M shared-memory bank conflicts of this capture came from the producers' scalar stores into the A-strided addend rows; they were replaced by 128-bit stores afterwards, which did not move the time (573 us): the kernel is chain bound, not store bound.  74 rebuilds per C2 step = 41 ms (3.4 %).", "%s_k_outprofile_rebuild_ncu_full.md" % TAG)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "late":
+        late()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "ml":
         ml()
         sys.exit(0)

@@ -797,16 +797,17 @@ k_outprofile_rebuild(Store<P> s, const int64_t *__restrict__ ids, int64_t n) {
             const P w = rw[q];
             const uint32_t c = rc[q];
             sW[buf * TN * PP + e] = xmul((double) w, inweight);
+            P add[A];
 #pragma unroll
             for (int a = 0; a < A; a++) {
-                P add = 0;
+                add[a] = 0;
                 if (w > 0) {
-                    if (c == VFT_DEV_NOCODE) add = pmul(rv[q][a], w);
-                    else if (MATRIX) add = pmul(s.codeFreq[c * 20 + a], w);
-                    else if (c == (uint32_t) a) add = w;
+                    if (c == VFT_DEV_NOCODE) add[a] = pmul(rv[q][a], w);
+                    else if (MATRIX) add[a] = pmul(s.codeFreq[c * 20 + a], w);
+                    else if (c == (uint32_t) a) add[a] = w;
                 }
-                sV[((size_t) buf * TN * PP + e) * A + a] = add;
             }
+            store_vec<P, A>(sV + ((size_t) buf * TN * PP + e) * A, add);      // 128-bit stores: scalar ones conflict 4 ways on the A-strided rows
         }
     };
     if (tid < TN) sId[tid] = tid < n ? (int) ids[tid] : 0;

@@ -380,6 +380,26 @@ __device__ __forceinline__ void load_vec(const P *__restrict__ src, P *v) {
     }
 }
 
+// n consecutive P's to a 16-byte aligned address with 128-bit stores
+template<typename P, int N_>
+__device__ __forceinline__ void store_vec(P *__restrict__ dst, const P *v) {
+    typedef typename VecLd<P>::type V;
+    constexpr int N = VecLd<P>::N;
+    if constexpr (N_ % N == 0) {
+        V *q = reinterpret_cast<V *>(dst);
+#pragma unroll
+        for (int k = 0; k < N_ / N; k++) {
+            V t;
+            if constexpr (N == 4) { t.x = v[4 * k]; t.y = v[4 * k + 1]; t.z = v[4 * k + 2]; t.w = v[4 * k + 3]; }
+            else { t.x = v[2 * k]; t.y = v[2 * k + 1]; }
+            q[k] = t;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N_; k++) dst[k] = v[k];
+    }
+}
+
 // WIDE variant (one pair per CTA, the mid-sized lists of long alignments): the calling warp evaluates the chunks
 // chunk0, chunk0+chunkStep, ... of ONE pair into a full-length term row (T, W: [Lp rounded up to C] each) and does
 // not accumulate; the caller adds the row in order once every warp of the CTA is done (cta_ordered_sum).
