@@ -1971,7 +1971,7 @@ extern "C" int vft_sh_support_batch(vft_ctx *c, int64_t n, int64_t nBootstrap, c
             if (p < 0 || p >= L) return fail(VFT_EINVAL, "bad column index");
             colT[(size_t) (j * nBootstrap + b)] = (int32_t) p;
         }
-    const int64_t CH = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t) (256 << 20) / (24 * L)));     // quartets per launch
+    const int64_t CH = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 65535), (int64_t) (256 << 20) / (24 * L)));     // quartets per launch (grid.y)
     void *dCol = nullptr, *dSl = nullptr, *dLk = nullptr, *dVotes = nullptr;
     CK(mem_alloc(&dCol, colT.size() * 4, MEM_DEVICE)); CK(mem_alloc(&dSl, (size_t) CH * 3 * L * 8, MEM_DEVICE));
     CK(mem_alloc(&dLk, (size_t) CH * 24, MEM_DEVICE)); CK(mem_alloc(&dVotes, (size_t) CH * 4, MEM_DEVICE));
