@@ -292,6 +292,15 @@ int  vft_ml_pair_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t
 int  vft_ml_quartet_nni_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
                               double *criteria, int32_t *choice, int32_t *starTest, int64_t firstScratchRow,
                               vft_ml_stats *stats);
+/* The per-split body of testSplitsML (traverseTestSplitsML, NJ.tcc:6884-6952) for n independent splits: ids[4n] = A,B,C,D
+   (setupABCD order), len[5n] numeric_t = the current lengths (already optimised for AB|CD).  loglk[3n]: MLQuartetLogLk
+   (NJ.tcc:5410-5427) of AB|CD as it is, MLQuartetOptimize of AC|BD and AD|BC (the better one a second time when it is within
+   closeLogLkLimit); siteLk[n][3][nPos]: the per-site likelihoods of each (the input of vft_sh_support_batch);
+   choice[n]: the most likely topology; badSplit[n]: it beats AB|CD by more than treeLogLkDelta (0.1) -- the reference then
+   reports support 0.  Scratch rows firstScratchRow .. +3n-1. */
+int  vft_ml_split_test_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, const void *len,
+                             double *loglk, double *siteLk, int32_t *choice, int32_t *badSplit, int64_t firstScratchRow,
+                             vft_ml_stats *stats);
 /* chooseNNI (NJ.tcc:4836-4852), the minimum-evolution counterpart: for n quartets ids[4n] = A,B,C,D (node ids), the six
    profile distances of each (correctedPairDistances, NJ.tcc:1460-1488: bare profileDist, Options.pseudoWeight prior,
    logCorrect NJ.tcc:322-330 when logdist) evaluated as ONE vft_dist_pairs batch; criteria[3n] = d(AB)+d(CD), d(AC)+d(BD),

@@ -250,6 +250,12 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
         }
         {
             std::vector<std::unique_ptr<Profile>> upProfiles(nj2.maxnodes);
+            // the per-split body of testSplitsML (NJ.tcc:6884-6952) + SHSupport on the same quartets, 100 resamples
+            options.nBootstrap = 100;
+            std::vector<int64_t> shCol;
+            nj2.resampleColumns(shCol);
+            std::vector<double> spLk, spSite, spSupport;
+            std::vector<int64_t> spChoice, spBad;
             std::vector<int64_t> qids, qnode, qchoice;
             std::vector<P> qlen0, qlen1;
             std::vector<double> qcrit;
@@ -269,6 +275,28 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
                     for (int i = 0; i < 3; i++) qcrit.push_back(crit[i]);
                     qchoice.push_back(choice);
                 }
+                {
+                    double l5[5] = {(double) nj2.branchlength[abcd[0]], (double) nj2.branchlength[abcd[1]], (double) nj2.branchlength[abcd[2]],
+                                    (double) nj2.branchlength[abcd[3]], (double) nj2.branchlength[node]};
+                    double lAB[5] = {l5[0], l5[1], l5[2], l5[3], l5[4]}, lAC[5] = {l5[0], l5[2], l5[1], l5[3], l5[4]}, lAD[5] = {l5[0], l5[3], l5[2], l5[1], l5[4]};
+                    std::vector<double> site(3 * L);
+                    double lk3[3];
+                    lk3[0] = nj2.MLQuartetLogLk(*p4[0], *p4[1], *p4[2], *p4[3], lAB, &site[0]);
+                    lk3[1] = nj2.MLQuartetOptimize(*p4[0], *p4[2], *p4[1], *p4[3], lAC, nullptr, &site[L]);
+                    lk3[2] = nj2.MLQuartetOptimize(*p4[0], *p4[3], *p4[2], *p4[1], lAD, nullptr, &site[2 * L]);
+                    if (lk3[1] > lk3[2]) {
+                        if (options.mlAccuracy > 1 || lk3[1] > lk3[0] - Constants::closeLogLkLimit)
+                            lk3[1] = nj2.MLQuartetOptimize(*p4[0], *p4[2], *p4[1], *p4[3], lAC, nullptr, &site[L]);
+                    } else {
+                        if (options.mlAccuracy > 1 || lk3[2] > lk3[0] - Constants::closeLogLkLimit)
+                            lk3[2] = nj2.MLQuartetOptimize(*p4[0], *p4[3], *p4[2], *p4[1], lAD, nullptr, &site[2 * L]);
+                    }
+                    int ch = lk3[0] >= lk3[1] && lk3[0] >= lk3[2] ? 0 : (lk3[1] >= lk3[0] && lk3[1] >= lk3[2] ? 1 : 2);
+                    bool bad = lk3[ch] > lk3[0] + Constants::treeLogLkDelta;
+                    spLk.insert(spLk.end(), lk3, lk3 + 3); spSite.insert(spSite.end(), site.begin(), site.end());
+                    spChoice.push_back(ch); spBad.push_back(bad ? 1 : 0);
+                    spSupport.push_back(bad ? 0.0 : nj2.SHSupport(shCol, lk3, site));
+                }
                 for (int i = 0; i < 4; i++) qids.push_back(abcd[i]);
                 qnode.push_back(node);
                 nQ++;
@@ -277,6 +305,11 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
             putv<P>("ml.opt.q.len0", qlen0, {nQ, 2, 5}); putv<P>("ml.opt.q.len1", qlen1, {nQ, 2, 5});
             put("ml.opt.q.criteria", 'd', {nQ, 2, 3}, qcrit.data());
             putq("ml.opt.q.nStar", {(int64_t) options.debug.nStarTests});
+            putq("ml.split.col", shCol, {(int64_t) options.nBootstrap, L});
+            put("ml.split.loglk", 'd', {nQ, 3}, spLk.data()); put("ml.split.site", 'd', {nQ, 3, L}, spSite.data());
+            putq("ml.split.choice", spChoice); putq("ml.split.bad", spBad);
+            put("ml.split.support", 'd', {nQ}, spSupport.data());
+            options.nBootstrap = 1000;
             // the per-node body of traverseOptimizeAllBranchLengths on a few nodes (state untouched: local lengths)
             std::vector<int64_t> snode, sids;
             std::vector<P> slen0, slen1;

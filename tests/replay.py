@@ -376,6 +376,28 @@ def replay_ml_opt(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precis
         if not (bits_equal(ln[keep], first[0][keep]) and bits_equal(crit[keep], first[1][keep]) and np.array_equal(choice[keep], first[2][keep])):
             bad.append("fastNNI=0 differs where no star test fired")
         opt.fastNNI = int(fl[1])
+        # the per-split body of testSplitsML (MLQuartetLogLk + MLQuartetOptimize x2(+1) with per-site likelihoods), then SHSupport
+        if "ml.split.loglk" in dump:
+            lk3, site3, ch, bd, st = ctx.ml_split_test(opt, ids, dump["ml.opt.q.len0"][:, 0, :], base + nQ)
+            info["split.stats"] = st
+            want_lk, want_site = dump["ml.split.loglk"], dump["ml.split.site"]
+            if exact:
+                if not bits_equal(lk3, np.ascontiguousarray(want_lk)): bad.append("ml.split.loglk")
+                if not bits_equal(site3, np.ascontiguousarray(want_site)): bad.append("ml.split.site")
+                if not np.array_equal(ch, dump["ml.split.choice"]): bad.append("ml.split.choice")
+                if not np.array_equal(bd, dump["ml.split.bad"]): bad.append("ml.split.bad")
+            else:
+                cmp_lk("ml.split.loglk", lk3, want_lk)
+                near = np.abs(np.sort(want_lk, axis=1)[:, -1] - np.sort(want_lk, axis=1)[:, -2]) < 10 * lk_tol * np.abs(want_lk[:, 0]) + 0.11
+                if np.any((ch != dump["ml.split.choice"]) & ~near): bad.append("ml.split.choice")
+                same = ch == dump["ml.split.choice"]
+                if not np.allclose(site3[same], want_site[same], rtol=2e-2, atol=0): bad.append("ml.split.site~")
+            sup = ctx.sh_support(dump["ml.split.col"], lk3, site3)
+            sup = np.where(bd != 0, 0.0, sup)                                  # a bad split gets support 0 (NJ.tcc:6991)
+            info["split.support"] = [round(float(x), 2) for x in sup[:8]]
+            if exact:
+                if not bits_equal(sup, np.ascontiguousarray(dump["ml.split.support"])): bad.append("ml.split.support")
+            elif np.max(np.abs(sup - dump["ml.split.support"])[bd == dump["ml.split.bad"]], initial=0.0) > 0.1: bad.append("ml.split.support~")
         # the per-node body of optimizeAllBranchLengths
         sbase = base + 4 * nQ
         sid = np.array(s_ids, dtype=np.int64)

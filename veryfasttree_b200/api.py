@@ -87,6 +87,7 @@ ABI_SYMBOLS = [
     "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
     "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
+    "vft_ml_split_test_batch",
 ]
 
 
@@ -142,6 +143,7 @@ class Lib:
             d.vft_ml_star_optimize_batch.argtypes = [vp, mo, i64, vp, vp, i64, ms]
             d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
             d.vft_choose_nni_batch.argtypes = [vp, i64, vp, dbl, i32, vp, vp]
+            d.vft_ml_split_test_batch.argtypes = [vp, mo, i64, vp, vp, vp, vp, vp, vp, i64, ms]
             d.vft_sh_support_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp]
             d.vft_spec_join_launch.argtypes = [vp, i64, i64, i64, dbl, i64, vp, i64, vp, i64]
             d.vft_spec_join_take.argtypes = [vp, dbl, vp, vp, vp, vp, vp]
@@ -405,6 +407,18 @@ class Context:
         self.lib.check(self.lib.dll.vft_sh_support_batch(self.h, n, col.shape[0], _ptr(col), _ptr(loglk), _ptr(site_lk), _ptr(out)),
                        "vft_sh_support_batch")
         return out
+
+    def ml_split_test(self, opt, ids, length, first_scratch_row):
+        """vft_ml_split_test_batch: (loglk[n,3], siteLk[n,3,nPos], choice[n], bad[n], stats)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1, 4)
+        n = len(ids)
+        ln = np.ascontiguousarray(length, dtype=self.dt).reshape(n, 5)
+        lk = np.zeros((n, 3), dtype=np.float64); site = np.zeros((n, 3, self.cfg.nPos), dtype=np.float64)
+        choice = np.zeros(n, dtype=np.int32); bad = np.zeros(n, dtype=np.int32)
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_split_test_batch(self.h, C.byref(opt), n, _ptr(ids), _ptr(ln), _ptr(lk), _ptr(site), _ptr(choice),
+                                                            _ptr(bad), int(first_scratch_row), C.byref(st)), "vft_ml_split_test_batch")
+        return lk, site, choice, bad, st.as_dict()
 
     def ml_star_optimize(self, opt, ids, length, first_scratch_row):
         """vft_ml_star_optimize_batch: (len[n,3], stats)."""

@@ -230,6 +230,11 @@ public:
     void chooseNNIBatch(int64_t n, const int64_t *ids, double pseudoWeight, bool logdist, double *criteria, int32_t *choice) {
         check(vft_choose_nni_batch(ctx.get(), n, ids, pseudoWeight, logdist ? 1 : 0, criteria, choice));
     }
+    // the per-split body of testSplitsML (NJ.tcc:6884-6952): likelihoods + per-site likelihoods of the three topologies
+    void mlSplitTestBatch(const vft_ml_options &opt, int64_t n, const int64_t *ids, const numeric_t *len, double *loglk, double *siteLk,
+                          int32_t *choice, int32_t *badSplit, int64_t firstScratchRow) {
+        check(vft_ml_split_test_batch(ctx.get(), &opt, n, ids, len, loglk, siteLk, choice, badSplit, firstScratchRow, nullptr));
+    }
     void shSupportBatch(int64_t n, int64_t nBootstrap, const int64_t *col, const double *loglk, const double *siteLk, double *support) {
         check(vft_sh_support_batch(ctx.get(), n, nBootstrap, col, loglk, siteLk, support));
     }

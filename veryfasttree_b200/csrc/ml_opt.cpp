@@ -74,17 +74,19 @@ struct Batcher {
     vft_ctx *ctx;
     std::vector<int64_t> lkA, lkB;
     std::vector<double> lkX;
-    std::vector<double *> lkOut;
+    std::vector<double *> lkOut, lkSite;                     // lkSite[k]: per-site likelihoods are multiplied into this array (or nullptr)
+    int64_t L = 0;                                           // nPos, needed only when a site array is asked for
+    std::vector<double> siteBuf;
     std::vector<std::coroutine_handle<>> waiters;
     std::vector<int64_t> poOut, poA, poB;
     std::vector<double> poL1, poL2, lkVal;
     vft_ml_stats stats{};
 
     struct LkWait {
-        Batcher *b; int n; int64_t a[2], bb[2]; double x[2], val[2];
+        Batcher *b; int n; int64_t a[2], bb[2]; double x[2], val[2]; double *site = nullptr;
         bool await_ready() const noexcept { return false; }
         void await_suspend(std::coroutine_handle<> h) {
-            for (int k = 0; k < n; k++) { b->lkA.push_back(a[k]); b->lkB.push_back(bb[k]); b->lkX.push_back(x[k]); b->lkOut.push_back(&val[k]); }
+            for (int k = 0; k < n; k++) { b->lkA.push_back(a[k]); b->lkB.push_back(bb[k]); b->lkX.push_back(x[k]); b->lkOut.push_back(&val[k]); b->lkSite.push_back(site); }
             b->waiters.push_back(h);
         }
         std::pair<double, double> await_resume() const noexcept { return {val[0], val[1]}; }
@@ -99,8 +101,12 @@ struct Batcher {
         void await_resume() const noexcept {}
     };
     // pairLogLk(a, b, x) and a pair of them evaluated in the same round
-    LkWait lk(int64_t a, int64_t b, double x) { return LkWait{this, 1, {a, 0}, {b, 0}, {x, 0}, {0, 0}}; }
-    LkWait lk2(int64_t a0, int64_t b0, double x0, int64_t a1, int64_t b1, double x1) { return LkWait{this, 2, {a0, a1}, {b0, b1}, {x0, x1}, {0, 0}}; }
+    // site != nullptr: pairLogLk's site_likelihoods[] argument (NJ.tcc:1263-1265, :1436): every per-site value is multiplied in,
+    // the first item of a pair before the second
+    LkWait lk(int64_t a, int64_t b, double x, double *site = nullptr) { return LkWait{this, 1, {a, 0}, {b, 0}, {x, 0}, {0, 0}, site}; }
+    LkWait lk2(int64_t a0, int64_t b0, double x0, int64_t a1, int64_t b1, double x1, double *site = nullptr) {
+        return LkWait{this, 2, {a0, a1}, {b0, b1}, {x0, x1}, {0, 0}, site};
+    }
     // posteriorProfile(out <- p1, p2); two independent ones in the same round
     PostWait post(int64_t o, int64_t p1, int64_t p2, double l1, double l2) { return PostWait{this, 1, {o, 0}, {p1, 0}, {p2, 0}, {l1, 0}, {l2, 0}}; }
     PostWait post2(int64_t o0, int64_t p0, int64_t q0, double l0, double m0, int64_t o1, int64_t p1, int64_t q1, double l1, double m1) {
@@ -117,12 +123,39 @@ struct Batcher {
             poOut.clear(); poA.clear(); poB.clear(); poL1.clear(); poL2.clear();
         }
         if (!lkA.empty()) {
+            // the (rare) items that want their per-site likelihoods go in a call of their own, so that the bulk of a round
+            // carries no [n][nPos] result array
+            size_t nSite = 0;
+            for (double *p : lkSite) nSite += p != nullptr;
+            if (nSite > 0 && nSite < lkA.size()) {               // stable partition: plain items first
+                std::vector<size_t> order;
+                for (size_t k = 0; k < lkA.size(); k++) if (!lkSite[k]) order.push_back(k);
+                for (size_t k = 0; k < lkA.size(); k++) if (lkSite[k]) order.push_back(k);
+                auto perm = [&](auto &v) { auto c = v; for (size_t k = 0; k < order.size(); k++) v[k] = c[order[k]]; };
+                perm(lkA); perm(lkB); perm(lkX); perm(lkOut); perm(lkSite);
+            }
+            const size_t nPlain = lkA.size() - nSite;
             lkVal.resize(lkA.size());
-            int rc = vft_pair_loglk_batch(ctx, lkA.data(), lkB.data(), lkX.data(), (int64_t) lkA.size(), lkVal.data(), nullptr);
-            if (rc != VFT_OK) return rc;
-            stats.loglkCalls++; stats.loglkItems += (int64_t) lkA.size();
+            if (nPlain > 0) {
+                int rc = vft_pair_loglk_batch(ctx, lkA.data(), lkB.data(), lkX.data(), (int64_t) nPlain, lkVal.data(), nullptr);
+                if (rc != VFT_OK) return rc;
+                stats.loglkCalls++;
+            }
+            if (nSite > 0) {
+                siteBuf.resize(nSite * (size_t) L);
+                int rc = vft_pair_loglk_batch(ctx, lkA.data() + nPlain, lkB.data() + nPlain, lkX.data() + nPlain, (int64_t) nSite,
+                                              lkVal.data() + nPlain, siteBuf.data());
+                if (rc != VFT_OK) return rc;
+                stats.loglkCalls++;
+                for (size_t k = 0; k < nSite; k++) {              // in request order: a task's first item before its second
+                    double *dst = lkSite[nPlain + k];
+                    const double *row = siteBuf.data() + k * (size_t) L;
+                    for (int64_t j = 0; j < L; j++) dst[j] *= row[j];
+                }
+            }
+            stats.loglkItems += (int64_t) lkA.size();
             for (size_t k = 0; k < lkA.size(); k++) *lkOut[k] = lkVal[k];
-            lkA.clear(); lkB.clear(); lkX.clear(); lkOut.clear();
+            lkA.clear(); lkB.clear(); lkX.clear(); lkOut.clear(); lkSite.clear();
         }
         now.swap(waiters);
         waiters.clear();
@@ -241,7 +274,8 @@ enum { LEN_A = 0, LEN_B, LEN_C, LEN_D, LEN_I };            // NJ.h: order of the
 
 // MLQuartetOptimize, NJ.tcc:1650-1788.  rows[3]: scratch profile rows for AB, CD and the changing third profile
 // (BCD, ACD, ABD, ABC in turn -- the reference's stack Profiles).
-Task<double> quartetOptimize(Batcher &B, const Opt &o, const int64_t q[4], double len[5], bool *starTest, const int64_t rows[3]) {
+Task<double> quartetOptimize(Batcher &B, const Opt &o, const int64_t q[4], double len[5], bool *starTest, const int64_t rows[3],
+                             double *site = nullptr) {
     const int64_t pA = q[0], pB = q[1], pC = q[2], pD = q[3], AB = rows[0], CD = rows[1], X = rows[2];
     for (int j = 0; j < 5; j++) if (len[j] < o.minLen) len[j] = o.minLen;
     if (starTest) *starTest = false;
@@ -266,8 +300,13 @@ Task<double> quartetOptimize(Batcher &B, const Opt &o, const int64_t q[4], doubl
     len[LEN_C] = co_await oneDimMin(B, pC, X, o.minLen, len[LEN_C], 6.0, o.ftol, o.atol, &neg);
     co_await B.post(X, AB, pC, len[LEN_I], len[LEN_C]);       // ABC, :1749-1762
     len[LEN_D] = co_await oneDimMin(B, pD, X, o.minLen, len[LEN_D], 6.0, o.ftol, o.atol, &neg);
-    // PairLogLk(ABC,D) + PairLogLk(AB,C) + PairLogLk(A,B), :1764-1775
-    const auto rest = co_await B.lk2(AB, pC, len[LEN_I] + len[LEN_C], pA, pB, len[LEN_A] + len[LEN_B]);
+    // PairLogLk(ABC,D) + PairLogLk(AB,C) + PairLogLk(A,B), :1764-1775; with site likelihoods the first term is evaluated once
+    // more to collect them (:1767-1772), the value of the optimisation is what enters the sum
+    if (site) {
+        for (int64_t j = 0; j < B.L; j++) site[j] = 1.0;
+        (void) co_await B.lk(X, pD, len[LEN_D], site);
+    }
+    const auto rest = co_await B.lk2(AB, pC, len[LEN_I] + len[LEN_C], pA, pB, len[LEN_A] + len[LEN_B], site);
     co_return (-neg + rest.first) + rest.second;
 }
 
@@ -311,6 +350,43 @@ Task<int> quartetNNI(Batcher &B, const Opt &o, QuartetJob *job) {
     if (crit[1] > crit[0] && crit[1] > crit[2]) { best = ac; job->choice = 1; }
     else if (crit[2] > crit[0] && crit[2] > crit[1]) { best = ad; job->choice = 2; }
     for (int i = 0; i < 5; i++) len[i] = o.store(best[i]);
+    co_return 0;
+}
+
+// MLQuartetLogLk, NJ.tcc:5410-5427: the quartet likelihood at the given lengths, no optimisation; rows[0..1] = AB, CD
+Task<double> quartetLogLk(Batcher &B, const int64_t q[4], const double len[5], const int64_t rows[3], double *site) {
+    co_await B.post2(rows[0], q[0], q[1], len[0], len[1], rows[1], q[2], q[3], len[2], len[3]);
+    if (site) for (int64_t j = 0; j < B.L; j++) site[j] = 1.0;
+    const auto ab = co_await B.lk2(q[0], q[1], len[0] + len[1], q[2], q[3], len[2] + len[3], site);
+    const double abcd = (co_await B.lk(rows[0], rows[1], len[4], site)).first;
+    co_return (ab.first + ab.second) + abcd;
+}
+
+// The per-split body of traverseTestSplitsML, NJ.tcc:6884-6952: likelihood of the split as it is, the two alternatives
+// optimised (the better one a second time when it is close), each with its per-site likelihoods -- the input of SHSupport
+struct SplitJob { int64_t q[4]; double len[5]; double loglk[3]; int32_t choice, bad; int64_t rows[3]; double *site; };
+
+Task<int> splitTest(Batcher &B, const Opt &o, SplitJob *job) {
+    const int64_t *q = job->q;
+    const double *len = job->len;
+    double ab[5] = {len[LEN_A], len[LEN_B], len[LEN_C], len[LEN_D], len[LEN_I]};
+    double ac[5] = {len[LEN_A], len[LEN_C], len[LEN_B], len[LEN_D], len[LEN_I]};
+    double ad[5] = {len[LEN_A], len[LEN_D], len[LEN_C], len[LEN_B], len[LEN_I]};
+    const int64_t qAC[4] = {q[0], q[2], q[1], q[3]}, qAD[4] = {q[0], q[3], q[2], q[1]};
+    double *s0 = job->site, *s1 = s0 + B.L, *s2 = s1 + B.L;
+    double *lk = job->loglk;
+    lk[0] = co_await quartetLogLk(B, q, ab, job->rows, s0);
+    lk[1] = co_await quartetOptimize(B, o, qAC, ac, nullptr, job->rows, s1);
+    lk[2] = co_await quartetOptimize(B, o, qAD, ad, nullptr, job->rows, s2);
+    if (lk[1] > lk[2]) {                                                                      // :6929-6941
+        if (o.mlAccuracy > 1 || lk[1] > lk[0] - o.closeLimit) lk[1] = co_await quartetOptimize(B, o, qAC, ac, nullptr, job->rows, s1);
+    } else {
+        if (o.mlAccuracy > 1 || lk[2] > lk[0] - o.closeLimit) lk[2] = co_await quartetOptimize(B, o, qAD, ad, nullptr, job->rows, s2);
+    }
+    if (lk[0] >= lk[1] && lk[0] >= lk[2]) job->choice = 0;                                    // :6943-6950
+    else if (lk[1] >= lk[0] && lk[1] >= lk[2]) job->choice = 1;
+    else job->choice = 2;
+    job->bad = lk[job->choice] > lk[0] + 0.1;                                                 // Constants::treeLogLkDelta, :6952
     co_return 0;
 }
 
@@ -650,6 +726,35 @@ extern "C" int vft_choose_nni_batch(vft_ctx *ctx, int64_t n, const int64_t *ids,
         else if (c[2] < c[0] && c[2] <= c[1]) choice[k] = 2;
     }
     return VFT_OK;
+}
+
+extern "C" int vft_ml_split_test_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, const void *len,
+                                      double *loglk, double *siteLk, int32_t *choice, int32_t *badSplit, int64_t firstScratchRow,
+                                      vft_ml_stats *stats) {
+    Opt o; vft_config cfg;
+    if (!readOpt(ctx, opt, o, cfg) || n < 0 || (n > 0 && (!ids || !len || !loglk || !siteLk || !choice || !badSplit))) return VFT_EINVAL;
+    if (firstScratchRow < 2 * cfg.nSeqs || firstScratchRow + 3 * n > 2 * cfg.nSeqs + cfg.nScratch) return VFT_EINVAL;
+    Batcher B{ctx};
+    B.L = cfg.nPos;
+    std::vector<SplitJob> jobs((size_t) n);
+    std::vector<Task<int>> tasks;
+    tasks.reserve((size_t) n);
+    for (int64_t k = 0; k < n; k++) {
+        SplitJob &j = jobs[(size_t) k];
+        for (int i = 0; i < 4; i++) j.q[i] = ids[4 * k + i];
+        for (int i = 0; i < 5; i++) j.len[i] = rdP(len, 5 * k + i, o.single);
+        for (int i = 0; i < 3; i++) j.rows[i] = firstScratchRow + 3 * k + i;
+        j.site = siteLk + (size_t) k * 3 * (size_t) cfg.nPos;
+        tasks.push_back(splitTest(B, o, &j));
+    }
+    const int rc = B.run(tasks);
+    if (rc == VFT_OK)
+        for (int64_t k = 0; k < n; k++) {
+            for (int i = 0; i < 3; i++) loglk[3 * k + i] = jobs[(size_t) k].loglk[i];
+            choice[k] = jobs[(size_t) k].choice; badSplit[k] = jobs[(size_t) k].bad;
+        }
+    if (stats) *stats = B.stats;
+    return rc;
 }
 
 extern "C" int vft_ml_star_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
