@@ -301,6 +301,15 @@ int  vft_ml_quartet_nni_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n
 int  vft_ml_split_test_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, const void *len,
                              double *loglk, double *siteLk, int32_t *choice, int32_t *badSplit, int64_t firstScratchRow,
                              vft_ml_stats *stats);
+/* testSplitsML (NJ.tcc:6800-7000) over a whole tree (arrays as in vft_tree_loglk; node profiles current): the SH-like local
+   support of every internal split.  The tests do not change the tree, so they are all independent: the up-profiles of the
+   whole tree are built first (what getUpProfile builds lazily), then every split goes through vft_ml_split_test_batch's
+   body in lock-step chunks and vft_sh_support_batch.  col[nBootstrap*nPos] from the caller's RNG (resampleColumns,
+   NJ.tcc:705-716); support[maxnode] numeric_t: -1 where the reference sets none (leaves, root), 0 for a bad split;
+   *nBadSplits as SplitCount.nBadSplits.  Needs one scratch row per internal node + 3 per split of a chunk. */
+int  vft_ml_test_splits(vft_ctx *ctx, const vft_ml_options *opt, int64_t root, int64_t maxnode, const int32_t *nChild,
+                        const int64_t *child, const void *branchlength, int64_t nBootstrap, const int64_t *col, void *support,
+                        int64_t *nBadSplits, vft_ml_stats *stats);
 /* chooseNNI (NJ.tcc:4836-4852), the minimum-evolution counterpart: for n quartets ids[4n] = A,B,C,D (node ids), the six
    profile distances of each (correctedPairDistances, NJ.tcc:1460-1488: bare profileDist, Options.pseudoWeight prior,
    logCorrect NJ.tcc:322-330 when logdist) evaluated as ONE vft_dist_pairs batch; criteria[3n] = d(AB)+d(CD), d(AC)+d(BD),

@@ -34,6 +34,7 @@
 #include "NeighbourJoining.h"
 
 using namespace veryfasttree;
+void ran_start(long seed);            // Knuth.cpp: the global generator behind knuth_rand()
 
 static FILE *g_out;
 
@@ -347,6 +348,23 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
         putv<P>("ml.opt.tree.branchlength", blOpt);
         double lkOpt = nj2.treeLogLk(nullptr);
         put("ml.opt.tree.loglk", 'd', {1}, &lkOpt);
+        // testSplitsML (NJ.tcc:6800-7000) on the optimised tree: the reference draws its resampled columns from the global
+        // Knuth generator, so the generator is seeded, the columns drawn here, and seeded again for the call itself
+        {
+            options.nBootstrap = 100;
+            ran_start(20260117L);
+            std::vector<int64_t> colT;
+            nj2.resampleColumns(colT);
+            ran_start(20260117L);
+            typename NJ::SplitCount sc;
+            nj2.testSplitsML(sc);
+            std::vector<P> sup(M2);
+            for (int64_t i = 0; i < M2; i++) sup[i] = nj2.support[i];
+            putq("ml.splits.col", colT, {(int64_t) options.nBootstrap, L});
+            putv<P>("ml.splits.support", sup);
+            putq("ml.splits.nBad", {(int64_t) sc.nBadSplits, (int64_t) sc.nSplits});
+            options.nBootstrap = 1000;
+        }
     }
     return 0;
 }

@@ -413,6 +413,13 @@ def replay_ml_opt(lib: api.Lib, dump: dict, chars: np.ndarray, kind: str, precis
         cmp_len("ml.opt.tree.branchlength", bl1, np.ascontiguousarray(dump["ml.opt.tree.branchlength"], dtype=dt), minlen)
         lk1, _ = ctx.tree_loglk(root, n_child, child, bl1, recompute=False, leaf_codes=codes)
         cmp_lk("ml.opt.tree.loglk", lk1, dump["ml.opt.tree.loglk"][0])
+        # testSplitsML over the optimised tree: SH-like support of every internal split (CPU double only: the device pieces --
+        # split test, SHSupport -- are checked above; a whole-tree tolerance test would add nothing but flakiness)
+        if exact and "ml.splits.support" in dump:
+            sup, nbad, st = ctx.ml_test_splits(opt, root, n_child, child, bl1, dump["ml.splits.col"])
+            info["splits.stats"] = st
+            if not bits_equal(sup, np.ascontiguousarray(dump["ml.splits.support"], dtype=dt)): bad.append("ml.splits.support")
+            if nbad != int(dump["ml.splits.nBad"][0]): bad.append("ml.splits.nBad")
         # the level-synchronous schedule from the same start: a different (Jacobi-style) visiting order, so not the same
         # lengths -- but it must improve the likelihood about as much as the reference's sweep does
         lk0b, _ = ctx.tree_loglk(root, n_child, child, bl, recompute=True, leaf_codes=codes)

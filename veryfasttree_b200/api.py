@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "vft_put_profile", "vft_ml_default_options", "vft_ml_pair_optimize_batch", "vft_ml_quartet_nni_batch",
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
     "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
-    "vft_ml_split_test_batch",
+    "vft_ml_split_test_batch", "vft_ml_test_splits",
 ]
 
 
@@ -144,6 +144,7 @@ class Lib:
             d.vft_ml_optimize_branch_lengths.argtypes = [vp, mo, i64, i64, vp, vp, vp, i32, ms]
             d.vft_choose_nni_batch.argtypes = [vp, i64, vp, dbl, i32, vp, vp]
             d.vft_ml_split_test_batch.argtypes = [vp, mo, i64, vp, vp, vp, vp, vp, vp, i64, ms]
+            d.vft_ml_test_splits.argtypes = [vp, mo, i64, i64, vp, vp, vp, i64, vp, vp, C.POINTER(i64), ms]
             d.vft_sh_support_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp]
             d.vft_spec_join_launch.argtypes = [vp, i64, i64, i64, dbl, i64, vp, i64, vp, i64]
             d.vft_spec_join_take.argtypes = [vp, dbl, vp, vp, vp, vp, vp]
@@ -419,6 +420,17 @@ class Context:
         self.lib.check(self.lib.dll.vft_ml_split_test_batch(self.h, C.byref(opt), n, _ptr(ids), _ptr(ln), _ptr(lk), _ptr(site), _ptr(choice),
                                                             _ptr(bad), int(first_scratch_row), C.byref(st)), "vft_ml_split_test_batch")
         return lk, site, choice, bad, st.as_dict()
+
+    def ml_test_splits(self, opt, root, n_child, child, branchlength, col):
+        """vft_ml_test_splits: (support[maxnode], nBadSplits, stats)."""
+        n_child = np.ascontiguousarray(n_child, dtype=np.int32); child = np.ascontiguousarray(child, dtype=np.int64)
+        bl = np.ascontiguousarray(branchlength, dtype=self.dt); col = np.ascontiguousarray(col, dtype=np.int64)
+        sup = np.zeros(len(n_child), dtype=self.dt)
+        nbad = C.c_int64()
+        st = VftMlStats()
+        self.lib.check(self.lib.dll.vft_ml_test_splits(self.h, C.byref(opt), int(root), len(n_child), _ptr(n_child), _ptr(child), _ptr(bl),
+                                                       col.shape[0], _ptr(col), _ptr(sup), C.byref(nbad), C.byref(st)), "vft_ml_test_splits")
+        return sup, nbad.value, st.as_dict()
 
     def ml_star_optimize(self, opt, ids, length, first_scratch_row):
         """vft_ml_star_optimize_batch: (len[n,3], stats)."""

@@ -235,6 +235,13 @@ public:
                           int32_t *choice, int32_t *badSplit, int64_t firstScratchRow) {
         check(vft_ml_split_test_batch(ctx.get(), &opt, n, ids, len, loglk, siteLk, choice, badSplit, firstScratchRow, nullptr));
     }
+    // testSplitsML (NJ.tcc:6800-7000) over the whole tree: support[maxnode], returns SplitCount.nBadSplits
+    int64_t mlTestSplits(const vft_ml_options &opt, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child,
+                         const numeric_t *branchlength, int64_t nBootstrap, const int64_t *col, numeric_t *support) {
+        int64_t nBad = 0;
+        check(vft_ml_test_splits(ctx.get(), &opt, root, maxnode, nChild, child, branchlength, nBootstrap, col, support, &nBad, nullptr));
+        return nBad;
+    }
     void shSupportBatch(int64_t n, int64_t nBootstrap, const int64_t *col, const double *loglk, const double *siteLk, double *support) {
         check(vft_sh_support_batch(ctx.get(), n, nBootstrap, col, loglk, siteLk, support));
     }

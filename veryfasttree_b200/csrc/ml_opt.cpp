@@ -757,6 +757,104 @@ extern "C" int vft_ml_split_test_batch(vft_ctx *ctx, const vft_ml_options *opt, 
     return rc;
 }
 
+// testSplitsML, NJ.tcc:6800-6855 + traverseTestSplitsML :6856-7000 (no constraints): the splits do not change the tree, so
+// every internal node's test is independent once the up-profiles exist.  Up-profiles of the whole tree first (top-down, one
+// posterior batch per depth: the values getUpProfile would build lazily, NJ.tcc:3382-3434), then the split tests in lock-step
+// chunks, then SHSupport for the chunk.  support[node] as the reference sets it (:6991): 0 for a bad split.
+template<typename P>
+int testSplits(vft_ctx *ctx, const Opt &o, const vft_config &cfg, const Tree &t, const P *bl, int64_t nBootstrap, const int64_t *col,
+               P *support, int64_t *nBadSplits, vft_ml_stats *stats) {
+    const int64_t M = t.maxnode, first = 2 * cfg.nSeqs, L = cfg.nPos;
+    std::vector<int32_t> depth((size_t) M, 0);
+    int32_t D = 0;
+    for (auto it = t.order.rbegin(); it != t.order.rend(); ++it)
+        if (*it != t.root) { depth[*it] = depth[t.parent[*it]] + 1; D = std::max(D, depth[*it]); }
+    std::vector<int64_t> up((size_t) M, -1);
+    int64_t nUp = 0;
+    for (int64_t node : t.order) if (t.nChild[node] > 0 && node != t.root) up[node] = first + nUp++;
+    const int64_t CH = (cfg.nScratch - nUp) / 3;
+    if (CH < 1) return VFT_ENOMEM;
+    Batcher B{ctx};
+    B.L = L;
+    std::vector<std::vector<int64_t>> byDepth((size_t) D + 1);
+    for (int64_t node : t.order) if (t.nChild[node] > 0 && node != t.root) byDepth[depth[node]].push_back(node);
+    auto rootSibs = [&](int64_t node, int64_t sibs[2]) {
+        int ns = 0;
+        for (int j = 0; j < 3; j++) if (t.child[3 * t.root + j] != node) sibs[ns++] = t.child[3 * t.root + j];
+    };
+    std::vector<int64_t> po, pa, pb;
+    std::vector<double> l1, l2;
+    for (int32_t d = 1; d <= D; d++) {
+        po.clear(); pa.clear(); pb.clear(); l1.clear(); l2.clear();
+        for (int64_t node : byDepth[d]) {
+            const int64_t par = t.parent[node];
+            int64_t c, dd, dRow;
+            if (par == t.root) { int64_t sibs[2]; rootSibs(node, sibs); c = sibs[0]; dd = sibs[1]; dRow = dd; }
+            else { c = t.sibling(node); dd = par; dRow = up[par]; }
+            po.push_back(up[node]); pa.push_back(c); pb.push_back(dRow); l1.push_back((double) bl[c]); l2.push_back((double) bl[dd]);
+        }
+        if (po.empty()) continue;
+        const int rc = vft_posterior_profile_batch(ctx, (int64_t) po.size(), po.data(), pa.data(), pb.data(), l1.data(), l2.data());
+        if (rc != VFT_OK) return rc;
+        B.stats.posteriorCalls++; B.stats.posteriorItems += (int64_t) po.size();
+    }
+    // the splits, in the reference's post-order (only the order of the outputs depends on it)
+    std::vector<int64_t> nodes;
+    for (int64_t node : t.order) if (t.nChild[node] > 0 && node != t.root) nodes.push_back(node);
+    for (int64_t i = 0; i < M; i++) support[i] = (P) -1.0;                                   // NJ.tcc: support.resize(maxnodes, -1)
+    *nBadSplits = 0;
+    std::vector<SplitJob> jobs;
+    std::vector<double> site, lk3, sup;
+    for (size_t k0 = 0; k0 < nodes.size(); k0 += (size_t) CH) {
+        const size_t n = std::min(nodes.size() - k0, (size_t) CH);
+        jobs.assign(n, SplitJob{});
+        site.assign(n * 3 * (size_t) L, 0.0);
+        std::vector<Task<int>> tasks;
+        tasks.reserve(n);
+        for (size_t k = 0; k < n; k++) {
+            const int64_t node = nodes[k0 + k], par = t.parent[node];
+            SplitJob &j = jobs[k];
+            j.q[0] = t.child[3 * node]; j.q[1] = t.child[3 * node + 1];                         // setupABCD, NJ.tcc:1942-1974
+            int64_t lenDNode;
+            if (par == t.root) { int64_t sibs[2]; rootSibs(node, sibs); j.q[2] = sibs[0]; j.q[3] = sibs[1]; lenDNode = sibs[1]; }
+            else { j.q[2] = t.sibling(node); j.q[3] = up[par]; lenDNode = par; }
+            j.len[0] = (double) bl[j.q[0]]; j.len[1] = (double) bl[j.q[1]]; j.len[2] = (double) bl[j.q[2]];
+            j.len[3] = (double) bl[lenDNode]; j.len[4] = (double) bl[node];                     // :6886-6890
+            for (int i = 0; i < 3; i++) j.rows[i] = first + nUp + 3 * (int64_t) k + i;
+            j.site = site.data() + k * 3 * (size_t) L;
+            tasks.push_back(splitTest(B, o, &j));
+        }
+        int rc = B.run(tasks);
+        if (rc != VFT_OK) return rc;
+        lk3.resize(3 * n); sup.resize(n);
+        for (size_t k = 0; k < n; k++) for (int i = 0; i < 3; i++) lk3[3 * k + i] = jobs[k].loglk[i];
+        if (nBootstrap > 0) {
+            rc = vft_sh_support_batch(ctx, (int64_t) n, nBootstrap, col, lk3.data(), site.data(), sup.data());
+            if (rc != VFT_OK) return rc;
+        }
+        for (size_t k = 0; k < n; k++) {
+            *nBadSplits += jobs[k].bad;
+            if (nBootstrap > 0) support[nodes[k0 + k]] = (P) (jobs[k].bad ? 0.0 : sup[k]);       // :6991
+        }
+    }
+    if (stats) *stats = B.stats;
+    return VFT_OK;
+}
+
+extern "C" int vft_ml_test_splits(vft_ctx *ctx, const vft_ml_options *opt, int64_t root, int64_t maxnode, const int32_t *nChild,
+                                  const int64_t *child, const void *branchlength, int64_t nBootstrap, const int64_t *col, void *support,
+                                  int64_t *nBadSplits, vft_ml_stats *stats) {
+    Opt o; vft_config cfg;
+    if (!readOpt(ctx, opt, o, cfg) || !nChild || !child || !branchlength || !support || !nBadSplits || root < 0 || root >= maxnode
+        || maxnode > 2 * cfg.nSeqs || nBootstrap < 0 || (nBootstrap > 0 && !col) || cfg.nSeqs < 4)
+        return VFT_EINVAL;
+    Tree t{root, maxnode, cfg.nSeqs, nChild, child, {}, {}};
+    const int rc = t.build();
+    if (rc != VFT_OK) return rc;
+    if (cfg.precision == 32) return testSplits<float>(ctx, o, cfg, t, (const float *) branchlength, nBootstrap, col, (float *) support, nBadSplits, stats);
+    return testSplits<double>(ctx, o, cfg, t, (const double *) branchlength, nBootstrap, col, (double *) support, nBadSplits, stats);
+}
+
 extern "C" int vft_ml_star_optimize_batch(vft_ctx *ctx, const vft_ml_options *opt, int64_t n, const int64_t *ids, void *len,
                                           int64_t firstScratchRow, vft_ml_stats *stats) {
     Opt o; vft_config cfg;
