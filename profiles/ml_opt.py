@@ -95,6 +95,15 @@ with api.Context(lib, cfg) as ctx:
     for nm, a, b, x, y in zip(api.KERNEL_NAMES, list(c1.msKernel), list(c0.msKernel), list(c1.nKernel), list(c0.nKernel)):
         if x - y:
             print('   %-22s %6d launches %9.2f ms' % (nm, x - y, a - b))
+    # SH-like supports of every internal split (testSplitsML): up-profiles + split tests + SHSupport, 1 000 resamples
+    rng = np.random.default_rng(7)
+    col = rng.integers(0, L, size=(1000, L), dtype=np.int64)
+    t0 = time.time()
+    sup, nbad, st = ctx.ml_test_splits(opt, tree.root, n_child, child, bl, col)
+    dts = time.time() - t0
+    print('testSplitsML: %d splits in %.3f s (%d bad); %d lock-step rounds, %d pairLogLk items in %d calls, %d posteriors; support quartiles %s'
+          % (int((sup >= 0).sum()), dts, nbad, st['rounds'], st['loglkItems'], st['loglkCalls'], st['posteriorItems'],
+             np.round(np.quantile(sup[sup >= 0], [0.25, 0.5, 0.75]), 2)), flush=True)
 if ref_threads > 0 and os.path.exists(replay.REF_BIN):
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, 'a.fa')
