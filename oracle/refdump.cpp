@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -37,6 +38,7 @@ using namespace veryfasttree;
 void ran_start(long seed);            // Knuth.cpp: the global generator behind knuth_rand()
 
 static FILE *g_out;
+static int64_t envInt(const char *name, int64_t dflt) { const char *e = std::getenv(name); return e && *e ? std::atoll(e) : dflt; }
 
 static void put(const std::string &name, char dtype, const std::vector<int64_t> &dims, const void *data) {
     uint32_t nl = (uint32_t) name.size(), nd = (uint32_t) dims.size();
@@ -215,7 +217,7 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
         Dumper<P> DT(nj2);
         DT.profile("ml.tree.lastnode", nj2.profiles[nj2.root - 1]);
         // setMLRates (NJ.tcc:5429-5488) with 6 candidate rates on the same tree
-        options.nRateCats = 6;
+        options.nRateCats = envInt("VFT_REFDUMP_NCAT", 6);        // the large on-the-fly cases of tests/test_gpu_parity.py ask for the default 20
         nj2.setMLRates();
         std::vector<P> r6(nj2.rates.rates.begin(), nj2.rates.rates.end());
         std::vector<int64_t> rc6(nj2.rates.ratecat.begin(), nj2.rates.ratecat.end());
@@ -261,7 +263,8 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
             std::vector<P> qlen0, qlen1;
             std::vector<double> qcrit;
             int64_t nQ = 0;
-            for (int64_t node = N; node < M2; node++) {
+            const int64_t qStride = envInt("VFT_REFDUMP_QSTRIDE", 1);   // every qStride-th internal node (bounds the dump of a large case)
+            for (int64_t node = N; node < M2; node += qStride) {
                 if (node == nj2.root || nj2.child[node].nChild != 2) continue;
                 Profile *p4[4];
                 int64_t abcd[4];
@@ -315,7 +318,7 @@ static int runML(const std::string &fasta, bool aa, const std::string &model, in
             std::vector<int64_t> snode, sids;
             std::vector<P> slen0, slen1;
             int64_t nS = 0;
-            for (int64_t node = N; node < M2; node += 3) {
+            for (int64_t node = N; node < M2; node += 3 * qStride) {
                 const int64_t nChild = nj2.child[node].nChild;
                 if (nChild < 2) continue;
                 int64_t nodes[3] = {nj2.child[node].child[0], nj2.child[node].child[1], nChild == 3 ? nj2.child[node].child[2] : node};
