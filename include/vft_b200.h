@@ -409,6 +409,11 @@ typedef struct vft_nj_options {
     int32_t hostThreads;        /* OpenMP threads for the per-list host work of the refreshes and the
                                    leaf transfers (the reference parallelises the same loops,
                                    NJ.tcc:4477, :3838); 0 = min(16, cores).  Results do not depend on it. */
+    int32_t deviceLoop;         /* 1 = the join loop (NJ.tcc:2857-3100) runs on the device: top-hit lists, visible sets
+                                   and the lazily refreshed out-distances live in HBM, one thread block replays the
+                                   reference's decisions and the grid evaluates the distances (nj_loop_logic.h);
+                                   0 = the host-driven loop of round 1 (one synchronous call per join).  Same tree. */
+    int32_t reserved;
 } vft_nj_options;
 
 void vft_nj_default_options(vft_nj_options *opt);

@@ -58,7 +58,7 @@ class VftNjOptions(C.Structure):
     _fields_ = [("tophitsMult", C.c_double), ("tophitsClose", C.c_double), ("topvisibleMult", C.c_double),
                 ("tophitsRefresh", C.c_double), ("staleOutLimit", C.c_double), ("fResetOutProfile", C.c_double),
                 ("nResetOutProfile", C.c_int32), ("bionj", C.c_int32), ("prefetch", C.c_int32),
-                ("hostThreads", C.c_int32)]
+                ("hostThreads", C.c_int32), ("deviceLoop", C.c_int32), ("reserved", C.c_int32)]
 
 
 class VftNjResult(C.Structure):
@@ -503,7 +503,8 @@ class NJTree:
 
 def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | None = None,
              tables=None, device: int = 0, prefetch: bool = True, trace: bool = True,
-             reduction: int = 1, profile: bool = False, host_threads: int = 0, bionj: bool = False) -> NJTree:
+             reduction: int = 1, profile: bool = False, host_threads: int = 0, bionj: bool = False,
+             device_loop: int | None = None) -> NJTree:
     """The metric phase (NJ ctor tail + fastNJ) through vft_nj_build with HOST buffers."""
     lib = lib or load()
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -516,6 +517,8 @@ def nj_build(codes: np.ndarray, n_codes: int, precision: int = 32, lib: Lib | No
     opt.prefetch = int(prefetch)
     opt.hostThreads = host_threads
     opt.bionj = int(bionj)
+    if device_loop is not None:
+        opt.deviceLoop = int(device_loop)
     M = 2 * n
     parent = np.full(M, -1, dtype=np.int64)
     n_child = np.zeros(M, dtype=np.int32)

@@ -19,6 +19,7 @@
 // Not supported (rejected with VFT_EINVAL, documented in DESIGN.md): -fastest / 2nd-level top
 // hits, topological constraints, -slow.  -bionj is supported (BIONJ weights, NJ.tcc:2921-2966).
 #include "../../include/vft_b200.h"
+#include "nj_loop.h"
 
 #include <algorithm>
 #include <omp.h>
@@ -461,6 +462,9 @@ private:
     void getBestFromTopHits(int64_t iNode, int64_t nActive, Besthit &bestjoin);
     void topHitJoin(int64_t newnode, int64_t nActive);
     void refreshListsOnDevice(int64_t newnode, int64_t nActive, const std::vector<Besthit> &allhits);
+    void refreshLists(int64_t newnode, int64_t nActive);
+    void repairVisible(int64_t nActive);
+    bool runDeviceLoop();
     std::vector<Besthit> thjCombined, thjUnique;          // scratch of topHitJoin
     std::vector<int64_t> thjSlots;
     // scratch of resetTopVisible
@@ -974,6 +978,26 @@ void NJ<P>::speculateSearch(int64_t nActive) {
     }
 }
 
+// the visible-set repair of topHitNJSearch, NJ.tcc:4171-4201
+template<typename P>
+void NJ<P>::repairVisible(int64_t nActive) {
+    for (int64_t iNode = 0; iNode < maxnode; iNode++) {
+        if (parent[iNode] >= 0) continue;
+        Hit &v = visible[iNode];
+        int64_t newj = activeAncestor(v.j);
+        if (newj >= 0 && newj != v.j) {
+            if (newj == iNode) {
+                newj = 0;
+                while (parent[newj] >= 0 || newj == iNode) newj++;
+            }
+            Besthit bh = {(id_t) iNode, (id_t) newj, (P) -1e20, (P) -1e20, (P) -1e20};
+            setDistCriterion(nActive, bh);
+            v.j = newj;
+            v.dist = bh.dist;
+        }
+    }
+}
+
 // topHitNJSearch, NJ.tcc:4137-4264
 template<typename P>
 void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
@@ -1002,23 +1026,7 @@ void NJ<P>::topHitNJSearch(int64_t nActive, Besthit &join) {
     topvisibleAge++;
     if (2 * topvisibleAge > m
         || (3 * nCandidate < (int64_t) topvisible.size() && 3 * nCandidate < nActive)) {
-        if (topvisibleAge <= 2) {                                        // :4171-4201
-            for (int64_t iNode = 0; iNode < maxnode; iNode++) {
-                if (parent[iNode] >= 0) continue;
-                Hit &v = visible[iNode];
-                int64_t newj = activeAncestor(v.j);
-                if (newj >= 0 && newj != v.j) {
-                    if (newj == iNode) {
-                        newj = 0;
-                        while (parent[newj] >= 0 || newj == iNode) newj++;
-                    }
-                    Besthit bh = {(id_t) iNode, (id_t) newj, (P) -1e20, (P) -1e20, (P) -1e20};
-                    setDistCriterion(nActive, bh);
-                    v.j = newj;
-                    v.dist = bh.dist;
-                }
-            }
-        }
+        if (topvisibleAge <= 2) repairVisible(nActive);                  // :4171-4201
         resetTopVisible(nActive);
         topHitNJSearch(nActive, join);
         return;
@@ -1076,7 +1084,13 @@ void NJ<P>::topHitJoin(int64_t newnode, int64_t nActive) {
         return;
     }
 
-    // ---- refresh, NJ.tcc:4439-4517 ------------------------------------------------------------
+    refreshLists(newnode, nActive);
+}
+
+// the refresh branch of topHitJoin, NJ.tcc:4439-4517
+template<typename P>
+void NJ<P>::refreshLists(int64_t newnode, int64_t nActive) {
+    TopHitsList &lNew = topHitsLists[newnode];
     Section secRefresh(this, 5);
     res->nRefreshTopHits++;
     if (spec.valid) { spec.valid = false; check(vft_spec_join_discard(ctx)); }      // a refresh rewrites the lists the guess was built from
@@ -1332,6 +1346,93 @@ void NJ<P>::specInject(int64_t newnode, int64_t nActive) {
     }
 }
 
+// The join loop on the device (nj_loop.h): the state built by the leaf phase goes to the loop backend, which runs joins
+// until three nodes are left.  What the backend does not do itself comes back as a status: the image is downloaded, the
+// host code above performs that one operation (the rebuild of the top-visible set, a top-hits refresh) exactly as the
+// host-driven loop would, and the image goes back.  Returns false when the loop is not applicable (the caller then
+// runs the host-driven loop).
+template<typename P>
+bool NJ<P>::runDeviceLoop() {
+    if (m <= 0 || opt.bionj || !opt.deviceLoop) return false;
+    const int64_t M = maxnodes, nTV = (int64_t) topvisible.size();
+    vftx_loop *lp = nullptr;
+    if (vftx_loop_create(ctx, &opt, m, nTV, &lp) != VFT_OK) return false;
+    std::vector<int32_t> iParent(M), iUp(M), iChild(3 * M), iNOut(M), iHitJ((size_t) M * m), iHitCount(M), iAge(M), iVisJ(M), iTop(nTV);
+    std::vector<P> iBl(M), iDiam(M), iOut(M), iHitD((size_t) M * m), iVisD(M);
+    vftx_loop_image img{};
+    img.nSeqs = nSeqs; img.maxnodes = M; img.m = m; img.nTV = nTV;
+    img.parent = iParent.data(); img.up = iUp.data(); img.child = iChild.data(); img.branchlength = iBl.data(); img.diameter = iDiam.data();
+    img.outDist = iOut.data(); img.nOutAct = iNOut.data(); img.hitJ = iHitJ.data(); img.hitDist = iHitD.data(); img.hitCount = iHitCount.data();
+    img.age = iAge.data(); img.visJ = iVisJ.data(); img.visDist = iVisD.data(); img.topvisible = iTop.data();
+    int64_t nActive = nSeqs;
+    auto exportImage = [&] {
+        for (int64_t i = 0; i < M; i++) {
+            iParent[i] = (int32_t) parent[i]; iUp[i] = up[i];
+            for (int k = 0; k < 3; k++) iChild[3 * i + k] = (int32_t) child[i].child[k];
+            iBl[i] = branchlength[i]; iDiam[i] = diameter[i]; iOut[i] = outDistances[i]; iNOut[i] = nOutDistActive[i];
+            const std::vector<Hit> &h = topHitsLists[i].hits;
+            iHitCount[i] = (int32_t) h.size(); iAge[i] = (int32_t) topHitsLists[i].age;
+            for (size_t k = 0; k < h.size(); k++) { iHitJ[(size_t) i * m + k] = h[k].j; iHitD[(size_t) i * m + k] = h[k].dist; }
+            iVisJ[i] = visible[i].j; iVisD[i] = visible[i].dist;
+        }
+        for (int64_t k = 0; k < nTV; k++) iTop[k] = (int32_t) topvisible[k];
+        img.maxnode = maxnode; img.nActive = nActive; img.topvisibleAge = topvisibleAge; img.nActiveOutProfileReset = nActiveOutProfileReset;
+        img.totdiam = totdiam;
+    };
+    auto importImage = [&] {
+        maxnode = img.maxnode; nActive = img.nActive; topvisibleAge = img.topvisibleAge; nActiveOutProfileReset = img.nActiveOutProfileReset;
+        totdiam = img.totdiam;
+        for (int64_t i = 0; i < M; i++) {
+            parent[i] = iParent[i]; up[i] = iUp[i];
+            int nc = 0;
+            for (int k = 0; k < 3; k++) { child[i].child[k] = iChild[3 * i + k]; nc += iChild[3 * i + k] >= 0; }
+            child[i].nChild = nc;
+            branchlength[i] = iBl[i]; diameter[i] = iDiam[i]; outDistances[i] = iOut[i]; nOutDistActive[i] = iNOut[i];
+            std::vector<Hit> &h = topHitsLists[i].hits;
+            h.resize((size_t) iHitCount[i]); topHitsLists[i].age = iAge[i];
+            for (size_t k = 0; k < h.size(); k++) { h[k].j = iHitJ[(size_t) i * m + k]; h[k].dist = iHitD[(size_t) i * m + k]; }
+            hintedEpoch[i] = -1;
+            visible[i].j = iVisJ[i]; visible[i].dist = iVisD[i];
+        }
+        for (int64_t k = 0; k < nTV; k++) topvisible[k] = iTop[k];
+        newEpoch(nActive);
+        searchHinted = false;
+    };
+    int rc = VFT_OK;
+    int32_t resume = 0;
+    vftx_loop_status stt{};
+    for (;;) {
+        exportImage();
+        rc = vftx_loop_upload(lp, &img, resume);
+        if (rc != VFT_OK) break;
+        rc = timed([&] { return vftx_loop_run(lp, &stt); });
+        res->nDeviceCalls++;
+        if (rc != VFT_OK) break;
+        rc = vftx_loop_download(lp, &img);
+        if (rc != VFT_OK) break;
+        importImage();
+        if (stt.status == 1 /* DONE */) break;
+        if (stt.status == 2 /* NEED_RESET */) {
+            Section sec(this, 2);
+            if (stt.visfixPending) repairVisible(nActive);
+            resetTopVisible(nActive);
+        } else if (stt.status == 3 /* NEED_REFRESH */) {
+            Section sec(this, 4);
+            refreshLists(stt.newnode, nActive);
+        } else { rc = VFT_EINVAL; break; }
+        resume = 0;
+    }
+    if (rc == VFT_OK) {
+        res->nRefreshTopHits += 0;      // (counted by refreshLists)
+        res->nVisibleUpdate += stt.nVisibleUpdate; res->nHillBetter += stt.nHillBetter;
+        res->nOutSingleFetch += stt.nInlineOut; res->nPairSingleFetch += stt.nInlinePair; res->nPairPrefetchHit += stt.nPairHit;
+        if (res->joins) vftx_loop_joins(lp, res->joins, nSeqs - 3);
+    }
+    vftx_loop_destroy(lp);
+    if (rc != VFT_OK) throw DeviceError{rc};
+    return true;
+}
+
 // fastNJ, NJ.tcc:2796-3155
 template<typename P>
 void NJ<P>::fastNJ() {
@@ -1374,7 +1475,8 @@ void NJ<P>::fastNJ() {
     res->secondsLeafTopHits = std::chrono::duration<double>(t1 - t0).count();
 
     nActiveOutProfileReset = nSeqs;
-    for (int64_t nActive = nSeqs; nActive > 3; nActive--) {
+    const bool onDevice = runDeviceLoop();
+    for (int64_t nActive = nSeqs; !onDevice && nActive > 3; nActive--) {
         Besthit join;
         {
             Section sec(this, 2);
@@ -1567,6 +1669,8 @@ extern "C" void vft_nj_default_options(vft_nj_options *o) {
     o->bionj = 0;
     o->prefetch = 1;
     o->hostThreads = 0;
+    o->deviceLoop = 0;
+    if (const char *e = std::getenv("VFT_DEVICE_LOOP")) o->deviceLoop = std::atoi(e);
 }
 
 extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in, const uint8_t *codes,
