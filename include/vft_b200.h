@@ -376,7 +376,7 @@ typedef struct vft_counters {
 } vft_counters;
 #define VFT_KERNEL_NAMES "k_eval(inline list)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", \
                          "k_merge_prep+finish", "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", \
-                         "k_posterior", "-"
+                         "k_posterior", "k_nj_step"
 #define VFT_CFG_PROFILE 1    /* vft_config.reserved bit: time every kernel with CUDA events */
 int  vft_get_counters(vft_ctx *ctx, vft_counters *out);
 

@@ -37,7 +37,7 @@ class VftCounters(C.Structure):
 
 
 KERNEL_NAMES = ["k_eval(inline list)", "k_eval(batch)", "k_one_vs_all", "k_out_distance_all", "k_topk_select", "k_merge_prep+finish",
-                "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", "k_posterior", "-"]
+                "k_average", "k_outprofile_update", "k_outprofile_rebuild", "k_pair_loglk", "k_posterior", "k_nj_step"]
 
 
 class VftMlOptions(C.Structure):

@@ -1423,7 +1423,7 @@ bool NJ<P>::runDeviceLoop() {
         resume = 0;
     }
     if (rc == VFT_OK) {
-        res->nRefreshTopHits += 0;      // (counted by refreshLists)
+        res->nRefreshTopHits = stt.nRefresh;      // every refresh the loop asked for, wherever it was carried out
         res->nVisibleUpdate += stt.nVisibleUpdate; res->nHillBetter += stt.nHillBetter;
         res->nOutSingleFetch += stt.nInlineOut; res->nPairSingleFetch += stt.nInlinePair; res->nPairPrefetchHit += stt.nPairHit;
         if (res->joins) vftx_loop_joins(lp, res->joins, nSeqs - 3);

@@ -59,6 +59,7 @@ struct Scalars {
     int32_t nUnique;                      // candidates of the pending topHitJoin
     int32_t hintNode[2], hintEpoch, hintJoinSlot, hintJoinI, hintJoinJ;
     int32_t visfixPending;
+    int32_t rtvVisible;                   // candidates of the last top-visible rebuild
     // counters
     int64_t nJoins, nRefresh, nVisibleUpdate, nHillBetter, nReset, nInlineOut, nInlinePair, nOutHit, nPairHit, nRebuild;
     int64_t seqOps, profileOps, outprofileOps, algoBytes;
@@ -95,6 +96,9 @@ struct Scratch {
     int32_t *ctl;                         // [32] block-uniform control words
 };
 template<typename P>
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 inline size_t scratch_bytes(int cap, int nt) {
     return (size_t) cap * (3 * 4 + 2 * sizeof(P) + 8) + (size_t) 8 * cap * 4 + (size_t) nt * 12 + 32 * 4 + 64;
 }
@@ -132,6 +136,34 @@ NJL_D double q_mul(double a, double b) { return a * b; }
 // orderable keys: ascending unsigned order == ascending floating order (-0 == +0, as the reference's `<` sees them)
 NJL_D uint64_t okey(float x) { if (x == 0) x = 0; uint32_t u; memcpy(&u, &x, 4); return (u & 0x80000000u) ? (uint32_t) ~u : (u | 0x80000000u); }
 NJL_D uint64_t okey(double x) { if (x == 0) x = 0; uint64_t u; memcpy(&u, &x, 8); return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull); }
+
+// the same rules as free functions, for the grid-wide kernels of the rebuild / refresh paths
+NJL_D bool stale_fn(int32_t nOutAct, int32_t nActive, double staleOutLimit) {
+    const int64_t allow = (int64_t) ((double) (int64_t) nActive * staleOutLimit);
+    return (int64_t) nOutAct - (int64_t) nActive > allow;
+}
+NJL_D int32_t ancestor_fn(int32_t *up, int32_t i) {
+    if (i < 0) return i;
+    for (;;) {
+        const int32_t u = up[i];
+        if (u == i) return i;
+        const int32_t g = up[u];
+        up[i] = g;
+        i = g;
+    }
+}
+// setCriterion (NJ.tcc:1085-1113) WITHOUT committing its refreshes: a stale node enters with its fresh value
+template<typename P>
+NJL_D P crit_effective(const State<P> &st, int32_t i, int32_t j, P dist, int32_t nActive) {
+    const double lim = st.sc->staleOutLimit;
+    int32_t ni = st.nOutAct[i], nj = st.nOutAct[j];
+    double outI, outJ;
+    if (stale_fn(ni, nActive, lim)) { outI = (double) st.freshVal[i]; ni = nActive; } else outI = (double) st.outDist[i];
+    if (stale_fn(nj, nActive, lim)) { outJ = (double) st.freshVal[j]; nj = nActive; } else outJ = (double) st.outDist[j];
+    if (ni != nActive) outI = q_mul(outI, (double) (int64_t) (nActive - 1) / (double) ((int64_t) ni - 1));
+    if (nj != nActive) outJ = q_mul(outJ, (double) (int64_t) (nActive - 1) / (double) ((int64_t) nj - 1));
+    return (P) q_sub((double) dist, q_add(outI, outJ) / (double) (int64_t) (nActive - 2));
+}
 
 template<typename P, class X>
 struct Logic {
@@ -254,11 +286,11 @@ struct Logic {
         int32_t *ent = sm.miss, *pairs = sm.miss + sc.cap;
         if (x.tid() == 0) sm.ctl[1] = 0;
         x.sync();
-        int64_t nSeq = 0, nProf = 0, nLeafB = 0;
+        int64_t nSeq = 0, nProf = 0, nLeafB = 0, nHit = 0;
         for (int e = x.tid(); e < n; e += x.nt()) {
             const int32_t a = sm.cAux[e];
             if (a == -2) ent[x.atomicAddI(&sm.ctl[1], 1)] = e;
-            else if (a >= 0) sm.cDist[e] = st.pairD[a];
+            else if (a >= 0) { sm.cDist[e] = st.pairD[a]; nHit++; }
             if (a == -2 || a >= 0) {
                 const int32_t j = sm.cJ[e];
                 if (iNode < sc.nSeqs && j < sc.nSeqs) nSeq++; else { nProf++; if (j < sc.nSeqs) nLeafB++; }
@@ -266,6 +298,7 @@ struct Logic {
         }
         if (nSeq) x.atomicAddL(&sc.seqOps, nSeq);
         if (nProf) x.atomicAddL(&sc.profileOps, nProf);
+        if (nHit) x.atomicAddL(&sc.nPairHit, nHit);
         if (nSeq + nProf) x.atomicAddL(&sc.algoBytes, (nSeq + nLeafB) * sc.Lbytes + (nProf - nLeafB) * sc.profBytes);
         x.sync();
         const int nMiss = sm.ctl[1];
@@ -304,11 +337,6 @@ struct Logic {
             sm.list[k] = aux == -3 ? -1 : j;
         }
         x.sync();
-        if (x.tid() == 0) {
-            int hits = 0;
-            for (int k = 0; k < n; k++) hits += sm.cAux[k] >= 0 ? 1 : 0;
-            sc.nPairHit += hits;
-        }
         resolvePairs(iNode, n);
         ensureCommit(n, nActive, false);
         uint64_t bk = ~0ull; int32_t bi = -1;
@@ -379,7 +407,7 @@ struct Logic {
         if (x.tid() == 0) {
             sm.cJ[0] = jj; sm.cAux[0] = -2;
             if (sc.hintEpoch == sc.epoch && sc.hintJoinSlot >= 0 && ((sc.hintJoinI == ji && sc.hintJoinJ == jj) || (sc.hintJoinI == jj && sc.hintJoinJ == ji))) {
-                sm.cAux[0] = sc.hintJoinSlot; sc.nPairHit++;
+                sm.cAux[0] = sc.hintJoinSlot;
             }
         }
         x.sync();

@@ -26,8 +26,11 @@
 #include "../../include/vft_b200.h"
 #include "vft_device.cuh"
 #include "vft_ml.cuh"
+#include "nj_loop.h"
+#include "nj_loop_logic.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -581,10 +584,18 @@ k_merge_finish(Store<P> s, const int32_t *__restrict__ iNode, int64_t nActive, i
 template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
 k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
-          double *__restrict__ gTerms, unsigned int *__restrict__ doneCount, P *dOw, P *dOv, P *dOcd, P *specSelf) {
+          double *__restrict__ gTerms, unsigned int *__restrict__ doneCount, P *dOw, P *dOv, P *dOcd, P *specSelf,
+          const njl::Scalars *jd = nullptr) {
     // dOw/dOv/dOcd: where the UPDATEd out-profile goes (the live arrays, or the shadow copy of a speculative join);
     // specSelf != nullptr: speculative -- the self distance goes there and no per-node state is committed
+    // jd != nullptr: the device-resident join loop (nj_loop_logic.h) -- the join is read from the loop's scalars
     extern __shared__ __align__(16) unsigned char smem[];
+    bool doUpdate = UPDATE;
+    if (jd != nullptr) {
+        if (!jd->jdValid) return;
+        oid = jd->jdNew; id1 = jd->jdI; id2 = jd->jdJ; diameterOut = (P) jd->jdDiameter; nActiveOld = jd->jdNActiveOld;
+        doUpdate = UPDATE && jd->jdUpdate != 0;
+    }
     const bool single = gridDim.x == 1;                          // short alignments: one CTA, the terms never leave shared memory
     double *termW = single ? reinterpret_cast<double *>(smem) : gTerms;   // [Lp] w*w   (global when the CTAs split the positions)
     double *termT = termW + s.Lp;                                // [Lp] w*w*piece
@@ -620,7 +631,7 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
             oc[pos] = (uint8_t) co;
 #pragma unroll
             for (int k = 0; k < A; k++) ov[pos * A + k] = f[k];
-            if (UPDATE) {
+            if (UPDATE && doUpdate) {
                 // updateOutProfile for this position (NJ.tcc:943-1010), fused: the three profiles it
                 // needs are already in registers
                 P g[A];
@@ -1009,7 +1020,7 @@ struct vft_ctx {
 
 enum { CLS_DIST = 0, CLS_SELECT = 1, CLS_PROFILE = 2 };
 // finer split of the same timings: index into vft_counters.msKernel / nKernel (names: VFT_KERNEL_NAMES in the header)
-enum { K_EVAL_SMALL = 0, K_EVAL_LARGE, K_ONE_VS_ALL, K_OUT_DIST_ALL, K_SELECT, K_MERGE, K_AVERAGE, K_OUTPROFILE_UPDATE, K_REBUILD, K_LOGLK, K_POSTERIOR };
+enum { K_EVAL_SMALL = 0, K_EVAL_LARGE, K_ONE_VS_ALL, K_OUT_DIST_ALL, K_SELECT, K_MERGE, K_AVERAGE, K_OUTPROFILE_UPDATE, K_REBUILD, K_LOGLK, K_POSTERIOR, K_NJ_STEP };
 
 // attributes the algorithmic bytes accounted inside a scope to one kernel (vft_counters.bytesKernel)
 struct BytesScope {
@@ -2027,3 +2038,5 @@ extern "C" int vft_timer_stop(vft_ctx *c, double *ms) {
     *ms = f;
     return VFT_OK;
 }
+
+#include "nj_loop_gpu.cuh"
