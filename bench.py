@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- taxa/sec on the initial NJ + TopHits build (BASELINE.json `metric`).
 
-A "step" is one pass of the hot path over one synthetic alignment: NeighbourJoining ctor tail
-(out-profile + initial out-distances) + fastNJ() with top-hits, i.e. what the reference reports
-as "Initial topology".  Workload at N=1: BASELINE.json configs[1], 16 000 taxa x 200 nt columns,
-fp32 (nt fp32 in the reference is its SSE3 path).
+A "step" is one pass of the hot path over one synthetic alignment: NeighbourJoining ctor tail (out-profile + initial
+out-distances) + fastNJ() with top-hits, i.e. what the reference reports as "Initial topology".
 
-  value    taxa/s with the leaf codes already resident in HBM (device stopwatch, CUDA events on the
-           context's stream, around ctor tail + fastNJ)
-  e2e      taxa/s through the public C-ABI call vft_nj_build with HOST buffers: context creation,
-           pinned staging + H2D of the alignment, every per-batch H2D/D2H and the tree read-back inside
-  roofline the distance sweep (k_dist_pairs / k_one_vs_all / k_out_distance): algorithmic bytes
-           (counted by the library per call) / its device time from CUDA events on the
-           launching stream, measured in one extra profiled pass after the timed steps
-  cpu_baseline / --impl reference: the UNMODIFIED reference binary built under oracle/_ref
-           (-threads all host cores), timed on the same alignment: "Initial topology" stamp minus
-           the "Identified unique sequences" stamp.
+Workload at N=1 (`--workload c3`, the default): C3-SHAPED -- amino acid, 1287 columns, BLOSUM45 distances, fp32, the
+regime BASELINE.json's >=50x target is quoted on -- at 20 000 taxa, the largest size for which the 25 reference runs of the
+driver's reference arm fit its time limit (the reference needs ~21 s per run at 16 threads; 100 000 taxa would need hours).
+`--workload c2` is BASELINE.json configs[1] (16 000 x 200 nt), the workload of round 1.
 
-Multi-GPU (torchrun, one rank per GPU): each rank builds the tree of its own alignment (seed =
-1+rank): replicas, weak scaling, no data-path collective.  NCCL is used
-for the barrier and the max-over-ranks reduction only.
+  value    taxa/s with the leaf codes already resident in HBM (device stopwatch, CUDA events on the context's stream,
+           around ctor tail + fastNJ)
+  e2e      taxa/s through the public C-ABI call vft_nj_build with HOST buffers: context creation, pinned staging + H2D of
+           the alignment, every list copy and the tree read-back inside the timed region
+  roofline the kernel with the largest share of the step's device time that moves profile data: algorithmic bytes (SURVEY
+           8d, counted by the library per launch) / its device time from CUDA events on the launching stream, measured in one
+           extra profiled pass after the timed steps.  `traffic` is null here: DRAM bytes need ncu, see profiles/
+  parity_checked  the product's Newick against the `NJ` line of the reference's -log.  The reference's tree depends on its
+           thread count (psort tie placement, SURVEY 9.4: measured, -threads 4 != -threads 1 on this workload), so the check
+           runs the reference at `-threads 1 -ext AVX2` on a bounded prefix of the SAME alignment (first 3 000 taxa); the
+           full sizes are checked by tests/test_gpu_at_size.py
+  cpu_baseline / --impl reference: the UNMODIFIED reference binary (oracle/_ref, -mavx2 build) with -ext AVX2 -fastexp 3 on the
+           same alignment: "Initial topology" stamp minus the "Identified unique sequences" stamp; its thread count is the
+           fastest of {cores/2, cores} measured ON THE FULL WORKLOAD (the reference gets slower with too many threads).
+
+Multi-GPU (torchrun, one rank per GPU): `--gpus N` builds N trees, one per rank (seed = 1 + rank): REPLICAS, weak scaling, no
+data-path collective; NCCL is used for the barrier and the max-over-ranks reduction only.  The reference arm at N > 1 builds
+N trees too (N concurrent processes sharing the host cores), so that both arms do the same work.
 """
 from __future__ import annotations
 
@@ -48,15 +55,28 @@ import numpy as np  # noqa: E402
 
 from veryfasttree_b200 import api, synth  # noqa: E402
 
-WORKLOAD = {"name": "16k-taxa x 200-col nucleotide, JC/%different distances, fp32 (BASELINE.json configs[1])",
-            "n": 16000, "pos": 200, "kind": "nt", "precision": 32}
+WORKLOADS = {
+    "c3": {"name": "C3-shaped: 20k-taxa x 1287-col amino acid, BLOSUM45 distances, fp32 (BASELINE.json configs[2] at the largest N "
+                   "whose 25 reference runs fit the driver's reference arm)",
+           "n": 20000, "pos": 1287, "kind": "aa", "precision": 32, "ref_flags": ["-ext", "AVX2", "-fastexp", "3"]},
+    "c2": {"name": "16k-taxa x 200-col nucleotide, JC/%different distances, fp32 (BASELINE.json configs[1])",
+           "n": 16000, "pos": 200, "kind": "nt", "precision": 32, "ref_flags": ["-nt"]},
+}
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "VeryFastTree")
+PARITY_PREFIX = 3000
 
 
-def make_workload(seed: int, n: int):
-    chars = synth.make_alignment(n, WORKLOAD["pos"], WORKLOAD["kind"], seed)
+def make_workload(wl, seed: int, n: int):
+    chars = synth.make_alignment(n, wl["pos"], wl["kind"], seed)
     chars = chars[synth.unique_rows(chars)]          # the reference's Uniquify; report nUnique
     return chars
+
+
+def tables_for(wl):
+    if wl["kind"] != "aa":
+        return None
+    z = np.load(os.path.join(ROOT, "tests", "golden", "blosum45_f%d.npz" % wl["precision"]))
+    return [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
 
 
 class ClockSampler(threading.Thread):
@@ -89,89 +109,64 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def best_thread_count(host_cores: int, seed: int = 99):
-    """The reference's OpenMP build gets SLOWER with many threads on this path (measured: 128 threads
-    are >10x slower than 1 on a 128-core host), so "all the host threads it can use" is calibrated:
-    the thread count that is fastest on a 3000-taxon sample of the same workload is the one timed."""
-    sample = make_workload(seed, 3000)
-    best, best_t = 1, None
-    for th in [1, 2, 4, 8, 16, 32, 64, 128]:
-        if th > host_cores:
-            break
-        t, _ = run_reference(sample, th, timeout=120)
-        if t is None:
-            continue
-        if best_t is None or t < best_t:
-            best, best_t = th, t
-        elif t > 2.0 * best_t:
-            break
-    return best
-
-
-def run_reference(chars, threads: int, timeout: float = 900):
-    """Times the unmodified reference on `chars`; returns (seconds of the NJ+TopHits phase, nUnique)."""
+def run_reference(wl, chars, threads: int, timeout: float = 1500, want_tree: bool = False, extra=None):
+    """Times the unmodified reference on `chars`; returns (seconds of the NJ+TopHits phase, nUnique[, NJ tree])."""
+    none = (None, None, None) if want_tree else (None, None)
     if not os.path.exists(REF_BIN):
-        return None, None
+        return none
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, "a.fa")
         synth.write_fasta(fa, chars)
-        args = [REF_BIN, "-nt", "-threads", str(threads), "-noml", "-nni", "0", "-spr", "0", "-nosupport",
-                "-log", os.path.join(td, "log"), fa]
+        args = [REF_BIN] + list(extra if extra is not None else wl["ref_flags"]) + ["-threads", str(threads), "-noml", "-nni", "0", "-spr", "0",
+                                                                                   "-nosupport", "-log", os.path.join(td, "log"), fa]
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         try:
             p = subprocess.run(args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env, timeout=timeout)
         except subprocess.TimeoutExpired:
-            return None, None
+            return none
         if p.returncode != 0:
-            return None, None
+            return none
         log = open(os.path.join(td, "log")).read()
         m = re.search(r"Initial topology in ([0-9.]+) seconds", log)
         # stderr progress stamps: "   0.05 seconds: Identified unique sequences"
         u = re.search(r"([0-9.]+) seconds: Identified unique sequences", p.stderr.replace("\r", "\n"))
         if not m:
-            return None, None
+            return none
         t = float(m.group(1)) - (float(u.group(1)) if u else 0.0)
+        if want_tree:
+            nj = [line.split("\t", 1)[1].strip() for line in log.splitlines() if line.startswith("NJ\t")]
+            return t, chars.shape[0], (nj[0] if nj else None)
         return t, chars.shape[0]
 
 
-def batch_regime(lib, codes, device, n_pairs=262144, n_joins=6000):
-    """The same distance kernel in its bandwidth regime: one refresh-shaped request of n_pairs candidate pairs
-    (lists of internal nodes) through vft_dist_pairs; device time from CUDA events on the context's stream."""
-    n, L = codes.shape
-    cfg = api.make_config(n, L, 4, WORKLOAD["precision"], device=device)
-    cfg.reserved = 1
-    rs = np.random.RandomState(3)
-    with api.Context(lib, cfg) as ctx:
-        ctx.upload_leaves(codes)
-        ctx.outprofile_rebuild()
-        ctx.out_distance_all(n, 0.0)
-        active = list(range(n))
-        n_joins = min(n_joins, n // 2 - 2)
-        for k in range(n_joins):
-            a = active.pop(rs.randint(len(active))); b = active.pop(rs.randint(len(active)))
-            ctx.profile_average_update(n + k, a, b, n - k, -1.0, 0.001)
-            active.append(n + k)
-        internal = np.arange(n, n + n_joins)
-        m = 128
-        pi = np.repeat(internal[rs.randint(0, n_joins, size=m)], n_pairs // m)
-        pj = internal[rs.randint(0, n_joins, size=n_pairs)]
-        best = None
-        for _ in range(4):
-            c0 = ctx.counters()
-            ctx.dist_pairs(pi, pj)
-            c1 = ctx.counters()
-            ms, by = c1.msDist - c0.msDist, c1.algoBytes - c0.algoBytes
-            if best is None or ms < best[0]:
-                best = (ms, by)
-    peak = 6650.0
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        pass
-    gbps = best[1] / best[0] / 1e6
-    return {"what": "one vft_dist_pairs request of %d internal-node pairs (%d lists), k_eval(batch)" % (n_pairs, 128),
-            "ms": round(best[0], 3), "algorithmic_bytes": int(best[1]), "achieved": round(gbps, 1), "unit": "GB/s",
-            "frac": round(gbps / peak, 4)}
+def calibrate_threads(wl, chars, host_cores: int):
+    """The reference's OpenMP build gets SLOWER with too many threads on this path, so "all the host threads it can use" is
+    calibrated ON THE FULL WORKLOAD: the faster of cores/2 and cores.  Returns (threads, {threads: seconds})."""
+    cands = sorted({max(1, host_cores // 2), host_cores})
+    seen = {}
+    for th in cands:
+        t, _ = run_reference(wl, chars, th)
+        if t is not None:
+            seen[th] = t
+    if not seen:
+        return host_cores, {}
+    return min(seen, key=seen.get), seen
+
+
+def parity_check(wl, chars, lib, device):
+    """Product tree == reference tree (-threads 1 -ext AVX2) on the first PARITY_PREFIX taxa of the bench alignment."""
+    sub = chars[:PARITY_PREFIX]
+    extra = (["-nt"] if wl["kind"] == "nt" else []) + ["-ext", "AVX2"]
+    t, nu, want = run_reference(wl, sub, 1, timeout=600, want_tree=True, extra=extra)
+    if want is None:
+        return {"checked": False, "why": "oracle/_ref/VeryFastTree not available"}
+    A = 4 if wl["kind"] == "nt" else 20
+    tree = api.nj_build(api.encode(sub, wl["kind"]), A, wl["precision"], lib=lib, device=device, tables=tables_for(wl), trace=False)
+    got = tree.newick(["t%d" % i for i in range(sub.shape[0])])
+    return {"checked": True, "identical": got == want,
+            "sample": "first %d taxa of the bench alignment, reference %s -threads 1 (%.1f s); whole Newick string of the NJ phase compared "
+                      "(topology, join order and branch lengths)" % (sub.shape[0], " ".join(extra), t),
+            "full_size": "tests/test_gpu_at_size.py (16 000 x 200 nt and 4 000 x 1287 aa trees vs the reference at -threads 1)"}
 
 
 def main():
@@ -180,8 +175,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--taxa", type=int, default=WORKLOAD["n"], help="override the workload size (debug only)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--taxa", type=int, default=0, help="override the workload size (debug only)")
+    ap.add_argument("--device-loop", type=int, default=-1, help="-1: library default; 0/1: host-driven / device-resident join loop")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    n_taxa = args.taxa or wl["n"]
 
     # stdout carries exactly ONE line, the JSON: anything a library prints on fd 1 meanwhile (NCCL's version banner)
     # is sent to stderr
@@ -198,33 +197,57 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     host_cores = os.cpu_count() or 1
+    metric = "taxa/sec on initial NJ+TopHits build"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        chars = make_workload(1, args.taxa)
         if not os.path.exists(REF_BIN):
             emit({"impl": "reference", "unavailable": "oracle/_ref/VeryFastTree was not built (no /root/reference at build time)"})
             return 0
-        times = []
-        threads = best_thread_count(host_cores)
+        n_rep = max(1, args.gpus)
+        workloads = [make_workload(wl, 1 + r, n_taxa) for r in range(n_rep)]
+        threads, seen = calibrate_threads(wl, workloads[0], host_cores)
+        per_proc = max(1, threads // n_rep)
+        times, taxa = [], 0
+
+        def one_round():
+            """n_rep trees at once (one process each, the host cores shared), as the repo arm's replicas: seconds = the slowest"""
+            res = [None] * n_rep
+
+            def work(r):
+                res[r] = run_reference(wl, workloads[r], per_proc)
+            ths = [threading.Thread(target=work, args=(r,)) for r in range(n_rep)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            if any(x is None or x[0] is None for x in res):
+                return None, 0
+            return max(x[0] for x in res), sum(x[1] for x in res)
         for it in range(args.warmup + args.steps):
-            t, nu = run_reference(chars, threads)
+            t, nu = one_round()
             if t is None:
                 emit({"impl": "reference", "unavailable": "reference binary failed to run"})
                 return 0
             if it >= args.warmup:
                 times.append(t)
+                taxa = nu
         total = sum(times)
-        value = nu * len(times) / total
-        line = {"impl": "reference", "metric": "taxa/sec on initial NJ+TopHits build", "value": value, "unit": "taxa/s",
+        value = taxa * len(times) / total
+        flags = " ".join(wl["ref_flags"])
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": "taxa/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD["name"], "taxa": int(nu), "columns": WORKLOAD["pos"],
-                           "reference_flags": "-nt -threads %d -noml -nni 0 -spr 0 -nosupport (AUTO ext = SSE3 for nt fp32)" % threads,
-                           "host_cores": host_cores},
-                "cpu_baseline": {"value": value, "unit": "taxa/s", "cores": threads, "kind": "reference",
-                                 "sample": "the full workload, %d timed runs of the unmodified reference binary; threads = fastest of a 1..%d sweep on a 3000-taxon sample" % (len(times), host_cores)},
+                "config": {"workload": wl["name"], "taxa_per_gpu": int(taxa // n_rep), "columns": wl["pos"],
+                           "parallelism": "replicas x%d" % n_rep,
+                           "reference_flags": "%s -threads %d -noml -nni 0 -spr 0 -nosupport%s" % (
+                               flags, per_proc, " (nt fp32: the reference silently runs its SSE3 path)" if wl["kind"] == "nt" else ""),
+                           "reference_build": "oracle/_ref: the unmodified sources, g++ -O3 -mavx2 (no FMA; the parity oracle)",
+                           "thread_calibration_s": {str(k): round(v, 2) for k, v in seen.items()}, "host_cores": host_cores},
+                "cpu_baseline": {"value": value, "unit": "taxa/s", "cores": per_proc * n_rep, "kind": "reference",
+                                 "sample": "the full workload, %d timed runs of the unmodified reference binary (%d tree%s at a time); threads = the faster "
+                                           "of cores/2 and cores on the full workload" % (len(times), n_rep, "s" if n_rep > 1 else "")},
                 "e2e": {"value": value, "unit": "taxa/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -238,9 +261,12 @@ def main():
     lib = api.load()
     # host threads of the driver's list-processing regions: this rank's share of the cores
     host_threads = max(1, min(16, host_cores // max(1, world)))
+    A = 4 if wl["kind"] == "nt" else 20
+    tables = tables_for(wl)
+    dev_loop = None if args.device_loop < 0 else args.device_loop
 
-    chars = make_workload(1 + rank, args.taxa)
-    codes = api.encode(chars, WORKLOAD["kind"])
+    chars = make_workload(wl, 1 + rank, n_taxa)
+    codes = api.encode(chars, wl["kind"])
     n_unique = codes.shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
@@ -253,8 +279,8 @@ def main():
     def one_step(profile=False):
         flush.fill_(1)                       # L2 flush between iterations
         torch.cuda.synchronize()
-        return api.nj_build(codes, 4, WORKLOAD["precision"], lib=lib, device=local_rank, trace=False, profile=profile,
-                            host_threads=host_threads)
+        return api.nj_build(codes, A, wl["precision"], lib=lib, device=local_rank, trace=False, profile=profile,
+                            host_threads=host_threads, tables=tables, device_loop=dev_loop)
 
     for _ in range(args.warmup):
         one_step()
@@ -281,7 +307,7 @@ def main():
     from veryfasttree_b200 import dist as vdist
     dev_ms_max, e2e_max, taxa_total, launches_total = vdist.aggregate_step_times(dev_ms, e2e_s, float(n_unique), float(launches), device="cuda")
 
-    # one extra profiled pass: per-kernel-class device time from CUDA events on the launching stream
+    # one extra profiled pass: per-kernel device time from CUDA events on the launching stream
     ptree = one_step(profile=True)
     prof = ptree.stats["counters"]
     if rank == 0:
@@ -292,7 +318,7 @@ def main():
         print("[bench] per step (device ms, end-to-end ms):", per_step, file=sys.stderr)
         for nm, ms, cnt in zip(api.KERNEL_NAMES, prof["msKernel"], prof["nKernel"]):
             if cnt:
-                print("[bench] profiled pass  %-24s %7d launches %9.2f ms  %8.2f us/launch" % (nm, cnt, ms, 1e3 * ms / cnt), file=sys.stderr)
+                print("[bench] profiled pass  %-24s %7d events %9.2f ms  %8.2f us/event" % (nm, cnt, ms, 1e3 * ms / cnt), file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,50 +327,52 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # per-kernel table of the profiled pass (CUDA events on the launching stream around every launch)
     kernels = {}
+    prof_ms_total = sum(prof["msKernel"])
     for nm, ms, cnt, by in zip(api.KERNEL_NAMES, prof["msKernel"], prof["nKernel"], prof["bytesKernel"]):
         if cnt:
-            kernels[nm] = {"launches": int(cnt), "ms": round(ms, 2), "us_per_launch": round(1e3 * ms / cnt, 2),
+            kernels[nm] = {"launches": int(cnt), "ms": round(ms, 2), "us_per_launch": round(1e3 * ms / cnt, 2), "share_of_device_time": round(ms / prof_ms_total, 3),
                            "algorithmic_gb": round(by / 1e9, 3), "gbps": round(by / ms / 1e6, 1) if by and ms > 0 else None}
     dist_kernels = [k for k in kernels if kernels[k]["algorithmic_gb"]]
     dom = max(dist_kernels, key=lambda k: kernels[k]["ms"])
     achieved = kernels[dom]["gbps"]
-    batch = batch_regime(lib, codes, local_rank) if rank == 0 else None
-    roofline = {"bound": "hbm", "kernel": dom + " -- the dominant kernel of the step: one launch per per-join candidate list "
-                "(40-250 pairs of 0.2-4.4 KB), latency bound, the slab is L2 resident",
+    roofline = {"bound": "hbm", "kernel": dom + " -- the profile-moving kernel with the largest share of the step's device time (%.0f %%)" % (100 * kernels[dom]["share_of_device_time"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_launch": int(1e9 * kernels[dom]["algorithmic_gb"] / kernels[dom]["launches"]),
                 "us_per_launch": kernels[dom]["us_per_launch"],
-                "traffic": 256, "traffic_note": "dram__bytes_read+write per launch from profiles/r1_k_eval_small_ncu_full.md: "
-                "the 75 MB slab stays in the 126 MB L2, so DRAM traffic is ~0 and far BELOW the algorithmic bytes",
+                "bytes_rule": "SURVEY 8d dense rule: L B per leaf, L*(A*4+4+1) B per internal node, the list's query once.  An internal profile holds a "
+                              "vector only where its code is NOCODE, so DRAM traffic is BELOW this figure (ncu, profiles/): the fraction is an upper bound "
+                              "of HBM utilisation; the kernels are bound by the ordered double-precision sums (one dependent DADD per position), not by HBM",
+                "traffic": None, "traffic_note": "dram__bytes per launch are in the committed ncu summaries under profiles/ (not measurable inside bench.py)",
                 "distance_sweep_all_kernels": {"algorithmic_bytes_per_step": prof["distBytes"], "ms_per_step": prof["msDist"],
-                                               "gbps": (prof["distBytes"] / (prof["msDist"] * 1e-3)) / 1e9 if prof["msDist"] > 0 else None},
-                "batch_regime": batch}
+                                               "gbps": (prof["distBytes"] / (prof["msDist"] * 1e-3)) / 1e9 if prof["msDist"] > 0 else None}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    cpu = None
+    cpu, parity = None, None
     if args.gpus == 1:
-        threads = best_thread_count(host_cores)
-        t, nu = run_reference(chars, threads)
-        if t is not None:
-            cpu = {"value": nu / t, "unit": "taxa/s", "cores": threads, "kind": "reference", "host_cores": host_cores,
-                   "sample": "the full workload once (%d unique taxa x %d columns), unmodified reference binary, -threads %d "
-                             "(fastest of a 1..%d sweep on a 3000-taxon sample), %.2f s" % (nu, WORKLOAD["pos"], threads, host_cores, t)}
+        threads, seen = calibrate_threads(wl, chars, host_cores)
+        if seen:
+            t = seen[threads]
+            cpu = {"value": n_unique / t, "unit": "taxa/s", "cores": threads, "kind": "reference", "host_cores": host_cores,
+                   "sample": "the full workload once per candidate thread count (%d unique taxa x %d columns), unmodified reference binary %s: %s; fastest kept"
+                             % (n_unique, wl["pos"], " ".join(wl["ref_flags"]), ", ".join("-threads %d %.2f s" % kv for kv in sorted(seen.items())))}
         else:
             cpu = {"value": None, "unit": "taxa/s", "cores": host_cores, "kind": "reference", "sample": "oracle/_ref/VeryFastTree not available"}
+        parity = parity_check(wl, chars, lib, local_rank)
 
     value = taxa_total * args.steps / (dev_ms_max * 1e-3)
-    line = {"metric": "taxa/sec on initial NJ+TopHits build", "value": value, "unit": "taxa/s", "n_gpus": args.gpus,
+    line = {"metric": metric, "value": value, "unit": "taxa/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"], "taxa_per_gpu": int(n_unique), "columns": WORKLOAD["pos"],
+            "config": {"workload": wl["name"], "taxa_per_gpu": int(n_unique), "columns": wl["pos"],
                        "parallelism": "replicas x%d" % args.gpus, "host_threads_per_rank": host_threads,
+                       "join_loop": "device-resident" if ptree.stats["counters"]["nKernel"][11] else "host-driven",
                        "l2": "flushed between steps (256 MiB write)",
-                       "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)",
-                       "parity": "join order, top-hit lists and branch lengths identical to the reference at -threads 1"},
+                       "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)"},
+            "parity_checked": parity,
             "e2e": {"value": taxa_total * args.steps / e2e_max, "unit": "taxa/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(launches_total), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,

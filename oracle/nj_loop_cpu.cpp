@@ -26,6 +26,9 @@ struct CpuEnv {
     int atomicAddI(int32_t *p, int v) { const int o = *p; *p += v; return o; }
     int atomicExchI(int32_t *p, int v) { const int o = *p; *p = v; return o; }
     void atomicAddL(int64_t *p, int64_t v) { *p += v; }
+    bool syncOr(int pred) { return pred != 0; }
+    int32_t blockMin(uint64_t *, int32_t *, uint64_t k, int32_t idx, uint64_t *keyOut) { if (keyOut) *keyOut = k; return idx; }
+    int32_t blockSum(int32_t *, int32_t v) { return v; }
     void evalOut(const int32_t *ids, int n, int32_t nActive) {
         std::vector<int64_t> id((size_t) n);
         std::vector<P> out((size_t) n);
@@ -41,6 +44,7 @@ struct CpuEnv {
         for (int k = 0; k < n; k++) { a[(size_t) k] = pairs[2 * k]; b[(size_t) k] = pairs[2 * k + 1]; }
         const int r = vft_dist_pairs(ctx, a.data(), b.data(), n, VFT_PAIRS_JOIN, outD, w.data());
         if (r != VFT_OK) rc = r;
+        for (int k = 0; k < n; k++) { if (a[(size_t) k] < st->sc->nSeqs && b[(size_t) k] < st->sc->nSeqs) st->sc->seqOps++; else st->sc->profileOps++; }
     }
 };
 
@@ -123,7 +127,8 @@ struct Loop {
         const int rc = vft_eval_batch(ctx, ids.data(), nOut, sc.nActive, sc.totdiam, od.data(), a.data(), b.data(), nPair, VFT_PAIRS_JOIN, pairD.data(), pairW.data());
         if (rc != VFT_OK) return rc;
         for (int k = 0; k < nOut; k++) { freshVal[(size_t) reqOut[(size_t) k]] = od[(size_t) k]; freshEpoch[(size_t) reqOut[(size_t) k]] = sc.epoch; }
-        sc.outprofileOps += nOut;
+        sc.outprofileOps += nOut; sc.nPairHit += nPair;
+        for (int k = 0; k < nPair; k++) { if (a[(size_t) k] < sc.nSeqs && b[(size_t) k] < sc.nSeqs) sc.seqOps++; else sc.profileOps++; }
         return VFT_OK;
     }
 

@@ -23,6 +23,40 @@ struct GpuEnv {
     __device__ __forceinline__ int atomicAddI(int32_t *p, int v) { return atomicAdd(p, v); }
     __device__ __forceinline__ int atomicExchI(int32_t *p, int v) { return atomicExch(p, v); }
     __device__ __forceinline__ void atomicAddL(int64_t *p, int64_t v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long) v); }
+    __device__ __forceinline__ bool syncOr(int pred) { return __syncthreads_or(pred) != 0; }
+    // minimum of (key, idx) over the block, idx < 0 = no candidate: warp shuffles, then one pass over the warps' results
+    __device__ __forceinline__ int32_t blockMin(uint64_t *redK, int32_t *redI, uint64_t k, int32_t idx, uint64_t *keyOut) {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t kb = __shfl_down_sync(full, k, o);
+            const int32_t ib = __shfl_down_sync(full, idx, o);
+            if (ib >= 0 && (idx < 0 || kb < k || (kb == k && ib < idx))) { k = kb; idx = ib; }
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+        if (lane == 0) { redK[warp] = k; redI[warp] = idx; }
+        __syncthreads();
+        uint64_t bk = redK[0]; int32_t bi = redI[0];
+        for (int w = 1; w < nWarps; w++) {
+            const uint64_t kb = redK[w]; const int32_t ib = redI[w];
+            if (ib >= 0 && (bi < 0 || kb < bk || (kb == bk && ib < bi))) { bk = kb; bi = ib; }
+        }
+        if (keyOut) *keyOut = bk;
+        __syncthreads();
+        return bi;
+    }
+    __device__ __forceinline__ int32_t blockSum(int32_t *redI, int32_t v) {
+        const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(full, v, o);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+        if (lane == 0) redI[warp] = v;
+        __syncthreads();
+        int32_t tot = 0;
+        for (int w = 0; w < nWarps; w++) tot += redI[w];
+        __syncthreads();
+        return tot;
+    }
 
     // one item per warp, the warps of the block side by side
     __device__ __noinline__ void evalItem(int64_t a, int64_t b, bool isOut, int32_t nActive, P &d, P &w) {
@@ -51,13 +85,19 @@ struct GpuEnv {
         }
         __syncwarp();
     }
+    // SURVEY 8d accounting of one evaluated pair (the query's own bytes are left out: it is shared by the list)
+    __device__ __forceinline__ void account(int64_t a, int64_t b) {
+        Scalars *sc = st.sc;
+        if (a < s.nSeqs && b < s.nSeqs) { atomicAddL(&sc->seqOps, 1); atomicAddL(&sc->algoBytes, sc->Lbytes); }
+        else { atomicAddL(&sc->profileOps, 1); atomicAddL(&sc->algoBytes, b < s.nSeqs ? sc->Lbytes : sc->profBytes); }
+    }
     __device__ __noinline__ void evalOut(const int32_t *ids, int n, int32_t nActive) {
         const int warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5, lane = threadIdx.x & 31;
         for (int q = warp; q < n; q += nWarps) {
             const int32_t id = ids[q];
             P d, w;
             evalItem(id, -1, true, nActive, d, w);
-            if (lane == 0) { st.freshVal[id] = d; st.freshEpoch[id] = st.sc->epoch; }
+            if (lane == 0) { st.freshVal[id] = d; st.freshEpoch[id] = st.sc->epoch; atomicAddL(&st.sc->algoBytes, id < s.nSeqs ? st.sc->Lbytes : st.sc->profBytes); }
         }
         if (threadIdx.x == 0) st.sc->outprofileOps += n;
     }
@@ -65,8 +105,9 @@ struct GpuEnv {
         const int warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5, lane = threadIdx.x & 31;
         for (int q = warp; q < n; q += nWarps) {
             P d, w;
-            evalItem(pairs[2 * q], pairs[2 * q + 1], false, 0, d, w);
-            if (lane == 0) outD[q] = d;
+            const int64_t a = pairs[2 * q], b = pairs[2 * q + 1];
+            evalItem(a, b, false, 0, d, w);
+            if (lane == 0) { outD[q] = d; account(a, b); }
         }
     }
 };
@@ -109,6 +150,7 @@ k_nj_eval(Store<P> s, njl::State<P> st, int minItems) {
     G = G < 1 ? 1 : (G > R ? R : G);
     unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(R);
     const int64_t warp0 = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+    int64_t tSeq = 0, tProf = 0, tBytes = 0;
     for (int64_t warp = warp0; warp * G < n; warp += totalWarps) {
         const int64_t item = warp * G + lane;
         const bool inRange = lane < G && item < n;
@@ -135,10 +177,17 @@ k_nj_eval(Store<P> s, njl::State<P> st, int minItems) {
         if (valid) {
             if (isOut) { st.freshVal[a] = d; st.freshEpoch[a] = epoch; }
             else { st.pairD[item - nOut] = d; st.pairW[item - nOut] = w; }
+            if (isSeq) { tSeq++; tBytes += sc->Lbytes; } else { if (!isOut) tProf++; tBytes += (isOut ? a : b) < s.nSeqs ? sc->Lbytes : sc->profBytes; }
         }
         __syncwarp();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; }
+    for (int o = 16; o > 0; o >>= 1) { tSeq += __shfl_down_sync(full, tSeq, o); tProf += __shfl_down_sync(full, tProf, o); tBytes += __shfl_down_sync(full, tBytes, o); }
+    if (lane == 0 && tBytes > 0) {
+        if (tSeq) atomicAdd(reinterpret_cast<unsigned long long *>(&sc->seqOps), (unsigned long long) tSeq);
+        if (tProf) atomicAdd(reinterpret_cast<unsigned long long *>(&sc->profileOps), (unsigned long long) tProf);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sc->algoBytes), (unsigned long long) tBytes);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; sc->nPairHit += n - nOut; }
 }
 
 // the same list, one CTA per item (long alignments: a few hundred items cannot fill the machine with a warp each)
@@ -150,7 +199,7 @@ k_nj_eval_wide(Store<P> s, njl::State<P> st, int maxItems) {
     if (sc->status != njl::ST_RUNNING) return;
     const int nOut = sc->nOutReq, n = nOut + sc->nPairReq;
     if (n > maxItems) return;                            // long lists go to the grouped kernel
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; sc->nPairHit += n - nOut; }
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
         const bool isOut = item < nOut;
         const int64_t a = isOut ? st.reqOut[item] : st.reqA[item - nOut], b = isOut ? -1 : st.reqB[item - nOut];
@@ -169,6 +218,11 @@ k_nj_eval_wide(Store<P> s, njl::State<P> st, int maxItems) {
                 else { d = join_correct<P>(s, a, b, dd); w = ww; }
                 if (isOut) { st.freshVal[a] = d; st.freshEpoch[a] = sc->epoch; }
                 else { st.pairD[item - nOut] = d; st.pairW[item - nOut] = w; }
+                if (isSeq) { atomicAdd(reinterpret_cast<unsigned long long *>(&sc->seqOps), 1ull); atomicAdd(reinterpret_cast<unsigned long long *>(&sc->algoBytes), (unsigned long long) sc->Lbytes); }
+                else {
+                    if (!isOut) atomicAdd(reinterpret_cast<unsigned long long *>(&sc->profileOps), 1ull);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&sc->algoBytes), (unsigned long long) ((isOut ? a : b) < s.nSeqs ? sc->Lbytes : sc->profBytes));
+                }
             }
         }
         __syncthreads();

@@ -208,9 +208,22 @@ struct Logic {
     // -- `always` -- every one not at this nActive (setOutDistance, NJ.tcc:1012-1053).  Values come from the hint
     // evaluation of this epoch when present, else the block computes them.  Block-wide; n is block-uniform.
     NJL_DN void ensureCommit(int n, int32_t nActive, bool always) {
+        const int32_t epoch = sc.epoch;
+        // common case, one pass: every value needed is in hand (hinted) and is committed at once
+        int missing = 0;
+        for (int e = x.tid(); e < n; e += x.nt()) {
+            const int32_t i = sm.list[e];
+            if (i < 0) continue;
+            const bool need = always ? st.nOutAct[i] != nActive : stale(i, nActive);
+            if (!need) continue;
+            if (st.freshEpoch[i] == epoch) { st.outDist[i] = st.freshVal[i]; st.nOutAct[i] = nActive; }      // concurrent writers store the same values
+            else missing = 1;
+        }
+        if (!x.syncOr(missing)) return;
+        // some values were not hinted: the block computes them itself
         if (x.tid() == 0) { sm.ctl[0] = 0; sc.stamp++; }
         x.sync();
-        const int32_t stamp = sc.stamp, epoch = sc.epoch;
+        const int32_t stamp = sc.stamp;
         for (int e = x.tid(); e < n; e += x.nt()) {
             const int32_t i = sm.list[e];
             if (i < 0) continue;
@@ -220,16 +233,14 @@ struct Logic {
         }
         x.sync();
         const int nMiss = sm.ctl[0];
-        if (nMiss > 0) {
-            x.evalOut(sm.miss, nMiss, nActive);               // writes freshVal / freshEpoch
-            if (x.tid() == 0) sc.nInlineOut += nMiss;
-            x.sync();
-        }
+        x.evalOut(sm.miss, nMiss, nActive);                   // writes freshVal / freshEpoch
+        if (x.tid() == 0) sc.nInlineOut += nMiss;
+        x.sync();
         for (int e = x.tid(); e < n; e += x.nt()) {
             const int32_t i = sm.list[e];
             if (i < 0) continue;
             const bool need = always ? st.nOutAct[i] != nActive : stale(i, nActive);
-            if (need) { st.outDist[i] = st.freshVal[i]; st.nOutAct[i] = nActive; }      // concurrent writers store the same values
+            if (need) { st.outDist[i] = st.freshVal[i]; st.nOutAct[i] = nActive; }
         }
         x.sync();
     }
@@ -237,35 +248,8 @@ struct Logic {
     // ---- block reductions ----------------------------------------------------------------------------------------
     // minimum of (key, idx) over the threads' candidates; idx < 0 = no candidate.  Returns the winning idx (or -1) to
     // every thread; *keyOut its key.
-    NJL_DN int32_t blockMin(uint64_t k, int32_t idx, uint64_t *keyOut = nullptr) {
-        sm.redK[x.tid()] = k; sm.redI[x.tid()] = idx;
-        x.sync();
-        for (int s = 1; s < x.nt(); s <<= 1) {
-            const int t = x.tid();
-            if ((t & (2 * s - 1)) == 0 && t + s < x.nt()) {
-                const int32_t ia = sm.redI[t], ib = sm.redI[t + s];
-                const uint64_t ka = sm.redK[t], kb = sm.redK[t + s];
-                if (ib >= 0 && (ia < 0 || kb < ka || (kb == ka && ib < ia))) { sm.redK[t] = kb; sm.redI[t] = ib; }
-            }
-            x.sync();
-        }
-        const int32_t r = sm.redI[0];
-        if (keyOut) *keyOut = sm.redK[0];
-        x.sync();
-        return r;
-    }
-    NJL_DN int32_t blockSum(int32_t v) {
-        sm.redI[x.tid()] = v;
-        x.sync();
-        for (int s = 1; s < x.nt(); s <<= 1) {
-            const int t = x.tid();
-            if ((t & (2 * s - 1)) == 0 && t + s < x.nt()) sm.redI[t] += sm.redI[t + s];
-            x.sync();
-        }
-        const int32_t r = sm.redI[0];
-        x.sync();
-        return r;
-    }
+    NJL_D int32_t blockMin(uint64_t k, int32_t idx, uint64_t *keyOut = nullptr) { return x.blockMin(sm.redK, sm.redI, k, idx, keyOut); }
+    NJL_D int32_t blockSum(int32_t v) { return x.blockSum(sm.redI, v); }
     // psort order of sm.key[0..n): perm[rank] = element; rank = #smaller keys + #equal keys at LATER positions
     NJL_DN void rankSort(int n) {
         for (int e = x.tid(); e < n; e += x.nt()) {
@@ -286,20 +270,11 @@ struct Logic {
         int32_t *ent = sm.miss, *pairs = sm.miss + sc.cap;
         if (x.tid() == 0) sm.ctl[1] = 0;
         x.sync();
-        int64_t nSeq = 0, nProf = 0, nLeafB = 0, nHit = 0;
         for (int e = x.tid(); e < n; e += x.nt()) {
             const int32_t a = sm.cAux[e];
             if (a == -2) ent[x.atomicAddI(&sm.ctl[1], 1)] = e;
-            else if (a >= 0) { sm.cDist[e] = st.pairD[a]; nHit++; }
-            if (a == -2 || a >= 0) {
-                const int32_t j = sm.cJ[e];
-                if (iNode < sc.nSeqs && j < sc.nSeqs) nSeq++; else { nProf++; if (j < sc.nSeqs) nLeafB++; }
-            }
+            else if (a >= 0) sm.cDist[e] = st.pairD[a];
         }
-        if (nSeq) x.atomicAddL(&sc.seqOps, nSeq);
-        if (nProf) x.atomicAddL(&sc.profileOps, nProf);
-        if (nHit) x.atomicAddL(&sc.nPairHit, nHit);
-        if (nSeq + nProf) x.atomicAddL(&sc.algoBytes, (nSeq + nLeafB) * sc.Lbytes + (nProf - nLeafB) * sc.profBytes);
         x.sync();
         const int nMiss = sm.ctl[1];
         if (nMiss > 0) {
@@ -441,7 +416,7 @@ struct Logic {
             sc.epoch++;                                          // newEpoch(nActive - 1)
             sc.nActive = nActive - 1;
             sc.nJoins++;
-            sc.profileOps++; sc.algoBytes += sc.profBytes;       // averageProfile's self distance
+            sc.profileOps++;                                     // averageProfile's self distance
             if (rebuild) { sc.status = ST_NEED_REBUILD; sc.nRebuild++; }
         }
         x.sync();
@@ -638,7 +613,6 @@ struct Logic {
             sm.cCrit[u] = c; sm.key[u] = okey(c);
         }
         if (x.tid() == 0) {
-            sc.algoBytes += sc.profBytes;                                // the list shares its query
             st.age[newnode] = (st.age[c0] + st.age[c1] + 1) / 2 + 1;     // :4342
             st.hitCount[c0] = 0; st.hitCount[c1] = 0;
         }
@@ -681,9 +655,19 @@ struct Logic {
             sm.perm[r] = flag ? (sm.cAux[r] ? 2 : 1) : 0;
         }
         x.sync();
-        for (int r = 0; r < nSave; r++) {
-            const int f = sm.perm[r];                             // (updateTopVisible leaves sm.perm alone)
-            if (!f) continue;
+        // the hits that replace a visible entry, in list order (ordered compaction of the flags into sm.key)
+        int mineF = 0;
+        for (int r = x.tid(); r < nSave; r += x.nt()) {
+            if (!sm.perm[r]) continue;
+            int pos = 0;
+            for (int q = 0; q < r; q++) pos += sm.perm[q] ? 1 : 0;
+            sm.key[pos] = (uint64_t) r;
+            mineF++;
+        }
+        const int32_t nFlag = blockSum(mineF);
+        for (int q = 0; q < nFlag; q++) {
+            const int r = (int) sm.key[q];                        // (updateTopVisible leaves sm.key and sm.perm alone)
+            const int f = sm.perm[r];
             const int32_t j = hj[r];
             const P d = hd[r];
             if (x.tid() == 0) { if (f == 2) sc.nVisibleUpdate++; st.visJ[j] = newnode; st.visDist[j] = d; }
