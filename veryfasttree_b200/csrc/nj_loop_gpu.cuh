@@ -24,26 +24,30 @@ struct GpuEnv {
     __device__ __forceinline__ int atomicExchI(int32_t *p, int v) { return atomicExch(p, v); }
     __device__ __forceinline__ void atomicAddL(int64_t *p, int64_t v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long) v); }
     __device__ __forceinline__ bool syncOr(int pred) { return __syncthreads_or(pred) != 0; }
-    // minimum of (key, idx) over the block, idx < 0 = no candidate: warp shuffles, then one pass over the warps' results
+    // minimum of (key, idx) over the block, idx < 0 = no candidate: warp shuffles, the warps' results folded by warp 0
     __device__ __forceinline__ int32_t blockMin(uint64_t *redK, int32_t *redI, uint64_t k, int32_t idx, uint64_t *keyOut) {
         const unsigned full = 0xFFFFFFFFu;
+        auto fold = [&](uint64_t &k0, int32_t &i0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t kb = __shfl_down_sync(full, k, o);
-            const int32_t ib = __shfl_down_sync(full, idx, o);
-            if (ib >= 0 && (idx < 0 || kb < k || (kb == k && ib < idx))) { k = kb; idx = ib; }
-        }
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t kb = __shfl_down_sync(full, k0, o);
+                const int32_t ib = __shfl_down_sync(full, i0, o);
+                if (ib >= 0 && (i0 < 0 || kb < k0 || (kb == k0 && ib < i0))) { k0 = kb; i0 = ib; }
+            }
+        };
+        fold(k, idx);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
         if (lane == 0) { redK[warp] = k; redI[warp] = idx; }
         __syncthreads();
-        uint64_t bk = redK[0]; int32_t bi = redI[0];
-        for (int w = 1; w < nWarps; w++) {
-            const uint64_t kb = redK[w]; const int32_t ib = redI[w];
-            if (ib >= 0 && (bi < 0 || kb < bk || (kb == bk && ib < bi))) { bk = kb; bi = ib; }
+        if (warp == 0) {
+            uint64_t bk = lane < nWarps ? redK[lane] : ~0ull;
+            int32_t bi = lane < nWarps ? redI[lane] : -1;
+            fold(bk, bi);
+            if (lane == 0) { redK[32] = bk; redI[32] = bi; }
         }
-        if (keyOut) *keyOut = bk;
         __syncthreads();
-        return bi;
+        if (keyOut) *keyOut = redK[32];
+        return redI[32];
     }
     __device__ __forceinline__ int32_t blockSum(int32_t *redI, int32_t v) {
         const unsigned full = 0xFFFFFFFFu;
@@ -52,12 +56,15 @@ struct GpuEnv {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
         if (lane == 0) redI[warp] = v;
         __syncthreads();
-        int32_t tot = 0;
-        for (int w = 0; w < nWarps; w++) tot += redI[w];
+        if (warp == 0) {
+            int32_t t = lane < nWarps ? redI[lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(full, t, o);
+            if (lane == 0) redI[33] = t;
+        }
         __syncthreads();
-        return tot;
+        return redI[33];
     }
-
     // one item per warp, the warps of the block side by side
     __device__ __noinline__ void evalItem(int64_t a, int64_t b, bool isOut, int32_t nActive, P &d, P &w) {
         const unsigned full = 0xFFFFFFFFu;
@@ -112,7 +119,7 @@ struct GpuEnv {
     }
 };
 
-constexpr int NJ_STEP_T = 512;
+constexpr int NJ_STEP_T = 256;
 
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(NJ_STEP_T, 1)
@@ -142,6 +149,7 @@ k_nj_eval(Store<P> s, njl::State<P> st, int minItems) {
     const int32_t nActive = sc->nActive;
     const double totdiam = sc->totdiam;
     const int32_t epoch = sc->epoch;
+    const int32_t selfNode = sc->jdSelfPending ? sc->jdNew : -1;
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     constexpr int R = TileShape<A, MATRIX>::R;
@@ -167,6 +175,13 @@ k_nj_eval(Store<P> s, njl::State<P> st, int minItems) {
         const bool isProf = valid && !isSeq;
         const unsigned mask = __ballot_sync(full, isProf);
         double den, top;
+        // the new node's own out-distance needs its self distance (NJ.tcc:3040-3043), which k_average leaves to this kernel
+        const unsigned selfMask = __ballot_sync(full, isOut && a == selfNode);
+        if (selfMask) {
+            group_profile_dist<P, A, MATRIX>(s, a, a, selfMask, G, smw, den, top);
+            if (isOut && a == selfNode) { P sd, sw; finish_dist<P>(den, top, sd, sw); s.selfdist[a] = sd; s.selfweight[a] = sw; }
+            __syncwarp();
+        }
         group_profile_dist<P, A, MATRIX>(s, a, isOut ? (int64_t) -1 : b, mask, G, smw, den, top);
         if (isProf) {
             P dd, ww;
@@ -188,6 +203,7 @@ k_nj_eval(Store<P> s, njl::State<P> st, int minItems) {
         atomicAdd(reinterpret_cast<unsigned long long *>(&sc->algoBytes), (unsigned long long) tBytes);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; sc->nPairHit += n - nOut; }
+    // (jdSelfPending is cleared by the next k_nj_step: other CTAs of this launch may still read it)
 }
 
 // the same list, one CTA per item (long alignments: a few hundred items cannot fill the machine with a warp each)
@@ -199,6 +215,7 @@ k_nj_eval_wide(Store<P> s, njl::State<P> st, int maxItems) {
     if (sc->status != njl::ST_RUNNING) return;
     const int nOut = sc->nOutReq, n = nOut + sc->nPairReq;
     if (n > maxItems) return;                            // long lists go to the grouped kernel
+    const int32_t selfNode = sc->jdSelfPending ? sc->jdNew : -1;
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->jdValid = 0; sc->outprofileOps += nOut; sc->nPairHit += n - nOut; }
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
         const bool isOut = item < nOut;
@@ -206,6 +223,15 @@ k_nj_eval_wide(Store<P> s, njl::State<P> st, int maxItems) {
         if (a < 0) continue;
         const bool isSeq = !isOut && a < s.nSeqs && b < s.nSeqs;
         double den, top;
+        if (isOut && a == selfNode) {                    // the new node: its self distance first (see k_nj_eval)
+            group_profile_dist<P, A, MATRIX, true>(s, a, a, 1u, 1, smemRaw, den, top, (int) (threadIdx.x >> 5), (int) (blockDim.x >> 5));
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                cta_ordered_sum<P, A, MATRIX>(s, smemRaw, den, top);
+                if (threadIdx.x == 0) { P sd, sw; finish_dist<P>(den, top, sd, sw); s.selfdist[a] = sd; s.selfweight[a] = sw; }
+            }
+            __syncthreads();
+        }
         group_profile_dist<P, A, MATRIX, true>(s, a, isOut ? (int64_t) -1 : b, 1u, 1, smemRaw, den, top, (int) (threadIdx.x >> 5), (int) (blockDim.x >> 5));
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -522,7 +548,7 @@ extern "C" int vftx_loop_upload(vftx_loop *lp, const vftx_loop_image *g, int32_t
     if (lp->traceBase < 0) lp->traceBase = c->N - g->nActive;
     sc.maxnode = (int32_t) g->maxnode; sc.nActive = (int32_t) g->nActive; sc.topvisibleAge = (int32_t) g->topvisibleAge;
     sc.nActiveOutProfileReset = (int32_t) g->nActiveOutProfileReset; sc.totdiam = g->totdiam;
-    sc.status = njl::ST_RUNNING; sc.resume = resume; sc.epoch++; sc.hintEpoch = -1; sc.hintJoinSlot = -1; sc.jdValid = 0; sc.nOutReq = 0; sc.nPairReq = 0;
+    sc.status = njl::ST_RUNNING; sc.resume = resume; sc.epoch++; sc.hintEpoch = -1; sc.hintJoinSlot = -1; sc.jdValid = 0; sc.jdSelfPending = 0; sc.nOutReq = 0; sc.nPairReq = 0;
     CK(cudaMemcpyAsync(d.sc, &sc, sizeof sc, cudaMemcpyHostToDevice, c->stream));
     CK(sync_stream(c));
     return VFT_OK;
@@ -617,7 +643,7 @@ static LoopGeom loop_geom(vftx_loop *lp) {
         k_average<P, A_, MX, true><<<g.avgBlocks, g.AVG_T, g.smemAvg, c->stream>>>(make_store<P>(c), 0, 0, 0, 0.5, (P) 0, 0, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr, (Scalars *) lp->d.sc); } while (0)
 // the request list: one CTA per item while the list is short and the rows are long, G items per warp otherwise (each kernel
 // returns at once outside its regime: the list size is only known on the device)
-#define LOOP_EVAL(P, A_, MX) do { if (lp->wide) k_nj_eval_wide<P, A_, MX><<<g.wideBlocks, 128, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), loop_state<P>(lp), 2048); \
+#define LOOP_EVAL(P, A_, MX) do { if (lp->wide) k_nj_eval_wide<P, A_, MX><<<g.wideBlocks, 256, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), loop_state<P>(lp), 2048); \
         k_nj_eval<P, A_, MX><<<g.evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(TileShape<A_, MX>::R), c->stream>>>(make_store<P>(c), loop_state<P>(lp), lp->wide ? 2048 : -1); } while (0)
 
 // resetTopVisible on the device (kernels above); the loop's scalars in lp->hSc are current
@@ -630,13 +656,13 @@ static int loop_reset_topvisible(vftx_loop *lp) {
     const int64_t n = sc.maxnode;
     const unsigned nb = (unsigned) ((n + 255) / 256);
     const int K = (int) std::min<int64_t>(n, RTV_K);
-    const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12, finSmem = (size_t) RTV_K * 20 + (size_t) RTV_HS * 8;
+    const size_t finSmem = (size_t) RTV_K * 20 + (size_t) RTV_HS * 8;
 #define LOOP_RTV(P, A_, MX) do { \
         prof_begin(c, CLS_SELECT, K_NJ_STEP); k_nj_rtv_mark<P><<<nb, 256, 0, c->stream>>>(loop_state<P>(lp), (int32_t *) lp->d.touchStamp); prof_end(c); \
         prof_begin(c, CLS_DIST, K_EVAL_LARGE); LOOP_EVAL(P, A_, MX); prof_end(c); \
         prof_begin(c, CLS_SELECT, K_NJ_STEP); k_nj_rtv_keys<P><<<nb, 256, 0, c->stream>>>(loop_state<P>(lp), c->d_keys); \
         k_nj_rtv_commit<P><<<nb, 256, 0, c->stream>>>(loop_state<P>(lp), (const int32_t *) lp->d.touchStamp); prof_end(c); \
-        prof_begin(c, CLS_SELECT, K_SELECT); k_topk_select<P, (int) sizeof(P)><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, K, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, (Rec<P> *) lp->d.rec); prof_end(c); \
+        prof_begin(c, CLS_SELECT, K_SELECT); launch_topk<P, (int) sizeof(P)>(c, c->d_keys, n, K, (Rec<P> *) lp->d.rec); prof_end(c); \
         cudaFuncSetAttribute(k_nj_rtv_finish<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) finSmem); \
         prof_begin(c, CLS_SELECT, K_NJ_STEP); k_nj_rtv_finish<P><<<1, 1024, finSmem, c->stream>>>(loop_state<P>(lp), (const Rec<P> *) lp->d.rec, c->d_keys, K); prof_end(c); } while (0)
     VFT_DISPATCH(c, LOOP_RTV);
@@ -675,7 +701,7 @@ static int loop_refresh(vftx_loop *lp, bool *done) {
     const int64_t warpsAll = (n + Gall - 1) / Gall;
     const int Gm = pick_group(c, (int64_t) slots);
     const int64_t warpsM = ((int64_t) slots + Gm - 1) / Gm;
-    const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12, smemSort = (size_t) np2 * 12;
+    const size_t smemSort = (size_t) np2 * 12;
     InlineItems inl;
     inl.a[0] = 0;
     LoopArrays &d = lp->d;
@@ -685,7 +711,7 @@ static int loop_refresh(vftx_loop *lp, bool *done) {
         k_nj_commit_all<P><<<nb, 256, 0, c->stream>>>(make_store<P>(c), loop_state<P>(lp)); \
         prof_begin(c, CLS_DIST, K_ONE_VS_ALL); \
         k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsAll + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gall), c->stream>>>(make_store<P>(c), newnode, nActive, n, 0, n, Gall, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys); prof_end(c); \
-        prof_begin(c, CLS_SELECT, K_SELECT); k_topk_select<P, (int) sizeof(P)><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) (2 * m), (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, (Rec<P> *) d.rec); prof_end(c); \
+        prof_begin(c, CLS_SELECT, K_SELECT); launch_topk<P, (int) sizeof(P)>(c, c->d_keys, n, (int) (2 * m), (Rec<P> *) d.rec); prof_end(c); \
         prof_begin(c, CLS_SELECT, K_MERGE); \
         k_nj_refresh_self<P><<<1, 1024, (size_t) 2 * m * 4, c->stream>>>(loop_state<P>(lp), (const Rec<P> *) d.rec, (int32_t *) d.mNode, (int32_t *) d.mOff, (int32_t *) d.allJ, (P *) d.allDist); \
         k_nj_refresh_pack<P><<<(unsigned) m, 128, 0, c->stream>>>(loop_state<P>(lp), (const int32_t *) d.mNode, (const int32_t *) d.mOff, (int32_t *) d.ownJ, (P *) d.ownDist); \

@@ -52,7 +52,7 @@ struct Scalars {
     int32_t maxnode, epoch, stamp, topvisibleAge, nActiveOutProfileReset;
     double totdiam;
     // the join being carried out: consumed by the averageProfile kernel and by thj_finish
-    int32_t jdValid, jdNew, jdI, jdJ, jdNActiveOld, jdUpdate;
+    int32_t jdValid, jdNew, jdI, jdJ, jdNActiveOld, jdUpdate, jdSelfPending;
     double jdDiameter;
     // request list for the grid-wide evaluation
     int32_t nOutReq, nPairReq;
@@ -407,7 +407,7 @@ struct Logic {
             const int64_t changedActive = (int64_t) sc.nActiveOutProfileReset - ((int64_t) nActive - 1);
             const bool rebuild = changedActive >= sc.nResetOutProfile && (double) changedActive >= sc.fResetOutProfile * (double) sc.nActiveOutProfileReset;
             if (!rebuild) sc.totdiam = q_add(sc.totdiam, (double) q_sub(q_sub(dn, st.diameter[ji]), st.diameter[jj]));
-            sc.jdValid = 1; sc.jdNew = newnode; sc.jdI = ji; sc.jdJ = jj; sc.jdNActiveOld = nActive; sc.jdUpdate = rebuild ? 0 : 1;
+            sc.jdValid = 1; sc.jdSelfPending = 1; sc.jdNew = newnode; sc.jdI = ji; sc.jdJ = jj; sc.jdNActiveOld = nActive; sc.jdUpdate = rebuild ? 0 : 1;
             sc.jdDiameter = (double) dn;
             st.nOutAct[newnode] = 2000000000;                   // never computed: stale at any nActive
             st.outDist[newnode] = 0;
@@ -680,6 +680,7 @@ struct Logic {
     // ---- one step of the loop: [finish the pending topHitJoin] -> search -> join -> prepare its topHitJoin ------------
     NJL_DN void step() {
         if (sc.status != ST_RUNNING) return;
+        if (x.tid() == 0) sc.jdSelfPending = 0;                   // (consumed by the evaluation of the previous step's request list)
         if (sc.resume == RS_THJ_FINISH) {
             if (!thjFinish()) {
                 if (x.tid() == 0) { sc.status = ST_NEED_REFRESH; sc.nRefresh++; }

@@ -331,11 +331,22 @@ struct Rec { int64_t j; P dist, weight, crit; };
 // records straight into mapped host memory.  KEYBYTES = 4 (float criterion) or 8 (double).
 constexpr int SEL_T = 1024;
 constexpr int SEL_MAXK = 4096;
+constexpr int SEL_CTAS = 32;                 // chunks of the multi-CTA select
 
 template<typename P, int KEYBYTES>
 __global__ void __launch_bounds__(SEL_T)
-k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__restrict__ dist, const P *__restrict__ weight,
-              const P *__restrict__ crit, Rec<P> *__restrict__ out) {
+k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P *__restrict__ dist, const P *__restrict__ weight,
+              const P *__restrict__ crit, Rec<P> *__restrict__ out, const uint32_t *__restrict__ idxIn = nullptr,
+              uint64_t *__restrict__ candK = nullptr, uint32_t *__restrict__ candI = nullptr) {
+    // Multi-CTA use (long key arrays): stage 1 -- gridDim.x CTAs, each selects the K best of ITS chunk and writes them as
+    // (key, original index) candidates (candK/candI, K per CTA, padded with never-selected keys); stage 2 -- one CTA runs the
+    // same selection over the candidates (idxIn = their original indices).  The K best overall are among the per-chunk K
+    // best, and the composite (key, index) order is the same at both stages.
+    const int64_t chunk = (nAll + gridDim.x - 1) / gridDim.x;
+    const int64_t base = (int64_t) blockIdx.x * chunk;
+    const int64_t n = base >= nAll ? 0 : (nAll - base < chunk ? nAll - base : chunk);
+    const uint64_t *__restrict__ keys = keysAll + base;
+    if (idxIn != nullptr) idxIn += base;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned int *hist = reinterpret_cast<unsigned int *>(smem);                    // [32 warps][256]
     uint64_t *sk = reinterpret_cast<uint64_t *>(smem + 32 * 256 * 4);              // [SEL_MAXK] sort keys
@@ -360,7 +371,7 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
             unsigned int digit = 0;
             if (i < n) {
                 const uint64_t k = keys[i];
-                const uint32_t ni = 0xFFFFFFFFu - (uint32_t) i;
+                const uint32_t ni = 0xFFFFFFFFu - (idxIn ? idxIn[i] : (uint32_t) (base + i));
                 in = ((k & mk) == pk) && ((ni & mi) == pi);
                 digit = onKey ? (unsigned int) ((k >> shift) & 0xFFu) : ((ni >> shift) & 0xFFu);
             }
@@ -419,10 +430,11 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
         const int64_t i = base + tid;
         if (i < n) {
             const uint64_t k = keys[i];
-            const uint32_t ni = 0xFFFFFFFFu - (uint32_t) i;
+            const uint32_t oi = idxIn ? idxIn[i] : (uint32_t) (base + i);
+            const uint32_t ni = 0xFFFFFFFFu - oi;
             if (k < tk || (k == tk && ni <= ti)) {
                 const unsigned int slot = atomicAdd(&cnt, 1u);
-                if (slot < SEL_MAXK) { sk[slot] = k; sv[slot] = (uint32_t) i; }
+                if (slot < SEL_MAXK) { sk[slot] = k; sv[slot] = oi; }
             }
         }
     }
@@ -446,11 +458,23 @@ k_topk_select(const uint64_t *__restrict__ keys, int64_t n, int K, const P *__re
         }
     }
     __syncthreads();
+    if (candK != nullptr) {                              // stage 1: this chunk's candidates
+        for (int t = tid; t < K; t += SEL_T) {
+            candK[(size_t) blockIdx.x * K + t] = t < have ? sk[t] : ~0ull;
+            candI[(size_t) blockIdx.x * K + t] = t < have ? sv[t] : 0xFFFFFFFFu;
+        }
+        return;
+    }
     for (int t = tid; t < K && t < have; t += SEL_T) {
         const uint32_t j = sv[t];
-        out[t].j = j; out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j];
+        out[t].j = j;
+        if (j != 0xFFFFFFFFu) { out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j]; }      // (padding of a short chunk: never a real node)
     }
 }
+
+// the K best of n keys in psort order: one CTA for short arrays, chunked over CTAs + a merge stage for long ones
+template<typename P, int KEYBYTES>
+static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out);
 
 // ---- top-hits refresh on the device: vft_tophits_merge -------------------------------------------------
 // One CTA per list.  psort order (key ascending, ties in reverse input order) = ascending order of the
@@ -662,7 +686,13 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
 #pragma unroll
             for (int k = 0; k < A; k++) ov[pos * A + k] = 0;
         }
-        termW[pos] = tw; termT[pos] = tt;
+        if (jd == nullptr) { termW[pos] = tw; termT[pos] = tt; }
+    }
+    if (jd != nullptr) {
+        // device-resident loop: profileDist(new, new) is evaluated with the join's request list (k_nj_eval), in parallel with
+        // the other distances of the new node, instead of as a second chain behind this kernel
+        if (blockIdx.x == 0 && threadIdx.x == 0) { s.diameter[oid] = diameterOut; s.active[id1] = 0; s.active[id2] = 0; s.active[oid] = 1; }
+        return;
     }
     // the last CTA to finish adds the self-distance terms in position order
     double *sT = reinterpret_cast<double *>(smem);               // [2*Lp] both term arrays
@@ -982,6 +1012,7 @@ struct vft_ctx {
     void *codes, *weights, *vecs, *ow, *ov, *ocd, *diameter, *selfdist, *selfweight, *outDist, *active, *tables;
     void *d_dist, *d_weight, *d_crit;          // [M] one-vs-all scratch
     uint64_t *d_keys;                          // [M]
+    uint64_t *d_candK = nullptr; uint32_t *d_candI = nullptr;   // [SEL_CTAS * SEL_MAXK] candidates of the chunked top-K select
     int64_t *d_ids, *d_pi, *d_pj;              // staging for lists
     void *d_out1, *d_out2;
     int64_t listCap;
@@ -1162,6 +1193,7 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     CK(mem_alloc((void **) &c->tables, 840 * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_dist, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_weight, M * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_crit, M * ps, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_keys, M * 8, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_candK, (size_t) SEL_CTAS * SEL_MAXK * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_candI, (size_t) SEL_CTAS * SEL_MAXK * 4, MEM_DEVICE));
     CK(cudaMemsetAsync(c->codes, VFT_NOCODE, (M + S) * Lp, c->stream));
     CK(cudaMemsetAsync(c->weights, 0, (N + S) * Lp * ps, c->stream));
     CK(cudaMemsetAsync(c->ow, 0, Lp * ps, c->stream));
@@ -1216,7 +1248,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
     mem_free(c->h_in); mem_free(c->h_out);
-    mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms);
+    mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms); mem_free(c->d_candK); mem_free(c->d_candI);
     for (void *q : {c->ow2, c->ov2, c->ocd2, c->d_specR0, c->d_specR1, c->d_specSelf, c->h_specIn, c->h_specOut}) mem_free(q);
     if (c->specDone) cudaEventDestroy(c->specDone);
     mem_free((void *) c->h_flag);
@@ -1563,6 +1595,22 @@ extern "C" int vft_spec_join_discard(vft_ctx *c) {
     return VFT_OK;
 }
 
+template<typename P, int KEYBYTES>
+static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out) {
+    const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12;
+    const int nCta = (int) std::min<int64_t>(SEL_CTAS, n / 8192);
+    if (nCta < 2 || (int64_t) nCta * K > n) {
+        k_topk_select<P, KEYBYTES><<<1, SEL_T, selSmem, c->stream>>>(keys, n, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, out);
+        c->cnt.launches++;
+        return;
+    }
+    k_topk_select<P, KEYBYTES><<<nCta, SEL_T, selSmem, c->stream>>>(keys, n, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, (Rec<P> *) nullptr,
+                                                                    (const uint32_t *) nullptr, c->d_candK, c->d_candI);
+    k_topk_select<P, KEYBYTES><<<1, SEL_T, selSmem, c->stream>>>(c->d_candK, (int64_t) nCta * K, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, out,
+                                                                 c->d_candI);
+    c->cnt.launches += 2;
+}
+
 extern "C" int vft_out_distance_batch(vft_ctx *c, const int64_t *ids, int64_t n, int64_t nActive, double totdiam,
                                       void *outDist) {
     return vft_eval_batch(c, ids, n, nActive, totdiam, outDist, nullptr, nullptr, 0, 0, nullptr, nullptr);
@@ -1633,13 +1681,11 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     const size_t recSz = c->ps == 4 ? sizeof(Rec<float>) : sizeof(Rec<double>);
     int rc = ensure_pinned(c, (size_t) std::max<int64_t>(nRet, 1) * recSz); if (rc) return rc;
     if (nRet > 0) {
-        const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12;
         prof_begin(c, CLS_SELECT, K_SELECT);
-        if (c->ps == 4) k_topk_select<float, 4><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, (Rec<float> *) c->h_out);
-        else k_topk_select<double, 8><<<1, SEL_T, selSmem, c->stream>>>(c->d_keys, n, (int) nRet, (double *) c->d_dist, (double *) c->d_weight, (double *) c->d_crit, (Rec<double> *) c->h_out);
+        if (c->ps == 4) launch_topk<float, 4>(c, c->d_keys, n, (int) nRet, (Rec<float> *) c->h_out);
+        else launch_topk<double, 8>(c, c->d_keys, n, (int) nRet, (Rec<double> *) c->h_out);
         prof_end(c);
         CK(cudaGetLastError());
-        c->cnt.launches++;
         c->cnt.d2hBytes += (int64_t) (nRet * recSz);
     }
     CK(sync_stream(c));
