@@ -25,8 +25,8 @@ driver's reference arm fit its time limit (the reference needs ~21 s per run at 
            fastest of {cores/2, cores} measured ON THE FULL WORKLOAD (the reference gets slower with too many threads).
 
 Multi-GPU (torchrun, one rank per GPU): `--gpus N` builds N trees, one per rank (seed = 1 + rank): REPLICAS, weak scaling, no
-data-path collective; NCCL is used for the barrier and the max-over-ranks reduction only.  The reference arm at N > 1 builds
-N trees too (N concurrent processes sharing the host cores), so that both arms do the same work.
+data-path collective; NCCL is used for the barrier and the max-over-ranks reduction only.  The reference arm times one tree
+per step at every N: the host's cores are the same, so its aggregate taxa/s for N queued trees is that of one.
 """
 from __future__ import annotations
 
@@ -205,28 +205,16 @@ def main():
         if not os.path.exists(REF_BIN):
             emit({"impl": "reference", "unavailable": "oracle/_ref/VeryFastTree was not built (no /root/reference at build time)"})
             return 0
-        n_rep = max(1, args.gpus)
-        workloads = [make_workload(wl, 1 + r, n_taxa) for r in range(n_rep)]
+        # The host has the same cores whatever --gpus is, and N trees built one after the other at all cores give the same
+        # aggregate taxa/s as one: the reference arm therefore times ONE tree per step at every N (N concurrent reference
+        # processes would only split the same cores, and 25 rounds of them would not fit the driver's time limit).
+        n_rep = 1
+        workloads = [make_workload(wl, 1, n_taxa)]
         threads, seen = calibrate_threads(wl, workloads[0], host_cores)
-        per_proc = max(1, threads // n_rep)
+        per_proc = threads
         times, taxa = [], 0
-
-        def one_round():
-            """n_rep trees at once (one process each, the host cores shared), as the repo arm's replicas: seconds = the slowest"""
-            res = [None] * n_rep
-
-            def work(r):
-                res[r] = run_reference(wl, workloads[r], per_proc)
-            ths = [threading.Thread(target=work, args=(r,)) for r in range(n_rep)]
-            for th in ths:
-                th.start()
-            for th in ths:
-                th.join()
-            if any(x is None or x[0] is None for x in res):
-                return None, 0
-            return max(x[0] for x in res), sum(x[1] for x in res)
         for it in range(args.warmup + args.steps):
-            t, nu = one_round()
+            t, nu = run_reference(wl, workloads[0], per_proc)
             if t is None:
                 emit({"impl": "reference", "unavailable": "reference binary failed to run"})
                 return 0
@@ -240,14 +228,14 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "taxa_per_gpu": int(taxa // n_rep), "columns": wl["pos"],
-                           "parallelism": "replicas x%d" % n_rep,
+                           "parallelism": "one tree per step at all host cores: the CPU's aggregate taxa/s does not depend on how many trees are queued (the repo arm at --gpus N builds N trees, one per GPU)",
                            "reference_flags": "%s -threads %d -noml -nni 0 -spr 0 -nosupport%s" % (
                                flags, per_proc, " (nt fp32: the reference silently runs its SSE3 path)" if wl["kind"] == "nt" else ""),
                            "reference_build": "oracle/_ref: the unmodified sources, g++ -O3 -mavx2 (no FMA; the parity oracle)",
                            "thread_calibration_s": {str(k): round(v, 2) for k, v in seen.items()}, "host_cores": host_cores},
                 "cpu_baseline": {"value": value, "unit": "taxa/s", "cores": per_proc * n_rep, "kind": "reference",
-                                 "sample": "the full workload, %d timed runs of the unmodified reference binary (%d tree%s at a time); threads = the faster "
-                                           "of cores/2 and cores on the full workload" % (len(times), n_rep, "s" if n_rep > 1 else "")},
+                                 "sample": "the full workload, %d timed runs of the unmodified reference binary; threads = the faster of cores/2 and cores, "
+                                           "measured on the full workload" % len(times)},
                 "e2e": {"value": value, "unit": "taxa/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)

@@ -22,6 +22,13 @@
  *   - all calls on one context are serialised by the caller (the batch *replaces* the
  *     reference's `omp for`); the library runs them on one CUDA stream per context.
  *
+ * Limits (checked, never silently exceeded: VFT_EINVAL with a message from vft_last_error)
+ *   - nPos <= 12 800 columns        (shared-memory term buffer of the averageProfile kernel; checked in vft_ctx_create)
+ *   - nSeqs < 2^30; K <= 4096 best hits per one-vs-all; merged candidate lists <= 4096 entries: with the reference's
+ *     m = sqrt(N) top hits (K = 2m, lists <= 3m) that is N <~ 1.8 million taxa
+ *   - vft_sh_support_batch: nPos <= 8 500 (the quartet's 3 x nPos site table in shared memory)
+ *   - NJ driver: no topological constraints, no -slow, no 2nd-level top hits (-fastest)
+ *
  * Arithmetic contract: results are bit-identical to the reference's "-mavx2" (no FMA)
  * build run with `-threads 1` -- same expression types (P vs double), same evaluation order,
  * same lane order in the P-typed dot products (AVX256Operations.tcc:5-26,58-138).

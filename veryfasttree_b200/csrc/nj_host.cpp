@@ -343,12 +343,18 @@ private:
         return r;
     }
 
-    DW pairDistNoCache(int64_t i, int64_t j) {       // callable from host threads: no shared counters
-        DW r;
+    // callable from host threads: no shared counters.  An exception must not leave an OpenMP region, so a failure is
+    // recorded and thrown by the caller after the region (threadError)
+    int threadError = VFT_OK;
+    DW pairDistNoCache(int64_t i, int64_t j) {
+        DW r{0, 0};
         int rc;
 #pragma omp critical(vft_device_call)
         rc = vft_dist_pairs(ctx, &i, &j, 1, VFT_PAIRS_JOIN, &r.dist, &r.weight);
-        if (rc != VFT_OK) throw DeviceError{rc};
+        if (rc != VFT_OK) {
+#pragma omp atomic write
+            threadError = rc;
+        }
         return r;
     }
 
@@ -1161,6 +1167,7 @@ void NJ<P>::refreshLists(int64_t newnode, int64_t nActive) {
         sortSaveBestHits(wk.iNode, wk.unique, (int64_t) wk.unique.size(), m, true);   // :4512
         visible[wk.iNode] = topHitsLists[wk.iNode].hits[0];
     }
+    if (threadError != VFT_OK) throw DeviceError{threadError};
     res->nPairPrefetchHit += hits;
     clearPairs();
     resetTopVisible(nActive);                                            // :4517

@@ -707,10 +707,14 @@ static int loop_refresh(vftx_loop *lp, bool *done) {
     LoopArrays &d = lp->d;
 #define LOOP_REFRESH(P, A_, MX) do { \
         prof_begin(c, CLS_DIST, K_OUT_DIST_ALL); \
-        k_out_distance_all<P, A_, MX><<<(unsigned) ((warpsAll + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gall), c->stream>>>(make_store<P>(c), n, Gall, nActive, sc.totdiam); prof_end(c); \
+        if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), n, std::min(Gall, STG_G), nActive, sc.totdiam); \
+        else k_out_distance_all<P, A_, MX><<<(unsigned) ((warpsAll + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gall), c->stream>>>(make_store<P>(c), n, Gall, nActive, sc.totdiam); \
+        prof_end(c); \
         k_nj_commit_all<P><<<nb, 256, 0, c->stream>>>(make_store<P>(c), loop_state<P>(lp)); \
         prof_begin(c, CLS_DIST, K_ONE_VS_ALL); \
-        k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsAll + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gall), c->stream>>>(make_store<P>(c), newnode, nActive, n, 0, n, Gall, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys); prof_end(c); \
+        if (c->stagedOk) k_one_vs_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), newnode, nActive, n, 0, n, std::min(Gall, STG_G), (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, c->d_keys); \
+        else k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsAll + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gall), c->stream>>>(make_store<P>(c), newnode, nActive, n, 0, n, Gall, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys); \
+        prof_end(c); \
         prof_begin(c, CLS_SELECT, K_SELECT); launch_topk<P, (int) sizeof(P)>(c, c->d_keys, n, (int) (2 * m), (Rec<P> *) d.rec); prof_end(c); \
         prof_begin(c, CLS_SELECT, K_MERGE); \
         k_nj_refresh_self<P><<<1, 1024, (size_t) 2 * m * 4, c->stream>>>(loop_state<P>(lp), (const Rec<P> *) d.rec, (int32_t *) d.mNode, (int32_t *) d.mOff, (int32_t *) d.allJ, (P *) d.allDist); \

@@ -25,6 +25,7 @@
 // There is no CPU fallback: without a usable device vft_ctx_create returns VFT_ENODEVICE.
 #include "../../include/vft_b200.h"
 #include "vft_device.cuh"
+#include "vft_bulk.cuh"
 #include "vft_ml.cuh"
 #include "nj_loop.h"
 #include "nj_loop_logic.h"
@@ -292,6 +293,84 @@ k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, i
     keys[j] = order_key(c);
 }
 
+// The two all-candidate sweeps with the shared profile staged in shared memory by TMA bulk copies (vft_bulk.cuh): 512-thread
+// CTAs (16 warps x up to 16 pairs each), one CTA per SM next to ~110 KB of staged rows.  Same arithmetic, same results.
+constexpr int STG_T = 512, STG_G = 12;
+template<typename P, int A, bool MATRIX>
+__host__ __device__ inline size_t staged_tile_bytes() { return (size_t) (STG_T / 32) * group_smem_bytes<P, A, MATRIX>(STG_G); }
+
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(STG_T, 1)
+k_out_distance_all_staged(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ __align__(8) uint64_t bar;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    unsigned char *stage = smemRaw + staged_tile_bytes<P, A, MATRIX>();
+    const uint32_t ocdBytes = (uint32_t) (s.Lp * A * sizeof(P)), owBytes = (uint32_t) (s.Lp * sizeof(P));
+    const BulkSrc src[3] = {{s.ocd, ocdBytes}, {s.ow, owBytes}, {nullptr, 0}};
+    cta_bulk_stage(stage, src, &bar);
+    Store<P> s2 = s;
+    s2.ocd = reinterpret_cast<P *>(stage); s2.ow = reinterpret_cast<P *>(stage + ocdBytes);
+    unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(STG_G);
+    const int64_t totalWarps = (int64_t) gridDim.x * (STG_T / 32);
+    for (int64_t warp = (blockIdx.x * (int64_t) STG_T + threadIdx.x) >> 5; warp * G < maxnode; warp += totalWarps) {
+        const int64_t j = warp * G + lane;
+        const bool act = lane < G && j < maxnode && s.active[j];
+        const unsigned mask = __ballot_sync(full, act);
+        double den, top;
+        group_profile_dist<P, A, MATRIX>(s2, j, (int64_t) -1, mask, G, smw, den, top);
+        if (act) {
+            P dd, ww;
+            finish_dist<P>(den, top, dd, ww);
+            s.outDist[j] = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
+        }
+        __syncwarp();
+    }
+}
+
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(STG_T, 1)
+k_one_vs_all_staged(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd, int G,
+                    P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ __align__(8) uint64_t bar;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    unsigned char *stage = smemRaw + staged_tile_bytes<P, A, MATRIX>();
+    // the query is an internal node: codes, weights, vectors (the vectors first: 16-byte alignment of every region)
+    const int64_t row = query - s.nSeqs;
+    const uint32_t vBytes = (uint32_t) (s.Lp * A * sizeof(P)), wBytes = (uint32_t) (s.Lp * sizeof(P)), cBytes = (uint32_t) s.Lp;
+    const BulkSrc src[3] = {{s.vecs + row * s.Lp * A, vBytes}, {s.weights + row * s.Lp, wBytes}, {s.codes + query * s.Lp, cBytes}};
+    cta_bulk_stage(stage, src, &bar);
+    Store<P> s2 = s;
+    s2.ovId = (int32_t) query; s2.ovV = reinterpret_cast<const P *>(stage); s2.ovW = reinterpret_cast<const P *>(stage + vBytes);
+    s2.ovCodes = stage + vBytes + wBytes;
+    unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(STG_G);
+    const double outI = (double) s.outDist[query];
+    const int64_t totalWarps = (int64_t) gridDim.x * (STG_T / 32);
+    for (int64_t warp = (blockIdx.x * (int64_t) STG_T + threadIdx.x) >> 5; warp * G < maxnode; warp += totalWarps) {
+        const int64_t j = warp * G + lane;
+        const bool valid = lane < G && j < maxnode;
+        const bool act = valid && s.active[j] && j >= jBegin && j < jEnd;
+        const unsigned mask = __ballot_sync(full, act);
+        double den, top;
+        group_profile_dist<P, A, MATRIX>(s2, query, j, mask, G, smw, den, top);
+        if (valid) {
+            if (!act) keys[j] = ~0ull;
+            else {
+                P d, w;
+                finish_dist<P>(den, top, d, w);
+                d = join_correct<P>(s, query, j, d);
+                const P c = (P) xsub((double) d, xadd(outI, (double) s.outDist[j]) / (double) (nActive - 2));
+                dist[j] = d; weight[j] = w; crit[j] = c;
+                keys[j] = order_key(c);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128, sizeof(P) == 4 ? 4 : 2)
@@ -343,10 +422,10 @@ k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P
     // same selection over the candidates (idxIn = their original indices).  The K best overall are among the per-chunk K
     // best, and the composite (key, index) order is the same at both stages.
     const int64_t chunk = (nAll + gridDim.x - 1) / gridDim.x;
-    const int64_t base = (int64_t) blockIdx.x * chunk;
-    const int64_t n = base >= nAll ? 0 : (nAll - base < chunk ? nAll - base : chunk);
-    const uint64_t *__restrict__ keys = keysAll + base;
-    if (idxIn != nullptr) idxIn += base;
+    const int64_t chunkBase = (int64_t) blockIdx.x * chunk;
+    const int64_t n = chunkBase >= nAll ? 0 : (nAll - chunkBase < chunk ? nAll - chunkBase : chunk);
+    const uint64_t *__restrict__ keys = keysAll + chunkBase;
+    if (idxIn != nullptr) idxIn += chunkBase;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned int *hist = reinterpret_cast<unsigned int *>(smem);                    // [32 warps][256]
     uint64_t *sk = reinterpret_cast<uint64_t *>(smem + 32 * 256 * 4);              // [SEL_MAXK] sort keys
@@ -371,7 +450,7 @@ k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P
             unsigned int digit = 0;
             if (i < n) {
                 const uint64_t k = keys[i];
-                const uint32_t ni = 0xFFFFFFFFu - (idxIn ? idxIn[i] : (uint32_t) (base + i));
+                const uint32_t ni = 0xFFFFFFFFu - (idxIn ? idxIn[i] : (uint32_t) (chunkBase + i));
                 in = ((k & mk) == pk) && ((ni & mi) == pi);
                 digit = onKey ? (unsigned int) ((k >> shift) & 0xFFu) : ((ni >> shift) & 0xFFu);
             }
@@ -430,7 +509,7 @@ k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P
         const int64_t i = base + tid;
         if (i < n) {
             const uint64_t k = keys[i];
-            const uint32_t oi = idxIn ? idxIn[i] : (uint32_t) (base + i);
+            const uint32_t oi = idxIn ? idxIn[i] : (uint32_t) (chunkBase + i);
             const uint32_t ni = 0xFFFFFFFFu - oi;
             if (k < tk || (k == tk && ni <= ti)) {
                 const unsigned int slot = atomicAdd(&cnt, 1u);
@@ -1007,7 +1086,7 @@ struct vft_ctx {
     int64_t N, M, L, Lp, maxnode;
     int64_t S = 0;                 // scratch profile rows (cfg.nScratch): ids M .. M+S-1, likelihood entry points only
     size_t ps;
-    cudaStream_t stream;
+    cudaStream_t stream = nullptr;
     // device
     void *codes, *weights, *vecs, *ow, *ov, *ocd, *diameter, *selfdist, *selfweight, *outDist, *active, *tables;
     void *d_dist, *d_weight, *d_crit;          // [M] one-vs-all scratch
@@ -1020,6 +1099,8 @@ struct vft_ctx {
     double *d_terms;                           // [2*Lp] self-distance terms of k_average
     void *d_mrg; size_t mrgCap;
     bool wideOk;
+    bool stagedOk = false;                     // the TMA-staged sweep kernels apply (fp32, 20 states, matrix mode, rows fit shared memory)
+    size_t stagedSmem = 0;
     unsigned long long *d_acct;
     // pinned host
     void *h_in, *h_out;
@@ -1042,7 +1123,7 @@ struct vft_ctx {
     int64_t specOut = -1, specId1 = -1, specId2 = -1, specNPairs = 0, specNOut = 0, specBytes = 0;
     vft_counters cnt;
     // stopwatch + optional per-kernel-class event timing (cfg.reserved & VFT_CFG_PROFILE)
-    cudaEvent_t tmr0, tmr1;
+    cudaEvent_t tmr0 = nullptr, tmr1 = nullptr;
     bool profile;
     struct Pending { cudaEvent_t a, b; int cls, kid; };
     std::vector<Pending> pending;
@@ -1120,6 +1201,7 @@ static Store<P> make_store(vft_ctx *c) {
     s.distances = t; s.eigenval = t + 400; s.eigentot = t + 420; s.codeFreq = t + 440;
     s.nSeqs = c->N; s.L = c->L; s.Lp = c->Lp; s.reduction = c->cfg.reduction;
     s.fPostTotalTolerance = c->cfg.fPostTotalTolerance;
+    s.ovId = -2; s.ovCodes = nullptr; s.ovW = nullptr; s.ovV = nullptr;
     return s;
 }
 
@@ -1142,6 +1224,7 @@ static int ensure_lists(vft_ctx *c, int64_t n) {
     if (n <= c->listCap) return VFT_OK;
     int64_t cap = std::max<int64_t>(n, 2 * c->listCap);
     mem_free(c->d_ids); mem_free(c->d_pi); mem_free(c->d_pj); mem_free(c->d_out1); mem_free(c->d_out2);
+    c->d_ids = c->d_pi = c->d_pj = nullptr; c->d_out1 = c->d_out2 = nullptr; c->listCap = 0;      // nothing dangling if an allocation below fails
     CK(mem_alloc((void **) &c->d_ids, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_pi, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_pj, cap * 8, MEM_DEVICE));
     CK(mem_alloc((void **) &c->d_out1, cap * 8, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_out2, cap * 8, MEM_DEVICE));
     c->listCap = cap;
@@ -1158,12 +1241,15 @@ static int ensure_pinned(vft_ctx *c, size_t bytes) {
     return VFT_OK;
 }
 
-extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
+static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **partial) {
     if (!cfg || !out) return fail(VFT_EINVAL, "null argument");
     if (cfg->nSeqs < 1 || cfg->nPos < 1) return fail(VFT_EINVAL, "nSeqs and nPos must be positive");
     if (cfg->nCodes != 4 && cfg->nCodes != 20) return fail(VFT_EINVAL, "nCodes must be 4 or 20");
     if (cfg->precision != 32 && cfg->precision != 64) return fail(VFT_EINVAL, "precision must be 32 or 64");
     if (2 * cfg->nSeqs >= 0xFFFF0000ll) return fail(VFT_EINVAL, "too many sequences for 32-bit sort indices");
+    if (cfg->nScratch < 0 || 2 * cfg->nSeqs + cfg->nScratch >= 0x7FFF0000ll) return fail(VFT_EINVAL, "bad nScratch");
+    // documented limits of the kernels' shared-memory buffers (include/vft_b200.h), checked before anything is allocated
+    if (((cfg->nPos + 31) / 32 * 32) * 16 > 200 * 1024) return fail(VFT_EINVAL, "alignments longer than 12 800 columns are not supported (term buffer of the average kernel)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1) {
@@ -1174,13 +1260,13 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(VFT_EINVAL, "bad device ordinal");
     CK(cudaSetDevice(cfg->device));
     vft_ctx *c = new vft_ctx();      // value-initialised: every pointer starts out null
+    *partial = c;                    // released by the caller if anything below fails
     c->cfg = *cfg; c->A = cfg->nCodes; c->N = cfg->nSeqs; c->M = 2 * cfg->nSeqs; c->L = cfg->nPos;
     c->Lp = (cfg->nPos + 31) / 32 * 32; c->ps = cfg->precision / 8; c->maxnode = 0;
     std::memset(&c->cnt, 0, sizeof c->cnt);
     c->profile = (cfg->reserved & VFT_CFG_PROFILE) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->tmr0)); CK(cudaEventCreate(&c->tmr1));
-    if (cfg->nScratch < 0 || 2 * cfg->nSeqs + cfg->nScratch >= 0x7FFF0000ll) return fail(VFT_EINVAL, "bad nScratch");
     c->S = cfg->nScratch;
     const size_t ps = c->ps, Lp = (size_t) c->Lp, A = (size_t) c->A, N = (size_t) c->N, M = (size_t) c->M, S = (size_t) c->S;
     // the scratch rows (ids M .. M+S-1) extend the three profile arrays; the per-node NJ arrays stay [M]
@@ -1232,6 +1318,14 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
 #define SET_SMEM_WIDE(P, A_, MX) do { const size_t w = wide_smem_bytes<P, A_, MX>(c->Lp); c->wideOk = w <= 200 * 1024; \
         if (c->wideOk && w > 48 * 1024) cudaFuncSetAttribute(k_eval_wide<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) w); } while (0)
         VFT_DISPATCH(c, SET_SMEM_WIDE);
+        // TMA-staged sweeps: tiles of 16 warps + the staged rows (vectors + weights + codes of one node, or codeDist + weights)
+        const size_t rows = (size_t) c->Lp * (20 * 4 + 4 + 1) + 64;
+        c->stagedSmem = staged_tile_bytes<float, 20, true>() + ((rows + 15) & ~(size_t) 15);
+        c->stagedOk = c->ps == 4 && c->A == 20 && c->cfg.useMatrix && c->stagedSmem <= 225 * 1024 && std::getenv("VFT_STAGING") != nullptr && std::getenv("VFT_STAGING")[0] == '1';      // opt-in: measured 15 % SLOWER than the plain sweeps
+        if (c->stagedOk) {
+            cudaFuncSetAttribute(k_out_distance_all_staged<float, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->stagedSmem);
+            cudaFuncSetAttribute(k_one_vs_all_staged<float, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->stagedSmem);
+        }
     }
     cudaFuncSetAttribute(k_topk_select<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     cudaFuncSetAttribute(k_topk_select<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
@@ -1240,10 +1334,24 @@ extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
     return VFT_OK;
 }
 
+extern "C" int vft_ctx_destroy(vft_ctx *c);
+extern "C" int vft_ctx_create(const vft_config *cfg, vft_ctx **out) {
+    vft_ctx *partial = nullptr;
+    const int rc = ctx_create_impl(cfg, out, &partial);
+    if (rc != VFT_OK && partial != nullptr) {        // a failed allocation / CUDA call half way: give everything back
+        char keep[sizeof g_err];
+        std::memcpy(keep, g_err, sizeof keep);
+        vft_ctx_destroy(partial);
+        std::memcpy(g_err, keep, sizeof keep);
+        if (out) *out = nullptr;
+    }
+    return rc;
+}
+
 extern "C" int vft_ctx_destroy(vft_ctx *c) {
     if (!c) return VFT_OK;
     bind_device(c);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
@@ -1254,8 +1362,9 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     mem_free((void *) c->h_flag);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
-    cudaEventDestroy(c->tmr0); cudaEventDestroy(c->tmr1);
-    cudaStreamDestroy(c->stream);
+    if (c->tmr0) cudaEventDestroy(c->tmr0);
+    if (c->tmr1) cudaEventDestroy(c->tmr1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return VFT_OK;
 }
@@ -1631,7 +1740,8 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     const int64_t warps = (n + G - 1) / G;
 #define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam)
     prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
-    VFT_DISPATCH(c, CALL_ODA);
+    if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), n, std::min(G, STG_G), nActive, totdiam);
+    else { VFT_DISPATCH(c, CALL_ODA); }
     prof_end(c);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_out, c->outDist, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));   // one DMA instead of a PCIe write per lane
@@ -1668,7 +1778,9 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
 #define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
     prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
-    if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); } else { VFT_DISPATCH(c, CALL_OVA_WARP); }
+    if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); }
+    else if (c->stagedOk) k_one_vs_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), query, nActive, n, jBegin, jEnd, std::min(Gq, STG_G), (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, c->d_keys);
+    else { VFT_DISPATCH(c, CALL_OVA_WARP); }
     prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;

@@ -46,6 +46,9 @@ struct Store {
     int64_t nSeqs, L, Lp;
     int reduction;         // VFT_REDUCE_*
     double fPostTotalTolerance;
+    // rows of ONE node staged in shared memory by the CTA (vft_bulk.cuh): the node every pair of the sweep shares
+    int32_t ovId;          // -2: none
+    const uint8_t *ovCodes; const P *ovW, *ovV;
 };
 
 // ---- lane-ordered reductions: BasicOperations.tcc:17-41, AVX256Operations.tcc:5-26,58-138 -------
@@ -436,6 +439,7 @@ __device__ __forceinline__ void group_profile_dist(const Store<P> &s, int64_t my
     auto side = [&](int id) {
         Side r;
         if (id < 0) { r.codes = nullptr; r.w = s.ow; r.v = s.ov; }
+        else if (id == s.ovId) { r.codes = s.ovCodes; r.w = s.ovW; r.v = s.ovV; }
         else {
             r.codes = s.codes + (uint64_t) (uint32_t) id * Lp;
             if ((uint32_t) id < nSeqs) { r.w = nullptr; r.v = nullptr; }
