@@ -23,7 +23,8 @@
  *     reference's `omp for`); the library runs them on one CUDA stream per context.
  *
  * Limits (checked, never silently exceeded: VFT_EINVAL with a message from vft_last_error)
- *   - nPos <= 12 800 columns        (shared-memory term buffer of the averageProfile kernel; checked in vft_ctx_create)
+ *   - NJ phase: nPos <= 12 800 columns (shared-memory term buffer of the averageProfile kernel; checked by vft_nj_build
+ *     up front, by vft_profile_average otherwise)
  *   - nSeqs < 2^30; K <= 4096 best hits per one-vs-all; merged candidate lists <= 4096 entries: with the reference's
  *     m = sqrt(N) top hits (K = 2m, lists <= 3m) that is N <~ 1.8 million taxa
  *   - vft_sh_support_batch: nPos <= 8 500 (the quartet's 3 x nPos site table in shared memory)

@@ -27,6 +27,7 @@ struct CpuEnv {
     int atomicExchI(int32_t *p, int v) { const int o = *p; *p = v; return o; }
     void atomicAddL(int64_t *p, int64_t v) { *p += v; }
     bool syncOr(int pred) { return pred != 0; }
+    int64_t clock() const { return 0; }
     int32_t blockMin(uint64_t *, int32_t *, uint64_t k, int32_t idx, uint64_t *keyOut) { if (keyOut) *keyOut = k; return idx; }
     int32_t blockSum(int32_t *, int32_t v) { return v; }
     void evalOut(const int32_t *ids, int n, int32_t nActive) {

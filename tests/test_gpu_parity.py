@@ -259,3 +259,42 @@ def test_second_device_and_host_threads(glib):
     want = open(os.path.join(replay.GOLDEN, "nt1000_f32.nj.tree")).read().strip()
     tree = api.nj_build(api.encode(chars, kind), 4, 32, lib=glib, device=1, host_threads=8)
     assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+
+
+# ---- the device-resident join loop (vft_nj_options.deviceLoop = 1: k_nj_step / k_nj_eval / the device-side rebuild and refresh) ----
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60", "c1", "aa300", "nt1000"])
+def test_device_resident_loop_gives_the_reference_tree(glib, name, prec):
+    chars, kind = replay.golden_case(name)
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
+    tree = api.nj_build(api.encode(chars, kind), 4 if kind == "nt" else 20, prec, lib=glib, tables=tables_for(kind, prec), device_loop=1)
+    assert tree.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+    assert tree.stats["counters"]["nKernel"] is not None and tree.stats["nDeviceCalls"] < chars.shape[0]      # far fewer host interventions than joins
+
+
+@pytest.mark.parametrize("kind,n,L", [("nt", 16000, 200), ("aa", 6000, 1287)])
+def test_device_resident_loop_identical_to_host_driven_loop_at_size(glib, kind, n, L):
+    """Join order, tree and branch lengths of the device-resident loop == the host-driven loop (itself pinned to the reference at
+    these shapes by tests/test_gpu_at_size.py), incl. the device-side top-visible rebuilds and refreshes (hundreds per tree)."""
+    chars = synth.make_alignment(n, L, kind, seed=1)
+    chars = chars[synth.unique_rows(chars)]
+    codes = api.encode(chars, kind)
+    A = 4 if kind == "nt" else 20
+    dev = api.nj_build(codes, A, 32, lib=glib, tables=tables_for(kind, 32), device_loop=1)
+    host = api.nj_build(codes, A, 32, lib=glib, tables=tables_for(kind, 32), device_loop=0)
+    assert np.array_equal(dev.joins, host.joins) and np.array_equal(dev.parent, host.parent)
+    assert dev.branchlength.tobytes() == host.branchlength.tobytes()
+    assert dev.stats["nRefreshTopHits"] == host.stats["nRefreshTopHits"] > 100
+
+
+def test_tma_staged_sweeps_bit_identical(glib, olib, monkeypatch):
+    """VFT_STAGING=1: the all-candidate sweeps with the shared profile staged in shared memory by cp.async.bulk (vft_bulk.cuh);
+    every output of the seeded script identical to the CPU restatement."""
+    monkeypatch.setenv("VFT_STAGING", "1")
+    chars = synth.make_alignment(400, 610, "aa", seed=77)
+    chars[::13, ::7] = ord("-")
+    codes = api.encode(chars, "aa")
+    a = run_script(glib, codes, 20, 32, tables_for("aa", 32), 7, 150, 40)
+    b = run_script(olib, codes, 20, 32, tables_for("aa", 32), 7, 150, 40)
+    bad = [ka for (ka, va), (kb, vb) in zip(flatten(a), flatten(b)) if not replay.bits_equal(va, vb)]
+    assert bad == []

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import replay
-from veryfasttree_b200 import api
+from veryfasttree_b200 import api, synth
 
 
 @pytest.fixture(scope="module")
@@ -198,3 +198,37 @@ def test_new_entry_points_validate_their_arguments(olib):
         crit = np.zeros(3); ch = np.zeros(1, dtype=np.int32)
         bad = np.array([0, 1, 2, 10 * N], dtype=np.int64)
         assert d.vft_choose_nni_batch(ctx.h, 1, api._ptr(bad), 0.0, 1, api._ptr(crit), api._ptr(ch)) == -1
+
+
+# ---- the device-resident join loop (csrc/nj_loop_logic.h) through its one-thread CPU double (oracle/nj_loop_cpu.cpp) ----
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", ["nt60", "aa60", "c1", "aa300", "nt1000"])
+def test_device_loop_logic_gives_the_reference_tree(olib, name, prec):
+    """The block-parallel re-expression of topHitNJSearch / topHitJoin / updateVisible ... over flat device state, run with
+    one thread: the reference's NJ tree byte for byte, and joins, branch lengths and decision counters identical to the
+    host-driven loop."""
+    chars, kind = replay.golden_case(name)
+    want = open(os.path.join(replay.GOLDEN, "%s_f%d.nj.tree" % (name, prec))).read().strip()
+    A = 4 if kind == "nt" else 20
+    tables = None
+    if kind == "aa":
+        z = np.load(os.path.join(replay.GOLDEN, "blosum45_f%d.npz" % prec))
+        tables = [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
+    codes = api.encode(chars, kind)
+    dev = api.nj_build(codes, A, prec, lib=olib, tables=tables, device_loop=1)
+    host = api.nj_build(codes, A, prec, lib=olib, tables=tables, device_loop=0)
+    assert dev.newick(["t%d" % i for i in range(chars.shape[0])]) == want
+    assert np.array_equal(dev.joins, host.joins) and np.array_equal(dev.parent, host.parent)
+    assert dev.branchlength.tobytes() == host.branchlength.tobytes()
+    for k in ("nRefreshTopHits", "nVisibleUpdate", "nHillBetter"):
+        assert dev.stats[k] == host.stats[k], k
+
+
+def test_device_loop_logic_on_a_larger_tree(olib):
+    chars = synth.make_alignment(2500, 120, "nt", seed=9)
+    chars = chars[synth.unique_rows(chars)]
+    codes = api.encode(chars, "nt")
+    dev = api.nj_build(codes, 4, 32, lib=olib, device_loop=1)
+    host = api.nj_build(codes, 4, 32, lib=olib, device_loop=0)
+    assert np.array_equal(dev.joins, host.joins) and dev.branchlength.tobytes() == host.branchlength.tobytes()
+    assert dev.stats["nRefreshTopHits"] == host.stats["nRefreshTopHits"] > 50

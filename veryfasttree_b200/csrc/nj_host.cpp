@@ -20,6 +20,7 @@
 // hits, topological constraints, -slow.  -bionj is supported (BIONJ weights, NJ.tcc:2921-2966).
 #include "../../include/vft_b200.h"
 #include "nj_loop.h"
+extern "C" void vftx_set_error(const char *msg);      // the library's vft_last_error text (vft_cuda.cu / oracle)
 
 #include <algorithm>
 #include <omp.h>
@@ -1682,11 +1683,18 @@ extern "C" void vft_nj_default_options(vft_nj_options *o) {
 
 extern "C" int vft_nj_build(const vft_config *cfg, const vft_nj_options *opt_in, const uint8_t *codes,
                             const void *const tables[4], vft_nj_result *res) {
-    if (!cfg || !codes || !res || !res->parent || !res->nChild || !res->child || !res->branchlength) return VFT_EINVAL;
-    if (cfg->nSeqs >= (int64_t) 1 << 30) return VFT_EINVAL;
+    auto bad = [](const char *msg) { vftx_set_error(msg); return VFT_EINVAL; };
+    if (!cfg || !codes || !res || !res->parent || !res->nChild || !res->child || !res->branchlength) return bad("vft_nj_build: null argument");
+    if (cfg->nSeqs >= (int64_t) 1 << 30) return bad("vft_nj_build: too many sequences");
     vft_nj_options opt;
     if (opt_in) opt = *opt_in; else vft_nj_default_options(&opt);
-    if (cfg->useMatrix && !tables) return VFT_EINVAL;
+    if (cfg->useMatrix && !tables) return bad("vft_nj_build: useMatrix needs the four tables");
+    // limits of the kernels this phase uses (include/vft_b200.h), checked before anything is allocated or computed
+    if (((cfg->nPos + 31) / 32 * 32) * 16 > 200 * 1024) return bad("vft_nj_build: alignments longer than 12 800 columns are not supported (term buffer of the average kernel)");
+    {
+        const double mm = opt.tophitsMult > 0 ? 0.5 + opt.tophitsMult * std::sqrt((double) cfg->nSeqs) : 0;
+        if (3 * mm > 4096) return bad("vft_nj_build: top-hit lists longer than 1 365 entries are not supported (m = tophitsMult * sqrt(nSeqs); ~1.8 million taxa at the default)");
+    }
     // zero the output counters, keep the caller's buffers
     res->root = -1; res->maxnode = 0; res->m = 0;
     res->nSeeds = res->nCloseUsed = res->nRefreshTopHits = res->nVisibleUpdate = res->nHillBetter = 0;

@@ -24,6 +24,7 @@ struct GpuEnv {
     __device__ __forceinline__ int atomicExchI(int32_t *p, int v) { return atomicExch(p, v); }
     __device__ __forceinline__ void atomicAddL(int64_t *p, int64_t v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long) v); }
     __device__ __forceinline__ bool syncOr(int pred) { return __syncthreads_or(pred) != 0; }
+    __device__ __forceinline__ int64_t clock() const { return (int64_t) clock64(); }
     // minimum of (key, idx) over the block, idx < 0 = no candidate: warp shuffles, the warps' results folded by warp 0
     __device__ __forceinline__ int32_t blockMin(uint64_t *redK, int32_t *redI, uint64_t k, int32_t idx, uint64_t *keyOut) {
         const unsigned full = 0xFFFFFFFFu;
@@ -806,6 +807,14 @@ extern "C" int vftx_loop_run(vftx_loop *lp, vftx_loop_status *out) {
         out->nActive = sc.nActive; out->maxnode = sc.maxnode; out->nJoins = sc.nJoins; out->nRefresh = sc.nRefresh;
         out->nVisibleUpdate = sc.nVisibleUpdate; out->nHillBetter = sc.nHillBetter; out->nReset = sc.nReset; out->nInlineOut = sc.nInlineOut;
         out->nInlinePair = sc.nInlinePair; out->nPairHit = sc.nPairHit; out->nRebuild = sc.nRebuild; out->nSteps = lp->nSteps;
+    }
+    if (std::getenv("VFT_LOOP_TIMING") && sc.status != njl::ST_RUNNING) {
+        static const char *nm[12] = {"thjFinish: resolvePairs", "thjFinish: ensureCommit", "thjFinish: crit+sort+save", "updateTopVisible(new)", "updateVisible: flags",
+                                     "updateVisible: replacements", "search: scan", "search: hill-climb (getBest x2)", "(search exit)", "joinBookkeeping", "thjPrepare", "hintSearch"};
+        double tot = 0;
+        for (int k = 0; k < 12; k++) tot += (double) sc.tPhase[k];
+        std::fprintf(stderr, "[k_nj_step phases] joins %lld, cycles per join by phase (tid 0's clock64):\n", (long long) sc.nJoins);
+        for (int k = 0; k < 12; k++) std::fprintf(stderr, "   %-34s %9.0f  %5.1f %%\n", nm[k], (double) sc.tPhase[k] / (double) std::max<int64_t>(1, sc.nJoins), 100.0 * (double) sc.tPhase[k] / std::max(1.0, tot));
     }
     // the loop's own distance work, for the context's counters (Debug.h:12-15)
     c->cnt.seqOps += sc.seqOps - lp->seenSeqOps; c->cnt.profileOps += (sc.profileOps + sc.outprofileOps) - lp->seenProfileOps;

@@ -63,6 +63,7 @@ struct Scalars {
     // counters
     int64_t nJoins, nRefresh, nVisibleUpdate, nHillBetter, nReset, nInlineOut, nInlinePair, nOutHit, nPairHit, nRebuild;
     int64_t seqOps, profileOps, outprofileOps, algoBytes;
+    int64_t tPhase[16], tLast;            // cycles per phase of the step (diagnostic: VFT_LOOP_TIMING)
 };
 
 template<typename P>
@@ -359,6 +360,7 @@ struct Logic {
         }
         ji = st.topvisible[wk]; jj = st.visJ[ji]; jdist = st.visDist[ji];
         P jcrit = crit(ji, jj, jdist, nActive);
+        tmark(6);
         // hill-climbing, NJ.tcc:4222-4263
         bool changed;
         do {
@@ -369,6 +371,7 @@ struct Logic {
             if (b.j != ji && b.crit < jcrit) { changed = true; const int32_t oi = jj; ji = oi; jj = b.j; jdist = b.dist; jcrit = b.crit; }
             if (changed && x.tid() == 0) sc.nHillBetter++;
         } while (changed);
+        tmark(7);
         return true;
     }
 
@@ -607,7 +610,9 @@ struct Logic {
         if (x.tid() == 0) sm.list[nUnique] = newnode;
         x.sync();
         resolvePairs(newnode, nUnique);
+        tmark(0);
         ensureCommit(nUnique + 1, nActive, false);
+        tmark(1);
         for (int u = x.tid(); u < nUnique; u += x.nt()) {
             const P c = crit(newnode, sm.cJ[u], sm.cDist[u], nActive);
             sm.cCrit[u] = c; sm.key[u] = okey(c);
@@ -634,7 +639,9 @@ struct Logic {
             st.visJ[newnode] = sm.cJ[e0]; st.visDist[newnode] = sm.cDist[e0];
         }
         x.sync();
+        tmark(2);
         updateTopVisible(newnode, st.visJ[newnode], st.visDist[newnode], nActive);
+        tmark(3);
         // updateVisible (:4635-4658) over the saved hits, in order.  Which hits replace a visible entry is decided for all of
         // them first (each test reads only its own node's entry), the replacements -- each followed by an updateTopVisible
         // -- are then made one after the other
@@ -665,6 +672,7 @@ struct Logic {
             mineF++;
         }
         const int32_t nFlag = blockSum(mineF);
+        tmark(4);
         for (int q = 0; q < nFlag; q++) {
             const int r = (int) sm.key[q];                        // (updateTopVisible leaves sm.key and sm.perm alone)
             const int f = sm.perm[r];
@@ -674,13 +682,17 @@ struct Logic {
             x.sync();
             updateTopVisible(j, newnode, d, nActive);
         }
+        tmark(5);
         return true;
     }
 
+    NJL_D void tmark(int k) {
+        if (x.tid() == 0) { const int64_t t = x.clock(); sc.tPhase[k] += t - sc.tLast; sc.tLast = t; }
+    }
     // ---- one step of the loop: [finish the pending topHitJoin] -> search -> join -> prepare its topHitJoin ------------
     NJL_DN void step() {
         if (sc.status != ST_RUNNING) return;
-        if (x.tid() == 0) sc.jdSelfPending = 0;                   // (consumed by the evaluation of the previous step's request list)
+        if (x.tid() == 0) { sc.jdSelfPending = 0; sc.tLast = x.clock(); }   // (the self distance was consumed by the evaluation of the previous step's request list)
         if (sc.resume == RS_THJ_FINISH) {
             if (!thjFinish()) {
                 if (x.tid() == 0) { sc.status = ST_NEED_REFRESH; sc.nRefresh++; }
@@ -701,10 +713,14 @@ struct Logic {
             x.sync();
             return;
         }
+        tmark(8);
         joinBookkeeping(ji, jj);
+        tmark(9);
         beginRequests();
         thjPrepare();
+        tmark(10);
         if (sc.nActive > 3) hintSearch();
+        tmark(11);
         if (x.tid() == 0) sc.resume = RS_THJ_FINISH;
         x.sync();
     }

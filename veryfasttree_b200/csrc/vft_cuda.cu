@@ -206,7 +206,7 @@ k_eval(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__res
 // path: with unit weights profileDist's terms ARE seqDist's (NJ.tcc:1601-1624), only the no-overlap
 // weight differs (0 instead of 0.01).
 template<typename P, int A, bool MATRIX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(sizeof(P) == 4 ? 384 : 256)
 k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
             int64_t n, int64_t nOutItems, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
             unsigned int *__restrict__ doneCount, P *__restrict__ hostOut, volatile unsigned int *hostFlag = nullptr, unsigned int flagVal = 0) {
@@ -1218,6 +1218,7 @@ static Store<P> make_store(vft_ctx *c) {
     } while (0)
 
 extern "C" const char *vft_last_error(void) { return g_err; }
+extern "C" void vftx_set_error(const char *msg) { std::snprintf(g_err, sizeof g_err, "%s", msg); }      // for the host drivers above the kernel-level ABI
 extern "C" const char *vft_backend_name(void) { return "cuda-sm100a"; }
 
 static int ensure_lists(vft_ctx *c, int64_t n) {
@@ -1248,8 +1249,6 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
     if (cfg->precision != 32 && cfg->precision != 64) return fail(VFT_EINVAL, "precision must be 32 or 64");
     if (2 * cfg->nSeqs >= 0xFFFF0000ll) return fail(VFT_EINVAL, "too many sequences for 32-bit sort indices");
     if (cfg->nScratch < 0 || 2 * cfg->nSeqs + cfg->nScratch >= 0x7FFF0000ll) return fail(VFT_EINVAL, "bad nScratch");
-    // documented limits of the kernels' shared-memory buffers (include/vft_b200.h), checked before anything is allocated
-    if (((cfg->nPos + 31) / 32 * 32) * 16 > 200 * 1024) return fail(VFT_EINVAL, "alignments longer than 12 800 columns are not supported (term buffer of the average kernel)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1) {
@@ -1573,7 +1572,8 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         else k_eval<P, A_, MX, false><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(EVAL_ARGS(P)); } while (0)
     // long alignments, lists that cannot fill the machine with a warp per pair: a CTA per pair
     const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
-    const int wideThreads = n <= 160 ? 256 : 128;
+    // threads per pair: as many warps as keep the machine full (148 SMs x 1536 threads), so that each warp walks few chunks
+    const int wideThreads = (c->ps == 4 && n <= 592) ? 384 : (n <= 888 ? 256 : 128);
 #define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut, flag, seq)
     prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     if (wide) { VFT_DISPATCH(c, CALL_EVAL_WIDE); } else { VFT_DISPATCH(c, CALL_EVAL); }
