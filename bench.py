@@ -24,9 +24,13 @@ driver's reference arm fit its time limit (the reference needs ~21 s per run at 
            same alignment: "Initial topology" stamp minus the "Identified unique sequences" stamp; its thread count is the
            fastest of {cores/2, cores} measured ON THE FULL WORKLOAD (the reference gets slower with too many threads).
 
-Multi-GPU (torchrun, one rank per GPU): `--gpus N` builds N trees, one per rank (seed = 1 + rank): REPLICAS, weak scaling, no
-data-path collective; NCCL is used for the barrier and the max-over-ranks reduction only.  The reference arm times one tree
-per step at every N: the host's cores are the same, so its aggregate taxa/s for N queued trees is that of one.
+Multi-GPU (torchrun, one rank per GPU): `--gpus N` builds ONE tree sharded over the N GPUs (`--multi sharded`, the default;
+SURVEY 8e): every rank runs the same host loop on a replicated slab, the candidate axis of the all-candidate sweeps
+(setBestHit, the all-node out-distances, the list merges of a refresh) is split over the ranks and their results are
+all-gathered over NVLink peer memory (csrc/vft_dist.cuh; VFT_EXCHANGE=nccl for ncclAllGather).  STRONG scaling: the same
+20 000-taxon tree at every N, value = its taxa / the max over ranks of the device time; every rank's tree is checked to be the
+same (`trees_identical_across_ranks`).  The reference arm times the same one tree at every N.  `--multi replicas` keeps the
+earlier mode (N independent trees, no data-path collective, weak scaling).
 """
 from __future__ import annotations
 
@@ -178,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--taxa", type=int, default=0, help="override the workload size (debug only)")
     ap.add_argument("--device-loop", type=int, default=-1, help="-1: library default; 0/1: host-driven / device-resident join loop")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"], help="--gpus N > 1: one tree sharded over the GPUs, or N independent trees")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     n_taxa = args.taxa or wl["n"]
@@ -226,9 +231,10 @@ def main():
         flags = " ".join(wl["ref_flags"])
         line = {"impl": "reference", "metric": metric, "value": value, "unit": "taxa/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "taxa_per_gpu": int(taxa // n_rep), "columns": wl["pos"],
-                           "parallelism": "one tree per step at all host cores: the CPU's aggregate taxa/s does not depend on how many trees are queued (the repo arm at --gpus N builds N trees, one per GPU)",
+                "higher_is_better": True, "scaling": "strong" if args.multi == "sharded" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "taxa": int(taxa // n_rep), "columns": wl["pos"],
+                           "parallelism": "one tree per step at all host cores (the repo arm at --gpus N shards this same tree over N GPUs; with --multi replicas it builds N trees, "
+                                          "and the CPU's aggregate taxa/s does not depend on how many trees are queued)",
                            "reference_flags": "%s -threads %d -noml -nni 0 -spr 0 -nosupport%s" % (
                                flags, per_proc, " (nt fp32: the reference silently runs its SSE3 path)" if wl["kind"] == "nt" else ""),
                            "reference_build": "oracle/_ref: the unmodified sources, g++ -O3 -mavx2 (no FMA; the parity oracle)",
@@ -247,13 +253,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = api.load()
+    from veryfasttree_b200 import dist as vdist
+    sharded = world > 1 and args.multi == "sharded"
+    dist_info = vdist.init_sharded(lib, local_rank) if sharded else {"mode": "none"}
     # host threads of the driver's list-processing regions: this rank's share of the cores
     host_threads = max(1, min(16, host_cores // max(1, world)))
     A = 4 if wl["kind"] == "nt" else 20
     tables = tables_for(wl)
     dev_loop = None if args.device_loop < 0 else args.device_loop
 
-    chars = make_workload(wl, 1 + rank, n_taxa)
+    chars = make_workload(wl, 1 if sharded else 1 + rank, n_taxa)      # sharded: every rank holds the same alignment
     codes = api.encode(chars, wl["kind"])
     n_unique = codes.shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
@@ -292,8 +301,16 @@ def main():
     sampler.join(timeout=2)
 
     # max over ranks of the device-timed and end-to-end sums, sum of the units (veryfasttree_b200/dist.py)
-    from veryfasttree_b200 import dist as vdist
     dev_ms_max, e2e_max, taxa_total, launches_total = vdist.aggregate_step_times(dev_ms, e2e_s, float(n_unique), float(launches), device="cuda")
+    trees_identical = None
+    if sharded:
+        taxa_total = float(n_unique)                  # ONE tree: the ranks share its taxa
+        import zlib
+        sig = float(zlib.crc32(tr.parent.tobytes() + tr.branchlength.tobytes()))
+        t = torch.tensor([sig, -sig], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        trees_identical = bool(t[0].item() == -t[1].item())
+        dist_info = lib.dist_info()
 
     # one extra profiled pass: per-kernel device time from CUDA events on the launching stream
     ptree = one_step(profile=True)
@@ -335,6 +352,8 @@ def main():
                 "distance_sweep_all_kernels": {"algorithmic_bytes_per_step": prof["distBytes"], "ms_per_step": prof["msDist"],
                                                "gbps": (prof["distBytes"] / (prof["msDist"] * 1e-3)) / 1e9 if prof["msDist"] > 0 else None}}
     if rank != 0:
+        if sharded:
+            lib.dist_finalize()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -354,9 +373,15 @@ def main():
     value = taxa_total * args.steps / (dev_ms_max * 1e-3)
     line = {"metric": metric, "value": value, "unit": "taxa/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "taxa_per_gpu": int(n_unique), "columns": wl["pos"],
-                       "parallelism": "replicas x%d" % args.gpus, "host_threads_per_rank": host_threads,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "taxa": int(n_unique), "columns": wl["pos"],
+                       "parallelism": ("one tree sharded over %d GPUs: replicated slab and join loop, candidate-sharded sweeps, all-gather of top-2m records / "
+                                       "out-distances / merged lists via %s (%d exchanges, %.1f MB per step and rank)"
+                                       % (args.gpus, {"peer": "NVLink peer memory (one push-and-wait kernel per exchange)", "nccl": "ncclAllGather",
+                                                      "host": "a host all-gather"}.get(dist_info["mode"], dist_info["mode"]),
+                                          dist_info["exchanges"] // max(1, args.warmup + args.steps + 1),
+                                          dist_info["bytes"] / 1e6 / max(1, args.warmup + args.steps + 1))) if sharded else "replicas x%d" % args.gpus,
+                       "trees_identical_across_ranks": trees_identical, "host_threads_per_rank": host_threads,
                        "join_loop": "device-resident" if ptree.stats["counters"]["nKernel"][11] else "host-driven",
                        "l2": "flushed between steps (256 MiB write)",
                        "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)"},
@@ -366,6 +391,8 @@ def main():
             "gpu_launches": int(launches_total), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "wall_s": t_wall}
+    if sharded:
+        lib.dist_finalize()
     if world > 1:
         dist.destroy_process_group()
     emit(line)

@@ -183,6 +183,30 @@ int  vft_dist_one_vs_all_range(vft_ctx *ctx, int64_t query, int64_t nActive, int
                                int64_t jEnd, int64_t *j_out, void *dist, void *weight, void *criterion,
                                int64_t *nOut);
 
+/* -- one tree sharded over the GPUs of a node ----------------------------------------------------------------
+   One process per GPU.  Every rank makes the SAME sequence of calls on a replicated profile slab (the join chain is
+   deterministic, so no rank ever waits for another one's joins); the candidate axis of the three all-candidate sweeps is
+   sharded and their results exchanged with one all-gather each:
+     vft_dist_one_vs_all   rank r evaluates entries r, r+W, ... of the ascending active list, selects its K best; the W x K
+                           fixed-size records are all-gathered and merged -- every rank returns the same K records
+     vft_out_distance_all  the same strided share; the values are all-gathered into every rank's table
+     vft_tophits_merge     the lists in W contiguous chunks; the saved lists are all-gathered
+   Results are bit-identical to the unsharded calls (each distance is computed by exactly one rank with the same kernel).
+   The reference has nothing comparable (CudaOperations.cu:8-12 maps OpenMP threads to devices); the contract is SURVEY 8e.
+   vft_dist_init: collective over the `world` ranks; id128 = the 128-byte NCCL unique id made by vft_dist_unique_id on one
+   rank and handed to the others by the launcher (torch.distributed / MPI / a file).  Contexts created on `device` afterwards
+   are sharded.  Exchange: peer memory over NVLink (CUDA IPC + one push-and-wait kernel per exchange) when every GPU can map
+   its peers, else ncclAllGather; VFT_EXCHANGE=nccl forces the latter.  vft_dist_init_host: the exchange goes through a
+   caller-provided HOST all-gather instead (send: bytesPerRank bytes, recv: world x bytesPerRank, rank order; returns 0) --
+   MPI / gloo bring-up, and what the CPU double of the tests uses. */
+typedef int (*vft_allgather_fn)(const void *send, void *recv, int64_t bytesPerRank, void *user);
+int  vft_dist_unique_id(void *id128);
+int  vft_dist_init(int32_t rank, int32_t world, const void *id128, int32_t device);
+int  vft_dist_init_host(int32_t rank, int32_t world, vft_allgather_fn fn, void *user, int32_t device);
+int  vft_dist_finalize(void);
+/* mode: 0 none (world 1), 1 NCCL, 2 peer memory, 3 host callback; counters since vft_dist_init */
+int  vft_dist_info(int32_t *rank, int32_t *world, int32_t *mode, int64_t *nExchanges, int64_t *bytesExchanged);
+
 /* -- top-hits refresh: the list-merging loop of topHitJoin's refresh branch (NJ.tcc:4477-4515) ------
    After a refresh's one-vs-all of `newnode` (NJ.tcc:4470-4472) the reference rebuilds the top-hit list
    of each of its m best hits iNode[l] from  (own list of iNode) + (the nAvail best hits of newnode):

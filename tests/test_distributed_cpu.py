@@ -78,3 +78,68 @@ def test_candidate_blocks_cover_everything():
             blocks = [vdist.candidate_block(n, r, world) for r in range(world)]
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+
+
+# ---- ONE tree sharded over the ranks: the CPU double of csrc/vft_dist.cuh behind the same C-ABI, the exchange
+#      routed through torch.distributed.all_gather (gloo).  Every rank must return the unsharded tree, bit for bit.
+def _sharded_case(kind):
+    from veryfasttree_b200 import api, synth
+    if kind == "nt":
+        chars = synth.make_alignment(420, 160, "nt", seed=5)
+        chars = chars[synth.unique_rows(chars)]
+        return api.encode(chars, "nt"), 4, 32, None
+    chars = synth.make_alignment(330, 90, "aa", seed=6)
+    chars = chars[synth.unique_rows(chars)]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "blosum45_f64.npz"))
+    return api.encode(chars, "aa"), 20, 64, [z["distances"], z["eigenval"], z["eigentot"], z["codeFreq"]]
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import replay
+    from veryfasttree_b200 import api, dist as vdist
+    lib = api.load(replay.ORACLE_LIB)
+    out = {}
+    for kind in ("nt", "aa"):
+        codes, A, prec, tables = _sharded_case(kind)
+        info = vdist.init_sharded_host(lib)
+        assert info["world"] == world and info["rank"] == rank and info["mode"] == "host"
+        tree = api.nj_build(codes, A, prec, lib=lib, tables=tables, host_threads=1)
+        info = lib.dist_info()
+        lib.dist_finalize()
+        out[kind + "_joins"] = tree.joins
+        out[kind + "_bl"] = tree.branchlength
+        out[kind + "_lth"] = tree.leaf_top_hits
+        out[kind + "_exchanges"] = info["exchanges"]
+        out[kind + "_refresh"] = tree.stats["nRefreshTopHits"]
+    np.savez(os.path.join(out_dir, "s%d.npz" % rank), **out)
+    dist.destroy_process_group()
+
+
+def _run_sharded(tmp_path, world):
+    import replay
+    from veryfasttree_b200 import api
+    replay.ensure_oracle_built()
+    mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    lib = api.load(replay.ORACLE_LIB)
+    for kind in ("nt", "aa"):
+        codes, A, prec, tables = _sharded_case(kind)
+        ref = api.nj_build(codes, A, prec, lib=lib, tables=tables, host_threads=1)
+        for r in range(world):
+            z = np.load(tmp_path / ("s%d.npz" % r))
+            assert np.array_equal(z[kind + "_joins"], ref.joins), "join order differs on rank %d (%s)" % (r, kind)
+            assert z[kind + "_bl"].tobytes() == ref.branchlength.tobytes()
+            assert np.array_equal(z[kind + "_lth"], ref.leaf_top_hits)
+            # the data path really crossed ranks: one exchange per seed, at least two per refresh (out-distances, one-vs-all;
+            # the list merge when there are lists), the initial out-distances
+            assert int(z[kind + "_exchanges"]) > ref.stats["nSeeds"] + 2 * int(z[kind + "_refresh"])
+            assert int(z[kind + "_refresh"]) == ref.stats["nRefreshTopHits"] > 0
+
+
+def test_one_tree_sharded_over_two_ranks(tmp_path):
+    _run_sharded(tmp_path, 2)
+
+
+def test_one_tree_sharded_over_three_ranks(tmp_path):
+    _run_sharded(tmp_path, 3)        # uneven shares: list chunks and strided slots that do not divide

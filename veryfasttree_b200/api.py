@@ -88,11 +88,15 @@ ABI_SYMBOLS = [
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
     "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
     "vft_ml_split_test_batch", "vft_ml_test_splits",
+    "vft_dist_unique_id", "vft_dist_init", "vft_dist_init_host", "vft_dist_finalize", "vft_dist_info",
 ]
 
 
 class VftError(RuntimeError):
     pass
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class Lib:
@@ -151,6 +155,11 @@ class Lib:
             d.vft_spec_join_discard.argtypes = [vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+        if hasattr(d, "vft_dist_init"):
+            d.vft_dist_unique_id.argtypes = [vp]
+            d.vft_dist_init.argtypes = [i32, i32, vp, i32]
+            d.vft_dist_init_host.argtypes = [i32, i32, ALLGATHER_FN, vp, i32]
+            d.vft_dist_info.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
         d.vft_get_counters.argtypes = [vp, C.POINTER(VftCounters)]
         d.vft_nj_default_options.argtypes = [C.POINTER(VftNjOptions)]
         d.vft_nj_build.argtypes = [C.POINTER(VftConfig), C.POINTER(VftNjOptions), vp, vp, C.POINTER(VftNjResult)]
@@ -158,6 +167,41 @@ class Lib:
     @property
     def backend(self) -> str:
         return self.dll.vft_backend_name().decode()
+
+    # ---- one tree sharded over the ranks of a group (include/vft_b200.h, "one tree sharded over the GPUs of a node")
+    def dist_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.check(self.dll.vft_dist_unique_id(buf), "vft_dist_unique_id")
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes | None, device: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self.check(self.dll.vft_dist_init(rank, world, buf, device), "vft_dist_init")
+
+    def dist_init_host(self, rank: int, world: int, allgather, device: int = 0):
+        """allgather(send: bytes) -> bytes of world * len(send), rank order (e.g. over torch.distributed / gloo)."""
+        def _cb(send, recv, nbytes, _user):
+            try:
+                out = allgather(C.string_at(send, nbytes))
+                assert len(out) == nbytes * world
+                C.memmove(recv, out, len(out))
+                return 0
+            except Exception:           # the C side reports the failure
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allgather_cb = ALLGATHER_FN(_cb)          # keep the trampoline alive
+        self.check(self.dll.vft_dist_init_host(rank, world, self._allgather_cb, None, device), "vft_dist_init_host")
+
+    def dist_finalize(self):
+        self.check(self.dll.vft_dist_finalize(), "vft_dist_finalize")
+        self._allgather_cb = None
+
+    def dist_info(self) -> dict:
+        r, w, m = C.c_int32(), C.c_int32(), C.c_int32()
+        n, b = C.c_int64(), C.c_int64()
+        self.check(self.dll.vft_dist_info(C.byref(r), C.byref(w), C.byref(m), C.byref(n), C.byref(b)), "vft_dist_info")
+        return {"rank": r.value, "world": w.value, "mode": ["none", "nccl", "peer", "host"][m.value], "exchanges": n.value, "bytes": b.value}
 
     def check(self, rc: int, what: str):
         if rc != 0:

@@ -600,7 +600,7 @@ static int loop_note_joins(vftx_loop *lp) {
         const int64_t newnode = c->maxnode;
         for (int64_t ch : {lp->hJoins[(size_t) (2 * k)], lp->hJoins[(size_t) (2 * k + 1)]})
             if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
-        c->activeHost[newnode] = 1; c->nActInternal++;
+        c->activeHost[newnode] = 1; c->nActInternal++; c->actDirty = true;
         c->maxnode = newnode + 1;
         c->cnt.profileAvgOps++;
     }

@@ -249,48 +249,60 @@ k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *
     }
 }
 
-// setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist)
+// setBestHit (NJ.tcc:3571-3639) for a LEAF query: one thread per node slot (leaf x leaf = seqDist).
+// Candidate addressing of the three all-candidate sweeps: list == nullptr -- slot k IS node k (inactive nodes and nodes
+// outside [jBegin, jEnd) get a never-selected key); list != nullptr -- the COMPACT form: slot k is node
+// list[k * stride + offset] of the ascending active list, every slot is live, results are indexed by slot.  stride/offset
+// pick the strided share of one rank when a tree is sharded over GPUs (vft_dist_init): slot order == node order either way,
+// so the (criterion, node descending) tie rule of the select is unchanged.
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128)
 k_one_vs_all_leaf(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd,
-                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
-    const int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    if (j >= maxnode) return;
-    if (!s.active[j] || j < jBegin || j >= jEnd) { keys[j] = ~0ull; return; }
+                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys,
+                  const int32_t *__restrict__ list = nullptr, int stride = 1, int offset = 0) {
+    const int64_t k = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    if (k >= maxnode) return;
+    int64_t j = k;
+    if (list != nullptr) j = list[k * stride + offset];
+    else if (!s.active[j] || j < jBegin || j >= jEnd) { keys[k] = ~0ull; return; }
     P d, w;
     join_dist<P, A, MATRIX>(s, query, j, false, d, w);
     // setCriterion (NJ.tcc:1099-1107) with every out-distance fresh at this nActive
     const double outI = (double) s.outDist[query], outJ = (double) s.outDist[j];
     const P c = (P) xsub((double) d, xadd(outI, outJ) / (double) (nActive - 2));
-    dist[j] = d; weight[j] = w; crit[j] = c;
-    keys[j] = order_key(c);
+    dist[k] = d; weight[k] = w; crit[k] = c;
+    keys[k] = order_key(c);
 }
 
 // setBestHit for an INTERNAL query: every distance is a profileDist; each warp owns G node slots
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128, sizeof(P) == 4 ? 4 : 2)
 k_one_vs_all_warp(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd, int G,
-                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+                  P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys,
+                  const int32_t *__restrict__ list = nullptr, int stride = 1, int offset = 0) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-    const int64_t j = warp * G + lane;
-    const bool valid = lane < G && j < maxnode;
-    const bool act = valid && s.active[j] && j >= jBegin && j < jEnd;
+    const int64_t k = warp * G + lane;
+    const bool valid = lane < G && k < maxnode;
+    int64_t j = k;
+    bool act;
+    if (list != nullptr) { j = valid ? (int64_t) list[k * stride + offset] : 0; act = valid; }
+    else act = valid && s.active[j] && j >= jBegin && j < jEnd;
     const unsigned mask = __ballot_sync(full, act);
     double den, top;
     group_profile_dist<P, A, MATRIX>(s, query, j, mask, G, smw, den, top);
     if (!valid) return;
-    if (!act) { keys[j] = ~0ull; return; }
+    if (!act) { keys[k] = ~0ull; return; }
     P d, w;
     finish_dist<P>(den, top, d, w);
     d = join_correct<P>(s, query, j, d);
     const double outI = (double) s.outDist[query], outJ = (double) s.outDist[j];
     const P c = (P) xsub((double) d, xadd(outI, outJ) / (double) (nActive - 2));
-    dist[j] = d; weight[j] = w; crit[j] = c;
-    keys[j] = order_key(c);
+    dist[k] = d; weight[k] = w; crit[k] = c;
+    keys[k] = order_key(c);
 }
 
 // The two all-candidate sweeps with the shared profile staged in shared memory by TMA bulk copies (vft_bulk.cuh): 512-thread
@@ -301,7 +313,8 @@ __host__ __device__ inline size_t staged_tile_bytes() { return (size_t) (STG_T /
 
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(STG_T, 1)
-k_out_distance_all_staged(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam) {
+k_out_distance_all_staged(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam,
+                          const int32_t *__restrict__ list = nullptr, int stride = 1, int offset = 0, P *__restrict__ res = nullptr) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ __align__(8) uint64_t bar;
     const unsigned full = 0xFFFFFFFFu;
@@ -315,15 +328,19 @@ k_out_distance_all_staged(Store<P> s, int64_t maxnode, int G, int64_t nActive, d
     unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(STG_G);
     const int64_t totalWarps = (int64_t) gridDim.x * (STG_T / 32);
     for (int64_t warp = (blockIdx.x * (int64_t) STG_T + threadIdx.x) >> 5; warp * G < maxnode; warp += totalWarps) {
-        const int64_t j = warp * G + lane;
-        const bool act = lane < G && j < maxnode && s.active[j];
+        const int64_t k = warp * G + lane;
+        int64_t j = k;
+        bool act = lane < G && k < maxnode;
+        if (list != nullptr) j = act ? (int64_t) list[k * stride + offset] : 0;
+        else act = act && s.active[j];
         const unsigned mask = __ballot_sync(full, act);
         double den, top;
         group_profile_dist<P, A, MATRIX>(s2, j, (int64_t) -1, mask, G, smw, den, top);
         if (act) {
             P dd, ww;
             finish_dist<P>(den, top, dd, ww);
-            s.outDist[j] = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
+            const P v = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
+            if (res != nullptr) res[k] = v; else s.outDist[j] = v;
         }
         __syncwarp();
     }
@@ -332,7 +349,8 @@ k_out_distance_all_staged(Store<P> s, int64_t maxnode, int G, int64_t nActive, d
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(STG_T, 1)
 k_one_vs_all_staged(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode, int64_t jBegin, int64_t jEnd, int G,
-                    P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys) {
+                    P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys,
+                    const int32_t *__restrict__ list = nullptr, int stride = 1, int offset = 0) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ __align__(8) uint64_t bar;
     const unsigned full = 0xFFFFFFFFu;
@@ -350,38 +368,46 @@ k_one_vs_all_staged(Store<P> s, int64_t query, int64_t nActive, int64_t maxnode,
     const double outI = (double) s.outDist[query];
     const int64_t totalWarps = (int64_t) gridDim.x * (STG_T / 32);
     for (int64_t warp = (blockIdx.x * (int64_t) STG_T + threadIdx.x) >> 5; warp * G < maxnode; warp += totalWarps) {
-        const int64_t j = warp * G + lane;
-        const bool valid = lane < G && j < maxnode;
-        const bool act = valid && s.active[j] && j >= jBegin && j < jEnd;
+        const int64_t k = warp * G + lane;
+        const bool valid = lane < G && k < maxnode;
+        int64_t j = k;
+        bool act;
+        if (list != nullptr) { j = valid ? (int64_t) list[k * stride + offset] : 0; act = valid; }
+        else act = valid && s.active[j] && j >= jBegin && j < jEnd;
         const unsigned mask = __ballot_sync(full, act);
         double den, top;
         group_profile_dist<P, A, MATRIX>(s2, query, j, mask, G, smw, den, top);
         if (valid) {
-            if (!act) keys[j] = ~0ull;
+            if (!act) keys[k] = ~0ull;
             else {
                 P d, w;
                 finish_dist<P>(den, top, d, w);
                 d = join_correct<P>(s, query, j, d);
                 const P c = (P) xsub((double) d, xadd(outI, (double) s.outDist[j]) / (double) (nActive - 2));
-                dist[j] = d; weight[j] = w; crit[j] = c;
-                keys[j] = order_key(c);
+                dist[k] = d; weight[k] = w; crit[k] = c;
+                keys[k] = order_key(c);
             }
         }
         __syncwarp();
     }
 }
 
-// setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist
+// setOutDistance for every active node (NJ.tcc:257-260 / :4451-4464), committed to s.outDist -- or, in the compact form of a
+// sharded sweep, written to res[slot] (the rank's share; committed everywhere after the exchange)
 template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(128, sizeof(P) == 4 ? 4 : 2)
-k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam) {
+k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double totdiam,
+                   const int32_t *__restrict__ list = nullptr, int stride = 1, int offset = 0, P *__restrict__ res = nullptr) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned char *smw = smemRaw + (threadIdx.x >> 5) * group_smem_bytes<P, A, MATRIX>(G);
     const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-    const int64_t j = warp * G + lane;
-    const bool act = lane < G && j < maxnode && s.active[j];
+    const int64_t k = warp * G + lane;
+    int64_t j = k;
+    bool act = lane < G && k < maxnode;
+    if (list != nullptr) j = act ? (int64_t) list[k * stride + offset] : 0;
+    else act = act && s.active[j];
     const unsigned mask = __ballot_sync(full, act);
     double den, top;
     group_profile_dist<P, A, MATRIX>(s, j, (int64_t) -1, mask, G, smw, den, top);
@@ -389,7 +415,7 @@ k_out_distance_all(Store<P> s, int64_t maxnode, int G, int64_t nActive, double t
         P dd, ww;
         finish_dist<P>(den, top, dd, ww);
         const P v = out_distance_finish<P>(s, j, nActive, totdiam, dd, ww);
-        s.outDist[j] = v;
+        if (res != nullptr) res[k] = v; else s.outDist[j] = v;
     }
 }
 
@@ -416,7 +442,10 @@ template<typename P, int KEYBYTES>
 __global__ void __launch_bounds__(SEL_T)
 k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P *__restrict__ dist, const P *__restrict__ weight,
               const P *__restrict__ crit, Rec<P> *__restrict__ out, const uint32_t *__restrict__ idxIn = nullptr,
-              uint64_t *__restrict__ candK = nullptr, uint32_t *__restrict__ candI = nullptr) {
+              uint64_t *__restrict__ candK = nullptr, uint32_t *__restrict__ candI = nullptr,
+              const int32_t *__restrict__ list = nullptr, int lstride = 1, int loffset = 0) {
+    // list != nullptr: the keys are indexed by SLOT of a compact candidate list (see k_one_vs_all_leaf); slot order == node
+    // order, so the selection works on slots and only the record written at the end carries the node id
     // Multi-CTA use (long key arrays): stage 1 -- gridDim.x CTAs, each selects the K best of ITS chunk and writes them as
     // (key, original index) candidates (candK/candI, K per CTA, padded with never-selected keys); stage 2 -- one CTA runs the
     // same selection over the candidates (idxIn = their original indices).  The K best overall are among the per-chunk K
@@ -546,14 +575,16 @@ k_topk_select(const uint64_t *__restrict__ keysAll, int64_t nAll, int K, const P
     }
     for (int t = tid; t < K && t < have; t += SEL_T) {
         const uint32_t j = sv[t];
-        out[t].j = j;
-        if (j != 0xFFFFFFFFu) { out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j]; }      // (padding of a short chunk: never a real node)
+        if (j != 0xFFFFFFFFu) {                                                                                 // (padding of a short chunk: never a real node)
+            out[t].j = list != nullptr ? (int64_t) list[(int64_t) j * lstride + loffset] : (int64_t) j;
+            out[t].dist = dist[j]; out[t].weight = weight[j]; out[t].crit = crit[j];
+        } else out[t].j = j;
     }
 }
 
 // the K best of n keys in psort order: one CTA for short arrays, chunked over CTAs + a merge stage for long ones
 template<typename P, int KEYBYTES>
-static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out);
+static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out, const int32_t *list = nullptr, int lstride = 1, int loffset = 0);
 
 // ---- top-hits refresh on the device: vft_tophits_merge -------------------------------------------------
 // One CTA per list.  psort order (key ascending, ties in reverse input order) = ascending order of the
@@ -1080,6 +1111,8 @@ __global__ void k_init_leaves(Store<P> s) {
 // host side of the ABI
 // =================================================================================================
 
+#include "vft_dist.cuh"
+
 struct vft_ctx {
     vft_config cfg;
     int A;
@@ -1107,6 +1140,9 @@ struct vft_ctx {
     size_t hCap;
     std::vector<uint8_t> activeHost;
     int64_t nActLeaf, nActInternal;
+    // the ascending list of active nodes, kept on the device for the compact all-candidate sweeps (rebuilt lazily)
+    int32_t *d_act = nullptr, *h_act = nullptr; int64_t nAct = 0; bool actDirty = true;
+    bool sharded = false;                      // member of the process's dist group (vft_dist.cuh): sweeps cover this rank's share
     // ML model
     void *mlTables, *mlRates;
     int32_t *mlRatecat;
@@ -1289,6 +1325,8 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
     CK(cudaMemsetAsync(c->active, 0, M, c->stream));
     CK(cudaMemsetAsync(c->tables, 0, 840 * ps, c->stream));
     c->activeHost.assign(M, 0);
+    CK(mem_alloc((void **) &c->d_act, (M + 64) * 4, MEM_DEVICE)); CK(mem_alloc((void **) &c->h_act, (M + 64) * 4, MEM_PINNED));
+    c->sharded = g_dist.ready && g_dist.world > 1 && g_dist.device == cfg->device;
     CK(mem_alloc((void **) &c->mlTables, 1300 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRates, 64 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRatecat, Lp * 4, MEM_DEVICE));
     CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
     c->hasTransmat = false; c->hasRates = false;
@@ -1354,7 +1392,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
-    mem_free(c->h_in); mem_free(c->h_out);
+    mem_free(c->h_in); mem_free(c->h_out); mem_free(c->d_act); mem_free(c->h_act);
     mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms); mem_free(c->d_candK); mem_free(c->d_candI);
     for (void *q : {c->ow2, c->ov2, c->ocd2, c->d_specR0, c->d_specR1, c->d_specSelf, c->h_specIn, c->h_specOut}) mem_free(q);
     if (c->specDone) cudaEventDestroy(c->specDone);
@@ -1402,7 +1440,7 @@ extern "C" int vft_upload_leaves(vft_ctx *c, const uint8_t *codes) {
     std::fill(c->activeHost.begin(), c->activeHost.end(), 0);
     std::fill(c->activeHost.begin(), c->activeHost.begin() + c->N, 1);
     c->maxnode = c->N;
-    c->nActLeaf = c->N; c->nActInternal = 0;
+    c->nActLeaf = c->N; c->nActInternal = 0; c->actDirty = true;
     return VFT_OK;
 }
 
@@ -1479,6 +1517,7 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
         if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
     if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
+    c->actDirty = true;
     return VFT_OK;            // asynchronous: ordered on the context's stream
 }
 
@@ -1689,6 +1728,7 @@ extern "C" int vft_spec_join_take(vft_ctx *c, double diameter_out, void *pairDis
         if (c->activeHost[ch]) { c->activeHost[ch] = 0; if (ch < c->N) c->nActLeaf--; else c->nActInternal--; }
     if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
+    c->actDirty = true;
     const char *h0 = (const char *) c->h_specOut, *h1 = h0 + (size_t) n * c->ps;
     if (nOut && outDist) std::memcpy(outDist, h0, (size_t) nOut * c->ps);
     if (nOut && outWeight) std::memcpy(outWeight, h1, (size_t) nOut * c->ps);
@@ -1705,18 +1745,19 @@ extern "C" int vft_spec_join_discard(vft_ctx *c) {
 }
 
 template<typename P, int KEYBYTES>
-static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out) {
+static void launch_topk(vft_ctx *c, const uint64_t *keys, int64_t n, int K, Rec<P> *out, const int32_t *list, int lstride, int loffset) {
     const size_t selSmem = 32 * 256 * 4 + SEL_MAXK * 12;
     const int nCta = (int) std::min<int64_t>(SEL_CTAS, n / 8192);
     if (nCta < 2 || (int64_t) nCta * K > n) {
-        k_topk_select<P, KEYBYTES><<<1, SEL_T, selSmem, c->stream>>>(keys, n, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, out);
+        k_topk_select<P, KEYBYTES><<<1, SEL_T, selSmem, c->stream>>>(keys, n, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, out,
+                                                                     (const uint32_t *) nullptr, (uint64_t *) nullptr, (uint32_t *) nullptr, list, lstride, loffset);
         c->cnt.launches++;
         return;
     }
     k_topk_select<P, KEYBYTES><<<nCta, SEL_T, selSmem, c->stream>>>(keys, n, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, (Rec<P> *) nullptr,
                                                                     (const uint32_t *) nullptr, c->d_candK, c->d_candI);
     k_topk_select<P, KEYBYTES><<<1, SEL_T, selSmem, c->stream>>>(c->d_candK, (int64_t) nCta * K, K, (const P *) c->d_dist, (const P *) c->d_weight, (const P *) c->d_crit, out,
-                                                                 c->d_candI);
+                                                                 c->d_candI, (uint64_t *) nullptr, (uint32_t *) nullptr, list, lstride, loffset);
     c->cnt.launches += 2;
 }
 
@@ -1730,31 +1771,61 @@ extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, 
     return vft_eval_batch(c, nullptr, 0, 0, 0.0, nullptr, pi, pj, n, flags, dist, weight);
 }
 
+// the ascending active list on the device (the compact sweeps index it; a sharded context takes every W-th entry)
+static int ensure_active(vft_ctx *c) {
+    if (!c->actDirty) return VFT_OK;
+    int64_t n = 0;
+    const uint8_t *act = c->activeHost.data();
+    for (int64_t i = 0; i < c->maxnode; i++) if (act[i]) c->h_act[n++] = (int32_t) i;
+    CK(cudaMemcpyAsync(c->d_act, c->h_act, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+    c->cnt.h2dBytes += n * 4;
+    c->nAct = n; c->actDirty = false;
+    return VFT_OK;
+}
+static inline int shard_world(const vft_ctx *c) { return c->sharded ? g_dist.world : 1; }
+static inline int shard_rank(const vft_ctx *c) { return c->sharded ? g_dist.rank : 0; }
+static inline int64_t shard_len(int64_t nAct, int W, int r) { return nAct > r ? (nAct - r + W - 1) / W : 0; }
+
 extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam, void *outDist, int64_t maxnode) {
     if (!c || !outDist || maxnode < c->maxnode) return fail(VFT_EINVAL, "bad argument");
     bind_device(c);
     const int64_t n = c->maxnode;
     BytesScope bytesScope(c, K_OUT_DIST_ALL);
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
-    const int G = pick_group(c, n);
-    const int64_t warps = (n + G - 1) / G;
-#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), n, G, nActive, totdiam)
+    rc = ensure_active(c); if (rc) return rc;
+    const int W = shard_world(c), r = shard_rank(c);
+    const int64_t len = shard_len(c->nAct, W, r), chunk = (c->nAct + W - 1) / W;
+    const int G = pick_group(c, len);
+    const int64_t warps = (len + G - 1) / G;
+    void *res = nullptr;
+    if (W > 1) { rc = dist_reserve(c->stream, (size_t) chunk * c->ps); if (rc) return rc; res = g_dist.send; }
+#define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), len, G, nActive, totdiam, c->d_act, W, r, (P *) res)
     prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
-    if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), n, std::min(G, STG_G), nActive, totdiam);
-    else { VFT_DISPATCH(c, CALL_ODA); }
+    if (len > 0) {
+        if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), len, std::min(G, STG_G), nActive, totdiam, c->d_act, W, r, (float *) res);
+        else { VFT_DISPATCH(c, CALL_ODA); }
+    }
     prof_end(c);
     CK(cudaGetLastError());
+    if (W > 1) {
+        // every rank's share -> every rank's table
+        const char *base; size_t stride;
+        rc = dist_allgather(c->stream, (size_t) chunk * c->ps, &base, &stride); if (rc) return rc;
+        if (c->ps == 4) k_scatter_outdist<float><<<(unsigned) ((c->nAct + 255) / 256), 256, 0, c->stream>>>(base, stride, c->d_act, c->nAct, W, (float *) c->outDist);
+        else k_scatter_outdist<double><<<(unsigned) ((c->nAct + 255) / 256), 256, 0, c->stream>>>(base, stride, c->d_act, c->nAct, W, (double *) c->outDist);
+        CK(cudaGetLastError());
+        c->cnt.launches += g_dist.mode == DIST_PEER ? 2 : 1;
+    }
     CK(cudaMemcpyAsync(c->h_out, c->outDist, (size_t) n * c->ps, cudaMemcpyDeviceToHost, c->stream));   // one DMA instead of a PCIe write per lane
     CK(sync_stream(c));
-    int64_t nAct = 0;
-    for (int64_t i = 0; i < n; i++)
-        if (c->activeHost[i]) {
-            std::memcpy((char *) outDist + i * c->ps, (char *) c->h_out + i * c->ps, c->ps);
-            nAct++; c->cnt.algoBytes += profile_bytes(c, i);
-        }
-    c->cnt.launches++; c->cnt.profileOps += nAct; c->cnt.outprofileOps += nAct;
+    for (int64_t k = 0; k < c->nAct; k++) {
+        const int64_t i = c->h_act[k];
+        std::memcpy((char *) outDist + i * c->ps, (char *) c->h_out + i * c->ps, c->ps);
+        if (k % W == r) c->cnt.algoBytes += profile_bytes(c, i);                        // (a sharded context accounts its share)
+    }
+    c->cnt.launches++; c->cnt.profileOps += len; c->cnt.outprofileOps += len;
     c->cnt.algoBytes += profile_bytes(c, -1);
-    c->cnt.d2hBytes += nAct * (int64_t) c->ps;
+    c->cnt.d2hBytes += c->nAct * (int64_t) c->ps;
     return VFT_OK;
 }
 
@@ -1771,49 +1842,76 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     if (query < 0 || query >= c->maxnode || !c->activeHost[query]) return fail(VFT_EINVAL, "query must be an active node");
     if (K < 1) return fail(VFT_EINVAL, "K must be positive");
     BytesScope bytesScope(c, K_ONE_VS_ALL);
-    const int64_t n = c->maxnode;
+    const int64_t nAll = c->maxnode;
     if (K > SEL_MAXK) return fail(VFT_EINVAL, "K larger than 4096 is not supported");
+    // The whole candidate range goes through the COMPACT form (slot k = k-th active node; a sharded context takes slots
+    // r, r+W, ...); an explicit sub-range keeps the node-indexed form.
+    const bool compact = jBegin <= 0 && jEnd >= nAll;
+    int W = 1, r = 0;
+    int64_t n = nAll, inBlock = nActive;
+    const int32_t *list = nullptr;
+    if (compact) {
+        int rc = ensure_active(c); if (rc) return rc;
+        W = shard_world(c); r = shard_rank(c);
+        n = shard_len(c->nAct, W, r); inBlock = n; list = c->d_act;
+    } else {
+        inBlock = 0;
+        for (int64_t j = std::max<int64_t>(0, jBegin); j < std::min(jEnd, nAll); j++) inBlock += c->activeHost[j];
+    }
     const int Gq = pick_group(c, n);
     const int64_t warpsQ = (n + Gq - 1) / Gq;
-#define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
-#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys)
+#define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, list, W, r)
+#define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, list, W, r)
     prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
-    if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); }
-    else if (c->stagedOk) k_one_vs_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), query, nActive, n, jBegin, jEnd, std::min(Gq, STG_G), (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, c->d_keys);
-    else { VFT_DISPATCH(c, CALL_OVA_WARP); }
+    if (n > 0) {
+        if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); }
+        else if (c->stagedOk) k_one_vs_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), query, nActive, n, jBegin, jEnd, std::min(Gq, STG_G), (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, c->d_keys, list, W, r);
+        else { VFT_DISPATCH(c, CALL_OVA_WARP); }
+    }
     prof_end(c);
     CK(cudaGetLastError());
     c->cnt.launches++;
-    int64_t inBlock = nActive;
-    if (jBegin > 0 || jEnd < n) {
-        inBlock = 0;
-        for (int64_t j = std::max<int64_t>(0, jBegin); j < std::min(jEnd, n); j++) inBlock += c->activeHost[j];
-    }
-    const int64_t nRet = std::min<int64_t>(K, inBlock);
+    const int64_t nLocal = std::min<int64_t>(K, inBlock);                        // this rank's records
+    const int64_t nRet = W > 1 ? std::min<int64_t>(K, c->nAct) : nLocal;          // records returned
     const size_t recSz = c->ps == 4 ? sizeof(Rec<float>) : sizeof(Rec<double>);
     int rc = ensure_pinned(c, (size_t) std::max<int64_t>(nRet, 1) * recSz); if (rc) return rc;
-    if (nRet > 0) {
+    if (W > 1) { rc = dist_reserve(c->stream, (size_t) K * recSz); if (rc) return rc; }
+    if (nLocal > 0) {
         prof_begin(c, CLS_SELECT, K_SELECT);
-        if (c->ps == 4) launch_topk<float, 4>(c, c->d_keys, n, (int) nRet, (Rec<float> *) c->h_out);
-        else launch_topk<double, 8>(c, c->d_keys, n, (int) nRet, (Rec<double> *) c->h_out);
+        void *dst = W > 1 ? (void *) g_dist.send : c->h_out;
+        if (c->ps == 4) launch_topk<float, 4>(c, c->d_keys, n, (int) nLocal, (Rec<float> *) dst, list, W, r);
+        else launch_topk<double, 8>(c, c->d_keys, n, (int) nLocal, (Rec<double> *) dst, list, W, r);
         prof_end(c);
         CK(cudaGetLastError());
-        c->cnt.d2hBytes += (int64_t) (nRet * recSz);
     }
+    if (W > 1 && nRet > 0) {
+        // the exchange step of SURVEY 8e: W x K fixed-size records, then every rank merges them to the same K best
+        const char *base; size_t stride;
+        rc = dist_allgather(c->stream, (size_t) K * recSz, &base, &stride); if (rc) return rc;
+        prof_begin(c, CLS_SELECT, K_SELECT);
+        const unsigned blocks = (unsigned) (((int64_t) W * K + 255) / 256);
+        if (c->ps == 4) k_rank_merge<float><<<blocks, 256, 0, c->stream>>>(base, stride, W, c->nAct, (int) K, (Rec<float> *) c->h_out);
+        else k_rank_merge<double><<<blocks, 256, 0, c->stream>>>(base, stride, W, c->nAct, (int) K, (Rec<double> *) c->h_out);
+        prof_end(c);
+        CK(cudaGetLastError());
+        c->cnt.launches += g_dist.mode == DIST_PEER ? 2 : 1;
+    }
+    c->cnt.d2hBytes += (int64_t) (nRet * recSz);
     CK(sync_stream(c));
     if (c->ps == 4) {
-        const Rec<float> *r = (const Rec<float> *) c->h_out;
-        for (int64_t k = 0; k < nRet; k++) { j_out[k] = r[k].j; ((float *) dist)[k] = r[k].dist; ((float *) weight)[k] = r[k].weight; ((float *) criterion)[k] = r[k].crit; }
+        const Rec<float> *rr = (const Rec<float> *) c->h_out;
+        for (int64_t k = 0; k < nRet; k++) { j_out[k] = rr[k].j; ((float *) dist)[k] = rr[k].dist; ((float *) weight)[k] = rr[k].weight; ((float *) criterion)[k] = rr[k].crit; }
     } else {
-        const Rec<double> *r = (const Rec<double> *) c->h_out;
-        for (int64_t k = 0; k < nRet; k++) { j_out[k] = r[k].j; ((double *) dist)[k] = r[k].dist; ((double *) weight)[k] = r[k].weight; ((double *) criterion)[k] = r[k].crit; }
+        const Rec<double> *rr = (const Rec<double> *) c->h_out;
+        for (int64_t k = 0; k < nRet; k++) { j_out[k] = rr[k].j; ((double *) dist)[k] = rr[k].dist; ((double *) weight)[k] = rr[k].weight; ((double *) criterion)[k] = rr[k].crit; }
     }
     *nOut = nRet;
-    // accounting: one distance per active node
-    if (query < c->N) { c->cnt.seqOps += c->nActLeaf; c->cnt.algoBytes += c->nActLeaf * c->L; }
-    else { c->cnt.profileOps += c->nActLeaf; c->cnt.algoBytes += c->nActLeaf * profile_bytes(c, 0); }
-    c->cnt.profileOps += c->nActInternal;
-    c->cnt.algoBytes += c->nActInternal * profile_bytes(c, c->N);
+    // accounting: one distance per active node (a sharded context accounts its share)
+    const int64_t nLeaf = W > 1 ? c->nActLeaf / W : c->nActLeaf, nInt = W > 1 ? c->nActInternal / W : c->nActInternal;
+    if (query < c->N) { c->cnt.seqOps += nLeaf; c->cnt.algoBytes += nLeaf * c->L; }
+    else { c->cnt.profileOps += nLeaf; c->cnt.algoBytes += nLeaf * profile_bytes(c, 0); }
+    c->cnt.profileOps += nInt;
+    c->cnt.algoBytes += nInt * profile_bytes(c, c->N);
     c->cnt.algoBytes += profile_bytes(c, query);
     return VFT_OK;
 }
@@ -1844,7 +1942,14 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
     // response: int32 count[nLists] | j[nLists*m] | (8-aligned) P dist[nLists*m]
     const size_t offOD = (((size_t) nLists + (size_t) nLists * m) * 4 + 7) & ~(size_t) 7;
     const size_t outBytes = offOD + (size_t) nLists * m * ps + 32;
-    int rc = ensure_pinned(c, std::max(inBytes, outBytes)); if (rc) return rc;
+    // a sharded context takes the lists [l0, l1) of W contiguous chunks; its saved lists travel in the exchange buffer
+    const int W = shard_world(c), rk = shard_rank(c);
+    const int64_t chunkLists = (nLists + W - 1) / W;
+    const int64_t l0 = std::min(nLists, rk * chunkLists), l1 = std::min(nLists, l0 + chunkLists), myLists = l1 - l0;
+    const size_t xOffD = (((size_t) chunkLists + (size_t) chunkLists * m) * 4 + 7) & ~(size_t) 7;      // chunk image: count | j | (8-aligned) dist
+    const size_t xBytes = (xOffD + (size_t) chunkLists * m * ps + 15) & ~(size_t) 15;
+    int rc = ensure_pinned(c, std::max(std::max(inBytes, outBytes), W > 1 ? (size_t) W * xBytes : (size_t) 0)); if (rc) return rc;
+    if (W > 1) { rc = dist_reserve(c->stream, xBytes); if (rc) return rc; }
     int32_t *hi = (int32_t *) c->h_in;
     int32_t *hNode = hi, *hOff = hNode + nLists, *hOwnJ = hOff + nLists + 1, *hAllJ = hOwnJ + total;
     for (int64_t l = 0; l < nLists; l++) hNode[l] = (int32_t) iNode[l];
@@ -1875,43 +1980,61 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
     void *uD = dm, *r0 = dm + slots * ps, *r1 = dm + 2 * slots * ps;                      // P arrays first (8-byte aligned)
     int32_t *uJ = (int32_t *) (dm + 3 * slots * ps), *reqA = uJ + slots, *reqB = reqA + slots, *cnt = reqB + slots;
     const size_t smemSort = (size_t) np2 * 12;
+    // results: straight into mapped host memory, or (sharded) into this rank's chunk image of the exchange buffer
     int32_t *hoCount = (int32_t *) c->h_out, *hoJ = hoCount + nLists;
     void *hoD = (char *) c->h_out + offOD;
-    const int G = pick_group(c, (int64_t) slots);
-    const int64_t warps = ((int64_t) slots + G - 1) / G;
+    if (W > 1) { hoCount = (int32_t *) g_dist.send; hoJ = hoCount + chunkLists; hoD = g_dist.send + xOffD; }
+    const size_t mySlots = (size_t) myLists * cap, so = (size_t) l0 * cap;                 // this rank's slots start at `so`
+    const int G = pick_group(c, (int64_t) mySlots);
+    const int64_t warps = ((int64_t) mySlots + G - 1) / G;
     const unsigned evalBlocks = (unsigned) ((warps + 3) / 4);
     InlineItems inl;
     inl.a[0] = 0;
+    // (kernels index lists from 0: the request arrays are passed at list l0, the absolute ownOffset values still address
+    //  the whole ownJ / ownDist arrays)
 #define CALL_MERGE(P, A_, MX)                                                                                     \
     do {                                                                                                          \
         cudaFuncSetAttribute(k_merge_prep<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_MAX * 12);         \
         cudaFuncSetAttribute(k_merge_finish<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_MAX * 12);       \
         prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
-        k_merge_prep<P><<<(unsigned) nLists, MRG_T, smemSort, c->stream>>>(hNode, hOff, hOwnJ, (const P *) hP, (int) nAvail, hAllJ, \
-            (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ, (P *) uD, reqA, reqB, cnt, c->d_acct); \
+        k_merge_prep<P><<<(unsigned) myLists, MRG_T, smemSort, c->stream>>>(hNode + l0, hOff + l0, hOwnJ, (const P *) hP, (int) nAvail, hAllJ, \
+            (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ + so, (P *) uD + so, reqA + so, reqB + so, cnt + l0, c->d_acct); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
-        k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA, reqB, (int64_t) slots, 0, G, 0, nActive, 0.0, (P *) r0, (P *) r1, c->d_doneCount, (P *) nullptr); \
+        k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA + so, reqB + so, (int64_t) mySlots, 0, G, 0, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, c->d_doneCount, (P *) nullptr); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
-        k_merge_finish<P><<<(unsigned) nLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode, nActive, (int) m, (int) cap, np2, uJ, (P *) uD, reqA, (const P *) r0, cnt, hoCount, hoJ, (P *) hoD); \
+        k_merge_finish<P><<<(unsigned) myLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode + l0, nActive, (int) m, (int) cap, np2, uJ + so, (P *) uD + so, reqA + so, (const P *) r0 + so, cnt + l0, hoCount, hoJ, (P *) hoD); \
         prof_end(c);                                                                                              \
     } while (0)
-    VFT_DISPATCH(c, CALL_MERGE);
+    if (myLists > 0) { VFT_DISPATCH(c, CALL_MERGE); }
     CK(cudaGetLastError());
     unsigned long long acct[4];
     CK(cudaMemcpyAsync(acct, c->d_acct, 32, cudaMemcpyDeviceToHost, c->stream));
+    if (W > 1) {
+        const char *base; size_t stride;
+        rc = dist_allgather(c->stream, xBytes, &base, &stride); if (rc) return rc;
+        for (int w = 0; w < W; w++) CK(cudaMemcpyAsync((char *) c->h_out + (size_t) w * xBytes, base + (size_t) w * stride, xBytes, cudaMemcpyDeviceToHost, c->stream));
+        c->cnt.launches += g_dist.mode == DIST_PEER ? 1 : 0;
+    }
     CK(sync_stream(c));
     c->cnt.launches += 3;
     for (int64_t l = 0; l < nLists; l++) {
-        outCount[l] = hoCount[l];
-        for (int64_t k = 0; k < hoCount[l]; k++) outJ[l * m + k] = hoJ[l * m + k];
-        std::memcpy((char *) outDist + (size_t) l * m * ps, (char *) hoD + (size_t) l * m * ps, (size_t) hoCount[l] * ps);
-        c->cnt.algoBytes += profile_bytes(c, iNode[l]);                                  // a list shares its query
+        const int32_t *count = (const int32_t *) c->h_out, *jj = count + nLists;
+        const char *dd = (const char *) c->h_out + offOD;
+        int64_t li = l;
+        if (W > 1) {                                      // list l sits in the chunk image of rank l / chunkLists
+            const char *img = (const char *) c->h_out + (size_t) (l / chunkLists) * xBytes;
+            count = (const int32_t *) img; jj = count + chunkLists; dd = img + xOffD; li = l % chunkLists;
+        }
+        outCount[l] = count[li];
+        for (int64_t k = 0; k < count[li]; k++) outJ[l * m + k] = jj[li * m + k];
+        std::memcpy((char *) outDist + (size_t) l * m * ps, dd + (size_t) li * m * ps, (size_t) count[li] * ps);
+        if (l >= l0 && l < l1) c->cnt.algoBytes += profile_bytes(c, iNode[l]);           // a list shares its query
     }
     c->cnt.seqOps += (int64_t) acct[0]; c->cnt.profileOps += (int64_t) acct[1];
     c->cnt.algoBytes += (int64_t) acct[2] * c->L + (int64_t) acct[3] * profile_bytes(c, c->N);
-    c->cnt.h2dBytes += (int64_t) inBytes; c->cnt.d2hBytes += (int64_t) outBytes;
+    c->cnt.h2dBytes += (int64_t) inBytes; c->cnt.d2hBytes += (int64_t) (W > 1 ? (size_t) W * xBytes : outBytes);
     return VFT_OK;
 }
 
@@ -1972,7 +2095,7 @@ static inline bool ml_readable(const vft_ctx *c, int64_t id) { return id >= 0 &&
 static inline bool ml_writable(const vft_ctx *c, int64_t id) { return id >= c->N && id < c->M + c->S; }
 static inline void ml_written(vft_ctx *c, int64_t id) {
     if (id >= c->M) return;
-    if (!c->activeHost[id]) { c->activeHost[id] = 1; c->nActInternal++; }
+    if (!c->activeHost[id]) { c->activeHost[id] = 1; c->nActInternal++; c->actDirty = true; }
     if (id >= c->maxnode) c->maxnode = id + 1;
 }
 

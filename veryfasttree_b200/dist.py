@@ -1,12 +1,13 @@
 """Multi-rank plumbing of bench.py (torch.distributed: NCCL on GPUs, gloo in the CPU tests).
 
-Round 1 runs REPLICAS: every rank builds the tree of its own alignment, nothing crosses ranks on the
-data path.  What does cross ranks is measurement: a barrier on both sides of the timed region, the
-MAX over ranks of the per-rank device time, and the SUM of the units (taxa) processed.
+ONE tree is sharded over the ranks inside the C-ABI library (vft_dist_init, csrc/vft_dist.cuh): every rank runs
+the same host loop on a replicated slab, the candidate axis of the all-candidate sweeps is split and their
+results are all-gathered over NVLink peer memory (or NCCL).  This module only bootstraps that group from
+torch.distributed -- `init_sharded` hands the NCCL unique id from rank 0 to the others; `init_sharded_host`
+routes the exchange through a torch.distributed all_gather on host bytes (gloo: the CPU double of the tests) --
+and aggregates measurements (max time / sum of units) for bench.py.
 
-`sharded_one_vs_all` is the collective pattern the big sweeps shard by: every rank
-evaluates one query against ITS block of candidate nodes, the per-rank top-K records are all-gathered
-and merged in the reference's psort order (criterion ascending, ties by node id descending).
+`sharded_one_vs_all` is the older Python-level demonstration of the same exchange pattern (kept for its test).
 """
 from __future__ import annotations
 
@@ -65,3 +66,30 @@ def sharded_one_vs_all(ctx, query: int, n_active: int, k: int, device=None):
         a = a[~np.isnan(a[:, 0])]
         js.append(a[:, 0].astype(np.int64)); ds.append(a[:, 1].astype(d.dtype)); ws.append(a[:, 2].astype(d.dtype)); cs.append(a[:, 3].astype(d.dtype))
     return merge_top_k(js, ds, ws, cs, k)
+
+
+def init_sharded(lib, device: int):
+    """Collective: make the process group of torch.distributed a vft dist group on `device` (NCCL unique id from rank 0)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [lib.dist_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    lib.dist_init(rank, world, box[0], device)
+    return lib.dist_info()
+
+
+def init_sharded_host(lib, device: int = 0):
+    """The same group with the exchange routed through torch.distributed.all_gather on host bytes (any backend)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    def allgather(payload: bytes) -> bytes:
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return b"".join(o.numpy().tobytes() for o in out)
+
+    lib.dist_init_host(rank, world, allgather, device)
+    return lib.dist_info()
