@@ -140,6 +140,7 @@ extern "C" int vft_release_cached_memory(void) { mem_release_all(); return VFT_O
 // ia/ib/r0/r1 live in pinned host memory mapped into the device address space (zero-copy): a
 // request costs one launch and one stream synchronisation, no separate memcpy.
 constexpr int INLINE_ITEMS = 896;
+constexpr int WIDE_THREADS[6] = {384, 192, 128, 96, 64, 32};      // CTA sizes of the CTA-per-pair kernel (k_eval_wide), largest first
 constexpr size_t SPEC_MAX = 4096;                                     // items of one speculative join request
 struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 7 KB of kernel parameters
 
@@ -1132,6 +1133,7 @@ struct vft_ctx {
     double *d_terms;                           // [2*Lp] self-distance terms of k_average
     void *d_mrg; size_t mrgCap;
     bool wideOk;
+    int wideSlots[6] = {0, 0, 0, 0, 0, 0};        // co-resident CTAs of k_eval_wide on the whole GPU at WIDE_THREADS[k] threads per CTA
     bool stagedOk = false;                     // the TMA-staged sweep kernels apply (fp32, 20 states, matrix mode, rows fit shared memory)
     size_t stagedSmem = 0;
     unsigned long long *d_acct;
@@ -1353,7 +1355,10 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
         cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
         VFT_DISPATCH(c, SET_SMEM);
 #define SET_SMEM_WIDE(P, A_, MX) do { const size_t w = wide_smem_bytes<P, A_, MX>(c->Lp); c->wideOk = w <= 200 * 1024; \
-        if (c->wideOk && w > 48 * 1024) cudaFuncSetAttribute(k_eval_wide<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) w); } while (0)
+        if (c->wideOk && w > 48 * 1024) cudaFuncSetAttribute(k_eval_wide<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) w); \
+        int nSm = 148; cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, cfg->device); \
+        for (int k = 0; c->wideOk && k < 6; k++) { int nb = 0; \
+            if (WIDE_THREADS[k] <= (sizeof(P) == 4 ? 384 : 256) && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval_wide<P, A_, MX>, WIDE_THREADS[k], w) == cudaSuccess) c->wideSlots[k] = nb * nSm; } } while (0)
         VFT_DISPATCH(c, SET_SMEM_WIDE);
         // TMA-staged sweeps: tiles of 16 warps + the staged rows (vectors + weights + codes of one node, or codeDist + weights)
         const size_t rows = (size_t) c->Lp * (20 * 4 + 4 + 1) + 64;
@@ -1611,8 +1616,12 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
         else k_eval<P, A_, MX, false><<<blocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(EVAL_ARGS(P)); } while (0)
     // long alignments, lists that cannot fill the machine with a warp per pair: a CTA per pair
     const bool wide = c->wideOk && c->Lp >= 512 && n <= 2048;
-    // threads per pair: as many warps as keep the machine full (148 SMs x 1536 threads), so that each warp walks few chunks
-    const int wideThreads = (c->ps == 4 && n <= 592) ? 384 : (n <= 888 ? 256 : 128);
+    // threads per pair: the largest CTA for which ALL n CTAs are co-resident (registers decide: 154 per thread in the fp32
+    // 20-state build = 12 warps per SM).  One wave matters more than warps per pair: the list's latency is one CTA's
+    // (chunks per warp + the ordered sum), whereas a second wave doubles it.
+    int wideThreads = 32;
+    for (int k = 0; k < 6; k++) if (c->wideSlots[k] >= n) { wideThreads = WIDE_THREADS[k]; break; }
+    if (const char *e = std::getenv("VFT_WIDE_THREADS")) { const int t = std::atoi(e); if (t >= 32 && t <= (c->ps == 4 ? 384 : 256) && t % 32 == 0) wideThreads = t; }
 #define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut, flag, seq)
     prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     if (wide) { VFT_DISPATCH(c, CALL_EVAL_WIDE); } else { VFT_DISPATCH(c, CALL_EVAL); }
