@@ -1113,6 +1113,7 @@ __global__ void k_init_leaves(Store<P> s) {
 // =================================================================================================
 
 #include "vft_dist.cuh"
+#include "vft_sweep.cuh"
 
 struct vft_ctx {
     vft_config cfg;
@@ -1144,6 +1145,9 @@ struct vft_ctx {
     int64_t nActLeaf, nActInternal;
     // the ascending list of active nodes, kept on the device for the compact all-candidate sweeps (rebuilt lazily)
     int32_t *d_act = nullptr, *h_act = nullptr; int64_t nAct = 0; bool actDirty = true;
+    // query tables of the 20-state matrix sweeps (vft_sweep.cuh): [qtabCap][Lp][20] x2 + [qtabCap][Lp]
+    void *d_qcd = nullptr, *d_qv = nullptr, *d_qw = nullptr; int32_t *d_qnodes = nullptr; int64_t qtabCap = 0;
+    bool sweepOk = false;
     bool sharded = false;                      // member of the process's dist group (vft_dist.cuh): sweeps cover this rank's share
     // ML model
     void *mlTables, *mlRates;
@@ -1369,6 +1373,18 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
             cudaFuncSetAttribute(k_one_vs_all_staged<float, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->stagedSmem);
         }
     }
+    {
+        // the table-driven sweeps (vft_sweep.cuh) replace the generic grouped kernels in the 20-state matrix mode; VFT_SWEEP=0 keeps the old ones
+        const char *e = std::getenv("VFT_SWEEP");
+        c->sweepOk = c->A == 20 && c->cfg.useMatrix && !(e && e[0] == '0');
+        if (c->sweepOk) {
+#define SET_SWEEP(P) do { const int b = (int) (SWP_WARPS * SweepSmem<P>::perWarp); \
+            cudaFuncSetAttribute(k_sweep20<P, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); \
+            cudaFuncSetAttribute(k_sweep20<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); \
+            cudaFuncSetAttribute(k_sweep20<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); } while (0)
+            if (c->ps == 4) SET_SWEEP(float); else SET_SWEEP(double);
+        }
+    }
     cudaFuncSetAttribute(k_topk_select<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     cudaFuncSetAttribute(k_topk_select<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4 + SEL_MAXK * 12);
     CK(sync_stream(c));
@@ -1397,7 +1413,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
-    mem_free(c->h_in); mem_free(c->h_out); mem_free(c->d_act); mem_free(c->h_act);
+    mem_free(c->h_in); mem_free(c->h_out); mem_free(c->d_act); mem_free(c->h_act); mem_free(c->d_qcd); mem_free(c->d_qv); mem_free(c->d_qw); mem_free(c->d_qnodes);
     mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms); mem_free(c->d_candK); mem_free(c->d_candI);
     for (void *q : {c->ow2, c->ov2, c->ocd2, c->d_specR0, c->d_specR1, c->d_specSelf, c->h_specIn, c->h_specOut}) mem_free(q);
     if (c->specDone) cudaEventDestroy(c->specDone);
@@ -1780,6 +1796,31 @@ extern "C" int vft_dist_pairs(vft_ctx *c, const int64_t *pi, const int64_t *pj, 
     return vft_eval_batch(c, nullptr, 0, 0, 0.0, nullptr, pi, pj, n, flags, dist, weight);
 }
 
+// room for the query tables of nTab queries
+static int ensure_qtabs(vft_ctx *c, int64_t nTab) {
+    if (nTab <= c->qtabCap) return VFT_OK;
+    const int64_t cap = std::max<int64_t>(nTab, std::min<int64_t>(2 * c->qtabCap, nTab + 64));
+    mem_free(c->d_qcd); mem_free(c->d_qv); mem_free(c->d_qw); mem_free(c->d_qnodes);
+    c->d_qcd = c->d_qv = c->d_qw = nullptr; c->d_qnodes = nullptr; c->qtabCap = 0;
+    const size_t row = (size_t) c->Lp * c->ps;
+    CK(mem_alloc(&c->d_qcd, (size_t) cap * row * 20, MEM_DEVICE)); CK(mem_alloc(&c->d_qv, (size_t) cap * row * 20, MEM_DEVICE));
+    CK(mem_alloc(&c->d_qw, (size_t) cap * row, MEM_DEVICE)); CK(mem_alloc((void **) &c->d_qnodes, (size_t) cap * 4, MEM_DEVICE));
+    c->qtabCap = cap;
+    return VFT_OK;
+}
+template<typename P>
+static QTab<P> make_qtab(vft_ctx *c, bool outProfile) {
+    QTab<P> q;
+    if (outProfile) { q.cd = (const P *) c->ocd; q.v = (const P *) c->ov; q.w = (const P *) c->ow; }
+    else { q.cd = (const P *) c->d_qcd; q.v = (const P *) c->d_qv; q.w = (const P *) c->d_qw; }
+    q.stride = (size_t) c->Lp * 20;
+    return q;
+}
+static inline unsigned sweep_blocks(int64_t nSlots) {
+    const int64_t groups = (nSlots + 31) / 32;
+    return (unsigned) std::max<int64_t>(1, std::min<int64_t>((groups + SWP_WARPS - 1) / SWP_WARPS, 148 * 8));
+}
+
 // the ascending active list on the device (the compact sweeps index it; a sharded context takes every W-th entry)
 static int ensure_active(vft_ctx *c) {
     if (!c->actDirty) return VFT_OK;
@@ -1810,8 +1851,10 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     if (W > 1) { rc = dist_reserve(c->stream, (size_t) chunk * c->ps); if (rc) return rc; res = g_dist.send; }
 #define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), len, G, nActive, totdiam, c->d_act, W, r, (P *) res)
     prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
+#define CALL_ODA_SWEEP(P) k_sweep20<P, 1><<<sweep_blocks(len), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, true), c->d_act, W, r, nullptr, nullptr, 32, len, -1, nActive, totdiam, (P *) nullptr, (P *) nullptr, (P *) nullptr, (uint64_t *) nullptr, (P *) res)
     if (len > 0) {
-        if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), len, std::min(G, STG_G), nActive, totdiam, c->d_act, W, r, (float *) res);
+        if (c->sweepOk) { if (c->ps == 4) CALL_ODA_SWEEP(float); else CALL_ODA_SWEEP(double); }
+        else if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), len, std::min(G, STG_G), nActive, totdiam, c->d_act, W, r, (float *) res);
         else { VFT_DISPATCH(c, CALL_ODA); }
     }
     prof_end(c);
@@ -1872,7 +1915,14 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
 #define CALL_OVA_LEAF(P, A_, MX) k_one_vs_all_leaf<P, A_, MX><<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, list, W, r)
 #define CALL_OVA_WARP(P, A_, MX) k_one_vs_all_warp<P, A_, MX><<<(unsigned) ((warpsQ + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(Gq), c->stream>>>(make_store<P>(c), query, nActive, n, jBegin, jEnd, Gq, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, list, W, r)
     prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
-    if (n > 0) {
+#define CALL_OVA_SWEEP(P) do { \
+        k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), 1), 128, 0, c->stream>>>(make_store<P>(c), nullptr, query, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
+        k_sweep20<P, 0><<<sweep_blocks(n), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, false), list, W, r, nullptr, nullptr, 32, n, query, nActive, 0.0, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, (P *) nullptr); } while (0)
+    if (n > 0 && compact && c->sweepOk) {
+        int rq = ensure_qtabs(c, 1); if (rq) return rq;
+        if (c->ps == 4) CALL_OVA_SWEEP(float); else CALL_OVA_SWEEP(double);
+        c->cnt.launches++;
+    } else if (n > 0) {
         if (query < c->N) { VFT_DISPATCH(c, CALL_OVA_LEAF); }
         else if (c->stagedOk) k_one_vs_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), query, nActive, n, jBegin, jEnd, std::min(Gq, STG_G), (float *) c->d_dist, (float *) c->d_weight, (float *) c->d_crit, c->d_keys, list, W, r);
         else { VFT_DISPATCH(c, CALL_OVA_WARP); }
@@ -1938,7 +1988,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
         if (iNode[l] < 0 || iNode[l] >= c->maxnode || !c->activeHost[iNode[l]] || ownOffset[l + 1] < ownOffset[l]) return fail(VFT_EINVAL, "bad list");
         maxOwn = std::max(maxOwn, ownOffset[l + 1] - ownOffset[l]);
     }
-    const int64_t total = ownOffset[nLists], cap = maxOwn + nAvail;
+    const int64_t total = ownOffset[nLists], cap = (maxOwn + nAvail + 31) / 32 * 32;      // slot stride of a list: whole warps (k_sweep20)
     if (total > 0 && (!ownJ || !ownDist)) return fail(VFT_EINVAL, "null argument");
     int np2 = 32;
     while (np2 < cap) np2 <<= 1;
@@ -2010,12 +2060,17 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
             (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ + so, (P *) uD + so, reqA + so, reqB + so, cnt + l0, c->d_acct); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
+        if (c->sweepOk) {                                                                                         \
+            k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), (unsigned) myLists), 128, 0, c->stream>>>(make_store<P>(c), hNode + l0, -1, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
+            k_sweep20<P, 2><<<sweep_blocks((int64_t) mySlots), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, false), nullptr, 1, 0, reqA + so, reqB + so, (int) cap, (int64_t) mySlots, -1, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, (P *) nullptr, (uint64_t *) nullptr, (P *) nullptr); \
+        } else                                                                                                    \
         k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA + so, reqB + so, (int64_t) mySlots, 0, G, 0, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, c->d_doneCount, (P *) nullptr); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_SELECT, K_MERGE);                                                                                \
         k_merge_finish<P><<<(unsigned) myLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode + l0, nActive, (int) m, (int) cap, np2, uJ + so, (P *) uD + so, reqA + so, (const P *) r0 + so, cnt + l0, hoCount, hoJ, (P *) hoD); \
         prof_end(c);                                                                                              \
     } while (0)
+    if (myLists > 0 && c->sweepOk) { rc = ensure_qtabs(c, myLists); if (rc) return rc; }
     if (myLists > 0) { VFT_DISPATCH(c, CALL_MERGE); }
     CK(cudaGetLastError());
     unsigned long long acct[4];
