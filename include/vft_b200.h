@@ -93,6 +93,17 @@ int  vft_release_cached_memory(void);
 int  vft_upload_tables(vft_ctx *ctx, const void *distances, const void *eigenval,
                        const void *eigentot, const void *codeFreq);
 
+/* -- ingest: the character decoding of seqsToProfiles (NJ.tcc:415-457) + Uniquify (Alignment.cpp:494-526) ------
+   text[nSeqs][nPos]: the alignment rows as the reference holds them after readAlignment (ASCII, no terminators);
+   codesString: Options.codesString ("ACGT" for -nt, "ARNDCQEGHILKMFPSTWYV" otherwise; both cases decode, everything else
+   -- '-' included -- is a gap, VFT_NOCODE).  The text is decoded and hashed on the device; rows are grouped in input order and
+   every repeat is confirmed byte for byte, so the outputs are exactly the reference's: uniqueFirst[k] = the first row of the
+   k-th distinct sequence (k < *nUnique), alnToUniq[i] = the distinct sequence row i belongs to, codes[*nUnique][nPos] = the
+   decoded distinct rows in that order -- the `codes` argument of vft_upload_leaves / vft_nj_build.  All three arrays are
+   caller-allocated for nSeqs rows. */
+int  vft_ingest(const char *text, int64_t nSeqs, int64_t nPos, const char *codesString, int32_t device,
+                int64_t *uniqueFirst, int64_t *alnToUniq, uint8_t *codes, int64_t *nUnique);
+
 /* -- leaves: end of seqsToProfiles (NJ.tcc:382-534) ----------------------------------------- */
 /* codes[nSeqs][nPos]; sets weights {0,1}, selfweight = nPos-nGaps (NJ.tcc:249-252), marks all
    leaves active, no internal nodes */

@@ -17,8 +17,10 @@ A = 4 if kind == "nt" else 20
 for profile in (False, True):
     tr = api.nj_build(codes, A, 32, lib=lib, tables=tabs, device_loop=mode, profile=profile, trace=False)
     st = tr.stats; c = st["counters"]
-    print("%s %d x %d device_loop=%d profile=%s: device %.3f s, end-to-end %.3f s (leaf %.2f, joins %.2f, in calls %.2f) launches %d refreshes %d" % (
-        kind, codes.shape[0], L, mode, profile, st["deviceMsResident"] / 1e3, st["secondsEndToEnd"], st["secondsLeafTopHits"], st["secondsJoins"], st["secondsInCalls"], c["launches"], st["nRefreshTopHits"]), flush=True)
+    import zlib
+    print("%s %d x %d device_loop=%d profile=%s: device %.3f s, end-to-end %.3f s (leaf %.2f, joins %.2f, in calls %.2f) launches %d refreshes %d tree crc %08x" % (
+        kind, codes.shape[0], L, mode, profile, st["deviceMsResident"] / 1e3, st["secondsEndToEnd"], st["secondsLeafTopHits"], st["secondsJoins"], st["secondsInCalls"], c["launches"], st["nRefreshTopHits"],
+        zlib.crc32(tr.parent.tobytes() + tr.branchlength.tobytes())), flush=True)
     if profile:
         for nm, ms, cnt, by in zip(api.KERNEL_NAMES, c["msKernel"], c["nKernel"], c["bytesKernel"]):
             if cnt:

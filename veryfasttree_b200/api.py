@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
     "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
     "vft_ml_split_test_batch", "vft_ml_test_splits",
-    "vft_dist_unique_id", "vft_dist_init", "vft_dist_init_host", "vft_dist_finalize", "vft_dist_info",
+    "vft_ingest", "vft_dist_unique_id", "vft_dist_init", "vft_dist_init_host", "vft_dist_finalize", "vft_dist_info",
 ]
 
 
@@ -155,6 +155,8 @@ class Lib:
             d.vft_spec_join_discard.argtypes = [vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+        if hasattr(d, "vft_ingest"):
+            d.vft_ingest.argtypes = [vp, i64, i64, C.c_char_p, i32, vp, vp, vp, C.POINTER(i64)]
         if hasattr(d, "vft_dist_init"):
             d.vft_dist_unique_id.argtypes = [vp]
             d.vft_dist_init.argtypes = [i32, i32, vp, i32]
@@ -236,6 +238,21 @@ def encode(chars: np.ndarray, kind: str) -> np.ndarray:
         lut[ord("U")] = lut[ord("T")]
         lut[ord("u")] = lut[ord("T")]
     return np.ascontiguousarray(lut[chars])
+
+
+def ingest(chars: np.ndarray, kind: str, lib: "Lib | None" = None, device: int = 0):
+    """Alignment text [nSeqs][nPos] (uint8 ASCII) -> (codes of the distinct rows, uniqueFirst, alnToUniq) through vft_ingest:
+    seqsToProfiles' decoding (NeighbourJoining.tcc:415-457) + Uniquify (Alignment.cpp:494-526)."""
+    lib = lib or load()
+    text = np.ascontiguousarray(chars, dtype=np.uint8)
+    n, L = text.shape
+    first = np.empty(n, dtype=np.int64)
+    to_uniq = np.empty(n, dtype=np.int64)
+    codes = np.empty((n, L), dtype=np.uint8)
+    nu = C.c_int64()
+    alphabet = (CODES_NT if kind == "nt" else CODES_AA).encode()
+    lib.check(lib.dll.vft_ingest(_ptr(text), n, L, alphabet, device, _ptr(first), _ptr(to_uniq), _ptr(codes), C.byref(nu)), "vft_ingest")
+    return codes[:nu.value].copy(), first[:nu.value].copy(), to_uniq
 
 
 def _ptr(a):

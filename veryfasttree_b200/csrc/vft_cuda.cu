@@ -31,6 +31,7 @@
 #include "nj_loop_logic.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -720,7 +721,10 @@ template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
 k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
           double *__restrict__ gTerms, unsigned int *__restrict__ doneCount, P *dOw, P *dOv, P *dOcd, P *specSelf,
-          const njl::Scalars *jd = nullptr) {
+          const njl::Scalars *jd = nullptr, int ppc = 0) {
+    // ppc: positions per CTA and pass (0: one per thread).  With ppc < blockDim.x the first ppc threads build the profile
+    // (and the out-profile's new vector); then ALL threads share the 20 codeDist entries of each position (setCodeDist,
+    // 20 three-way products of 20 per position: 85 % of this kernel's arithmetic, serial per position otherwise)
     // dOw/dOv/dOcd: where the UPDATEd out-profile goes (the live arrays, or the shadow copy of a speculative join);
     // specSelf != nullptr: speculative -- the self distance goes there and no per-node state is committed
     // jd != nullptr: the device-resident join loop (nj_loop_logic.h) -- the join is read from the loop's scalars
@@ -739,7 +743,10 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
     uint8_t *oc = s.codes + oid * s.Lp;
     P *ow = s.weights + row * s.Lp;
     P *ov = s.vecs + row * s.Lp * A;
-    for (int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; pos < s.Lp; pos += (int64_t) gridDim.x * blockDim.x) {
+    const int PPC = ppc > 0 ? ppc : (int) blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t) PPC; base < s.Lp; base += (int64_t) gridDim.x * PPC) {
+      const int64_t pos = base + threadIdx.x;
+      if ((int) threadIdx.x < PPC && pos < s.Lp) {
         double tw = 0, tt = 0;
         if (pos < s.L) {
             const uint32_t c1 = p1.codes[pos], c2 = p2.codes[pos];
@@ -785,7 +792,7 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
                 normalize_freq<P, A, MATRIX>(s, g);                                        // :984
 #pragma unroll
                 for (int k = 0; k < A; k++) dOv[pos * A + k] = g[k];
-                if (MATRIX) code_dist_row<P, A, MATRIX>(s, g, dOcd + pos * A);             // :1001-1003
+                if (MATRIX && ppc == 0) code_dist_row<P, A, MATRIX>(s, g, dOcd + pos * A); // :1001-1003 (ppc > 0: by all threads, below)
             }
             if (wo > 0) {                                       // self-distance term, profileDist(out,out)
                 const double wt = (double) pmul(wo, wo);
@@ -798,6 +805,28 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
             for (int k = 0; k < A; k++) ov[pos * A + k] = 0;
         }
         if (jd == nullptr) { termW[pos] = tw; termT[pos] = tt; }
+      }
+      if (MATRIX && UPDATE && ppc > 0) {
+        // setCodeDist of the updated out-profile (NJ.tcc:873-898, :1001-1003): thread per (position, code)
+        __syncthreads();
+        if (doUpdate) {
+            P e[A];
+#pragma unroll
+            for (int k = 0; k < A; k++) e[k] = s.eigenval[k];
+            for (int task = threadIdx.x; task < PPC * A; task += blockDim.x) {
+                const int64_t p2 = base + task / A;
+                const int cc = task % A;
+                if (p2 < s.L) {
+                    P g[A], b[A];
+                    load_vec<P, A>(dOv + p2 * A, g);
+#pragma unroll
+                    for (int k = 0; k < A; k++) b[k] = s.codeFreq[cc * 20 + k];
+                    dOcd[p2 * A + cc] = (P) (double) vec_mul3_sum<P, A>(g, b, e, s.reduction);
+                }
+            }
+        }
+        __syncthreads();
+      }
     }
     if (jd != nullptr) {
         // device-resident loop: profileDist(new, new) is evaluated with the join's request list (k_nj_eval), in parallel with
@@ -1378,10 +1407,8 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
         const char *e = std::getenv("VFT_SWEEP");
         c->sweepOk = c->A == 20 && c->cfg.useMatrix && !(e && e[0] == '0');
         if (c->sweepOk) {
-#define SET_SWEEP(P) do { const int b = (int) (SWP_WARPS * SweepSmem<P>::perWarp); \
-            cudaFuncSetAttribute(k_sweep20<P, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); \
-            cudaFuncSetAttribute(k_sweep20<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); \
-            cudaFuncSetAttribute(k_sweep20<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b); } while (0)
+#define SET_SWEEP1(P, M_, R_) cudaFuncSetAttribute(k_sweep20<P, M_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SweepCfg<P, M_, R_>::bytes)
+#define SET_SWEEP(P) do { SET_SWEEP1(P, 0, 8); SET_SWEEP1(P, 0, 16); SET_SWEEP1(P, 0, 32); SET_SWEEP1(P, 1, 8); SET_SWEEP1(P, 1, 16); SET_SWEEP1(P, 1, 32); SET_SWEEP1(P, 2, 32); } while (0)
             if (c->ps == 4) SET_SWEEP(float); else SET_SWEEP(double);
         }
     }
@@ -1517,13 +1544,16 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
     const size_t smem = (size_t) c->Lp * 16;
     if (smem > 200 * 1024) return fail(VFT_EINVAL, "alignment too long for the average kernel's term buffer");
     // short alignments: one CTA (no cross-CTA hand-off); long ones: 64 positions per CTA, the last CTA adds the terms
-    const int AVG_T = c->Lp <= 512 ? 256 : 64;
-    const unsigned avgBlocks = c->Lp <= 512 ? 1u : (unsigned) ((c->Lp + AVG_T - 1) / AVG_T);
+    int AVG_T = c->Lp <= 512 ? 256 : 64, ppc = 0;
+    unsigned avgBlocks = c->Lp <= 512 ? 1u : (unsigned) ((c->Lp + AVG_T - 1) / AVG_T);
+    if (update && c->cfg.useMatrix && c->Lp > 512 && !(std::getenv("VFT_AVG_SPLIT") && std::getenv("VFT_AVG_SPLIT")[0] == '0')) {
+        AVG_T = 256; ppc = 16; avgBlocks = (unsigned) ((c->Lp + ppc - 1) / ppc);      // codeDist shared by all threads of the CTA
+    }
 #define CALL_AVG(P, A_, MX)                                                                                   \
     do {                                                                                                      \
         if (update) {                                                                                         \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr); \
+            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr, nullptr, ppc); \
         } else {                                                                                              \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
             k_average<P, A_, MX, false><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr); \
@@ -1816,10 +1846,14 @@ static QTab<P> make_qtab(vft_ctx *c, bool outProfile) {
     q.stride = (size_t) c->Lp * 20;
     return q;
 }
-static inline unsigned sweep_blocks(int64_t nSlots) {
-    const int64_t groups = (nSlots + 31) / 32;
-    return (unsigned) std::max<int64_t>(1, std::min<int64_t>((groups + SWP_WARPS - 1) / SWP_WARPS, 148 * 8));
+#define LAUNCH_SWEEP(P, M_, R_, nSl, ...) k_sweep20<P, M_, R_><<<sweep_grid<R_>(nSl), SweepCfg<P, M_, R_>::NW * 32, SweepCfg<P, M_, R_>::bytes, c->stream>>>(__VA_ARGS__)
+// rows per warp by the size of the sweep (VFT_SWEEP_ROWS=8|16|32 overrides, for experiments)
+static inline int sweep_rows_for(int64_t n) {
+    static const int forced = [] { const char *e = std::getenv("VFT_SWEEP_ROWS"); const int v = e ? std::atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
+    return forced ? forced : sweep_rows(n);
 }
+#define SWEEP_BY_ROWS(P, M_, nSl, ...) do { const int rr_ = sweep_rows_for(nSl); \
+        if (rr_ == 32) LAUNCH_SWEEP(P, M_, 32, nSl, __VA_ARGS__); else if (rr_ == 16) LAUNCH_SWEEP(P, M_, 16, nSl, __VA_ARGS__); else LAUNCH_SWEEP(P, M_, 8, nSl, __VA_ARGS__); } while (0)
 
 // the ascending active list on the device (the compact sweeps index it; a sharded context takes every W-th entry)
 static int ensure_active(vft_ctx *c) {
@@ -1851,7 +1885,7 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     if (W > 1) { rc = dist_reserve(c->stream, (size_t) chunk * c->ps); if (rc) return rc; res = g_dist.send; }
 #define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), len, G, nActive, totdiam, c->d_act, W, r, (P *) res)
     prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
-#define CALL_ODA_SWEEP(P) k_sweep20<P, 1><<<sweep_blocks(len), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, true), c->d_act, W, r, nullptr, nullptr, 32, len, -1, nActive, totdiam, (P *) nullptr, (P *) nullptr, (P *) nullptr, (uint64_t *) nullptr, (P *) res)
+#define CALL_ODA_SWEEP(P) SWEEP_BY_ROWS(P, 1, len, make_store<P>(c), make_qtab<P>(c, true), c->d_act, W, r, nullptr, nullptr, 32, len, -1, nActive, totdiam, (P *) nullptr, (P *) nullptr, (P *) nullptr, (uint64_t *) nullptr, (P *) res)
     if (len > 0) {
         if (c->sweepOk) { if (c->ps == 4) CALL_ODA_SWEEP(float); else CALL_ODA_SWEEP(double); }
         else if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), len, std::min(G, STG_G), nActive, totdiam, c->d_act, W, r, (float *) res);
@@ -1917,7 +1951,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
 #define CALL_OVA_SWEEP(P) do { \
         k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), 1), 128, 0, c->stream>>>(make_store<P>(c), nullptr, query, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
-        k_sweep20<P, 0><<<sweep_blocks(n), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, false), list, W, r, nullptr, nullptr, 32, n, query, nActive, 0.0, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, (P *) nullptr); } while (0)
+        SWEEP_BY_ROWS(P, 0, n, make_store<P>(c), make_qtab<P>(c, false), list, W, r, nullptr, nullptr, 32, n, query, nActive, 0.0, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, (P *) nullptr); } while (0)
     if (n > 0 && compact && c->sweepOk) {
         int rq = ensure_qtabs(c, 1); if (rq) return rq;
         if (c->ps == 4) CALL_OVA_SWEEP(float); else CALL_OVA_SWEEP(double);
@@ -2062,7 +2096,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
         prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
         if (c->sweepOk) {                                                                                         \
             k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), (unsigned) myLists), 128, 0, c->stream>>>(make_store<P>(c), hNode + l0, -1, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
-            k_sweep20<P, 2><<<sweep_blocks((int64_t) mySlots), SWP_WARPS * 32, SWP_WARPS * SweepSmem<P>::perWarp, c->stream>>>(make_store<P>(c), make_qtab<P>(c, false), nullptr, 1, 0, reqA + so, reqB + so, (int) cap, (int64_t) mySlots, -1, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, (P *) nullptr, (uint64_t *) nullptr, (P *) nullptr); \
+            LAUNCH_SWEEP(P, 2, 32, (int64_t) mySlots, make_store<P>(c), make_qtab<P>(c, false), nullptr, 1, 0, reqA + so, reqB + so, (int) cap, (int64_t) mySlots, -1, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, (P *) nullptr, (uint64_t *) nullptr, (P *) nullptr); \
         } else                                                                                                    \
         k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA + so, reqB + so, (int64_t) mySlots, 0, G, 0, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, c->d_doneCount, (P *) nullptr); \
         prof_end(c);                                                                                              \
@@ -2384,4 +2418,5 @@ extern "C" int vft_timer_stop(vft_ctx *c, double *ms) {
     return VFT_OK;
 }
 
+#include "vft_ingest.cuh"
 #include "nj_loop_gpu.cuh"

@@ -68,49 +68,58 @@ k_query_tables(Store<P> s, const int32_t *__restrict__ nodes, int64_t single, P 
     store_vec<P, 20>(v, f);
 }
 
-constexpr int SWP_WARPS = 4;
 constexpr int SWP_QCAP = 256;                    // queued vector positions per warp (flushed above 128; a unit adds <= 128)
-template<typename P> struct SweepSmem {
-    static constexpr int WS = sizeof(P) == 4 ? 36 : 34;       // tile row stride: 16-byte aligned rows, conflict-free 128-bit row reads
-    static constexpr size_t tile = 2 * 32 * WS * sizeof(P);   // w1*w2 and piece
-    static constexpr size_t qs = 32 * 21 * sizeof(P);         // the query's table slice of the chunk, row stride 21
-    static constexpr size_t perWarp = tile + qs + SWP_QCAP * 2 + 32 * 4;
+// R = candidates (tile rows) per warp: 32 when the sweep has enough candidates to fill the machine with 32-row warps, 16 or 8
+// for the shorter sweeps (20 000 candidates are only 625 32-row warps: 4 per SM, one per scheduler -- latency bound).
+// MODE 0/1: every warp of the CTA works on the same query, chunk by chunk in lock step, and the query's table slice is staged
+// ONCE per CTA (double-buffered, one __syncthreads per chunk); MODE 2 (a query per list): per warp.
+template<typename P, int MODE, int R> struct SweepCfg {
+    static constexpr int NW = R == 32 ? 4 : 8;                 // warps per CTA
+    static constexpr int WS = sizeof(P) == 4 ? 36 : 34;        // tile row stride: 16-byte aligned rows, conflict-free 128-bit row reads
+    static constexpr size_t tile = 2 * (size_t) R * WS * sizeof(P);   // w1*w2 and piece
+    static constexpr size_t qsOne = 32 * 21 * sizeof(P);       // one table slice, row stride 21
+    static constexpr size_t perWarp = tile + SWP_QCAP * 2 + R * 4 + (MODE == 2 ? qsOne : 0);
+    static constexpr size_t shared = MODE == 2 ? 0 : 2 * qsOne;
+    static constexpr size_t bytes = shared + NW * perWarp;
 };
 
-template<typename P, int MODE>
-__global__ void __launch_bounds__(SWP_WARPS * 32, sizeof(P) == 4 ? 4 : 2)
+template<typename P, int MODE, int R>
+__global__ void __launch_bounds__(SweepCfg<P, MODE, R>::NW * 32, sizeof(P) == 4 ? (R == 32 ? 4 : 2) : 1)
 k_sweep20(Store<P> s, QTab<P> qt, const int32_t *__restrict__ list, int stride, int offset,
           const int32_t *__restrict__ reqA, const int32_t *__restrict__ reqB, int cap,
           int64_t nSlots, int64_t query, int64_t nActive, double totdiam,
           P *__restrict__ dist, P *__restrict__ weight, P *__restrict__ crit, uint64_t *__restrict__ keys, P *__restrict__ res) {
+    typedef SweepCfg<P, MODE, R> Cfg;
+    static_assert(MODE != 2 || R == 32, "a query per list: 32-row warps");
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    constexpr int WS = SweepSmem<P>::WS;
+    constexpr int WS = Cfg::WS, NW = Cfg::NW, U = R / 4;
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char *sm = smemRaw + (size_t) wid * SweepSmem<P>::perWarp;
-    P *Wt = reinterpret_cast<P *>(sm);                                   // [32][WS]
-    P *Pc = Wt + 32 * WS;                                                // [32][WS]
-    P *qs = reinterpret_cast<P *>(sm + SweepSmem<P>::tile);             // [32][21]
-    uint16_t *queue = reinterpret_cast<uint16_t *>(sm + SweepSmem<P>::tile + SweepSmem<P>::qs);
-    int32_t *ids = reinterpret_cast<int32_t *>(sm + SweepSmem<P>::tile + SweepSmem<P>::qs + SWP_QCAP * 2);
+    unsigned char *sm = smemRaw + Cfg::shared + (size_t) wid * Cfg::perWarp;
+    P *Wt = reinterpret_cast<P *>(sm);                                   // [R][WS]
+    P *Pc = Wt + R * WS;                                                 // [R][WS]
+    uint16_t *queue = reinterpret_cast<uint16_t *>(sm + Cfg::tile);
+    int32_t *ids = reinterpret_cast<int32_t *>(sm + Cfg::tile + SWP_QCAP * 2);
+    P *qsWarp = reinterpret_cast<P *>(sm + Cfg::tile + SWP_QCAP * 2 + R * 4);     // MODE 2 only
+    P *qsCta = reinterpret_cast<P *>(smemRaw);                           // MODE 0/1: [2][32][21]
     const uint32_t Lp = (uint32_t) s.Lp, nSeqs = (uint32_t) s.nSeqs;
     const int nChunks = (int) (Lp / 32);
-    const int64_t nGroups = (nSlots + 31) / 32;
+    const int64_t nGroups = (nSlots + R - 1) / R, nSuper = (nGroups + NW - 1) / NW;
     const int sub = lane >> 3, pl = (lane & 7) * 4;                      // my row within a unit, my first position within a chunk
-    typedef typename Vec4T<P>::type V4;
 
-    for (int64_t g = (int64_t) blockIdx.x * SWP_WARPS + wid; g < nGroups; g += (int64_t) gridDim.x * SWP_WARPS) {
-        const int64_t k = g * 32 + lane;
+    for (int64_t sg = blockIdx.x; sg < nSuper; sg += gridDim.x) {
+        const int64_t g = sg * NW + wid;
+        const int64_t k = g * R + lane;
         int32_t id = -1;
-        if (k < nSlots) {
+        if (lane < R && k < nSlots) {
             if (MODE == 2) { if (reqA[k] >= 0) id = reqB[k]; }
             else id = list[k * stride + offset];
         }
-        const unsigned live = __ballot_sync(full, id >= 0);
-        if (live == 0) continue;
-        const size_t tab = MODE == 2 ? (size_t) ((g * 32) / cap) : 0;     // cap is a multiple of 32: one query per group
+        const bool alive = __ballot_sync(full, id >= 0) != 0;            // (MODE 0/1: a dead warp still takes part in the staging)
+        if (MODE == 2 && !alive) continue;
+        const size_t tab = MODE == 2 ? (size_t) ((g * R) / cap) : 0;      // cap is a multiple of 32: one query per group
         const P *tcd = qt.cd + tab * qt.stride, *tv = qt.v + tab * qt.stride, *tw = qt.w + tab * (qt.stride / 20);
-        ids[lane] = id;
+        if (lane < R) ids[lane] = id;
         __syncwarp();
         double den = 0, top = 0;
         int nq = 0;                                                       // queued items (warp-uniform)
@@ -133,87 +142,99 @@ k_sweep20(Store<P> s, QTab<P> qt, const int32_t *__restrict__ list, int stride, 
             nq = 0;
             __syncwarp();
         };
+        // the query's [32][20] table slice of chunk ch -> shared memory (coalesced reads, row stride 21 against bank conflicts)
+        auto stage = [&](int ch) {
+            const P *src = tcd + (uint64_t) ch * 32 * 20;
+            if constexpr (MODE == 2) {
+#pragma unroll
+                for (int t = 0; t < 20; t++) { const int idx = t * 32 + lane; qsWarp[(idx / 20) * 21 + (idx % 20)] = src[idx]; }
+            } else {
+                P *dst = qsCta + (size_t) (ch & 1) * 32 * 21;
+                for (int idx = threadIdx.x; idx < 640; idx += NW * 32) dst[(idx / 20) * 21 + (idx % 20)] = src[idx];
+            }
+        };
+        if constexpr (MODE != 2) { stage(0); __syncthreads(); }
         for (int ch = 0; ch < nChunks; ch++) {
             const uint32_t p0c = (uint32_t) ch * 32;
-            // the query's [32][20] table slice -> shared memory (coalesced reads, row stride 21 against bank conflicts)
+            const P *qs = qsWarp;
+            if constexpr (MODE == 2) stage(ch);
+            else { if (ch + 1 < nChunks) stage(ch + 1); qs = qsCta + (size_t) (ch & 1) * 32 * 21; }
+            if (alive) {
+                P qw[4];
+                load_vec<P, 4>(tw + p0c + pl, qw);
+                // phase 1 loads: codes + weights of my 4 positions in each of the U units
+                uint32_t c4[U];
+                P w4[U][4];
 #pragma unroll
-            for (int t = 0; t < 20; t++) {
-                const int idx = t * 32 + lane;
-                qs[(idx / 20) * 21 + (idx % 20)] = tcd[(uint64_t) p0c * 20 + idx];
-            }
-            P qw[4];
-            load_vec<P, 4>(tw + p0c + pl, qw);
-            // phase 1 loads: codes + weights of my 4 positions in each of the 8 units
-            uint32_t c4[8];
-            P w4[8][4];
+                for (int u = 0; u < U; u++) {
+                    const int32_t rid = __shfl_sync(full, id, u * 4 + sub);
+                    c4[u] = 0x7F7F7F7Fu;
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int32_t rid = __shfl_sync(full, id, u * 4 + sub);
-                c4[u] = 0x7F7F7F7Fu;
+                    for (int i = 0; i < 4; i++) w4[u][i] = 0;
+                    if (rid >= 0) {
+                        c4[u] = *reinterpret_cast<const uint32_t *>(s.codes + (uint64_t) (uint32_t) rid * Lp + p0c + pl);
+                        if ((uint32_t) rid >= nSeqs) load_vec<P, 4>(s.weights + (uint64_t) ((uint32_t) rid - nSeqs) * Lp + p0c + pl, w4[u]);
+                        else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) w4[u][i] = 0;
-                if (rid >= 0) {
-                    c4[u] = *reinterpret_cast<const uint32_t *>(s.codes + (uint64_t) (uint32_t) rid * Lp + p0c + pl);
-                    if ((uint32_t) rid >= nSeqs) load_vec<P, 4>(s.weights + (uint64_t) ((uint32_t) rid - nSeqs) * Lp + p0c + pl, w4[u]);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) w4[u][i] = ((c4[u] >> (8 * i)) & 0xFFu) != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+                            for (int i = 0; i < 4; i++) w4[u][i] = ((c4[u] >> (8 * i)) & 0xFFu) != VFT_DEV_NOCODE ? (P) 1 : (P) 0;
+                        }
                     }
                 }
-            }
-            __syncwarp();                                                 // qs staged
+                if constexpr (MODE == 2) __syncwarp();                    // qs staged
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int r = u * 4 + sub;
-                P wt[4], pc[4];
-                unsigned needMask[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t c = (c4[u] >> (8 * i)) & 0xFFu;
-                    const bool on = w4[u][i] > 0 && qw[i] > 0;
-                    // NJ.tcc:1176: weight = p1->weights[i] * p2->weights[i] (the product commutes)
-                    wt[i] = on ? pmul(w4[u][i], qw[i]) : (P) 0;
-                    pc[i] = (on && c < 20u) ? qs[(pl + i) * 21 + c] : (P) 0;
-                    needMask[i] = __ballot_sync(full, on && c == VFT_DEV_NOCODE);
-                }
-                if constexpr (sizeof(P) == 4) {
-                    *reinterpret_cast<float4 *>(Wt + r * WS + pl) = make_float4(wt[0], wt[1], wt[2], wt[3]);
-                    *reinterpret_cast<float4 *>(Pc + r * WS + pl) = make_float4(pc[0], pc[1], pc[2], pc[3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; i += 2) {
-                        *reinterpret_cast<double2 *>(Wt + r * WS + pl + i) = make_double2(wt[i], wt[i + 1]);
-                        *reinterpret_cast<double2 *>(Pc + r * WS + pl + i) = make_double2(pc[i], pc[i + 1]);
-                    }
-                }
-                if (needMask[0] | needMask[1] | needMask[2] | needMask[3]) {
+                for (int u = 0; u < U; u++) {
+                    const int r = u * 4 + sub;
+                    P wt[4], pc[4];
+                    unsigned needMask[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        if (needMask[i] >> lane & 1u) queue[nq + __popc(needMask[i] & ((1u << lane) - 1u))] = (uint16_t) ((r << 5) | (pl + i));
-                        nq += __popc(needMask[i]);
+                        const uint32_t c = (c4[u] >> (8 * i)) & 0xFFu;
+                        const bool on = w4[u][i] > 0 && qw[i] > 0;
+                        // NJ.tcc:1176: weight = p1->weights[i] * p2->weights[i] (the product commutes)
+                        wt[i] = on ? pmul(w4[u][i], qw[i]) : (P) 0;
+                        pc[i] = (on && c < 20u) ? qs[(pl + i) * 21 + c] : (P) 0;
+                        needMask[i] = __ballot_sync(full, on && c == VFT_DEV_NOCODE);
                     }
-                    if (nq > SWP_QCAP - 128) { __syncwarp(); flush(p0c); }
-                }
-            }
-            __syncwarp();
-            if (nq > 0) flush(p0c);
-            // phase 2: lane r adds row r in position order
-            if (id >= 0) {
-                const P *wr = Wt + lane * WS, *pr = Pc + lane * WS;
+                    if constexpr (sizeof(P) == 4) {
+                        *reinterpret_cast<float4 *>(Wt + r * WS + pl) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+                        *reinterpret_cast<float4 *>(Pc + r * WS + pl) = make_float4(pc[0], pc[1], pc[2], pc[3]);
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    P a[4], b[4];
-                    load_vec<P, 4>(wr + j, a);
-                    load_vec<P, 4>(pr + j, b);
+                        for (int i = 0; i < 4; i += 2) {
+                            *reinterpret_cast<double2 *>(Wt + r * WS + pl + i) = make_double2(wt[i], wt[i + 1]);
+                            *reinterpret_cast<double2 *>(Pc + r * WS + pl + i) = make_double2(pc[i], pc[i + 1]);
+                        }
+                    }
+                    if (needMask[0] | needMask[1] | needMask[2] | needMask[3]) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const double wd = (double) a[i];
-                        den = xadd(den, wd);                              // :1177 (skipped positions add +0.0: exact)
-                        top = xadd(top, xmul(wd, (double) b[i]));        // :1183
+                        for (int i = 0; i < 4; i++) {
+                            if (needMask[i] >> lane & 1u) queue[nq + __popc(needMask[i] & ((1u << lane) - 1u))] = (uint16_t) ((r << 5) | (pl + i));
+                            nq += __popc(needMask[i]);
+                        }
+                        if (nq > SWP_QCAP - 128) { __syncwarp(); flush(p0c); }
                     }
                 }
+                __syncwarp();
+                if (nq > 0) flush(p0c);
+                // phase 2: lane r adds row r in position order
+                if (id >= 0) {
+                    const P *wr = Wt + lane * WS, *pr = Pc + lane * WS;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        P a[4], b[4];
+                        load_vec<P, 4>(wr + j, a);
+                        load_vec<P, 4>(pr + j, b);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const double wd = (double) a[i];
+                            den = xadd(den, wd);                          // :1177 (skipped positions add +0.0: exact)
+                            top = xadd(top, xmul(wd, (double) b[i]));    // :1183
+                        }
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            if constexpr (MODE != 2) __syncthreads();                     // slice ch+1 staged by everybody, slice ch free again
         }
         if (id < 0) continue;
         P dd, ww;
@@ -234,6 +255,14 @@ k_sweep20(Store<P> s, QTab<P> qt, const int32_t *__restrict__ list, int stride, 
         dist[k] = d; weight[k] = w; crit[k] = c;
         keys[k] = order_key(c);
     }
+}
+
+// rows per warp of a sweep over n candidates: the largest of 32 / 16 / 8 that still gives ~16 warps per SM
+static inline int sweep_rows(int64_t n) { return n >= 32 * 2368 ? 32 : (n >= 16 * 2368 ? 16 : 8); }
+template<int R> static inline unsigned sweep_grid(int64_t nSlots) {
+    constexpr int NW = R == 32 ? 4 : 8;
+    const int64_t groups = (nSlots + R - 1) / R, super = (groups + NW - 1) / NW;
+    return (unsigned) std::max<int64_t>(1, std::min<int64_t>(super, 148 * 8));
 }
 
 }  // namespace
