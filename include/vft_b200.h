@@ -127,6 +127,16 @@ int  vft_profile_average(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2,
 int  vft_profile_average_update(vft_ctx *ctx, int64_t out_id, int64_t id1, int64_t id2,
                                 double bionjWeight, double diameter_out, int64_t nActiveOld);
 int  vft_get_self(vft_ctx *ctx, int64_t id, double *selfdist, double *selfweight);
+/* averageProfile (NJ.tcc:2067-2135, unweighted) for n INDEPENDENT items in one launch: profile out_id[k] = mean of id1[k], id2[k].
+   Only the profile rows are written (no diameter, self distance, active flag): one tree level of recomputeProfiles. */
+int  vft_profile_average_batch(vft_ctx *ctx, int64_t n, const int64_t *out_id, const int64_t *id1, const int64_t *id2);
+/* recomputeProfiles (NJ.tcc:3474-3506) over a whole tree (arrays as in vft_nj_result): every 2-child internal node becomes the
+   unweighted average of its children, children before parents -- as LEVEL-SYNCHRONOUS batches (one vft_profile_average_batch
+   per height above the leaves; the reference's own threaded variant walks the same levels, :3483-3496).  This is the
+   hand-over from the NJ slab to the ML phase: called after the tables were replaced by the transition matrix's
+   (vft_upload_tables with transmat-as-distance-matrix, VeryFastTreeImpl.tcc:253-256) it re-expresses every internal
+   profile in the new basis. */
+int  vft_recompute_profiles(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child);
 
 /* -- speculative join: the NEXT join's device work launched ahead of the host's decision ------------------------------
    The join loop is a dependency chain (search -> averageProfile -> distances of the new node -> bookkeeping -> search):

@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "vft_ml_star_optimize_batch", "vft_ml_optimize_branch_lengths", "vft_choose_nni_batch",
     "vft_spec_join_launch", "vft_spec_join_take", "vft_spec_join_discard", "vft_sh_support_batch",
     "vft_ml_split_test_batch", "vft_ml_test_splits",
-    "vft_ingest", "vft_dist_unique_id", "vft_dist_init", "vft_dist_init_host", "vft_dist_finalize", "vft_dist_info",
+    "vft_ingest", "vft_profile_average_batch", "vft_recompute_profiles", "vft_dist_unique_id", "vft_dist_init", "vft_dist_init_host", "vft_dist_finalize", "vft_dist_info",
 ]
 
 
@@ -155,6 +155,9 @@ class Lib:
             d.vft_spec_join_discard.argtypes = [vp]
         if hasattr(d, "vft_tophits_merge"):
             d.vft_tophits_merge.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+        if hasattr(d, "vft_recompute_profiles"):
+            d.vft_profile_average_batch.argtypes = [vp, i64, vp, vp, vp]
+            d.vft_recompute_profiles.argtypes = [vp, i64, i64, vp, vp]
         if hasattr(d, "vft_ingest"):
             d.vft_ingest.argtypes = [vp, i64, i64, C.c_char_p, i32, vp, vp, vp, C.POINTER(i64)]
         if hasattr(d, "vft_dist_init"):
@@ -321,6 +324,15 @@ class Context:
         self.lib.check(self.lib.dll.vft_profile_average_update(self.h, out_id, id1, id2, bionj_weight, diameter,
                                                                n_active_old), "vft_profile_average_update")
         self._maxnode = max(self._maxnode, out_id + 1)
+
+    def profile_average_batch(self, out_id, id1, id2):
+        o, a, b = (np.ascontiguousarray(x, dtype=np.int64) for x in (out_id, id1, id2))
+        self.lib.check(self.lib.dll.vft_profile_average_batch(self.h, len(o), _ptr(o), _ptr(a), _ptr(b)), "vft_profile_average_batch")
+
+    def recompute_profiles(self, root, n_child, child):
+        nc = np.ascontiguousarray(n_child, dtype=np.int32)
+        ch = np.ascontiguousarray(child, dtype=np.int64)
+        self.lib.check(self.lib.dll.vft_recompute_profiles(self.h, int(root), len(nc), _ptr(nc), _ptr(ch)), "vft_recompute_profiles")
 
     def get_self(self, node):
         d, w = C.c_double(), C.c_double()

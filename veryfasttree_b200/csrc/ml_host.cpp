@@ -233,3 +233,30 @@ extern "C" int vft_set_ml_rates(vft_ctx *ctx, int64_t root, int64_t maxnode, con
     return set_ml_rates<double>(ctx, cfg, !hasTransmat, root, maxnode, nChild, child, (const double *) branchlength, nRateCats,
                                 MLMinRelBranchLength, MLMinBranchLength, fastexpLevel, leafCodes, (double *) rates, ratecat, siteLoglk);
 }
+
+// recomputeProfiles, NJ.tcc:3474-3506 (the minimum-evolution counterpart of recomputeMLProfiles): one
+// vft_profile_average_batch per tree level
+extern "C" int vft_recompute_profiles(vft_ctx *ctx, int64_t root, int64_t maxnode, const int32_t *nChild, const int64_t *child) {
+    if (!ctx || !nChild || !child || root < 0 || root >= maxnode) return VFT_EINVAL;
+    std::vector<int64_t> order;
+    if (post_order(root, maxnode, nChild, child, order) != VFT_OK) return VFT_EINVAL;
+    std::vector<int32_t> height((size_t) maxnode, 0);
+    int32_t H = 0;
+    for (int64_t node : order) {
+        int32_t h = 0;
+        for (int k = 0; k < nChild[node]; k++) h = std::max(h, height[child[3 * node + k]] + 1);
+        height[node] = h; H = std::max(H, h);
+    }
+    std::vector<std::vector<int64_t>> levels((size_t) H + 1);
+    for (int64_t node : order) if (nChild[node] == 2) levels[height[node]].push_back(node);       // :3476
+    std::vector<int64_t> a, b;
+    for (int32_t h = 1; h <= H; h++) {
+        const auto &lv = levels[h];
+        if (lv.empty()) continue;
+        a.resize(lv.size()); b.resize(lv.size());
+        for (size_t k = 0; k < lv.size(); k++) { a[k] = child[3 * lv[k]]; b[k] = child[3 * lv[k] + 1]; }
+        const int rc = vft_profile_average_batch(ctx, (int64_t) lv.size(), lv.data(), a.data(), b.data());
+        if (rc != VFT_OK) return rc;
+    }
+    return VFT_OK;
+}

@@ -871,6 +871,46 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
     }
 }
 
+// averageProfile (NJ.tcc:2067-2135) for n independent (out, child, child) items: one tree level of the ME
+// recomputeProfiles (NJ.tcc:3474-3506).  Only the profile rows are written -- no diameter, self distance or active flags.
+template<typename P, int A, bool MATRIX>
+__global__ void __launch_bounds__(128)
+k_average_batch(Store<P> s, const int32_t *__restrict__ oids, const int32_t *__restrict__ id1s, const int32_t *__restrict__ id2s, int64_t itemBase) {
+    const int64_t item = itemBase + blockIdx.y;
+    const int64_t oid = oids[item], id1 = id1s[item], id2 = id2s[item];
+    const int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    if (pos >= s.Lp) return;
+    const View<P, A> p1 = make_view<P, A>(s, id1), p2 = make_view<P, A>(s, id2);
+    const int64_t row = oid - s.nSeqs;
+    uint8_t *oc = s.codes + oid * s.Lp;
+    P *ow = s.weights + row * s.Lp;
+    P *ov = s.vecs + row * s.Lp * A;
+    P f[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) f[k] = 0;
+    P wo = 0;
+    uint32_t co = VFT_DEV_NOCODE;
+    if (pos < s.L) {
+        const uint32_t c1 = p1.codes[pos], c2 = p2.codes[pos];
+        const P w1 = p1.w ? p1.w[pos] : (c1 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+        const P w2 = p2.w ? p2.w[pos] : (c2 != VFT_DEV_NOCODE ? (P) 1 : (P) 0);
+        wo = (P) xadd(xmul(0.5, (double) w1), xmul(0.5, (double) w2));                   // :2075, unweighted (-1 => 0.5)
+        if (wo > 0) {                                                                      // :2077-2085
+            if (w1 > 0 && c1 != VFT_DEV_NOCODE && (w2 <= 0 || c1 == c2)) co = c1;
+            else if (w1 <= 0 && w2 > 0 && c2 != VFT_DEV_NOCODE) co = c2;
+        }
+        if (wo > 0 && co == VFT_DEV_NOCODE) {                                              // :2104-2112
+            if (w1 > 0) add_to_freq<P, A, MATRIX>(s, f, xmul((double) w1, 0.5), c1, (c1 == VFT_DEV_NOCODE && p1.v) ? p1.v + pos * A : nullptr);
+            if (w2 > 0) add_to_freq<P, A, MATRIX>(s, f, xmul((double) w2, 0.5), c2, (c2 == VFT_DEV_NOCODE && p2.v) ? p2.v + pos * A : nullptr);
+            normalize_freq<P, A, MATRIX>(s, f);
+        }
+    }
+    ow[pos] = wo;
+    oc[pos] = (uint8_t) co;
+#pragma unroll
+    for (int k = 0; k < A; k++) ov[pos * A + k] = f[k];
+}
+
 // a speculative join that turned out right: its per-node state becomes real (vft_spec_join_take)
 template<typename P>
 __global__ void k_spec_commit(Store<P> s, int64_t oid, int64_t id1, int64_t id2, P diameterOut, const P *__restrict__ specSelf) {
@@ -1580,6 +1620,36 @@ extern "C" int vft_profile_average(vft_ctx *c, int64_t out_id, int64_t id1, int6
 extern "C" int vft_profile_average_update(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, double bionjWeight,
                                           double diameter_out, int64_t nActiveOld) {
     return launch_average(c, out_id, id1, id2, bionjWeight, diameter_out, nActiveOld, true);
+}
+
+extern "C" int vft_profile_average_batch(vft_ctx *c, int64_t n, const int64_t *out_id, const int64_t *id1, const int64_t *id2) {
+    if (!c || n < 0 || (n > 0 && (!out_id || !id1 || !id2))) return fail(VFT_EINVAL, "null argument");
+    if (n == 0) return VFT_OK;
+    bind_device(c);
+    int rc = ensure_pinned(c, (size_t) n * 12); if (rc) return rc;
+    rc = ensure_lists(c, n); if (rc) return rc;
+    int32_t *h = (int32_t *) c->h_in;
+    for (int64_t k = 0; k < n; k++) {
+        // items of one call must be independent: every input row is a leaf or an internal row that is not an output of the call
+        if (out_id[k] < c->N || out_id[k] >= c->M || id1[k] < 0 || id2[k] < 0 || id1[k] >= c->M || id2[k] >= c->M) return fail(VFT_EINVAL, "bad node id");
+        h[k] = (int32_t) out_id[k]; h[n + k] = (int32_t) id1[k]; h[2 * n + k] = (int32_t) id2[k];
+    }
+    CK(cudaMemcpyAsync(c->d_pi, h, (size_t) n * 12, cudaMemcpyHostToDevice, c->stream));
+    c->cnt.h2dBytes += n * 12;
+    const int32_t *d = (const int32_t *) c->d_pi;
+    prof_begin(c, CLS_PROFILE, K_AVERAGE);
+    for (int64_t base = 0; base < n; base += 32768) {
+        const unsigned ny = (unsigned) std::min<int64_t>(32768, n - base);
+#define CALL_AVGB(P, A_, MX) k_average_batch<P, A_, MX><<<dim3((unsigned) ((c->Lp + 127) / 128), ny), 128, 0, c->stream>>>(make_store<P>(c), d, d + n, d + 2 * n, base)
+        VFT_DISPATCH(c, CALL_AVGB);
+        c->cnt.launches++;
+    }
+    prof_end(c);
+    CK(cudaGetLastError());
+    CK(sync_stream(c));                    // h_in is reused by the next call
+    c->cnt.profileAvgOps += n;
+    for (int64_t k = 0; k < n; k++) if (out_id[k] >= c->maxnode) c->maxnode = out_id[k] + 1;
+    return VFT_OK;
 }
 
 extern "C" int vft_get_self(vft_ctx *c, int64_t id, double *selfdist, double *selfweight) {
