@@ -65,7 +65,13 @@ WORKLOADS = {
            "n": 20000, "pos": 1287, "kind": "aa", "precision": 32, "ref_flags": ["-ext", "AVX2", "-fastexp", "3"]},
     "c2": {"name": "16k-taxa x 200-col nucleotide, JC/%different distances, fp32 (BASELINE.json configs[1])",
            "n": 16000, "pos": 200, "kind": "nt", "precision": 32, "ref_flags": ["-nt"]},
+    # BASELINE.json configs[2] at its full size: by hand only (the reference needs ~4 min per run at this size)
+    "c3full": {"name": "C3: 100k-taxa x 1287-col amino acid, BLOSUM45 distances, fp32 (BASELINE.json configs[2])",
+               "n": 100000, "pos": 1287, "kind": "aa", "precision": 32, "ref_flags": ["-ext", "AVX2", "-fastexp", "3"]},
 }
+# DRAM bytes per launch of the kernels, from committed `ncu --set full` captures of this workload (profiles/r2/): the
+# "traffic" side of the roofline, which cannot be measured inside this script
+NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "VeryFastTree")
 PARITY_PREFIX = 3000
 
@@ -182,6 +188,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--taxa", type=int, default=0, help="override the workload size (debug only)")
     ap.add_argument("--device-loop", type=int, default=-1, help="-1: library default; 0/1: host-driven / device-resident join loop")
+    ap.add_argument("--skip-cpu", action="store_true", help="no cpu_baseline / parity legs (hand runs of the big workloads)")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"], help="--gpus N > 1: one tree sharded over the GPUs, or N independent trees")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -337,6 +344,11 @@ def main():
         if cnt:
             kernels[nm] = {"launches": int(cnt), "ms": round(ms, 2), "us_per_launch": round(1e3 * ms / cnt, 2), "share_of_device_time": round(ms / prof_ms_total, 3),
                            "algorithmic_gb": round(by / 1e9, 3), "gbps": round(by / ms / 1e6, 1) if by and ms > 0 else None}
+    traffic = {}
+    try:
+        traffic = json.load(open(NCU_TRAFFIC)).get(args.workload, {})
+    except Exception:
+        pass
     dist_kernels = [k for k in kernels if kernels[k]["algorithmic_gb"]]
     dom = max(dist_kernels, key=lambda k: kernels[k]["ms"])
     achieved = kernels[dom]["gbps"]
@@ -348,7 +360,8 @@ def main():
                 "bytes_rule": "SURVEY 8d dense rule: L B per leaf, L*(A*4+4+1) B per internal node, the list's query once.  An internal profile holds a "
                               "vector only where its code is NOCODE, so DRAM traffic is BELOW this figure (ncu, profiles/): the fraction is an upper bound "
                               "of HBM utilisation; the kernels are bound by the ordered double-precision sums (one dependent DADD per position), not by HBM",
-                "traffic": None, "traffic_note": "dram__bytes per launch are in the committed ncu summaries under profiles/ (not measurable inside bench.py)",
+                "traffic": traffic.get(dom, {}).get("dram_bytes_per_launch"),
+                "traffic_note": traffic.get(dom, {}).get("source", "no ncu capture of this kernel is committed under profiles/"),
                 "distance_sweep_all_kernels": {"algorithmic_bytes_per_step": prof["distBytes"], "ms_per_step": prof["msDist"],
                                                "gbps": (prof["distBytes"] / (prof["msDist"] * 1e-3)) / 1e9 if prof["msDist"] > 0 else None}}
     if rank != 0:
@@ -359,7 +372,7 @@ def main():
         return 0
 
     cpu, parity = None, None
-    if args.gpus == 1:
+    if args.gpus == 1 and not args.skip_cpu:
         threads, seen = calibrate_threads(wl, chars, host_cores)
         if seen:
             t = seen[threads]

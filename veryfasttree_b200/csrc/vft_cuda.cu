@@ -145,6 +145,35 @@ constexpr int WIDE_THREADS[6] = {384, 192, 128, 96, 64, 32};      // CTA sizes o
 constexpr size_t SPEC_MAX = 4096;                                     // items of one speculative join request
 struct InlineItems { int32_t a[INLINE_ITEMS], b[INLINE_ITEMS]; };     // 7 KB of kernel parameters
 
+// profileDist(new, new) from the per-position terms k_average left in global memory (deferred self distance): the ordered
+// sums of NJ.tcc:1172-1183 by one lane, terms staged through shared memory by the warp
+template<typename P>
+__device__ __forceinline__ void self_sum_from_terms(const Store<P> &s, const double *__restrict__ gTerms, int64_t oid, double *sT) {
+    for (int64_t k = threadIdx.x; k < 2 * s.Lp; k += blockDim.x) sT[k] = __ldcg(gTerms + k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double top = 0, denom = 0;
+        for (int64_t pos = 0; pos < s.Lp; pos += 8) {
+            double w8[8], t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const double2 a = *reinterpret_cast<const double2 *>(sT + pos + k), b = *reinterpret_cast<const double2 *>(sT + s.Lp + pos + k);
+                w8[k] = a.x; w8[k + 1] = a.y; t8[k] = b.x; t8[k + 1] = b.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { denom = xadd(denom, w8[k]); top = xadd(top, t8[k]); }
+        }
+        s.selfweight[oid] = (P) (denom > 0 ? denom : 0.01);
+        s.selfdist[oid] = (P) (denom > 0 ? top / denom : 1.0);
+    }
+}
+template<typename P>
+__global__ void __launch_bounds__(128)
+k_self_sum(Store<P> s, const double *__restrict__ gTerms, int64_t oid) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    self_sum_from_terms<P>(s, gTerms, oid, reinterpret_cast<double *>(smem));
+}
+
 // DENSE = the throughput build for batches (fp32: capped at 128 registers -> 16 warps/SM, a few bytes of spill);
 // the per-join lists (one item per warp, latency bound) use the uncapped build.
 template<typename P, int A, bool MATRIX, bool DENSE>
@@ -211,10 +240,20 @@ template<typename P, int A, bool MATRIX>
 __global__ void __launch_bounds__(sizeof(P) == 4 ? 384 : 256)
 k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *__restrict__ ia, const int32_t *__restrict__ ib,
             int64_t n, int64_t nOutItems, int raw, int64_t nActive, double totdiam, P *__restrict__ r0, P *__restrict__ r1,
-            unsigned int *__restrict__ doneCount, P *__restrict__ hostOut, volatile unsigned int *hostFlag = nullptr, unsigned int flagVal = 0) {
+            unsigned int *__restrict__ doneCount, P *__restrict__ hostOut, volatile unsigned int *hostFlag = nullptr, unsigned int flagVal = 0,
+            int64_t selfNode = -1, const double *__restrict__ gTerms = nullptr, unsigned int *selfFlag = nullptr, unsigned int selfSeq = 0) {
+    // selfNode >= 0: the newest node's self distance is still pending (k_average left its terms in gTerms): CTA n -- one more than
+    // the items -- adds them up while the item CTAs work; the item that needs the result (the node's out-distance) waits for the
+    // flag at the very end of its own chain.  Every CTA of the launch is co-resident (the host sizes the CTAs for that), so the
+    // wait cannot deadlock.
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int64_t item = blockIdx.x;
-    const int64_t a = ia ? ia[item] : inl.a[item], b = ib ? ib[item] : inl.b[item];
+    const bool selfCta = item == n;
+    const int64_t a = selfCta ? -1 : (ia ? ia[item] : inl.a[item]), b = selfCta ? -1 : (ib ? ib[item] : inl.b[item]);
+    if (selfCta) {
+        self_sum_from_terms<P>(s, gTerms, selfNode, reinterpret_cast<double *>(smemRaw));
+        if (threadIdx.x == 0) { __threadfence(); atomicExch(selfFlag, selfSeq); }
+    }
     if (a >= 0) {
         const bool isOut = item < nOutItems;
         const bool isSeq = !isOut && !raw && a < s.nSeqs && b < s.nSeqs;
@@ -227,6 +266,10 @@ k_eval_wide(Store<P> s, const __grid_constant__ InlineItems inl, const int32_t *
             if (threadIdx.x == 0) {
                 P dd, ww, d, w = 0;
                 finish_dist<P>(den, top, dd, ww);
+                if (isOut && a == selfNode) {                // needs selfdist / selfweight of the node whose self distance CTA n computes
+                    while (atomicAdd(selfFlag, 0u) != selfSeq) { }
+                    __threadfence();
+                }
                 if (isOut && !raw) d = out_distance_finish<P>(s, a, nActive, totdiam, dd, ww);
                 else if (isSeq) { d = (P) xadd((double) dd, 0.0); w = den > 0 ? ww : (P) 0; }     // :1621-1622, :1122
                 else { d = raw ? dd : join_correct<P>(s, a, b, dd); w = ww; }
@@ -721,7 +764,9 @@ template<typename P, int A, bool MATRIX, bool UPDATE>
 __global__ void __launch_bounds__(256)
 k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight, P diameterOut, int64_t nActiveOld,
           double *__restrict__ gTerms, unsigned int *__restrict__ doneCount, P *dOw, P *dOv, P *dOcd, P *specSelf,
-          const njl::Scalars *jd = nullptr, int ppc = 0) {
+          const njl::Scalars *jd = nullptr, int ppc = 0, int noSelf = 0) {
+    // noSelf: the self distance is DEFERRED -- the terms go to gTerms and are added by the next per-join kernel (k_eval_wide's
+    // extra CTA) or by k_self_sum, off this kernel's critical path
     // ppc: positions per CTA and pass (0: one per thread).  With ppc < blockDim.x the first ppc threads build the profile
     // (and the out-profile's new vector); then ALL threads share the 20 codeDist entries of each position (setCodeDist,
     // 20 three-way products of 20 per position: 85 % of this kernel's arithmetic, serial per position otherwise)
@@ -735,7 +780,7 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
         oid = jd->jdNew; id1 = jd->jdI; id2 = jd->jdJ; diameterOut = (P) jd->jdDiameter; nActiveOld = jd->jdNActiveOld;
         doUpdate = UPDATE && jd->jdUpdate != 0;
     }
-    const bool single = gridDim.x == 1;                          // short alignments: one CTA, the terms never leave shared memory
+    const bool single = gridDim.x == 1 && !noSelf;               // short alignments: one CTA, the terms never leave shared memory
     double *termW = single ? reinterpret_cast<double *>(smem) : gTerms;   // [Lp] w*w   (global when the CTAs split the positions)
     double *termT = termW + s.Lp;                                // [Lp] w*w*piece
     const View<P, A> p1 = make_view<P, A>(s, id1), p2 = make_view<P, A>(s, id2);
@@ -831,6 +876,10 @@ k_average(Store<P> s, int64_t oid, int64_t id1, int64_t id2, double bionjWeight,
     if (jd != nullptr) {
         // device-resident loop: profileDist(new, new) is evaluated with the join's request list (k_nj_eval), in parallel with
         // the other distances of the new node, instead of as a second chain behind this kernel
+        if (blockIdx.x == 0 && threadIdx.x == 0) { s.diameter[oid] = diameterOut; s.active[id1] = 0; s.active[id2] = 0; s.active[oid] = 1; }
+        return;
+    }
+    if (noSelf) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { s.diameter[oid] = diameterOut; s.active[id1] = 0; s.active[id2] = 0; s.active[oid] = 1; }
         return;
     }
@@ -1217,6 +1266,10 @@ struct vft_ctx {
     // query tables of the 20-state matrix sweeps (vft_sweep.cuh): [qtabCap][Lp][20] x2 + [qtabCap][Lp]
     void *d_qcd = nullptr, *d_qv = nullptr, *d_qw = nullptr; int32_t *d_qnodes = nullptr; int64_t qtabCap = 0;
     bool sweepOk = false;
+    // the self distance of the newest node, deferred: its per-position terms wait in d_terms and are added up (in order) by an
+    // extra CTA of the NEXT per-join distance kernel instead of at the tail of k_average (resolved by any other entry point)
+    int64_t pendingSelf = -1; bool deferSelf = true; unsigned int *d_selfFlag = nullptr; unsigned int selfSeq = 0;
+    int sweepModes = 7;                        // which sweeps use vft_sweep.cuh: bit 0 one-vs-all, bit 1 all-node out-distances, bit 2 refresh list merges (VFT_SWEEP_MODES)
     bool sharded = false;                      // member of the process's dist group (vft_dist.cuh): sweeps cover this rank's share
     // ML model
     void *mlTables, *mlRates;
@@ -1288,9 +1341,11 @@ static inline void cpu_relax() {
 #endif
 }
 // the calling thread may be a host-pool thread that never selected the context's device
-static inline void bind_device(vft_ctx *c) {
+static void resolve_pending_self(vft_ctx *c);
+static inline void bind_device(vft_ctx *c, bool keepPendingSelf = false) {
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != c->cfg.device) cudaSetDevice(c->cfg.device);
+    if (!keepPendingSelf && c->pendingSelf >= 0) resolve_pending_self(c);
 }
 static cudaError_t sync_stream(vft_ctx *c) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -1314,6 +1369,21 @@ static Store<P> make_store(vft_ctx *c) {
     s.fPostTotalTolerance = c->cfg.fPostTotalTolerance;
     s.ovId = -2; s.ovCodes = nullptr; s.ovW = nullptr; s.ovV = nullptr;
     return s;
+}
+
+// a deferred self distance that no per-join kernel picked up: one small kernel, ordered on the context's stream
+static void resolve_pending_self(vft_ctx *c) {
+    const int64_t oid = c->pendingSelf;
+    c->pendingSelf = -1;
+    const size_t smem = (size_t) c->Lp * 16;
+    if (c->ps == 4) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_self_sum<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k_self_sum<float><<<1, 128, smem, c->stream>>>(make_store<float>(c), c->d_terms, oid);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_self_sum<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k_self_sum<double><<<1, 128, smem, c->stream>>>(make_store<double>(c), c->d_terms, oid);
+    }
+    c->cnt.launches++;
 }
 
 // dispatch on (precision, nCodes, useMatrix)
@@ -1413,6 +1483,8 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
     CK(cudaEventCreateWithFlags(&c->specDone, cudaEventDisableTiming));
     { void *f = nullptr; CK(mem_alloc(&f, 64, MEM_PINNED)); c->h_flag = (volatile unsigned int *) f; *c->h_flag = 0; }
     CK(mem_alloc((void **) &c->d_terms, 2 * Lp * 8, MEM_DEVICE));
+    CK(mem_alloc((void **) &c->d_selfFlag, 4, MEM_DEVICE)); CK(cudaMemsetAsync(c->d_selfFlag, 0, 4, c->stream));
+    if (const char *e = std::getenv("VFT_SELF_DEFER")) c->deferSelf = e[0] != '0';
     CK(cudaMemsetAsync(c->d_doneCount, 0, 4, c->stream));
     int rc = ensure_lists(c, std::max<int64_t>(4096, c->M));
     // pinned request/response buffers sized once for the largest list the NJ driver produces
@@ -1427,7 +1499,8 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
         cudaFuncSetAttribute(k_one_vs_all_warp<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
         cudaFuncSetAttribute(k_out_distance_all<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); } while (0)
         VFT_DISPATCH(c, SET_SMEM);
-#define SET_SMEM_WIDE(P, A_, MX) do { const size_t w = wide_smem_bytes<P, A_, MX>(c->Lp); c->wideOk = w <= 200 * 1024; \
+#define SET_SMEM_WIDE(P, A_, MX) do { const size_t w = std::max(wide_smem_bytes<P, A_, MX>(c->Lp), (size_t) c->Lp * 16);   /* (the deferred self distance's CTA: two term rows) */ \
+        c->wideOk = w <= 200 * 1024; \
         if (c->wideOk && w > 48 * 1024) cudaFuncSetAttribute(k_eval_wide<P, A_, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) w); \
         int nSm = 148; cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, cfg->device); \
         for (int k = 0; c->wideOk && k < 6; k++) { int nb = 0; \
@@ -1446,9 +1519,11 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
         // the table-driven sweeps (vft_sweep.cuh) replace the generic grouped kernels in the 20-state matrix mode; VFT_SWEEP=0 keeps the old ones
         const char *e = std::getenv("VFT_SWEEP");
         c->sweepOk = c->A == 20 && c->cfg.useMatrix && !(e && e[0] == '0');
+        if (const char *m = std::getenv("VFT_SWEEP_MODES")) c->sweepModes = std::atoi(m) & 7;
         if (c->sweepOk) {
-#define SET_SWEEP1(P, M_, R_) cudaFuncSetAttribute(k_sweep20<P, M_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SweepCfg<P, M_, R_>::bytes)
-#define SET_SWEEP(P) do { SET_SWEEP1(P, 0, 8); SET_SWEEP1(P, 0, 16); SET_SWEEP1(P, 0, 32); SET_SWEEP1(P, 1, 8); SET_SWEEP1(P, 1, 16); SET_SWEEP1(P, 1, 32); SET_SWEEP1(P, 2, 32); } while (0)
+#define SET_SWEEP(P) do { cudaFuncSetAttribute(k_sweep20<P, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SweepCfg<P>::bytes); \
+            cudaFuncSetAttribute(k_sweep20<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SweepCfg<P>::bytes); \
+            cudaFuncSetAttribute(k_sweep20<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SweepCfg<P>::bytes); } while (0)
             if (c->ps == 4) SET_SWEEP(float); else SET_SWEEP(double);
         }
     }
@@ -1480,7 +1555,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);
-    mem_free(c->h_in); mem_free(c->h_out); mem_free(c->d_act); mem_free(c->h_act); mem_free(c->d_qcd); mem_free(c->d_qv); mem_free(c->d_qw); mem_free(c->d_qnodes);
+    mem_free(c->h_in); mem_free(c->h_out); mem_free(c->d_act); mem_free(c->h_act); mem_free(c->d_selfFlag); mem_free(c->d_qcd); mem_free(c->d_qv); mem_free(c->d_qw); mem_free(c->d_qnodes);
     mem_free(c->d_doneCount); mem_free(c->d_mrg); mem_free(c->d_acct); mem_free(c->d_terms); mem_free(c->d_candK); mem_free(c->d_candI);
     for (void *q : {c->ow2, c->ov2, c->ocd2, c->d_specR0, c->d_specR1, c->d_specSelf, c->h_specIn, c->h_specOut}) mem_free(q);
     if (c->specDone) cudaEventDestroy(c->specDone);
@@ -1589,11 +1664,13 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
     if (update && c->cfg.useMatrix && c->Lp > 512 && !(std::getenv("VFT_AVG_SPLIT") && std::getenv("VFT_AVG_SPLIT")[0] == '0')) {
         AVG_T = 256; ppc = 16; avgBlocks = (unsigned) ((c->Lp + ppc - 1) / ppc);      // codeDist shared by all threads of the CTA
     }
+    // joins of long alignments: the self distance leaves this kernel's tail (see vft_ctx::pendingSelf)
+    const int noSelf = (update && c->deferSelf && c->wideOk && c->Lp >= 512) ? 1 : 0;
 #define CALL_AVG(P, A_, MX)                                                                                   \
     do {                                                                                                      \
         if (update) {                                                                                         \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr, nullptr, ppc); \
+            k_average<P, A_, MX, true><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr, nullptr, ppc, noSelf); \
         } else {                                                                                              \
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_average<P, A_, MX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
             k_average<P, A_, MX, false><<<avgBlocks, AVG_T, smem, c->stream>>>(make_store<P>(c), out_id, id1, id2, bionjWeight, (P) diameter_out, nActiveOld, c->d_terms, c->d_doneCount, (P *) c->ow, (P *) c->ov, (P *) c->ocd, (P *) nullptr); \
@@ -1609,6 +1686,7 @@ static int launch_average(vft_ctx *c, int64_t out_id, int64_t id1, int64_t id2, 
     if (!c->activeHost[out_id]) { c->activeHost[out_id] = 1; c->nActInternal++; }
     if (out_id >= c->maxnode) c->maxnode = out_id + 1;
     c->actDirty = true;
+    if (noSelf) c->pendingSelf = out_id;
     return VFT_OK;            // asynchronous: ordered on the context's stream
 }
 
@@ -1682,7 +1760,7 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
                               void *outDist, const int64_t *pi, const int64_t *pj, int64_t nPairs, int32_t flags,
                               void *dist, void *weight) {
     if (!c) return fail(VFT_EINVAL, "null argument");
-    bind_device(c);
+    bind_device(c, /*keepPendingSelf=*/true);
     if ((nOut > 0 && (!out_ids || !outDist)) || (nPairs > 0 && (!pi || !pj || !dist || !weight)) || nOut < 0 || nPairs < 0)
         return fail(VFT_EINVAL, "null argument");
     const int64_t n = nOut + nPairs;
@@ -1735,10 +1813,17 @@ extern "C" int vft_eval_batch(vft_ctx *c, const int64_t *out_ids, int64_t nOut, 
     // threads per pair: the largest CTA for which ALL n CTAs are co-resident (registers decide: 154 per thread in the fp32
     // 20-state build = 12 warps per SM).  One wave matters more than warps per pair: the list's latency is one CTA's
     // (chunks per warp + the ordered sum), whereas a second wave doubles it.
+    // a pending self distance rides along as one more CTA -- only when every CTA (items + 1) is co-resident, because an item may
+    // wait for it; otherwise it is resolved by its own kernel first
+    int64_t selfNode = -1;
+    if (c->pendingSelf >= 0) {
+        if (wide && c->wideSlots[5] >= n + 1) { selfNode = c->pendingSelf; c->pendingSelf = -1; c->selfSeq++; }
+        else resolve_pending_self(c);
+    }
     int wideThreads = 32;
-    for (int k = 0; k < 6; k++) if (c->wideSlots[k] >= n) { wideThreads = WIDE_THREADS[k]; break; }
+    for (int k = 0; k < 6; k++) if (c->wideSlots[k] >= n + (selfNode >= 0 ? 1 : 0)) { wideThreads = WIDE_THREADS[k]; break; }
     if (const char *e = std::getenv("VFT_WIDE_THREADS")) { const int t = std::atoi(e); if (t >= 32 && t <= (c->ps == 4 ? 384 : 256) && t % 32 == 0) wideThreads = t; }
-#define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) n, wideThreads, wide_smem_bytes<P, A_, MX>(c->Lp), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut, flag, seq)
+#define CALL_EVAL_WIDE(P, A_, MX) k_eval_wide<P, A_, MX><<<(unsigned) (n + (selfNode >= 0 ? 1 : 0)), wideThreads, std::max(wide_smem_bytes<P, A_, MX>(c->Lp), (size_t) c->Lp * 16), c->stream>>>(make_store<P>(c), inl, inlineItems ? nullptr : qa, inlineItems ? nullptr : qb, n, nOut, raw ? 1 : 0, nActive, totdiam, (P *) r0, (P *) r1, c->d_doneCount, (P *) hostOut, flag, seq, selfNode, c->d_terms, c->d_selfFlag, c->selfSeq)
     prof_begin(c, CLS_DIST, n <= INLINE_ITEMS ? K_EVAL_SMALL : K_EVAL_LARGE);
     if (wide) { VFT_DISPATCH(c, CALL_EVAL_WIDE); } else { VFT_DISPATCH(c, CALL_EVAL); }
     prof_end(c);
@@ -1916,14 +2001,7 @@ static QTab<P> make_qtab(vft_ctx *c, bool outProfile) {
     q.stride = (size_t) c->Lp * 20;
     return q;
 }
-#define LAUNCH_SWEEP(P, M_, R_, nSl, ...) k_sweep20<P, M_, R_><<<sweep_grid<R_>(nSl), SweepCfg<P, M_, R_>::NW * 32, SweepCfg<P, M_, R_>::bytes, c->stream>>>(__VA_ARGS__)
-// rows per warp by the size of the sweep (VFT_SWEEP_ROWS=8|16|32 overrides, for experiments)
-static inline int sweep_rows_for(int64_t n) {
-    static const int forced = [] { const char *e = std::getenv("VFT_SWEEP_ROWS"); const int v = e ? std::atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
-    return forced ? forced : sweep_rows(n);
-}
-#define SWEEP_BY_ROWS(P, M_, nSl, ...) do { const int rr_ = sweep_rows_for(nSl); \
-        if (rr_ == 32) LAUNCH_SWEEP(P, M_, 32, nSl, __VA_ARGS__); else if (rr_ == 16) LAUNCH_SWEEP(P, M_, 16, nSl, __VA_ARGS__); else LAUNCH_SWEEP(P, M_, 8, nSl, __VA_ARGS__); } while (0)
+#define LAUNCH_SWEEP(P, M_, nSl, ...) k_sweep20<P, M_><<<sweep_grid(nSl), SweepCfg<P>::threads, SweepCfg<P>::bytes, c->stream>>>(__VA_ARGS__)
 
 // the ascending active list on the device (the compact sweeps index it; a sharded context takes every W-th entry)
 static int ensure_active(vft_ctx *c) {
@@ -1955,9 +2033,9 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     if (W > 1) { rc = dist_reserve(c->stream, (size_t) chunk * c->ps); if (rc) return rc; res = g_dist.send; }
 #define CALL_ODA(P, A_, MX) k_out_distance_all<P, A_, MX><<<(unsigned) ((warps + 3) / 4), 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), len, G, nActive, totdiam, c->d_act, W, r, (P *) res)
     prof_begin(c, CLS_DIST, K_OUT_DIST_ALL);
-#define CALL_ODA_SWEEP(P) SWEEP_BY_ROWS(P, 1, len, make_store<P>(c), make_qtab<P>(c, true), c->d_act, W, r, nullptr, nullptr, 32, len, -1, nActive, totdiam, (P *) nullptr, (P *) nullptr, (P *) nullptr, (uint64_t *) nullptr, (P *) res)
+#define CALL_ODA_SWEEP(P) LAUNCH_SWEEP(P, 1, len, make_store<P>(c), make_qtab<P>(c, true), c->d_act, W, r, nullptr, nullptr, 32, len, -1, nActive, totdiam, (P *) nullptr, (P *) nullptr, (P *) nullptr, (uint64_t *) nullptr, (P *) res)
     if (len > 0) {
-        if (c->sweepOk) { if (c->ps == 4) CALL_ODA_SWEEP(float); else CALL_ODA_SWEEP(double); }
+        if (c->sweepOk && (c->sweepModes & 2)) { if (c->ps == 4) CALL_ODA_SWEEP(float); else CALL_ODA_SWEEP(double); }
         else if (c->stagedOk) k_out_distance_all_staged<float, 20, true><<<148, STG_T, c->stagedSmem, c->stream>>>(make_store<float>(c), len, std::min(G, STG_G), nActive, totdiam, c->d_act, W, r, (float *) res);
         else { VFT_DISPATCH(c, CALL_ODA); }
     }
@@ -2021,8 +2099,8 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     prof_begin(c, CLS_DIST, K_ONE_VS_ALL);
 #define CALL_OVA_SWEEP(P) do { \
         k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), 1), 128, 0, c->stream>>>(make_store<P>(c), nullptr, query, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
-        SWEEP_BY_ROWS(P, 0, n, make_store<P>(c), make_qtab<P>(c, false), list, W, r, nullptr, nullptr, 32, n, query, nActive, 0.0, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, (P *) nullptr); } while (0)
-    if (n > 0 && compact && c->sweepOk) {
+        LAUNCH_SWEEP(P, 0, n, make_store<P>(c), make_qtab<P>(c, false), list, W, r, nullptr, nullptr, 32, n, query, nActive, 0.0, (P *) c->d_dist, (P *) c->d_weight, (P *) c->d_crit, c->d_keys, (P *) nullptr); } while (0)
+    if (n > 0 && compact && c->sweepOk && (c->sweepModes & 1)) {
         int rq = ensure_qtabs(c, 1); if (rq) return rq;
         if (c->ps == 4) CALL_OVA_SWEEP(float); else CALL_OVA_SWEEP(double);
         c->cnt.launches++;
@@ -2164,9 +2242,9 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
             (const P *) (hP + (size_t) total * ps), (int) newnode, (int) cap, np2, (int) c->N, uJ + so, (P *) uD + so, reqA + so, reqB + so, cnt + l0, c->d_acct); \
         prof_end(c);                                                                                              \
         prof_begin(c, CLS_DIST, K_EVAL_LARGE);                                                                                  \
-        if (c->sweepOk) {                                                                                         \
+        if (c->sweepOk && (c->sweepModes & 4)) {                                                                  \
             k_query_tables<P><<<dim3((unsigned) ((c->Lp + 127) / 128), (unsigned) myLists), 128, 0, c->stream>>>(make_store<P>(c), hNode + l0, -1, (P *) c->d_qcd, (P *) c->d_qv, (P *) c->d_qw); \
-            LAUNCH_SWEEP(P, 2, 32, (int64_t) mySlots, make_store<P>(c), make_qtab<P>(c, false), nullptr, 1, 0, reqA + so, reqB + so, (int) cap, (int64_t) mySlots, -1, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, (P *) nullptr, (uint64_t *) nullptr, (P *) nullptr); \
+            LAUNCH_SWEEP(P, 2, (int64_t) mySlots, make_store<P>(c), make_qtab<P>(c, false), nullptr, 1, 0, reqA + so, reqB + so, (int) cap, (int64_t) mySlots, -1, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, (P *) nullptr, (uint64_t *) nullptr, (P *) nullptr); \
         } else                                                                                                    \
         k_eval<P, A_, MX, true><<<evalBlocks, 128, 4 * group_smem_bytes<P, A_, MX>(G), c->stream>>>(make_store<P>(c), inl, reqA + so, reqB + so, (int64_t) mySlots, 0, G, 0, nActive, 0.0, (P *) r0 + so, (P *) r1 + so, c->d_doneCount, (P *) nullptr); \
         prof_end(c);                                                                                              \
@@ -2174,7 +2252,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
         k_merge_finish<P><<<(unsigned) myLists, MRG_T, smemSort, c->stream>>>(make_store<P>(c), hNode + l0, nActive, (int) m, (int) cap, np2, uJ + so, (P *) uD + so, reqA + so, (const P *) r0 + so, cnt + l0, hoCount, hoJ, (P *) hoD); \
         prof_end(c);                                                                                              \
     } while (0)
-    if (myLists > 0 && c->sweepOk) { rc = ensure_qtabs(c, myLists); if (rc) return rc; }
+    if (myLists > 0 && c->sweepOk && (c->sweepModes & 4)) { rc = ensure_qtabs(c, myLists); if (rc) return rc; }
     if (myLists > 0) { VFT_DISPATCH(c, CALL_MERGE); }
     CK(cudaGetLastError());
     unsigned long long acct[4];
