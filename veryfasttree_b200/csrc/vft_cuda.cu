@@ -2014,8 +2014,18 @@ static int ensure_active(vft_ctx *c) {
     c->nAct = n; c->actDirty = false;
     return VFT_OK;
 }
-static inline int shard_world(const vft_ctx *c) { return c->sharded ? g_dist.world : 1; }
-static inline int shard_rank(const vft_ctx *c) { return c->sharded ? g_dist.rank : 0; }
+// A sweep is sharded only when every rank's share is big enough to pay for the exchange (its kernels are latency bound below
+// that: half the candidates are not half the time) -- otherwise every rank evaluates all of it, with no communication.  The
+// decision depends only on replicated state (the number of active nodes / request slots), so every rank takes the same one.
+static inline int64_t shard_min() {
+    static const int64_t v = [] { const char *e = std::getenv("VFT_SHARD_MIN"); const long x = e ? std::atol(e) : 8192; return (int64_t) (x > 0 ? x : 1); }();
+    return v;
+}
+static inline int shard_world(const vft_ctx *c, int64_t units = -1) {
+    if (!c->sharded) return 1;
+    return (units >= 0 && units < (int64_t) g_dist.world * shard_min()) ? 1 : g_dist.world;
+}
+static inline int shard_rank(const vft_ctx *c, int W) { return (c->sharded && W > 1) ? g_dist.rank : 0; }
 static inline int64_t shard_len(int64_t nAct, int W, int r) { return nAct > r ? (nAct - r + W - 1) / W : 0; }
 
 extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam, void *outDist, int64_t maxnode) {
@@ -2025,7 +2035,7 @@ extern "C" int vft_out_distance_all(vft_ctx *c, int64_t nActive, double totdiam,
     BytesScope bytesScope(c, K_OUT_DIST_ALL);
     int rc = ensure_pinned(c, (size_t) n * 8); if (rc) return rc;
     rc = ensure_active(c); if (rc) return rc;
-    const int W = shard_world(c), r = shard_rank(c);
+    const int W = shard_world(c, c->nAct), r = shard_rank(c, W);
     const int64_t len = shard_len(c->nAct, W, r), chunk = (c->nAct + W - 1) / W;
     const int G = pick_group(c, len);
     const int64_t warps = (len + G - 1) / G;
@@ -2086,7 +2096,7 @@ extern "C" int vft_dist_one_vs_all_range(vft_ctx *c, int64_t query, int64_t nAct
     const int32_t *list = nullptr;
     if (compact) {
         int rc = ensure_active(c); if (rc) return rc;
-        W = shard_world(c); r = shard_rank(c);
+        W = shard_world(c, c->nAct); r = shard_rank(c, W);
         n = shard_len(c->nAct, W, r); inBlock = n; list = c->d_act;
     } else {
         inBlock = 0;
@@ -2184,7 +2194,7 @@ extern "C" int vft_tophits_merge(vft_ctx *c, int64_t newnode, int64_t nActive, i
     const size_t offOD = (((size_t) nLists + (size_t) nLists * m) * 4 + 7) & ~(size_t) 7;
     const size_t outBytes = offOD + (size_t) nLists * m * ps + 32;
     // a sharded context takes the lists [l0, l1) of W contiguous chunks; its saved lists travel in the exchange buffer
-    const int W = shard_world(c), rk = shard_rank(c);
+    const int W = shard_world(c, nLists * cap), rk = shard_rank(c, W);
     const int64_t chunkLists = (nLists + W - 1) / W;
     const int64_t l0 = std::min(nLists, rk * chunkLists), l1 = std::min(nLists, l0 + chunkLists), myLists = l1 - l0;
     const size_t xOffD = (((size_t) chunkLists + (size_t) chunkLists * m) * 4 + 7) & ~(size_t) 7;      // chunk image: count | j | (8-aligned) dist
