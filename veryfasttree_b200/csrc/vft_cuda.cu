@@ -1472,6 +1472,7 @@ static int ctx_create_impl(const vft_config *cfg, vft_ctx **out, vft_ctx **parti
     c->activeHost.assign(M, 0);
     CK(mem_alloc((void **) &c->d_act, (M + 64) * 4, MEM_DEVICE)); CK(mem_alloc((void **) &c->h_act, (M + 64) * 4, MEM_PINNED));
     c->sharded = g_dist.ready && g_dist.world > 1 && g_dist.device == cfg->device;
+    if (c->sharded) g_dist.liveContexts++;
     CK(mem_alloc((void **) &c->mlTables, 1300 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRates, 64 * ps, MEM_DEVICE)); CK(mem_alloc((void **) &c->mlRatecat, Lp * 4, MEM_DEVICE));
     CK(cudaMemsetAsync(c->mlRatecat, 0, Lp * 4, c->stream));
     c->hasTransmat = false; c->hasRates = false;
@@ -1552,6 +1553,7 @@ extern "C" int vft_ctx_destroy(vft_ctx *c) {
     if (!c) return VFT_OK;
     bind_device(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->sharded && g_dist.liveContexts > 0) g_dist.liveContexts--;
     void *ptrs[] = {c->codes, c->weights, c->vecs, c->ow, c->ov, c->ocd, c->diameter, c->selfdist, c->selfweight,
                     c->outDist, c->active, c->tables, c->d_dist, c->d_weight, c->d_crit, c->d_keys, c->d_ids, c->d_pi, c->d_pj, c->d_out1, c->d_out2, c->mlTables, c->mlRates, c->mlRatecat};
     for (void *p : ptrs) mem_free(p);

@@ -54,6 +54,7 @@ struct DistGroup {
     ExpectTable expect;
     unsigned long long seq = 0;
     int64_t nExchanges = 0; int64_t bytesExchanged = 0;
+    int liveContexts = 0;                                  // sharded contexts alive: vft_dist_finalize refuses while > 0
 };
 DistGroup g_dist;
 
@@ -107,8 +108,14 @@ k_peer_allgather(const char *__restrict__ src, size_t bytes, PeerTable pt, int r
     if (threadIdx.x == 0) {
         atomicAdd_system(pt.flags[w] + rank, 1ull);
         if (part == 0) {
+            // bounded wait (~30 s of SM clock): a peer that died must not hang this GPU; the timeout is latched in the
+            // error word behind the flags and reported by the next host-side check (dist_allgather / vft_dist_info)
             const unsigned long long *mine = pt.flags[rank] + w;
-            while (ld_acquire_sys(mine) < ex.v[w]) { }
+            const long long t0 = clock64();
+            while (ld_acquire_sys(mine) < ex.v[w]) {
+                if (clock64() - t0 > 60000000000ll) { atomicExch((unsigned long long *) (pt.flags[rank] + DIST_MAXW), 1ull); break; }
+                __nanosleep(64);
+            }
         }
     }
 }
@@ -256,6 +263,14 @@ int dist_allgather(cudaStream_t stream, size_t bytes, const char **base, size_t 
         return VFT_OK;
     }
     // PEER
+    {   // a peer that timed out in an earlier exchange left its mark: fail loudly instead of computing on garbage
+        unsigned long long err = 0;
+        if (g.nExchanges % 64 == 0) {
+            CK(cudaMemcpyAsync(&err, g.peers.flags[g.rank] + DIST_MAXW, 8, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (err) return fail(VFT_ECUDA, "peer-memory exchange timed out: a rank of the group stopped responding");
+        }
+    }
     const int CT = (int) std::min<size_t>(16, std::max<size_t>(1, bytes >> 16));           // one CTA per 64 KB and peer, at most 16
     const size_t parityOff = (size_t) (g.seq & 1) * g.world * g.slotBytes;
     for (int w = 0; w < g.world; w++) g.expect.v[w] += (unsigned long long) CT;
@@ -281,6 +296,7 @@ extern "C" int vft_dist_unique_id(void *id128) {
 extern "C" int vft_dist_finalize(void) {
     DistGroup &g = g_dist;
     if (!g.ready) return VFT_OK;
+    if (g.liveContexts > 0) return fail(VFT_EINVAL, "vft_dist_finalize: sharded contexts are still alive (destroy them first)");
     if (g.device >= 0) cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     dist_release_buffers();
