@@ -45,6 +45,21 @@ def test_no_gpu_means_error_not_fallback(product):
     assert b"no CPU fallback" in product.dll.vft_last_error()
 
 
+def test_new_entry_points_refuse_to_run_without_a_device(product):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    text = np.frombuffer(b"ACGTACGA", dtype=np.uint8).reshape(2, 4).copy()
+    out = [np.zeros(2, dtype=np.int64), np.zeros(2, dtype=np.int64), np.zeros((2, 4), dtype=np.uint8)]
+    nu = C.c_int64()
+    rc = product.dll.vft_ingest(text.ctypes.data_as(C.c_void_p), 2, 4, b"ACGT", 0, *[o.ctypes.data_as(C.c_void_p) for o in out], C.byref(nu))
+    assert rc == -2 and b"no CPU fallback" in product.dll.vft_last_error()
+    assert product.dll.vft_dist_init(0, 1, None, 0) == -2          # VFT_ENODEVICE: no group without a device either
+    info = product.dist_info()
+    assert info["world"] == 1 and info["mode"] == "none"
+
+
 def test_argument_validation(product):
     h = C.c_void_p()
     for bad in (api.make_config(0, 16, 4, 32), api.make_config(8, 16, 5, 32), api.make_config(8, 16, 4, 16)):

@@ -84,6 +84,10 @@ def test_candidate_blocks_cover_everything():
 #      routed through torch.distributed.all_gather (gloo).  Every rank must return the unsharded tree, bit for bit.
 def _sharded_case(kind):
     from veryfasttree_b200 import api, synth
+    if kind == "tiny":                      # fewer lists than ranks, shares that are empty on some ranks
+        chars = synth.make_alignment(14, 40, "nt", seed=2)
+        chars = chars[synth.unique_rows(chars)]
+        return api.encode(chars, "nt"), 4, 64, None
     if kind == "nt":
         chars = synth.make_alignment(420, 160, "nt", seed=5)
         chars = chars[synth.unique_rows(chars)]
@@ -102,7 +106,7 @@ def _sharded_worker(rank, world, port, out_dir):
     from veryfasttree_b200 import api, dist as vdist
     lib = api.load(replay.ORACLE_LIB)
     out = {}
-    for kind in ("nt", "aa"):
+    for kind in ("nt", "aa", "tiny"):
         codes, A, prec, tables = _sharded_case(kind)
         info = vdist.init_sharded_host(lib)
         assert info["world"] == world and info["rank"] == rank and info["mode"] == "host"
@@ -124,7 +128,7 @@ def _run_sharded(tmp_path, world):
     replay.ensure_oracle_built()
     mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     lib = api.load(replay.ORACLE_LIB)
-    for kind in ("nt", "aa"):
+    for kind in ("nt", "aa", "tiny"):
         codes, A, prec, tables = _sharded_case(kind)
         ref = api.nj_build(codes, A, prec, lib=lib, tables=tables, host_threads=1)
         for r in range(world):
@@ -132,6 +136,8 @@ def _run_sharded(tmp_path, world):
             assert np.array_equal(z[kind + "_joins"], ref.joins), "join order differs on rank %d (%s)" % (r, kind)
             assert z[kind + "_bl"].tobytes() == ref.branchlength.tobytes()
             assert np.array_equal(z[kind + "_lth"], ref.leaf_top_hits)
+            if kind == "tiny":
+                continue
             # the data path really crossed ranks: one exchange per seed, at least two per refresh (out-distances, one-vs-all;
             # the list merge when there are lists), the initial out-distances
             assert int(z[kind + "_exchanges"]) > ref.stats["nSeeds"] + 2 * int(z[kind + "_refresh"])
@@ -144,3 +150,35 @@ def test_one_tree_sharded_over_two_ranks(tmp_path):
 
 def test_one_tree_sharded_over_three_ranks(tmp_path):
     _run_sharded(tmp_path, 3)        # uneven shares: list chunks and strided slots that do not divide
+
+
+def _threshold_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ["VFT_SHARD_MIN"] = "150"      # some sweeps of this tree reach 150 units per rank, most do not: both paths in one run
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import replay
+    from veryfasttree_b200 import api, dist as vdist
+    lib = api.load(replay.ORACLE_LIB)
+    codes, A, prec, tables = _sharded_case("nt")
+    vdist.init_sharded_host(lib)
+    tree = api.nj_build(codes, A, prec, lib=lib, tables=tables, host_threads=1)
+    info = lib.dist_info()
+    lib.dist_finalize()
+    np.savez(os.path.join(out_dir, "t%d.npz" % rank), joins=tree.joins, bl=tree.branchlength, exchanges=info["exchanges"])
+    dist.destroy_process_group()
+
+
+def test_sharding_threshold_mixes_sharded_and_replicated_sweeps(tmp_path):
+    """The default policy shards a sweep only when every rank's share is large enough; the decision is taken from replicated
+    state, so the ranks stay in step whatever mix results."""
+    import replay
+    from veryfasttree_b200 import api
+    replay.ensure_oracle_built()
+    mp.spawn(_threshold_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    lib = api.load(replay.ORACLE_LIB)
+    codes, A, prec, tables = _sharded_case("nt")
+    ref = api.nj_build(codes, A, prec, lib=lib, tables=tables, host_threads=1)
+    for r in range(2):
+        z = np.load(tmp_path / ("t%d.npz" % r))
+        assert np.array_equal(z["joins"], ref.joins) and z["bl"].tobytes() == ref.branchlength.tobytes()
+        assert 0 < int(z["exchanges"]) < ref.stats["nSeeds"] + 3 * ref.stats["nRefreshTopHits"]      # some, not all
