@@ -10,11 +10,16 @@
 // Kernels (the ordered accumulation they share is in vft_device.cuh):
 //   k_eval / k_eval_wide  candidate lists + lazy out-distances (transferBestHits / uniqueBestHits / getBestFromTopHits):
 //                         up to R pairs per warp, or one CTA per pair for the per-join lists of long alignments
-//   k_one_vs_all_*        query vs every active node + criterion -> 64-bit sort keys   (setBestHit)
+//   k_sweep20 (vft_sweep.cuh)  the three all-candidate sweeps of the 20-state matrix mode (setBestHit, the all-node out-distances,
+//                         the list merges of a refresh): per-query tables, producer warps + a consumer warp per 32 candidates
+//   k_one_vs_all_*        query vs every active node + criterion -> 64-bit sort keys   (setBestHit; the other modes)
 //   k_topk_select         radix select + bitonic sort: the K best in the reference's psort order
 //   k_merge_prep/finish   the m list merges of a top-hits refresh (vft_tophits_merge)
 //   k_out_distance_all    profileDist(node, out-profile) + the setOutDistance algebra, every active node
-//   k_average             averageProfile (+ fused updateOutProfile) + self distance of the new node
+//   k_average             averageProfile (+ fused updateOutProfile); the self distance of the new node is added up here, or --
+//                         deferred -- by an extra CTA of the next k_eval_wide / by k_self_sum;  k_average_batch: recomputeProfiles
+//   k_peer_allgather, k_rank_merge, k_scatter_outdist (vft_dist.cuh)   one tree sharded over GPUs: the exchange step
+//   k_ingest, k_ingest_gather (vft_ingest.cuh)   character decoding + row hashes + compaction of the distinct rows
 //   k_outprofile_*        updateOutProfile / outProfile + setCodeDist
 //   k_pair_loglk, k_posterior   pairLogLk / posteriorProfile (vft_ml.cuh): one tree level, or one lock-step round of the
 //                         branch-length / NNI optimisers (ml_opt.cpp), per launch; 1-8 warps per (pair, length) item
