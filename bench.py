@@ -393,7 +393,7 @@ def main():
                                        % (args.gpus, {"peer": "NVLink peer memory (one push-and-wait kernel per exchange)", "nccl": "ncclAllGather",
                                                       "host": "a host all-gather"}.get(dist_info["mode"], dist_info["mode"]),
                                           dist_info["exchanges"] // max(1, args.warmup + args.steps + 1),
-                                          dist_info["bytes"] / 1e6 / max(1, args.warmup + args.steps + 1))) if sharded else "replicas x%d" % args.gpus,
+                                          dist_info["bytes"] / 1e6 / max(1, args.warmup + args.steps + 1))) if sharded else ("single GPU" if args.gpus == 1 else "replicas x%d: one independent tree per GPU" % args.gpus),
                        "trees_identical_across_ranks": trees_identical, "host_threads_per_rank": host_threads,
                        "join_loop": "device-resident" if ptree.stats["counters"]["nKernel"][11] else "host-driven",
                        "l2": "flushed between steps (256 MiB write)",
