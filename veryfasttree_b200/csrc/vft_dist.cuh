@@ -165,7 +165,11 @@ __global__ void k_rank_merge(const char *__restrict__ base, size_t stride, int W
 int dist_release_buffers() {
     DistGroup &g = g_dist;
     if (g.xbuf) {
-        for (int w = 0; w < g.world; w++) if (w != g.rank && g.peers.data[w]) cudaIpcCloseMemHandle(g.peers.data[w]);
+        for (int w = 0; w < g.world; w++) if (w != g.rank && g.peers.data[w]) { cudaIpcCloseMemHandle(g.peers.data[w]); g.peers.data[w] = nullptr; }
+        if (g.comm && g.send && g.recv) {             // nobody frees a buffer a peer may still have mapped (finalize is collective)
+            g.api.AllGather(g.send, g.recv, 16, ncclUint8, g.comm, (cudaStream_t) 0);
+            cudaDeviceSynchronize();
+        }
         cudaFree(g.xbuf);
         g.xbuf = nullptr; g.slotBytes = 0;
     }
@@ -181,7 +185,9 @@ int dist_reserve(cudaStream_t stream, size_t bytes) {
     DistGroup &g = g_dist;
     bytes = (bytes + 15) & ~(size_t) 15;
     if (bytes > g.sendCap) {
-        size_t cap = (size_t) 1 << 20;
+        // 1 MB to start with (VFT_XBUF_INIT_KB: a smaller start, so that the tests reach the growth path), doubled as needed
+        static const size_t initCap = [] { const char *e = std::getenv("VFT_XBUF_INIT_KB"); const long kb = e ? std::atol(e) : 1024; return (size_t) (kb >= 4 ? kb : 4) << 10; }();
+        size_t cap = initCap;
         while (cap < bytes) cap <<= 1;
         CK(cudaStreamSynchronize(stream));
         if (g.send) cudaFree(g.send);
@@ -209,7 +215,11 @@ int dist_reserve(cudaStream_t stream, size_t bytes) {
         // (re)build the peer-mapped exchange buffer: local allocation, handles all-gathered through NCCL, peers opened
         CK(cudaStreamSynchronize(stream));
         if (g.xbuf) {
-            for (int w = 0; w < g.world; w++) if (w != g.rank && g.peers.data[w]) cudaIpcCloseMemHandle(g.peers.data[w]);
+            // every rank first drops its mappings of the peers' old buffers; only when ALL have done so (a small all-gather as
+            // the barrier) does anybody free the buffer the others had mapped
+            for (int w = 0; w < g.world; w++) if (w != g.rank && g.peers.data[w]) { cudaIpcCloseMemHandle(g.peers.data[w]); g.peers.data[w] = nullptr; }
+            NK(g.api.AllGather(g.send, g.recv, 16, ncclUint8, g.comm, stream));
+            CK(cudaStreamSynchronize(stream));
             cudaFree(g.xbuf); g.xbuf = nullptr;
         }
         const size_t slot = g.sendCap, dataBytes = 2 * (size_t) g.world * slot;
@@ -333,7 +343,7 @@ extern "C" int vft_dist_init(int32_t rank, int32_t world, const void *id128, int
     }
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    rc = dist_reserve(st, 1 << 20);
+    rc = dist_reserve(st, 4096);
     if (rc == VFT_OK) {
         cudaMemcpyAsync(g.send, &ok, 1, cudaMemcpyHostToDevice, st);
         ncclResult_t r = g.api.AllGather(g.send, g.recv, 16, ncclUint8, g.comm, st);
@@ -345,7 +355,7 @@ extern "C" int vft_dist_init(int32_t rank, int32_t world, const void *id128, int
             for (int w = 0; w < world; w++) allOk = allOk && all[(size_t) w * 16] == 1;
             if (allOk) {
                 g.mode = DIST_PEER;
-                rc = dist_reserve(st, 1 << 20);                 // builds and maps the exchange buffer
+                rc = dist_reserve(st, 4096);                    // builds and maps the exchange buffer
                 if (rc != VFT_OK) { cudaGetLastError(); g.mode = DIST_NCCL; }
                 // the mapping must have worked everywhere
                 unsigned char ok2 = rc == VFT_OK ? 1 : 0;
