@@ -73,6 +73,7 @@ WORKLOADS = {
 # "traffic" side of the roofline, which cannot be measured inside this script
 NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "VeryFastTree")
+REF_BIN512 = os.path.join(ROOT, "oracle", "_ref", "VeryFastTree_avx512")      # the same sources with the reference's -ext AVX512 path compiled in
 PARITY_PREFIX = 3000
 
 
@@ -119,15 +120,16 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def run_reference(wl, chars, threads: int, timeout: float = 1500, want_tree: bool = False, extra=None):
+def run_reference(wl, chars, threads: int, timeout: float = 1500, want_tree: bool = False, extra=None, binary=None):
     """Times the unmodified reference on `chars`; returns (seconds of the NJ+TopHits phase, nUnique[, NJ tree])."""
     none = (None, None, None) if want_tree else (None, None)
-    if not os.path.exists(REF_BIN):
+    binary = binary or REF_BIN
+    if not os.path.exists(binary):
         return none
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, "a.fa")
         synth.write_fasta(fa, chars)
-        args = [REF_BIN] + list(extra if extra is not None else wl["ref_flags"]) + ["-threads", str(threads), "-noml", "-nni", "0", "-spr", "0",
+        args = [binary] + list(extra if extra is not None else wl["ref_flags"]) + ["-threads", str(threads), "-noml", "-nni", "0", "-spr", "0",
                                                                                    "-nosupport", "-log", os.path.join(td, "log"), fa]
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         try:
@@ -161,6 +163,16 @@ def calibrate_threads(wl, chars, host_cores: int):
     if not seen:
         return host_cores, {}
     return min(seen, key=seen.get), seen
+
+
+def avx512_variant(wl, chars, threads):
+    """The reference's AVX-512 path ("AVX2/AVX512 OpenMP build"), same sources built with -mavx512*, one run at
+    the calibrated thread count.  Returns (seconds or None, flags)."""
+    if wl["kind"] != "aa" or not os.path.exists(REF_BIN512):
+        return None, None
+    flags = [f if f != "AVX2" else "AVX512" for f in wl["ref_flags"]]
+    t, _ = run_reference(wl, chars, threads, extra=flags, binary=REF_BIN512)
+    return t, flags
 
 
 def parity_check(wl, chars, lib, device):
@@ -224,9 +236,12 @@ def main():
         workloads = [make_workload(wl, 1, n_taxa)]
         threads, seen = calibrate_threads(wl, workloads[0], host_cores)
         per_proc = threads
+        t512, flags512 = avx512_variant(wl, workloads[0], per_proc)
+        use512 = t512 is not None and seen and t512 < seen[threads]          # the faster of the two builds is the reference arm
+        ref_binary, ref_flags = (REF_BIN512, flags512) if use512 else (REF_BIN, wl["ref_flags"])
         times, taxa = [], 0
         for it in range(args.warmup + args.steps):
-            t, nu = run_reference(wl, workloads[0], per_proc)
+            t, nu = run_reference(wl, workloads[0], per_proc, extra=ref_flags, binary=ref_binary)
             if t is None:
                 emit({"impl": "reference", "unavailable": "reference binary failed to run"})
                 return 0
@@ -235,16 +250,18 @@ def main():
                 taxa = nu
         total = sum(times)
         value = taxa * len(times) / total
-        flags = " ".join(wl["ref_flags"])
+        flags = " ".join(ref_flags)
         line = {"impl": "reference", "metric": metric, "value": value, "unit": "taxa/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-                "higher_is_better": True, "scaling": "strong" if args.multi == "sharded" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if (args.multi == "sharded" and args.gpus > 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "taxa": int(taxa // n_rep), "columns": wl["pos"],
                            "parallelism": "one tree per step at all host cores (the repo arm at --gpus N shards this same tree over N GPUs; with --multi replicas it builds N trees, "
                                           "and the CPU's aggregate taxa/s does not depend on how many trees are queued)",
                            "reference_flags": "%s -threads %d -noml -nni 0 -spr 0 -nosupport%s" % (
                                flags, per_proc, " (nt fp32: the reference silently runs its SSE3 path)" if wl["kind"] == "nt" else ""),
-                           "reference_build": "oracle/_ref: the unmodified sources, g++ -O3 -mavx2 (no FMA; the parity oracle)",
+                           "reference_build": ("oracle/_ref/VeryFastTree_avx512: the unmodified sources, g++ -O3 -mavx2 -mavx512{f,bw,dq,vl}" if use512
+                                               else "oracle/_ref/VeryFastTree: the unmodified sources, g++ -O3 -mavx2 (no FMA; the parity oracle)"),
+                           "avx512_build_s": None if t512 is None else round(t512, 2),
                            "thread_calibration_s": {str(k): round(v, 2) for k, v in seen.items()}, "host_cores": host_cores},
                 "cpu_baseline": {"value": value, "unit": "taxa/s", "cores": per_proc * n_rep, "kind": "reference",
                                  "sample": "the full workload, %d timed runs of the unmodified reference binary; threads = the faster of cores/2 and cores, "
@@ -374,11 +391,13 @@ def main():
     cpu, parity = None, None
     if args.gpus == 1 and not args.skip_cpu:
         threads, seen = calibrate_threads(wl, chars, host_cores)
+        t512, flags512 = avx512_variant(wl, chars, threads) if seen else (None, None)
         if seen:
-            t = seen[threads]
+            t = seen[threads] if t512 is None else min(seen[threads], t512)
             cpu = {"value": n_unique / t, "unit": "taxa/s", "cores": threads, "kind": "reference", "host_cores": host_cores,
                    "sample": "the full workload once per candidate thread count (%d unique taxa x %d columns), unmodified reference binary %s: %s; fastest kept"
-                             % (n_unique, wl["pos"], " ".join(wl["ref_flags"]), ", ".join("-threads %d %.2f s" % kv for kv in sorted(seen.items())))}
+                             % (n_unique, wl["pos"], " ".join(wl["ref_flags"]), ", ".join("-threads %d %.2f s" % kv for kv in sorted(seen.items())))
+                             + ("" if t512 is None else "; the AVX-512 build (%s) at -threads %d: %.2f s" % (" ".join(flags512), threads, t512))}
         else:
             cpu = {"value": None, "unit": "taxa/s", "cores": host_cores, "kind": "reference", "sample": "oracle/_ref/VeryFastTree not available"}
         parity = parity_check(wl, chars, lib, local_rank)
