@@ -162,6 +162,7 @@ def run_reference(wl, chars, threads: int, timeout: float = 1500, want_tree: boo
         args = [binary] + list(extra if extra is not None else wl["ref_flags"]) + ["-threads", str(threads), "-noml", "-nni", "0", "-spr", "0",
                                                                                    "-nosupport", "-log", os.path.join(td, "log"), fa]
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        env.pop("OMP_WAIT_POLICY", None)      # (set above for the repo arm's ranks only: the reference runs with its own defaults at every N)
         try:
             p = subprocess.run(args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env, timeout=timeout)
         except subprocess.TimeoutExpired:
