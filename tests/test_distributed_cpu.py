@@ -100,7 +100,7 @@ def _sharded_case(kind):
 
 def _sharded_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    os.environ["VFT_SHARD_MIN"] = "1"        # shard every sweep, however small (the default shards only shares of >= 8192 units)
+    os.environ["VFT_SHARD_MIN"] = "1"        # shard every sweep, however small (the default shards only shares of >= 4096 units)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import replay
     from veryfasttree_b200 import api, dist as vdist

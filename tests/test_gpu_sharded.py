@@ -48,7 +48,7 @@ def _case(kind):
 
 def _worker(rank, world, port, out_dir, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    os.environ["VFT_SHARD_MIN"] = "1"        # shard every sweep, however small (the default shards only shares of >= 8192 units)
+    os.environ["VFT_SHARD_MIN"] = "1"        # shard every sweep, however small (the default shards only shares of >= 4096 units)
     os.environ["VFT_XBUF_INIT_KB"] = "4"     # start with a 4 KB exchange buffer: the growth path (re-mapping the peers) runs too
     if mode == "nccl":
         os.environ["VFT_EXCHANGE"] = "nccl"

@@ -2025,7 +2025,7 @@ static int ensure_active(vft_ctx *c) {
 // that: half the candidates are not half the time) -- otherwise every rank evaluates all of it, with no communication.  The
 // decision depends only on replicated state (the number of active nodes / request slots), so every rank takes the same one.
 static inline int64_t shard_min() {
-    static const int64_t v = [] { const char *e = std::getenv("VFT_SHARD_MIN"); const long x = e ? std::atol(e) : 8192; return (int64_t) (x > 0 ? x : 1); }();
+    static const int64_t v = [] { const char *e = std::getenv("VFT_SHARD_MIN"); const long x = e ? std::atol(e) : 4096; return (int64_t) (x > 0 ? x : 1); }();
     return v;
 }
 static inline int shard_world(const vft_ctx *c, int64_t units = -1) {
