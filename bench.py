@@ -43,6 +43,23 @@ import os
 # not land on stdout next to the JSON line.  Both are read when the libraries load, so they are set first.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     os.environ["OMP_WAIT_POLICY"] = "PASSIVE"
+
+
+def _bind_openmp():
+    """The step is bound by ONE host thread (the join loop) plus short OpenMP bursts (the refreshes): threads that stay on their
+    cores are worth 3 % of the step on one GPU (measured: 2.23 s -> 2.16 s with OMP_PLACES=cores).  With one rank per GPU a per-rank
+    slice of the CPUs measured slightly WORSE than no binding (2.26 s vs 2.23 s at N=2), so the ranks stay unbound.  Not applied
+    when the caller has set OMP_PROC_BIND / OMP_PLACES, and never passed on to the reference's processes."""
+    if "OMP_PROC_BIND" in os.environ or "OMP_PLACES" in os.environ or os.environ.get("VFT_BENCH_BIND", "1") == "0":
+        return
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        return
+    os.environ["OMP_PLACES"] = "cores"
+    os.environ["OMP_PROC_BIND"] = "true"
+    os.environ["VFT_BENCH_BOUND"] = "1"
+
+
+_bind_openmp()
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
 import re
@@ -163,6 +180,8 @@ def run_reference(wl, chars, threads: int, timeout: float = 1500, want_tree: boo
                                                                                    "-nosupport", "-log", os.path.join(td, "log"), fa]
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         env.pop("OMP_WAIT_POLICY", None)      # (set above for the repo arm's ranks only: the reference runs with its own defaults at every N)
+        if env.pop("VFT_BENCH_BOUND", None):
+            env.pop("OMP_PLACES", None); env.pop("OMP_PROC_BIND", None)
         try:
             p = subprocess.run(args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env, timeout=timeout)
         except subprocess.TimeoutExpired:
@@ -445,6 +464,7 @@ def main():
                                           dist_info["exchanges"] // max(1, args.warmup + args.steps + 1),
                                           dist_info["bytes"] / 1e6 / max(1, args.warmup + args.steps + 1))) if sharded else ("single GPU" if args.gpus == 1 else "replicas x%d: one independent tree per GPU" % args.gpus),
                        "trees_identical_across_ranks": trees_identical, "host_threads_per_rank": host_threads,
+                       "openmp_binding": os.environ.get("OMP_PLACES") if os.environ.get("OMP_PROC_BIND") else None,
                        "join_loop": "device-resident" if ptree.stats["counters"]["nKernel"][11] else "host-driven",
                        "l2": "flushed between steps (256 MiB write)",
                        "arithmetic": "f32 storage, f64 accumulation of top/denom and criteria -- the reference's own mix (SURVEY 9.1)"},
