@@ -1712,7 +1712,7 @@ extern "C" int vft_profile_average_batch(vft_ctx *c, int64_t n, const int64_t *o
     if (n == 0) return VFT_OK;
     bind_device(c);
     int rc = ensure_pinned(c, (size_t) n * 12); if (rc) return rc;
-    rc = ensure_lists(c, n); if (rc) return rc;
+    rc = ensure_lists(c, (3 * n + 1) / 2 + 1); if (rc) return rc;      // three int32 per item in the 8-byte-per-entry list buffer
     int32_t *h = (int32_t *) c->h_in;
     for (int64_t k = 0; k < n; k++) {
         // items of one call must be independent: every input row is a leaf or an internal row that is not an output of the call
