@@ -29,6 +29,8 @@
  *     m = sqrt(N) top hits (K = 2m, lists <= 3m) that is N <~ 1.8 million taxa
  *   - vft_sh_support_batch: nPos <= 8 500 (the quartet's 3 x nPos site table in shared memory)
  *   - NJ driver: no topological constraints, no -slow, no 2nd-level top hits (-fastest)
+ *   - vft_dist_*: one node, at most 16 ranks (one process per GPU); every rank must make the same sequence of calls
+ *   - vft_ingest: rows travel in chunks of ~256 MB of text; nPos >= 1, no per-row terminators
  *
  * Arithmetic contract: results are bit-identical to the reference's "-mavx2" (no FMA)
  * build run with `-threads 1` -- same expression types (P vs double), same evaluation order,
